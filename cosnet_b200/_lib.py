@@ -1,0 +1,64 @@
+"""ctypes binding of the C ABI in include/coattn_b200.h (libcoattn_b200.so, built in-tree).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcoattn_b200.so")
+ABI_VERSION = 1
+
+_lock = threading.Lock()
+_lib = None
+
+_vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+
+# name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
+SIGNATURES = {
+    "coattn_b200_abi_version": (_i, []),
+    "coattn_b200_strerror": (ctypes.c_char_p, [_i]),
+    "coattn_workspace_bytes": (_i64, [_i, _i, _i, _i]),
+    "coattn_workspace_segment": (_i, [ctypes.c_char_p, _i, _i, _i, _i, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "coattn_forward": (_i, [_vp] * 10 + [_i64, _i, _i, _i, _i, _vp]),
+    "coattn_stage_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "coattn_stage_project": (_i, [_vp, _i64, _i, _i, _i, _i, _vp]),
+    "coattn_stage_attend": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "coattn_stage_gate": (_i, [_vp] * 7 + [_i, _i, _i, _i, _vp]),
+}
+
+
+class CoattnError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise CoattnError(
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU / eager fallback for the co-attention path)")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            got = lib.coattn_b200_abi_version()
+            if got != ABI_VERSION:
+                raise CoattnError(f"libcoattn_b200 ABI {got} != expected {ABI_VERSION}: rebuild")
+            _lib = lib
+    return _lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = load().coattn_b200_strerror(code).decode()
+        raise CoattnError(f"{what} failed with code {code}: {msg}")

@@ -1,0 +1,87 @@
+"""Host-side operator for the co-attention block (torch is only used for memory and streams).
+
+`coattention(v_a, v_b, weight, gate_weight, gate_bias)` replaces the inline block of the reference
+forward (rgbd_segmentation_RAA.py:150-187 for RGB, :204-238 for depth) and returns the two concat
+tensors that feed `reduce_channels_A/B` (:188-189) / `depth_reduce_channels` (:239-241).
+"""
+from __future__ import annotations
+
+import threading
+
+import torch
+
+from . import _lib
+
+_ws_lock = threading.Lock()
+_ws_cache = {}  # (device index) -> uint8 tensor, grown on demand; one per device (DataParallel replicas)
+
+
+def workspace_bytes(n: int, c: int, h: int, w: int) -> int:
+    r = _lib.load().coattn_workspace_bytes(n, c, h, w)
+    if r < 0:
+        _lib.check(int(r), "coattn_workspace_bytes")
+    return int(r)
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    with _ws_lock:
+        buf = _ws_cache.get(key)
+        if buf is None or buf.numel() < nbytes + 1024:
+            buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            _ws_cache[key] = buf
+    return buf
+
+
+def _aligned_ptr(buf: torch.Tensor) -> int:
+    p = buf.data_ptr()
+    return (p + 1023) // 1024 * 1024
+
+
+def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
+    if not (v_a.is_cuda and v_b.is_cuda):
+        raise _lib.CoattnError("co-attention runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+    if v_a.shape != v_b.shape or v_a.dim() != 4:
+        raise ValueError(f"expected two [N, C, H, W] feature maps of equal shape, got {tuple(v_a.shape)} / {tuple(v_b.shape)}")
+    if v_a.dtype != torch.float32 or v_b.dtype != torch.float32:
+        raise TypeError("features must be float32 (the reference encoders emit fp32, deeplabv3_encoder.py:80-82)")
+    n, c, h, w = v_a.shape
+    if weight.shape != (c, c):
+        raise ValueError(f"weight must be [{c}, {c}], got {tuple(weight.shape)}")
+    if gate_weight.numel() != c:
+        raise ValueError(f"gate weight must have {c} elements, got {tuple(gate_weight.shape)}")
+    if gate_bias is not None and gate_bias.numel() != 1:
+        raise ValueError("gate bias must have one element")
+    return n, c, h, w
+
+
+def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None):
+    """Runs the four CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L]."""
+    n, c, h, w = _check_inputs(v_a, v_b, weight, gate_weight, gate_bias)
+    lib = _lib.load()
+    dev = v_a.device
+    with torch.cuda.device(dev):
+        v_a = v_a.contiguous()
+        v_b = v_b.contiguous()
+        wt = weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+        gw = gate_weight.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
+        gb = None if gate_bias is None else gate_bias.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
+        cat_a = torch.empty((n, 2 * c, h, w), dtype=torch.float32, device=dev)
+        cat_b = torch.empty((n, 2 * c, h, w), dtype=torch.float32, device=dev)
+        z = torch.empty((2, n, c, h * w), dtype=torch.float32, device=dev)
+        lse = torch.empty((2, n, h * w), dtype=torch.float32, device=dev)
+        nbytes = workspace_bytes(n, c, h, w)
+        ws = _workspace(dev, nbytes)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
+                                  None if gb is None else gb.data_ptr(), cat_a.data_ptr(), cat_b.data_ptr(),
+                                  z.data_ptr(), lse.data_ptr(), _aligned_ptr(ws), nbytes, n, c, h, w, stream)
+        _lib.check(code, "coattn_forward")
+    return cat_a, cat_b, z, lse
+
+
+def coattention(v_a, v_b, weight, gate_weight, gate_bias=None):
+    """Drop-in for rgbd_segmentation_RAA.py:150-187: returns (cat_a, cat_b), each [N, 2C, H, W]."""
+    cat_a, cat_b, _, _ = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias)
+    return cat_a, cat_b

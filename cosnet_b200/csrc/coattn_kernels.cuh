@@ -1,0 +1,562 @@
+// sm_100a kernels of the co-attention hot path (reference: rgbd_segmentation_RAA.py:150-187 / :204-238).
+//
+//   prep_kernel     fp32 NCHW features -> bf16 operands in both layouts, zero padded to Lp   (:154-158)
+//   project_kernel  Qt = At * W^T on tcgen05 (the nn.Linear of :159)                          (:159)
+//   attend_kernel   fused affinity + softmax + attend, flash style, S never leaves the SM     (:160-170)
+//   gate_kernel     1x1 gate conv + sigmoid + scale + concat with the original features       (:177-187)
+//
+// Notation: per sample A = V_a [C, L], B = V_b [C, L] (L = H'W' contiguous), Q = W A.
+//   S[i,j]   = sum_c Q[c,i] B[c,j]
+//   Z_a[:,i] = sum_j B[:,j] softmax_j(S[i,:])[j]      (pass 0: queries Q,  keys B, values B)
+//   Z_b[:,j] = sum_i A[:,i] softmax_i(S[:,j])[i]      (pass 1: queries B,  keys Q, values A)
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+
+namespace coattn {
+
+constexpr int kC = 256;       // channels (all_channel of the reference ctor, :22)
+constexpr int kLPad = 128;    // spatial padding granule of the bf16 workspace
+
+// ==============================================================================================
+// prep: cast + transpose + pad
+// ==============================================================================================
+// src  : fp32 [C][L]              (one sample of V_a or V_b)
+// x16  : bf16 [C][Lp]             same orientation (K-major "values" operand of the attend GEMM)
+// xt   : bf16 [Lp][C]             transposed       (K-major "queries/keys" operand of the affinity GEMM)
+constexpr int kPrepTileL = 64;
+constexpr int kPrepThreads = 256;
+constexpr int kPrepStride = kC + 2;  // bf16 elements; 129 words -> conflict-free column writes
+
+struct PrepParams {
+  const float* va;   // [N][C][L]
+  const float* vb;   // [N][C][L]
+  __nv_bfloat16* at;   // [N][Lp][C]
+  __nv_bfloat16* bt;   // [N][Lp][C]
+  __nv_bfloat16* a16;  // [N][C][Lp]
+  __nv_bfloat16* b16;  // [N][C][Lp]
+  int L, Lp;
+};
+
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepParams p) {
+  __shared__ __align__(16) __nv_bfloat16 tile[kPrepTileL * kPrepStride];
+  const int n = blockIdx.y >> 1;
+  const int which = blockIdx.y & 1;  // 0: A, 1: B
+  const int l0 = blockIdx.x * kPrepTileL;
+  const float* src = (which ? p.vb : p.va) + (size_t)n * kC * p.L;
+  __nv_bfloat16* x16 = (which ? p.b16 : p.a16) + (size_t)n * kC * p.Lp;
+  __nv_bfloat16* xt = (which ? p.bt : p.at) + (size_t)n * p.Lp * kC;
+
+  const int tl = threadIdx.x & 63;   // position within the tile
+  const int tc = threadIdx.x >> 6;   // 0..3
+  const int l = l0 + tl;
+  const bool valid = l < p.L;
+#pragma unroll 8
+  for (int k = 0; k < kC / 4; ++k) {
+    const int c = tc + 4 * k;
+    const float v = valid ? __ldg(src + (size_t)c * p.L + l) : 0.0f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    tile[tl * kPrepStride + c] = b;
+    // pack neighbouring positions: even lanes store 4 bytes
+    const unsigned short mine = __bfloat16_as_ushort(b);
+    const unsigned short next = __shfl_down_sync(0xffffffffu, mine, 1);
+    if ((tl & 1) == 0) {
+      *reinterpret_cast<uint32_t*>(x16 + (size_t)c * p.Lp + l) = (uint32_t)mine | ((uint32_t)next << 16);
+    }
+  }
+  __syncthreads();
+  const int cp = threadIdx.x & 127;  // channel pair
+  const int r0 = threadIdx.x >> 7;   // 0..1
+#pragma unroll 8
+  for (int k = 0; k < kPrepTileL / 2; ++k) {
+    const int r = r0 + 2 * k;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&tile[r * kPrepStride + 2 * cp]);
+    *reinterpret_cast<uint32_t*>(xt + (size_t)(l0 + r) * kC + 2 * cp) = w;
+  }
+}
+
+// fp32 [C][C] -> bf16 [C][C]
+__global__ void cast_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w16, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w16[i] = __float2bfloat16_rn(w[i]);
+}
+
+// ==============================================================================================
+// shared role layout of the two tcgen05 kernels: warps 0-3 own TMEM lane quadrants 0-3
+// (softmax / epilogue), warp 4 = TMA producer, warp 5 = MMA issuer + TMEM allocator.
+// ==============================================================================================
+constexpr int kNumThreads = 192;
+constexpr int kProducerWarp = 4;
+constexpr int kMmaWarp = 5;
+
+__device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
+  const uint32_t a = smem_u32(p);
+  return p + ((1024u - (a & 1023u)) & 1023u);
+}
+
+// ==============================================================================================
+// project: Qt[n][i][co] = sum_ci At[n][i][ci] * W[co][ci]          (bf16 x bf16 -> fp32 -> bf16)
+// one CTA per 128-row tile; A tile and the whole W live in shared memory (64 KB + 128 KB)
+// ==============================================================================================
+constexpr int kProjSmemBytes = 64 * 1024 + 128 * 1024 + 1024 /*align slack*/ + 64 /*barriers*/;
+
+struct ProjectParams {
+  __nv_bfloat16* qt;  // [N][Lp][C]
+  int Lp;
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+project_kernel(const __grid_constant__ CUtensorMap tmap_at,  // [N*Lp][C], box {64, 128}
+               const __grid_constant__ CUtensorMap tmap_w,   // [C][C],    box {64, 256}
+               ProjectParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint8_t* sA = smem;               // 4 k-blocks x [128 rows x 128 B]
+  uint8_t* sW = smem + 64 * 1024;   // 4 k-blocks x [256 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 192 * 1024);
+  uint64_t* ab_full = bars + 0;
+  uint64_t* d_full = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.y;
+  const int row0 = n * p.Lp + blockIdx.x * 128;
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_at);
+    tma_prefetch_desc(&tmap_w);
+    mbar_init(ab_full, 1);
+    mbar_init(d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(ab_full, 192 * 1024);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        tma_load_2d(sA + kb * 16384, &tmap_at, ab_full, kb * 64, row0);
+        tma_load_2d(sW + kb * 32768, &tmap_w, ab_full, kb * 64, 0);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      mbar_wait(ab_full, 0, 100);
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc_bf16(128, 256);
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        const uint64_t ad = make_sdesc_k_sw128(smem_u32(sA + (kk >> 2) * 16384 + (kk & 3) * 32));
+        const uint64_t bd = make_sdesc_k_sw128(smem_u32(sW + (kk >> 2) * 32768 + (kk & 3) * 32));
+        umma_ss(tmem, ad, bd, idesc, kk > 0);
+      }
+      umma_commit(d_full);
+    }
+  } else {
+    // epilogue: thread = one output row
+    mbar_wait(d_full, 0, 101);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    __nv_bfloat16* dst = p.qt + (size_t)(row0 + row) * kC;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(taddr + ch * 32, v);
+      tmem_ld_wait();
+      uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+        o.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+        o.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+        o.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+        d4[q] = o;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ==============================================================================================
+// attend: persistent flash-style kernel over work items (sample n, pass p, 128-row query tile)
+// ==============================================================================================
+constexpr int kBM = 128;      // query rows per tile (TMEM lanes)
+constexpr int kBN = 64;       // key/value positions per step
+constexpr int kKStages = 2;
+constexpr int kVStages = 2;
+constexpr int kQBytes = kBM * kC * 2;      // 64 KB : 4 k-blocks x [128 rows x 128 B]
+constexpr int kKBytes = kBN * kC * 2;      // 32 KB : 4 k-blocks x [ 64 rows x 128 B]
+constexpr int kVBytes = kC * kBN * 2;      // 32 KB : [256 rows x 128 B]
+constexpr int kAttendSmemBytes = kQBytes + kKStages * kKBytes + kVStages * kVBytes + 1024 + 256;
+constexpr uint32_t kTmemColsO = 0;         // O accumulator: 256 fp32 columns
+constexpr uint32_t kTmemColsS = 256;       // two S/P buffers of kBN columns
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: O is only rescaled when the row max jumps by > 2^8
+
+struct AttendParams {
+  float* z;     // [2][N][C][L]  raw attended features (pass 0: Z_a, pass 1: Z_b)
+  float* lse;   // [2][N][L]     log-sum-exp of each softmax row (natural log)
+  int N, L, Lp;
+  int q_tiles;   // ceil(L / 128)
+  int kv_tiles;  // ceil(L / 64)
+  int num_items; // 2 * N * q_tiles
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  box {64, 128}
+              const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  box {64, 64}
+              const __grid_constant__ CUtensorMap tmap_v,  // VV [2*N*C][Lp],  box {64, 256}
+              AttendParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kQBytes;
+  uint8_t* sV = sK + kKStages * kKBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kVStages * kVBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;                 // [kKStages]
+  uint64_t* k_empty = k_full + kKStages;       // [kKStages]
+  uint64_t* v_full = k_empty + kKStages;       // [kVStages]
+  uint64_t* v_empty = v_full + kVStages;       // [kVStages]
+  uint64_t* s_full = v_empty + kVStages;       // [2]
+  uint64_t* p_full = s_full + 2;               // [2]
+  uint64_t* o_full = p_full + 2;               // one completion per PV step
+  uint64_t* o_free = o_full + 1;               // softmax warps drained O of the item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < kKStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
+    for (int s = 0; s < kVStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(p_full + b, 128); }
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 128);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int T = p.kv_tiles;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0, kcnt = 0, vcnt = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int qt = item % p.q_tiles;
+        const int np = item / p.q_tiles;
+        const int pass = np & 1;
+        const int n = np >> 1;
+        const int qrow0 = ((1 - pass) * p.N + n) * p.Lp + qt * kBM;
+        const int krow0 = (pass * p.N + n) * p.Lp;
+        const int vrow0 = (pass * p.N + n) * kC;
+        mbar_wait(q_empty, (it & 1) ^ 1, 1);
+        mbar_arrive_expect_tx(q_full, kQBytes);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sQ + kb * (kBM * 128), &tmap_q, q_full, kb * 64, qrow0);
+        for (int j = 0; j < T; ++j) {
+          {
+            const uint32_t s = kcnt % kKStages, ph = (kcnt / kKStages) & 1;
+            mbar_wait(k_empty + s, ph ^ 1, 2);
+            mbar_arrive_expect_tx(k_full + s, kKBytes);
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb)
+              tma_load_2d(sK + s * kKBytes + kb * (kBN * 128), &tmap_k, k_full + s, kb * 64, krow0 + j * kBN);
+            ++kcnt;
+          }
+          {
+            const uint32_t s = vcnt % kVStages, ph = (vcnt / kVStages) & 1;
+            mbar_wait(v_empty + s, ph ^ 1, 3);
+            mbar_arrive_expect_tx(v_full + s, kVBytes);
+            tma_load_2d(sV + s * kVBytes, &tmap_v, v_full + s, j * kBN, vrow0);
+            ++vcnt;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kBM, kBN);
+      constexpr uint32_t idesc_o = make_idesc_bf16(kBM, kC);
+      uint32_t it = 0, kcnt = 0, vcnt = 0;
+      uint32_t pphase[2] = {0, 0};
+      const uint32_t tO = tmem + kTmemColsO;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        auto issue_s = [&](int j) {
+          const uint32_t s = kcnt % kKStages, ph = (kcnt / kKStages) & 1;
+          mbar_wait(k_full + s, ph, 10);
+          tc_fence_after();
+          const uint32_t tS = tmem + kTmemColsS + (uint32_t)(j & 1) * kBN;
+#pragma unroll
+          for (int kk = 0; kk < kC / 16; ++kk) {
+            const uint64_t ad = make_sdesc_k_sw128(smem_u32(sQ + (kk >> 2) * (kBM * 128) + (kk & 3) * 32));
+            const uint64_t bd =
+                make_sdesc_k_sw128(smem_u32(sK + s * kKBytes + (kk >> 2) * (kBN * 128) + (kk & 3) * 32));
+            umma_ss(tS, ad, bd, idesc_s, kk > 0);
+          }
+          umma_commit(k_empty + s);
+          umma_commit(s_full + (j & 1));
+          ++kcnt;
+        };
+        mbar_wait(q_full, it & 1, 11);
+        if (it > 0) mbar_wait(o_free, (it - 1) & 1, 12);
+        tc_fence_after();
+        issue_s(0);
+        for (int j = 0; j < T; ++j) {
+          if (j + 1 < T) issue_s(j + 1);
+          else umma_commit(q_empty);   // every affinity MMA of this item has been issued
+          const int b = j & 1;
+          mbar_wait(p_full + b, pphase[b], 13);
+          pphase[b] ^= 1;
+          const uint32_t s = vcnt % kVStages, ph = (vcnt / kVStages) & 1;
+          mbar_wait(v_full + s, ph, 14);
+          tc_fence_after();
+          const uint32_t tP = tmem + kTmemColsS + (uint32_t)b * kBN;
+#pragma unroll
+          for (int kk = 0; kk < kBN / 16; ++kk) {
+            const uint64_t bd = make_sdesc_k_sw128(smem_u32(sV + s * kVBytes + kk * 32));
+            umma_ts(tO, tP + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(v_empty + s);
+          umma_commit(o_full);
+          ++vcnt;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + drain (1 thread = 1 row)
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t tO = tmem + lane_base + kTmemColsO;
+    uint32_t sphase[2] = {0, 0};
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int qt = item % p.q_tiles;
+      const int np = item / p.q_tiles;
+      const int pass = np & 1;
+      const int n = np >> 1;
+      const int row = qt * kBM + warp * 32 + lane;
+      const uint32_t pv_base = it * (uint32_t)T;
+      float m = -INFINITY, l = 0.0f;
+      for (int j = 0; j < T; ++j) {
+        const int b = j & 1;
+        const uint32_t tS = tmem + lane_base + kTmemColsS + (uint32_t)b * kBN;
+        mbar_wait(s_full + b, sphase[b], 20);
+        sphase[b] ^= 1;
+        tc_fence_after();
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tS, s0);
+        tmem_ld32(tS + 32, s1);
+        tmem_ld_wait();
+        if (j == T - 1) {
+          const int nvalid = p.L - j * kBN;  // >= 1
+          if (nvalid < kBN) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              if (k >= nvalid) s0[k] = 0xff800000u;        // -inf
+              if (32 + k >= nvalid) s1[k] = 0xff800000u;
+            }
+          }
+        }
+        float tmax = __uint_as_float(s0[0]);
+#pragma unroll
+        for (int k = 1; k < 32; ++k) tmax = fmaxf(tmax, __uint_as_float(s0[k]));
+#pragma unroll
+        for (int k = 0; k < 32; ++k) tmax = fmaxf(tmax, __uint_as_float(s1[k]));
+        if (j == 0) {
+          m = tmax;
+        } else {
+          const bool need = (tmax - m) * kLog2e > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = fmaxf(m, tmax);
+            const float scale = fast_exp2((m - m_new) * kLog2e);
+            mbar_wait(o_full, (pv_base + (uint32_t)j - 1u) & 1u, 21);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < kC / 32; ++ch) {
+              uint32_t o[32];
+              tmem_ld32(tO + ch * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * scale);
+              tmem_st32(tO + ch * 32, o);
+            }
+            tmem_st_wait();
+            l *= scale;
+            m = m_new;
+          }
+        }
+        const float neg_m = -m * kLog2e;
+        uint32_t pk[32];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s0[2 * k]), kLog2e, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s0[2 * k + 1]), kLog2e, neg_m));
+          pk[k] = pack_bf16x2(p0, p1);
+          l += bf16lo_to_f32(pk[k]) + bf16hi_to_f32(pk[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s1[2 * k]), kLog2e, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s1[2 * k + 1]), kLog2e, neg_m));
+          pk[16 + k] = pack_bf16x2(p0, p1);
+          l += bf16lo_to_f32(pk[16 + k]) + bf16hi_to_f32(pk[16 + k]);
+        }
+        tmem_st32(tS, pk);   // P (bf16 pairs) overlays the first 32 columns of the S buffer
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full + b);
+      }
+      // drain: Z[c][row] = O[row][c] / l
+      mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, 22);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      const bool valid = row < p.L;
+      float* zcol = p.z + ((size_t)(pass * p.N + n) * kC) * p.L + row;
+#pragma unroll 1
+      for (int ch = 0; ch < kC / 32; ++ch) {
+        uint32_t o[32];
+        tmem_ld32(tO + ch * 32, o);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) zcol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * inv;
+        }
+      }
+      if (valid) p.lse[(size_t)(pass * p.N + n) * p.L + row] = m + __logf(l);
+      tc_fence_before();
+      mbar_arrive(o_free);
+    }
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ==============================================================================================
+// gate: m = sigmoid(g . Z[:,p] + b);  cat[0:C] = Z * m;  cat[C:2C] = V         (:177-187)
+// HBM-bound: 16 L C bytes per (sample, side).  One block = kGatePos positions x all 256 channels;
+// warp w owns channels [32w, 32w+32), lanes run along positions (coalesced, VEC floats each).
+// ==============================================================================================
+constexpr int kGateThreads = 256;
+
+struct GateParams {
+  const float* z;      // [2][N][C][L] raw attended features (side 0: Z_a, side 1: Z_b)
+  const float* v_a;    // [N][C][L] original features of frame A
+  const float* v_b;    // [N][C][L] original features of frame B
+  const float* gate_w; // [C]
+  const float* gate_b; // [1] or nullptr
+  float* cat_a;        // [N][2C][L]
+  float* cat_b;        // [N][2C][L]
+  int N, L;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kGateThreads) gate_kernel(GateParams p) {
+  __shared__ float part[8][32 * VEC];
+  __shared__ float gw[kC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int side = blockIdx.y / p.N;
+  const int n = blockIdx.y - side * p.N;
+  const int pos = (blockIdx.x * 32 + lane) * VEC;
+  gw[threadIdx.x] = p.gate_w[threadIdx.x];
+  __syncthreads();
+  const bool valid = pos < p.L;   // L % VEC == 0 is guaranteed by the launcher
+  const float* z = p.z + (size_t)blockIdx.y * kC * p.L + pos;
+  const float* v = (side ? p.v_b : p.v_a) + (size_t)n * kC * p.L + pos;
+  float* cat = (side ? p.cat_b : p.cat_a) + (size_t)n * 2 * kC * p.L + pos;
+
+  float zr[32][VEC];
+  float dot[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) dot[e] = 0.f;
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int c = warp * 32 + k;
+      if constexpr (VEC == 4) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(z + (size_t)c * p.L));
+        zr[k][0] = t.x; zr[k][1] = t.y; zr[k][2] = t.z; zr[k][3] = t.w;
+      } else {
+        zr[k][0] = __ldcs(z + (size_t)c * p.L);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float g = gw[warp * 32 + k];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) dot[e] = fmaf(g, zr[k][e], dot[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) part[warp][lane * VEC + e] = dot[e];
+  // passthrough copy of the original features while the partial sums settle
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int c = warp * 32 + k;
+      if constexpr (VEC == 4) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(v + (size_t)c * p.L));
+        __stcs(reinterpret_cast<float4*>(cat + (size_t)(kC + c) * p.L), t);
+      } else {
+        __stcs(cat + (size_t)(kC + c) * p.L, __ldcs(v + (size_t)c * p.L));
+      }
+    }
+  }
+  __syncthreads();
+  if (valid) {
+    const float bias = p.gate_b ? __ldg(p.gate_b) : 0.f;
+    float mask[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float t = bias;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w][lane * VEC + e];
+      mask[e] = 1.0f / (1.0f + __expf(-t));
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int c = warp * 32 + k;
+      if constexpr (VEC == 4) {
+        float4 t;
+        t.x = zr[k][0] * mask[0]; t.y = zr[k][1] * mask[1]; t.z = zr[k][2] * mask[2]; t.w = zr[k][3] * mask[3];
+        __stcs(reinterpret_cast<float4*>(cat + (size_t)c * p.L), t);
+      } else {
+        __stcs(cat + (size_t)c * p.L, zr[k][0] * mask[0]);
+      }
+    }
+  }
+}
+
+}  // namespace coattn

@@ -1,0 +1,96 @@
+/*
+ * coattn_b200 -- C ABI of the B200 (sm_100a) co-attention hot path.
+ *
+ * Drop-in boundary for the inline co-attention block of the reference model
+ *   /root/reference/rgbd_segmentation_RAA.py:150-187  (RGB)   and   :204-238 (depth)
+ * i.e. everything between the encoder outputs V_a, V_b and the inputs of reduce_channels_A/B.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the current CUDA device
+ *     unless stated otherwise; the caller owns all buffers (workspace included);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it;
+ *   - functions return 0 on success, a negative COATTN_E_* code for argument errors, or a positive
+ *     cudaError_t value passed through from the runtime.  No exceptions cross this boundary;
+ *   - no global mutable state: safe to call concurrently from several host threads on different
+ *     devices (nn.DataParallel, reference train.py:493).
+ *
+ * Layouts (all row-major / NCHW contiguous, fp32):
+ *   v_a, v_b   [N, 256, H, W]      encoder features of frame A / frame B          (:143-148)
+ *   w          [256, 256]          *_similarity_weights.weight  (out, in)          (:27, :38)
+ *   gate_w     [256]               gate.weight viewed [1,256,1,1]                  (:28, :39)
+ *   gate_b     [1] or NULL         depth_gate.bias; NULL for the bias-free RGB gate
+ *   cat_a/b    [N, 512, H, W]      concat([Z * sigmoid(gate(Z)), V], dim=1)        (:183-187)
+ *   z          [2, N, 256, H*W]    raw attended features, z[0] = Z_a, z[1] = Z_b   (:169-170)
+ *   lse        [2, N, H*W]         natural-log normalisers: lse[0][n][i] = log sum_j exp S[i,j]
+ *                                  (softmax of :165), lse[1][n][j] = log sum_i exp S[i,j] (:164)
+ */
+#ifndef COATTN_B200_H_
+#define COATTN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COATTN_B200_ABI_VERSION 1
+
+enum {
+  COATTN_OK = 0,
+  COATTN_E_NULL = -1,        /* a required pointer is NULL                                  */
+  COATTN_E_SHAPE = -2,       /* n, h or w < 1, or c != 256                                  */
+  COATTN_E_WORKSPACE = -3,   /* workspace too small or not 1024-byte aligned                */
+  COATTN_E_ARCH = -4,        /* current device is not compute capability 10.x (no fallback) */
+  COATTN_E_DRIVER = -5,      /* cuTensorMapEncodeTiled unavailable / failed                 */
+  COATTN_E_ALIGN = -6        /* a tensor pointer is not 16-byte aligned                     */
+};
+
+/* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
+int coattn_b200_abi_version(void);
+
+/* Static, human readable description of a return code of this library. */
+const char* coattn_b200_strerror(int code);
+
+/* Bytes of scratch `coattn_forward` needs for a batch of n pairs of [c, h, w] features. */
+int64_t coattn_workspace_bytes(int n, int c, int h, int w);
+
+/*
+ * Whole hot path for one modality (replaces :150-187 or :204-238):
+ *   prep (bf16 cast/transposes) -> project (Q = W A) -> attend (both softmax axes) -> gate/concat.
+ * z and lse are outputs kept for the backward pass; either may be NULL, in which case they live
+ * in the workspace (z) or are dropped (lse is always computed; NULL routes it to the workspace).
+ */
+int coattn_forward(const float* v_a, const float* v_b, const float* w, const float* gate_w,
+                   const float* gate_b, float* cat_a, float* cat_b, float* z, float* lse,
+                   void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
+                   void* stream);
+
+/* ---- the four stages, exported individually for unit parity tests and per-kernel timing ---- */
+
+/* stage 1 (:154-158): bf16 operands.  Fills the workspace segments At, Bt, A16, B16 and W16. */
+int coattn_stage_prep(const float* v_a, const float* v_b, const float* w, void* workspace,
+                      int64_t workspace_bytes, int n, int c, int h, int w_, void* stream);
+/* stage 2 (:159): Qt = At W^T on the tensor cores. */
+int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
+                         void* stream);
+/* stage 3 (:160-170): fused affinity / dual softmax / attend.  Writes z and lse. */
+int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace_bytes, int n,
+                        int c, int h, int w_, void* stream);
+/* stage 4 (:177-187): gate, sigmoid, scale, concat. */
+int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const float* gate_w,
+                      const float* gate_b, float* cat_a, float* cat_b, int n, int c, int h, int w_,
+                      void* stream);
+
+/*
+ * Debug/test view of the workspace: byte offset and byte size of a named segment
+ * ("at", "bt", "qt", "a16", "b16", "w16", "z", "lse") for the given problem size, so tests can
+ * compare intermediate operands with the oracle.  Returns 0 or COATTN_E_NULL for an unknown name.
+ */
+int coattn_workspace_segment(const char* name, int n, int c, int h, int w_, int64_t* offset,
+                             int64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COATTN_B200_H_ */
