@@ -15,7 +15,9 @@ ABI_VERSION = 1
 _lock = threading.Lock()
 _lib = None
 
-_vp, _i, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+_vp, _i, _i64, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint
+
+FLAG_BF16 = 1  # COATTN_FLAG_BF16
 
 # name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
 SIGNATURES = {
@@ -23,10 +25,10 @@ SIGNATURES = {
     "coattn_b200_strerror": (ctypes.c_char_p, [_i]),
     "coattn_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "coattn_workspace_segment": (_i, [ctypes.c_char_p, _i, _i, _i, _i, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
-    "coattn_forward": (_i, [_vp] * 10 + [_i64, _i, _i, _i, _i, _vp]),
-    "coattn_stage_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
-    "coattn_stage_project": (_i, [_vp, _i64, _i, _i, _i, _i, _vp]),
-    "coattn_stage_attend": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "coattn_forward": (_i, [_vp] * 10 + [_i64, _i, _i, _i, _i, _u, _vp]),
+    "coattn_stage_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
+    "coattn_stage_project": (_i, [_vp, _i64, _i, _i, _i, _i, _u, _vp]),
+    "coattn_stage_attend": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_gate": (_i, [_vp] * 7 + [_i, _i, _i, _i, _vp]),
 }
 

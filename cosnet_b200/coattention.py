@@ -56,8 +56,12 @@ def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
     return n, c, h, w
 
 
-def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None):
-    """Runs the four CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L]."""
+def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False):
+    """Runs the four CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L].
+
+    bf16_operands=False (default): fp16 tensor-core operands with fp32 accumulation (COATTN_FLAG_BF16 unset);
+    True: bf16 operands (see include/coattn_b200.h for the trade-off).
+    """
     n, c, h, w = _check_inputs(v_a, v_b, weight, gate_weight, gate_bias)
     lib = _lib.load()
     dev = v_a.device
@@ -76,12 +80,74 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None):
         stream = torch.cuda.current_stream(dev).cuda_stream
         code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
                                   None if gb is None else gb.data_ptr(), cat_a.data_ptr(), cat_b.data_ptr(),
-                                  z.data_ptr(), lse.data_ptr(), _aligned_ptr(ws), nbytes, n, c, h, w, stream)
+                                  z.data_ptr(), lse.data_ptr(), _aligned_ptr(ws), nbytes, n, c, h, w,
+                                  _lib.FLAG_BF16 if bf16_operands else 0, stream)
         _lib.check(code, "coattn_forward")
     return cat_a, cat_b, z, lse
 
 
-def coattention(v_a, v_b, weight, gate_weight, gate_bias=None):
+def coattention(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False):
     """Drop-in for rgbd_segmentation_RAA.py:150-187: returns (cat_a, cat_b), each [N, 2C, H, W]."""
-    cat_a, cat_b, _, _ = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias)
+    cat_a, cat_b, _, _ = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands)
     return cat_a, cat_b
+
+
+class HostPipeline:
+    """Host-buffer entry point: features live in (pinned) host memory, results return to host memory.
+
+    The batch is cut into chunks that rotate over `slots` CUDA streams; each stream runs
+    H2D -> four kernels -> D2H in order, so the copies of neighbouring chunks overlap the kernels.
+    Device buffers and workspaces are allocated once and reused across calls.
+    """
+
+    def __init__(self, n: int, c: int, h: int, w: int, chunk: int = 4, slots: int = 3, device="cuda:0",
+                 bf16_operands: bool = False):
+        self.n, self.c, self.h, self.w = n, c, h, w
+        self.flags = _lib.FLAG_BF16 if bf16_operands else 0
+        self.chunk = max(1, min(chunk, n))
+        self.device = torch.device(device)
+        self.lib = _lib.load()
+        self.slots = []
+        with torch.cuda.device(self.device):
+            nbytes = workspace_bytes(self.chunk, c, h, w)
+            for _ in range(slots):
+                s = {
+                    "stream": torch.cuda.Stream(self.device),
+                    "va": torch.empty((self.chunk, c, h, w), dtype=torch.float32, device=self.device),
+                    "vb": torch.empty((self.chunk, c, h, w), dtype=torch.float32, device=self.device),
+                    "ca": torch.empty((self.chunk, 2 * c, h, w), dtype=torch.float32, device=self.device),
+                    "cb": torch.empty((self.chunk, 2 * c, h, w), dtype=torch.float32, device=self.device),
+                    "ws": torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device),
+                    "nbytes": nbytes,
+                }
+                self.slots.append(s)
+        self.h2d_bytes = 2 * n * c * h * w * 4
+        self.d2h_bytes = 2 * n * 2 * c * h * w * 4
+        self.launches_per_call = 5 * ((n + self.chunk - 1) // self.chunk)
+
+    def __call__(self, v_a, v_b, weight, gate_weight, gate_bias, out_a, out_b):
+        """v_a, v_b, out_a, out_b: host tensors (pin them for asynchronous copies); weights on the device."""
+        n, c, h, w = self.n, self.c, self.h, self.w
+        gw = gate_weight.view(-1)
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        for k, lo in enumerate(range(0, n, self.chunk)):
+            hi = min(n, lo + self.chunk)
+            m = hi - lo
+            s = self.slots[k % len(self.slots)]
+            st = s["stream"]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                s["va"][:m].copy_(v_a[lo:hi], non_blocking=True)
+                s["vb"][:m].copy_(v_b[lo:hi], non_blocking=True)
+                code = self.lib.coattn_forward(
+                    s["va"].data_ptr(), s["vb"].data_ptr(), weight.data_ptr(), gw.data_ptr(),
+                    None if gate_bias is None else gate_bias.data_ptr(), s["ca"].data_ptr(), s["cb"].data_ptr(),
+                    None, None, _aligned_ptr(s["ws"]), s["nbytes"], m, c, h, w, self.flags, st.cuda_stream)
+                _lib.check(code, "coattn_forward")
+                out_a[lo:hi].copy_(s["ca"][:m], non_blocking=True)
+                out_b[lo:hi].copy_(s["cb"][:m], non_blocking=True)
+        for s in self.slots:
+            cur.wait_stream(s["stream"])
+        return out_a, out_b

@@ -82,14 +82,14 @@ EncodeTiledFn get_encode_fn() {
   return reinterpret_cast<EncodeTiledFn>(fn);
 }
 
-// 2-D bf16 row-major tensor [rows][cols]; box = {64 columns (128 B), box_rows}; 128-byte swizzle.
+// 2-D 16-bit row-major tensor [rows][cols]; box = {64 columns (128 B), box_rows}; 128-byte swizzle.
 int make_tmap(EncodeTiledFn enc, CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
-              uint32_t box_rows) {
+              uint32_t box_rows, bool bf16) {
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
   const cuuint32_t box[2] = {64, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+  const CUresult r = enc(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? COATTN_OK : COATTN_E_DRIVER;
@@ -139,7 +139,7 @@ int coattn_workspace_segment(const char* name, int n, int c, int h, int w, int64
 }
 
 int coattn_stage_prep(const float* v_a, const float* v_b, const float* w, void* workspace,
-                      int64_t workspace_bytes, int n, int c, int h, int w_, void* stream) {
+                      int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags, void* stream) {
   if (!v_a || !v_b || !w) return COATTN_E_NULL;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
@@ -150,19 +150,27 @@ int coattn_stage_prep(const float* v_a, const float* v_b, const float* w, void* 
   PrepParams p;
   p.va = v_a;
   p.vb = v_b;
-  p.bt = reinterpret_cast<__nv_bfloat16*>(seg(workspace, ly.off_t));
-  p.at = reinterpret_cast<__nv_bfloat16*>(seg(workspace, ly.off_at));
-  p.b16 = reinterpret_cast<__nv_bfloat16*>(seg(workspace, ly.off_vv));
+  p.bt = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_t));
+  p.at = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_at));
+  p.b16 = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv));
   p.a16 = p.b16 + plane_elems;
   p.L = ly.L;
   p.Lp = ly.Lp;
-  prep_kernel<<<dim3(ly.Lp / kPrepTileL, 2 * n), kPrepThreads, 0, st>>>(p);
-  cast_w_kernel<<<(kC * kC + 255) / 256, 256, 0, st>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(seg(workspace, ly.off_w16)), kC * kC);
+  unsigned short* w16 = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16));
+  const dim3 grid(ly.Lp / kPrepTileL, 2 * n);
+  if (flags & COATTN_FLAG_BF16) {
+    prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(p);
+    cast_w_kernel<true><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+  } else {
+    prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(p);
+    cast_w_kernel<false><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+  }
   return (int)cudaGetLastError();
 }
 
-int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_, void* stream) {
+int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
+                         void* stream) {
+  const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
   if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
@@ -171,19 +179,21 @@ int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c,
   if (!enc) return COATTN_E_DRIVER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tm_at, tm_w;
-  if (int e = make_tmap(enc, &tm_at, seg(workspace, ly.off_at), (uint64_t)n * ly.Lp, kC, 128)) return e;
-  if (int e = make_tmap(enc, &tm_w, seg(workspace, ly.off_w16), kC, kC, 256)) return e;
+  if (int e = make_tmap(enc, &tm_at, seg(workspace, ly.off_at), (uint64_t)n * ly.Lp, kC, 128, bf16)) return e;
+  if (int e = make_tmap(enc, &tm_w, seg(workspace, ly.off_w16), kC, kC, 256, bf16)) return e;
   ProjectParams p;
-  p.qt = reinterpret_cast<__nv_bfloat16*>(seg(workspace, ly.off_t)) + ly.t_pass_elems();
+  p.qt = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_t)) + ly.t_pass_elems();
   p.Lp = ly.Lp;
-  cudaError_t e = cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjSmemBytes);
+  auto kern = bf16 ? project_kernel<true> : project_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  project_kernel<<<dim3(ly.Lp / 128, n), kNumThreads, kProjSmemBytes, st>>>(tm_at, tm_w, p);
+  kern<<<dim3(ly.Lp / 128, n), kNumThreads, kProjSmemBytes, st>>>(tm_at, tm_w, p);
   return (int)cudaGetLastError();
 }
 
 int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace_bytes, int n, int c, int h,
-                        int w_, void* stream) {
+                        int w_, unsigned flags, void* stream) {
+  const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
   if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
@@ -192,12 +202,12 @@ int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return COATTN_E_DRIVER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CUtensorMap tm_q, tm_k, tm_v;
+  CUtensorMap tm_k, tm_v;
   const uint64_t t_rows = (uint64_t)2 * n * ly.Lp;
-  if (int e = make_tmap(enc, &tm_q, seg(workspace, ly.off_t), t_rows, kC, kBM)) return e;
-  if (int e = make_tmap(enc, &tm_k, seg(workspace, ly.off_t), t_rows, kC, kBN)) return e;
-  if (int e = make_tmap(enc, &tm_v, seg(workspace, ly.off_vv), (uint64_t)2 * n * kC, ly.Lp, kC)) return e;
+  if (int e = make_tmap(enc, &tm_k, seg(workspace, ly.off_t), t_rows, kC, kBN, bf16)) return e;
+  if (int e = make_tmap(enc, &tm_v, seg(workspace, ly.off_vv), (uint64_t)2 * n * kC, ly.Lp, kC, bf16)) return e;
   AttendParams p;
+  p.t = reinterpret_cast<const unsigned short*>(seg(workspace, ly.off_t));
   p.z = z ? z : reinterpret_cast<float*>(seg(workspace, ly.off_z));
   p.lse = lse ? lse : reinterpret_cast<float*>(seg(workspace, ly.off_lse));
   p.N = n;
@@ -206,10 +216,11 @@ int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace
   p.q_tiles = (ly.L + kBM - 1) / kBM;
   p.kv_tiles = (ly.L + kBN - 1) / kBN;
   p.num_items = 2 * n * p.q_tiles;
-  cudaError_t e = cudaFuncSetAttribute(attend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttendSmemBytes);
+  auto kern = bf16 ? attend_kernel<true> : attend_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttendSmemBytes);
   if (e != cudaSuccess) return (int)e;
   const int grid = p.num_items < sms ? p.num_items : sms;
-  attend_kernel<<<grid, kNumThreads, kAttendSmemBytes, st>>>(tm_q, tm_k, tm_v, p);
+  kern<<<grid, kAttendThreads, kAttendSmemBytes, st>>>(tm_k, tm_v, p);
   return (int)cudaGetLastError();
 }
 
@@ -235,15 +246,15 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
 
 int coattn_forward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* gate_b,
                    float* cat_a, float* cat_b, float* z, float* lse, void* workspace, int64_t workspace_bytes,
-                   int n, int c, int h, int w_, void* stream) {
+                   int n, int c, int h, int w_, unsigned flags, void* stream) {
   if (!v_a || !v_b || !w || !gate_w || !cat_a || !cat_b) return COATTN_E_NULL;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
   if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
   float* zbuf = z ? z : reinterpret_cast<float*>(seg(workspace, ly.off_z));
-  if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, stream)) return e;
-  if (int e = coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, stream)) return e;
-  if (int e = coattn_stage_attend(zbuf, lse, workspace, workspace_bytes, n, c, h, w_, stream)) return e;
+  if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+  if (int e = coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+  if (int e = coattn_stage_attend(zbuf, lse, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
   return coattn_stage_gate(zbuf, v_a, v_b, gate_w, gate_b, cat_a, cat_b, n, c, h, w_, stream);
 }
 

@@ -31,21 +31,22 @@ constexpr int kPrepStride = kC + 2;  // bf16 elements; 129 words -> conflict-fre
 struct PrepParams {
   const float* va;   // [N][C][L]
   const float* vb;   // [N][C][L]
-  __nv_bfloat16* at;   // [N][Lp][C]
-  __nv_bfloat16* bt;   // [N][Lp][C]
-  __nv_bfloat16* a16;  // [N][C][Lp]
-  __nv_bfloat16* b16;  // [N][C][Lp]
+  unsigned short* at;   // [N][Lp][C]   16-bit operands (f16 or bf16 bit patterns)
+  unsigned short* bt;   // [N][Lp][C]
+  unsigned short* a16;  // [N][C][Lp]
+  unsigned short* b16;  // [N][C][Lp]
   int L, Lp;
 };
 
+template <bool BF16>
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepParams p) {
-  __shared__ __align__(16) __nv_bfloat16 tile[kPrepTileL * kPrepStride];
+  __shared__ __align__(16) unsigned short tile[kPrepTileL * kPrepStride];
   const int n = blockIdx.y >> 1;
   const int which = blockIdx.y & 1;  // 0: A, 1: B
   const int l0 = blockIdx.x * kPrepTileL;
   const float* src = (which ? p.vb : p.va) + (size_t)n * kC * p.L;
-  __nv_bfloat16* x16 = (which ? p.b16 : p.a16) + (size_t)n * kC * p.Lp;
-  __nv_bfloat16* xt = (which ? p.bt : p.at) + (size_t)n * p.Lp * kC;
+  unsigned short* x16 = (which ? p.b16 : p.a16) + (size_t)n * kC * p.Lp;
+  unsigned short* xt = (which ? p.bt : p.at) + (size_t)n * p.Lp * kC;
 
   const int tl = threadIdx.x & 63;   // position within the tile
   const int tc = threadIdx.x >> 6;   // 0..3
@@ -55,10 +56,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepParams p) {
   for (int k = 0; k < kC / 4; ++k) {
     const int c = tc + 4 * k;
     const float v = valid ? __ldg(src + (size_t)c * p.L + l) : 0.0f;
-    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-    tile[tl * kPrepStride + c] = b;
+    const unsigned short mine = cvt16<BF16>(v);
+    tile[tl * kPrepStride + c] = mine;
     // pack neighbouring positions: even lanes store 4 bytes
-    const unsigned short mine = __bfloat16_as_ushort(b);
     const unsigned short next = __shfl_down_sync(0xffffffffu, mine, 1);
     if ((tl & 1) == 0) {
       *reinterpret_cast<uint32_t*>(x16 + (size_t)c * p.Lp + l) = (uint32_t)mine | ((uint32_t)next << 16);
@@ -75,10 +75,11 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepParams p) {
   }
 }
 
-// fp32 [C][C] -> bf16 [C][C]
-__global__ void cast_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w16, int n) {
+// fp32 [C][C] -> 16-bit [C][C]
+template <bool BF16>
+__global__ void cast_w_kernel(const float* __restrict__ w, unsigned short* __restrict__ w16, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) w16[i] = __float2bfloat16_rn(w[i]);
+  if (i < n) w16[i] = cvt16<BF16>(w[i]);
 }
 
 // ==============================================================================================
@@ -101,10 +102,11 @@ __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
 constexpr int kProjSmemBytes = 64 * 1024 + 128 * 1024 + 1024 /*align slack*/ + 64 /*barriers*/;
 
 struct ProjectParams {
-  __nv_bfloat16* qt;  // [N][Lp][C]
+  unsigned short* qt;  // [N][Lp][C]
   int Lp;
 };
 
+template <bool BF16>
 __global__ void __launch_bounds__(kNumThreads, 1)
 project_kernel(const __grid_constant__ CUtensorMap tmap_at,  // [N*Lp][C], box {64, 128}
                const __grid_constant__ CUtensorMap tmap_w,   // [C][C],    box {64, 256}
@@ -152,7 +154,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_at,  // [N*Lp][C], box {
     if (lane == 0) {
       mbar_wait(ab_full, 0, 100);
       tc_fence_after();
-      constexpr uint32_t idesc = make_idesc_bf16(128, 256);
+      constexpr uint32_t idesc = make_idesc_16(128, 256, BF16);
 #pragma unroll
       for (int kk = 0; kk < 16; ++kk) {
         const uint64_t ad = make_sdesc_k_sw128(smem_u32(sA + (kk >> 2) * 16384 + (kk & 3) * 32));
@@ -166,7 +168,7 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_at,  // [N*Lp][C], box {
     mbar_wait(d_full, 0, 101);
     tc_fence_after();
     const int row = warp * 32 + lane;
-    __nv_bfloat16* dst = p.qt + (size_t)(row0 + row) * kC;
+    unsigned short* dst = p.qt + (size_t)(row0 + row) * kC;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int ch = 0; ch < 8; ++ch) {
@@ -177,10 +179,10 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_at,  // [N*Lp][C], box {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
-        o.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
-        o.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
-        o.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+        o.x = pack16x2<BF16>(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+        o.y = pack16x2<BF16>(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+        o.z = pack16x2<BF16>(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+        o.w = pack16x2<BF16>(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
         d4[q] = o;
       }
     }
@@ -195,21 +197,35 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_at,  // [N*Lp][C], box {
 
 // ==============================================================================================
 // attend: persistent flash-style kernel over work items (sample n, pass p, 128-row query tile)
+//
+//   warps 0-3  softmax + drain: thread r owns query row r (TMEM lane r); they also stage the query tile:
+//              each thread copies its 512-byte row global -> registers -> TMEM (A operand of the affinity MMA)
+//   warp 4     TMA producer of key tiles   [64 positions x 256 channels]  (4-stage ring)
+//   warp 5     MMA issuer (one thread) and TMEM allocator
+//   warp 6     TMA producer of value tiles [256 channels x 64 positions]  (3-stage ring)
+//
+//   TMEM columns: [0,256) O accumulator (fp32) | [256,320) S/P buffer 0 | [320,384) S/P buffer 1 |
+//                 [384,512) query tile, 128 x 256 16-bit values packed two per column
+//   MMA order per item: S(0) | S(1) PV(0) | S(2) PV(1) | ... | PV(T-1); P(j) overwrites S(j) in place.
 // ==============================================================================================
 constexpr int kBM = 128;      // query rows per tile (TMEM lanes)
 constexpr int kBN = 64;       // key/value positions per step
-constexpr int kKStages = 2;
-constexpr int kVStages = 2;
-constexpr int kQBytes = kBM * kC * 2;      // 64 KB : 4 k-blocks x [128 rows x 128 B]
+constexpr int kKStages = 4;
+constexpr int kVStages = 3;
 constexpr int kKBytes = kBN * kC * 2;      // 32 KB : 4 k-blocks x [ 64 rows x 128 B]
 constexpr int kVBytes = kC * kBN * 2;      // 32 KB : [256 rows x 128 B]
-constexpr int kAttendSmemBytes = kQBytes + kKStages * kKBytes + kVStages * kVBytes + 1024 + 256;
+constexpr int kAttendThreads = 224;
+constexpr int kKProducerWarp = 4;
+constexpr int kVProducerWarp = 6;
+constexpr int kAttendSmemBytes = kKStages * kKBytes + kVStages * kVBytes + 1024 + 256;
 constexpr uint32_t kTmemColsO = 0;         // O accumulator: 256 fp32 columns
 constexpr uint32_t kTmemColsS = 256;       // two S/P buffers of kBN columns
+constexpr uint32_t kTmemColsQ = 384;       // query tile: 128 columns of packed pairs
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: O is only rescaled when the row max jumps by > 2^8
 
 struct AttendParams {
+  const unsigned short* t;  // [2][N][Lp][C] 16-bit: t[0] = Bt, t[1] = Qt (queries of pass p are t[1-p])
   float* z;     // [2][N][C][L]  raw attended features (pass 0: Z_a, pass 1: Z_b)
   float* lse;   // [2][N][L]     log-sum-exp of each softmax row (natural log)
   int N, L, Lp;
@@ -218,20 +234,18 @@ struct AttendParams {
   int num_items; // 2 * N * q_tiles
 };
 
-__global__ void __launch_bounds__(kNumThreads, 1)
-attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  box {64, 128}
-              const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  box {64, 64}
+template <bool BF16>
+__global__ void __launch_bounds__(kAttendThreads, 1)
+attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  box {64, 64}
               const __grid_constant__ CUtensorMap tmap_v,  // VV [2*N*C][Lp],  box {64, 256}
               AttendParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kQBytes;
+  uint8_t* sK = smem;
   uint8_t* sV = sK + kKStages * kKBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kVStages * kVBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;                 // [kKStages]
+  uint64_t* q_full = bars + 0;                 // query tile staged in TMEM (128 arrivals)
+  uint64_t* k_full = bars + 1;                 // [kKStages]
   uint64_t* k_empty = k_full + kKStages;       // [kKStages]
   uint64_t* v_full = k_empty + kKStages;       // [kVStages]
   uint64_t* v_empty = v_full + kVStages;       // [kVStages]
@@ -244,12 +258,10 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  b
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == kProducerWarp && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
+  if (warp == kKProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    mbar_init(q_full, 128);
     for (int s = 0; s < kKStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
     for (int s = 0; s < kVStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(p_full + b, 128); }
@@ -267,50 +279,47 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  b
   const uint32_t tmem = *tmem_slot;
   const int T = p.kv_tiles;
 
-  if (warp == kProducerWarp) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == kKProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer: key tiles
     if (lane == 0) {
-      uint32_t it = 0, kcnt = 0, vcnt = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        const int qt = item % p.q_tiles;
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int np = item / p.q_tiles;
-        const int pass = np & 1;
-        const int n = np >> 1;
-        const int qrow0 = ((1 - pass) * p.N + n) * p.Lp + qt * kBM;
-        const int krow0 = (pass * p.N + n) * p.Lp;
-        const int vrow0 = (pass * p.N + n) * kC;
-        mbar_wait(q_empty, (it & 1) ^ 1, 1);
-        mbar_arrive_expect_tx(q_full, kQBytes);
+        const int krow0 = ((np & 1) * p.N + (np >> 1)) * p.Lp;
+        for (int j = 0; j < T; ++j, ++cnt) {
+          const uint32_t s = cnt % kKStages, ph = (cnt / kKStages) & 1;
+          mbar_wait(k_empty + s, ph ^ 1, 2);
+          mbar_arrive_expect_tx(k_full + s, kKBytes);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sQ + kb * (kBM * 128), &tmap_q, q_full, kb * 64, qrow0);
-        for (int j = 0; j < T; ++j) {
-          {
-            const uint32_t s = kcnt % kKStages, ph = (kcnt / kKStages) & 1;
-            mbar_wait(k_empty + s, ph ^ 1, 2);
-            mbar_arrive_expect_tx(k_full + s, kKBytes);
-#pragma unroll
-            for (int kb = 0; kb < 4; ++kb)
-              tma_load_2d(sK + s * kKBytes + kb * (kBN * 128), &tmap_k, k_full + s, kb * 64, krow0 + j * kBN);
-            ++kcnt;
-          }
-          {
-            const uint32_t s = vcnt % kVStages, ph = (vcnt / kVStages) & 1;
-            mbar_wait(v_empty + s, ph ^ 1, 3);
-            mbar_arrive_expect_tx(v_full + s, kVBytes);
-            tma_load_2d(sV + s * kVBytes, &tmap_v, v_full + s, j * kBN, vrow0);
-            ++vcnt;
-          }
+          for (int kb = 0; kb < 4; ++kb)
+            tma_load_2d(sK + s * kKBytes + kb * (kBN * 128), &tmap_k, k_full + s, kb * 64, krow0 + j * kBN);
+        }
+      }
+    }
+  } else if (warp == kVProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer: value tiles
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int np = item / p.q_tiles;
+        const int vrow0 = ((np & 1) * p.N + (np >> 1)) * kC;
+        for (int j = 0; j < T; ++j, ++cnt) {
+          const uint32_t s = cnt % kVStages, ph = (cnt / kVStages) & 1;
+          mbar_wait(v_empty + s, ph ^ 1, 3);
+          mbar_arrive_expect_tx(v_full + s, kVBytes);
+          tma_load_2d(sV + s * kVBytes, &tmap_v, v_full + s, j * kBN, vrow0);
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kBM, kBN);
-      constexpr uint32_t idesc_o = make_idesc_bf16(kBM, kC);
+      constexpr uint32_t idesc_s = make_idesc_16(kBM, kBN, BF16);
+      constexpr uint32_t idesc_o = make_idesc_16(kBM, kC, BF16);
       uint32_t it = 0, kcnt = 0, vcnt = 0;
-      uint32_t pphase[2] = {0, 0};
+      uint32_t pphase0 = 0, pphase1 = 0;
       const uint32_t tO = tmem + kTmemColsO;
+      const uint32_t tQ = tmem + kTmemColsQ;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         auto issue_s = [&](int j) {
           const uint32_t s = kcnt % kKStages, ph = (kcnt / kKStages) & 1;
@@ -319,25 +328,23 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  b
           const uint32_t tS = tmem + kTmemColsS + (uint32_t)(j & 1) * kBN;
 #pragma unroll
           for (int kk = 0; kk < kC / 16; ++kk) {
-            const uint64_t ad = make_sdesc_k_sw128(smem_u32(sQ + (kk >> 2) * (kBM * 128) + (kk & 3) * 32));
             const uint64_t bd =
                 make_sdesc_k_sw128(smem_u32(sK + s * kKBytes + (kk >> 2) * (kBN * 128) + (kk & 3) * 32));
-            umma_ss(tS, ad, bd, idesc_s, kk > 0);
+            umma_ts(tS, tQ + kk * 8, bd, idesc_s, kk > 0);
           }
           umma_commit(k_empty + s);
           umma_commit(s_full + (j & 1));
           ++kcnt;
         };
+        // q_full(it) also implies that the softmax warps finished draining O of the previous item
         mbar_wait(q_full, it & 1, 11);
-        if (it > 0) mbar_wait(o_free, (it - 1) & 1, 12);
         tc_fence_after();
         issue_s(0);
         for (int j = 0; j < T; ++j) {
           if (j + 1 < T) issue_s(j + 1);
-          else umma_commit(q_empty);   // every affinity MMA of this item has been issued
           const int b = j & 1;
-          mbar_wait(p_full + b, pphase[b], 13);
-          pphase[b] ^= 1;
+          if (b == 0) { mbar_wait(p_full + 0, pphase0, 13); pphase0 ^= 1; }
+          else        { mbar_wait(p_full + 1, pphase1, 13); pphase1 ^= 1; }
           const uint32_t s = vcnt % kVStages, ph = (vcnt / kVStages) & 1;
           mbar_wait(v_full + s, ph, 14);
           tc_fence_after();
@@ -357,7 +364,8 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  b
     // ------------------------------------------------------------------ softmax + drain (1 thread = 1 row)
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const uint32_t tO = tmem + lane_base + kTmemColsO;
-    uint32_t sphase[2] = {0, 0};
+    const uint32_t tQ = tmem + lane_base + kTmemColsQ;
+    uint32_t sphase0 = 0, sphase1 = 0;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int qt = item % p.q_tiles;
@@ -366,12 +374,31 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  b
       const int n = np >> 1;
       const int row = qt * kBM + warp * 32 + lane;
       const uint32_t pv_base = it * (uint32_t)T;
+      // ---- stage this thread's query row into TMEM.  All affinity MMAs of the previous item have completed
+      // (s_full of its last tile was observed) and O has been drained, so Q and O may be overwritten.
+      {
+        const uint4* qsrc = reinterpret_cast<const uint4*>(
+            p.t + ((size_t)((1 - pass) * p.N + n) * p.Lp + row) * kC);   // rows < Lp always exist (zero padded)
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t q[32];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const uint4 t4 = __ldg(qsrc + ch * 8 + v);
+            q[4 * v + 0] = t4.x; q[4 * v + 1] = t4.y; q[4 * v + 2] = t4.z; q[4 * v + 3] = t4.w;
+          }
+          tmem_st32(tQ + ch * 32, q);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(q_full);
+      }
       float m = -INFINITY, l = 0.0f;
       for (int j = 0; j < T; ++j) {
         const int b = j & 1;
         const uint32_t tS = tmem + lane_base + kTmemColsS + (uint32_t)b * kBN;
-        mbar_wait(s_full + b, sphase[b], 20);
-        sphase[b] ^= 1;
+        if (b == 0) { mbar_wait(s_full + 0, sphase0, 20); sphase0 ^= 1; }
+        else        { mbar_wait(s_full + 1, sphase1, 20); sphase1 ^= 1; }
         tc_fence_after();
         uint32_t s0[32], s1[32];
         tmem_ld32(tS, s0);
@@ -399,6 +426,7 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  b
           if (__any_sync(0xffffffffu, need)) {
             const float m_new = fmaxf(m, tmax);
             const float scale = fast_exp2((m - m_new) * kLog2e);
+            // PV(j-2) is complete (s_full(j) was observed), so the barrier is in phase j-1 or later
             mbar_wait(o_full, (pv_base + (uint32_t)j - 1u) & 1u, 21);
             tc_fence_after();
 #pragma unroll 1
@@ -417,26 +445,33 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  b
         }
         const float neg_m = -m * kLog2e;
         uint32_t pk[32];
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;   // independent partial sums (ILP)
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(s0[2 * k]), kLog2e, neg_m));
           const float p1 = fast_exp2(fmaf(__uint_as_float(s0[2 * k + 1]), kLog2e, neg_m));
-          pk[k] = pack_bf16x2(p0, p1);
-          l += bf16lo_to_f32(pk[k]) + bf16hi_to_f32(pk[k]);
+          pk[k] = pack16x2<BF16>(p0, p1);
+          if constexpr (BF16) { l0 += bf16lo_to_f32(pk[k]); l1 += bf16hi_to_f32(pk[k]); }  // sum what the MMA sees
+          else { l0 += p0; l1 += p1; }
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(s1[2 * k]), kLog2e, neg_m));
           const float p1 = fast_exp2(fmaf(__uint_as_float(s1[2 * k + 1]), kLog2e, neg_m));
-          pk[16 + k] = pack_bf16x2(p0, p1);
-          l += bf16lo_to_f32(pk[16 + k]) + bf16hi_to_f32(pk[16 + k]);
+          pk[16 + k] = pack16x2<BF16>(p0, p1);
+          if constexpr (BF16) { l2 += bf16lo_to_f32(pk[16 + k]); l3 += bf16hi_to_f32(pk[16 + k]); }
+          else { l2 += p0; l3 += p1; }
         }
-        tmem_st32(tS, pk);   // P (bf16 pairs) overlays the first 32 columns of the S buffer
+        l += (l0 + l1) + (l2 + l3);
+        tmem_st32(tS, pk);   // P (16-bit pairs) overlays the first 32 columns of the S buffer
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_full + b);
       }
       // drain: Z[c][row] = O[row][c] / l
+      // Phases are waited one by one: after s_full(T-1) only PV(T-3) is known complete, so the barrier may
+      // still be in phase T-2; a parity wait for phase T-1 alone would alias and pass early.
+      if (T >= 2) mbar_wait(o_full, (pv_base + (uint32_t)T - 2u) & 1u, 23);
       mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, 22);
       tc_fence_after();
       const float inv = 1.0f / l;
@@ -453,10 +488,9 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  b
         }
       }
       if (valid) p.lse[(size_t)(pass * p.N + n) * p.L + row] = m + __logf(l);
-      tc_fence_before();
-      mbar_arrive(o_free);
     }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();

@@ -126,12 +126,13 @@ __device__ __forceinline__ void tc_fence_after() {
 // ----------------------------------------------------------------------------------------------
 // tcgen05: descriptors
 // ----------------------------------------------------------------------------------------------
-// Instruction descriptor for kind::f16, BF16 x BF16 -> FP32, both operands K-major, dense.
-//   bits [4,6)  c_format = 1 (F32)      bits [7,10)  a_format = 1 (BF16)   bits [10,13) b_format = 1 (BF16)
+// Instruction descriptor for kind::f16, {F16,BF16} x {F16,BF16} -> FP32, both operands K-major, dense.
+//   bits [4,6)  c_format = 1 (F32)      bits [7,10)  a_format             bits [10,13) b_format
 //   bit 15 a_major = 0 (K)              bit 16 b_major = 0 (K)
 //   bits [17,23) N >> 3                 bits [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+//   16-bit operand format code: 0 = F16, 1 = BF16 (same tensor pipe, same rate)
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t M, uint32_t N, bool bf16) {
+  return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // Shared-memory matrix descriptor: K-major operand tile stored as rows of 128 bytes (64 bf16) with the
@@ -227,6 +228,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+// two fp32 -> packed f16x2 (lo = a, hi = b), round-to-nearest-even, saturating to +-65504
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// format-generic helpers: BF16 = true -> bfloat16, false -> IEEE half (saturating)
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack16x2(float a, float b) {
+  if constexpr (BF16) return pack_bf16x2(a, b);
+  else return pack_f16x2(a, b);
+}
+template <bool BF16>
+__device__ __forceinline__ unsigned short cvt16(float a) {
+  return static_cast<unsigned short>(pack16x2<BF16>(a, 0.0f) & 0xFFFFu);
 }
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }

@@ -46,6 +46,16 @@ enum {
   COATTN_E_ALIGN = -6        /* a tensor pointer is not 16-byte aligned                     */
 };
 
+/*
+ * flags (bitwise or).  The 16-bit tensor-core operand format of the affinity/attend GEMMs:
+ *   default (0)            IEEE fp16 operands, fp32 accumulation.  Same tcgen05 kind::f16 pipe and rate as
+ *                          bf16 but a 2^-11 mantissa: meets rel-L2 <= 1e-3 on the module output at every
+ *                          tested feature scale.  fp32 -> fp16 conversion saturates at +-65504.
+ *   COATTN_FLAG_BF16       bf16 operands, fp32 accumulation (full fp32 exponent range; ~2e-3 rel-L2 at
+ *                          train-like logit scales).
+ */
+#define COATTN_FLAG_BF16 1u
+
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);
 
@@ -57,26 +67,27 @@ int64_t coattn_workspace_bytes(int n, int c, int h, int w);
 
 /*
  * Whole hot path for one modality (replaces :150-187 or :204-238):
- *   prep (bf16 cast/transposes) -> project (Q = W A) -> attend (both softmax axes) -> gate/concat.
+ *   prep (16-bit cast/transposes) -> project (Q = W A) -> attend (both softmax axes) -> gate/concat.
  * z and lse are outputs kept for the backward pass; either may be NULL, in which case they live
  * in the workspace (z) or are dropped (lse is always computed; NULL routes it to the workspace).
  */
 int coattn_forward(const float* v_a, const float* v_b, const float* w, const float* gate_w,
                    const float* gate_b, float* cat_a, float* cat_b, float* z, float* lse,
                    void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
-                   void* stream);
+                   unsigned flags, void* stream);
 
 /* ---- the four stages, exported individually for unit parity tests and per-kernel timing ---- */
 
-/* stage 1 (:154-158): bf16 operands.  Fills the workspace segments At, Bt, A16, B16 and W16. */
+/* stage 1 (:154-158): 16-bit operands.  Fills the workspace segments At, Bt, A16, B16 and W16. */
 int coattn_stage_prep(const float* v_a, const float* v_b, const float* w, void* workspace,
-                      int64_t workspace_bytes, int n, int c, int h, int w_, void* stream);
+                      int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
+                      void* stream);
 /* stage 2 (:159): Qt = At W^T on the tensor cores. */
 int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
-                         void* stream);
+                         unsigned flags, void* stream);
 /* stage 3 (:160-170): fused affinity / dual softmax / attend.  Writes z and lse. */
 int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace_bytes, int n,
-                        int c, int h, int w_, void* stream);
+                        int c, int h, int w_, unsigned flags, void* stream);
 /* stage 4 (:177-187): gate, sigmoid, scale, concat. */
 int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const float* gate_w,
                       const float* gate_b, float* cat_a, float* cat_b, int n, int c, int h, int w_,

@@ -36,8 +36,8 @@ def segment(ws, name, n, c, h, w, dtype, shape):
     return raw.view(dtype).view(*shape)
 
 
-def bf16_round(x):
-    return torch.from_numpy(np.asarray(x, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+def bf16_round(x, dt=torch.bfloat16):
+    return torch.from_numpy(np.asarray(x, dtype=np.float32)).to(dt).to(torch.float32).numpy()
 
 
 def main():
@@ -49,8 +49,11 @@ def main():
     ap.add_argument("--sigma", type=float, default=0.66)
     ap.add_argument("--bias", type=int, default=1)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--bf16", type=int, default=0)
     args = ap.parse_args()
     n, h, w, c = args.n, args.h, args.w, 256
+    FL = 1 if args.bf16 else 0
+    odt = torch.bfloat16 if args.bf16 else torch.float16
     L = h * w
     Lp = (L + 127) // 128 * 128
     lib = _lib.load()
@@ -67,23 +70,23 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
 
     if args.stage in ("prep", "project", "attend"):
-        _lib.check(lib.coattn_stage_prep(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, st), "prep")
+        _lib.check(lib.coattn_stage_prep(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "prep")
         torch.cuda.synchronize()
-        at = segment(ws, "at", n, c, h, w, torch.bfloat16, (n, Lp, c)).float().cpu().numpy()
-        bt = segment(ws, "bt", n, c, h, w, torch.bfloat16, (n, Lp, c)).float().cpu().numpy()
-        a16 = segment(ws, "a16", n, c, h, w, torch.bfloat16, (n, c, Lp)).float().cpu().numpy()
-        b16 = segment(ws, "b16", n, c, h, w, torch.bfloat16, (n, c, Lp)).float().cpu().numpy()
-        w16 = segment(ws, "w16", n, c, h, w, torch.bfloat16, (c, c)).float().cpu().numpy()
-        ra = bf16_round(v_a.reshape(n, c, L)); rb = bf16_round(v_b.reshape(n, c, L))
+        at = segment(ws, "at", n, c, h, w, odt, (n, Lp, c)).float().cpu().numpy()
+        bt = segment(ws, "bt", n, c, h, w, odt, (n, Lp, c)).float().cpu().numpy()
+        a16 = segment(ws, "a16", n, c, h, w, odt, (n, c, Lp)).float().cpu().numpy()
+        b16 = segment(ws, "b16", n, c, h, w, odt, (n, c, Lp)).float().cpu().numpy()
+        w16 = segment(ws, "w16", n, c, h, w, odt, (c, c)).float().cpu().numpy()
+        ra = bf16_round(v_a.reshape(n, c, L), odt); rb = bf16_round(v_b.reshape(n, c, L), odt)
         print("[prep] a16 exact:", np.array_equal(a16[:, :, :L], ra), " pad zero:", float(np.abs(a16[:, :, L:]).max(initial=0)))
         print("[prep] b16 exact:", np.array_equal(b16[:, :, :L], rb), " pad zero:", float(np.abs(b16[:, :, L:]).max(initial=0)))
         print("[prep] at  exact:", np.array_equal(at[:, :L], ra.transpose(0, 2, 1)), " pad zero:", float(np.abs(at[:, L:]).max(initial=0)))
         print("[prep] bt  exact:", np.array_equal(bt[:, :L], rb.transpose(0, 2, 1)), " pad zero:", float(np.abs(bt[:, L:]).max(initial=0)))
-        print("[prep] w16 exact:", np.array_equal(w16, bf16_round(W)), flush=True)
+        print("[prep] w16 exact:", np.array_equal(w16, bf16_round(W, odt)), flush=True)
     if args.stage in ("project", "attend"):
-        _lib.check(lib.coattn_stage_project(wsp, nbytes, n, c, h, w, st), "project")
+        _lib.check(lib.coattn_stage_project(wsp, nbytes, n, c, h, w, FL, st), "project")
         torch.cuda.synchronize()
-        qt = segment(ws, "qt", n, c, h, w, torch.bfloat16, (n, Lp, c)).float().cpu().numpy()
+        qt = segment(ws, "qt", n, c, h, w, odt, (n, Lp, c)).float().cpu().numpy()
         q_ref = np.matmul(at.astype(np.float64), w16.astype(np.float64).T)
         print("[project] rel_l2(qt, bf16-operand fp64 ref):", rel_l2(qt, q_ref), " max|ref|:", float(np.abs(q_ref).max()))
         print("[project] max abs err:", float(np.abs(qt - q_ref).max()), " pad rows max:", float(np.abs(qt[:, L:]).max(initial=0)), flush=True)
@@ -95,7 +98,7 @@ def main():
     if args.stage == "attend":
         z = torch.zeros(2, n, c, L, device=dev)
         lse = torch.zeros(2, n, L, device=dev)
-        _lib.check(lib.coattn_stage_attend(z.data_ptr(), lse.data_ptr(), wsp, nbytes, n, c, h, w, st), "attend")
+        _lib.check(lib.coattn_stage_attend(z.data_ptr(), lse.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "attend")
         torch.cuda.synchronize()
         z = z.cpu().numpy(); lse = lse.cpu().numpy()
         # reference on the SAME bf16 operands (isolates kernel logic from quantisation)
@@ -123,7 +126,7 @@ def main():
             ref = torch.cat([zs * torch.sigmoid(t), v], 1)
             print(f"[gate] side {side} max abs err:", float((cat - ref).abs().max()), " passthrough exact:", bool(torch.equal(cat[:, c:], v)), flush=True)
     if args.stage in ("forward", "time"):
-        cat_a, cat_b, z, lse = coattention_forward_raw(tva, tvb, tW, tg, tb)
+        cat_a, cat_b, z, lse = coattention_forward_raw(tva, tvb, tW, tg, tb, bool(args.bf16))
         torch.cuda.synchronize()
         if args.stage == "forward":
             full = orc.coattention(v_a, v_b, W, g, b)
@@ -140,9 +143,9 @@ def main():
         for itn in range(args.iters + 3):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             ev[0].record()
-            _lib.check(lib.coattn_stage_prep(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, st), "prep"); ev[1].record()
-            _lib.check(lib.coattn_stage_project(wsp, nbytes, n, c, h, w, st), "project"); ev[2].record()
-            _lib.check(lib.coattn_stage_attend(zt.data_ptr(), lt.data_ptr(), wsp, nbytes, n, c, h, w, st), "attend"); ev[3].record()
+            _lib.check(lib.coattn_stage_prep(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "prep"); ev[1].record()
+            _lib.check(lib.coattn_stage_project(wsp, nbytes, n, c, h, w, FL, st), "project"); ev[2].record()
+            _lib.check(lib.coattn_stage_attend(zt.data_ptr(), lt.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "attend"); ev[3].record()
             _lib.check(lib.coattn_stage_gate(zt.data_ptr(), tva.data_ptr(), tvb.data_ptr(), tg.data_ptr(), bp, ca.data_ptr(), cb.data_ptr(), n, c, h, w, st), "gate"); ev[4].record()
             torch.cuda.synchronize()
             if itn >= 3:

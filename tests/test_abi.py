@@ -1,0 +1,75 @@
+"""The C-ABI library loads and exports every symbol include/coattn_b200.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "coattn_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from cosnet_b200 import _lib
+    return _lib.load()
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(coattn_\w+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_functions()
+    assert "coattn_forward" in names and "coattn_stage_attend" in names
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+
+
+def test_binding_covers_header():
+    from cosnet_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+
+
+def test_version_and_errors(lib):
+    from cosnet_b200 import _lib
+    assert lib.coattn_b200_abi_version() == _lib.ABI_VERSION
+    assert lib.coattn_b200_strerror(0) == b"ok"
+    assert b"256" in lib.coattn_b200_strerror(-2)
+    assert b"fallback" in lib.coattn_b200_strerror(-4)
+
+
+def test_workspace_size_and_shape_errors(lib):
+    # 60x60 -> Lp = 3712: five bf16 planes of N*Lp*C plus W16, z, lse
+    n, c, h, w = 2, 256, 60, 60
+    lp = 3712
+    plane = n * lp * c * 2
+    expect_min = 5 * plane + c * c * 2 + 2 * n * c * h * w * 4 + 2 * n * h * w * 4
+    got = lib.coattn_workspace_bytes(n, c, h, w)
+    assert expect_min <= got <= expect_min + 8 * 1024
+    assert lib.coattn_workspace_bytes(n, 128, h, w) == -2      # C must be 256
+    assert lib.coattn_workspace_bytes(0, c, h, w) == -2
+    off, nb = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.coattn_workspace_segment(b"qt", n, c, h, w, ctypes.byref(off), ctypes.byref(nb)) == 0
+    assert off.value == plane and nb.value == plane
+    assert lib.coattn_workspace_segment(b"nope", n, c, h, w, ctypes.byref(off), ctypes.byref(nb)) == -1
+
+
+def test_argument_errors_before_any_cuda_work(lib):
+    # NULL pointers and bad shapes are rejected on the host, before touching a device
+    assert lib.coattn_forward(None, None, None, None, None, None, None, None, None, None, 0, 1, 256, 4, 4, 0, None) == -1
+    assert lib.coattn_stage_gate(None, None, None, None, None, None, None, 1, 256, 4, 4, None) == -1
+    assert lib.coattn_stage_project(None, 0, 1, 64, 4, 4, 0, None) == -2
+
+
+def test_host_operator_refuses_cpu_tensors():
+    import torch
+    from cosnet_b200 import coattention
+    from cosnet_b200._lib import CoattnError
+    x = torch.zeros(1, 256, 2, 2)
+    with pytest.raises(CoattnError):
+        coattention(x, x, torch.zeros(256, 256), torch.zeros(256))

@@ -1,0 +1,204 @@
+"""Parity of the CUDA co-attention (through the C ABI) against golden vectors of the reference and the
+CPU oracle.  Needs a B200: run with `pytest -m gpu`.
+
+Tolerances (floating point path, fp32 accumulation; rel-L2 on the module output, the [N,2C,H,W] concat):
+  TOL    = 1e-3  default operand format (fp16): the bound BASELINE.json states, at every feature-scale tier;
+  TOL_BF = 5e-3  COATTN_FLAG_BF16 operands: bf16 quantisation alone costs ~1e-3 at tiny L and ~2e-3 at
+                 train-like logit scales (sigma = 1.0, S std ~ 5) -- reported, not hidden.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import coattn_oracle as orc
+from tests.helpers import golden_inputs, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+TOL_BF = 5e-3
+C = 256
+
+
+@pytest.fixture(scope="module")
+def op():
+    import __graft_entry__ as ge
+    ge.build()
+    from cosnet_b200 import coattention_forward_raw
+    assert torch.cuda.is_available()
+    return coattention_forward_raw
+
+
+def run(op, v_a, v_b, w, g, b, bf16=False):
+    dev = torch.device("cuda:0")
+    t = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    cat_a, cat_b, z, lse = op(t(v_a), t(v_b), t(w), t(g), t(b), bf16)
+    torch.cuda.synchronize()
+    return cat_a.cpu().numpy(), cat_b.cpu().numpy(), z.cpu().numpy(), lse.cpu().numpy()
+
+
+@pytest.mark.parametrize("bf16,tol", [(False, TOL), (True, TOL_BF)])
+@pytest.mark.parametrize("name", ["fwd_n2_4x5_s066", "fwd_n1_3x43_s100"])
+def test_golden_vectors_of_the_reference(op, name, bf16, tol):
+    fx = load_golden(name)
+    inp = golden_inputs(fx)
+    for mod, (va, vb, w, g, b) in {
+        "rgb": (inp["v_a"], inp["v_b"], inp["w_rgb"], inp["g_rgb"], None),
+        "depth": (inp["d_a"], inp["d_b"], inp["w_dep"], inp["g_dep"], inp["b_dep"]),
+    }.items():
+        cat_a, cat_b, z, _ = run(op, va, vb, w, g, b, bf16)
+        ref_a = np.concatenate([fx[f"{mod}_gated_a"], va], axis=1)
+        ref_b = np.concatenate([fx[f"{mod}_gated_b"], vb], axis=1)
+        assert rel_l2(cat_a, ref_a) < tol, (mod, rel_l2(cat_a, ref_a))
+        assert rel_l2(cat_b, ref_b) < tol, (mod, rel_l2(cat_b, ref_b))
+        # the passthrough half is a bit-exact copy (:186-187)
+        assert np.array_equal(cat_a[:, C:], va) and np.array_equal(cat_b[:, C:], vb)
+        if mod == "rgb":
+            assert rel_l2(z[0].reshape(fx["rgb_z_a"].shape), fx["rgb_z_a"]) < 5 * tol
+            assert rel_l2(z[1].reshape(fx["rgb_z_b"].shape), fx["rgb_z_b"]) < 5 * tol
+
+
+SHAPES = [
+    # n, h, w           L      what it exercises
+    (1, 1, 1),        # 1      single position: both softmaxes are 1
+    (2, 8, 8),        # 64     exactly one key tile
+    (1, 8, 16),       # 128    exactly one query tile
+    (3, 12, 11),      # 132    ragged tail, odd batch
+    (1, 31, 41),      # 1271   240x320 input (config.yaml:81), L odd -> scalar gate path
+    (2, 60, 60),      # 3600   473x473 input (headline shape)
+    (1, 61, 81),      # 4941   480x640 input
+]
+
+
+@pytest.mark.parametrize("n,h,w", SHAPES)
+@pytest.mark.parametrize("bias", [False, True])
+def test_against_oracle(op, n, h, w, bias):
+    v_a, v_b = orc.synthetic_features(1000 + h * w, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(2000 + h * w, bias=bias)
+    ref = orc.coattention(v_a, v_b, W, g, b)
+    cat_a, cat_b, z, lse = run(op, v_a, v_b, W, g, b)
+    assert rel_l2(cat_a, ref["cat_a"]) < TOL
+    assert rel_l2(cat_b, ref["cat_b"]) < TOL
+    L = h * w
+    assert np.abs(lse[0] - ref["lse_a"]).max() < 5e-2
+    assert np.abs(lse[1] - ref["lse_b"]).max() < 5e-2
+    assert np.array_equal(cat_a[:, C:], v_a) and np.array_equal(cat_b[:, C:], v_b)
+    assert np.isfinite(cat_a).all() and np.isfinite(cat_b).all() and np.isfinite(z).all()
+
+
+def test_480x854_shape(op):
+    # 480x854 input -> 61x107 features (L = 6527, what the reference really produces)
+    n, h, w = 1, 61, 107
+    v_a, v_b = orc.synthetic_features(77, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(78, bias=True)
+    ref = orc.coattention(v_a, v_b, W, g, b, dtype=np.float32)
+    cat_a, cat_b, _, _ = run(op, v_a, v_b, W, g, b)
+    assert rel_l2(cat_a, ref["cat_a"]) < TOL
+    assert rel_l2(cat_b, ref["cat_b"]) < TOL
+
+
+@pytest.mark.parametrize("sigma,bf16,tol", [
+    (0.01, False, TOL), (0.25, False, TOL), (0.66, False, TOL), (1.0, False, TOL), (1.5, False, TOL),
+    (0.01, True, TOL_BF), (0.66, True, TOL_BF), (1.0, True, TOL_BF), (1.5, True, 2e-2)])
+def test_feature_scale_tiers(op, sigma, bf16, tol):
+    # T0 (degenerate uniform softmax) .. T2+ (peaky softmax, exercises the lazy O rescale), SURVEY.md 7.3-2
+    n, h, w = 1, 24, 24
+    v_a, v_b = orc.synthetic_features(31, n, h, w, sigma)
+    W, g, b = orc.synthetic_weights(32, bias=True)
+    ref = orc.coattention(v_a, v_b, W, g, b)
+    cat_a, cat_b, _, _ = run(op, v_a, v_b, W, g, b, bf16)
+    assert rel_l2(cat_a, ref["cat_a"]) < tol, rel_l2(cat_a, ref["cat_a"])
+    assert rel_l2(cat_b, ref["cat_b"]) < tol, rel_l2(cat_b, ref["cat_b"])
+
+
+def test_large_logits_stay_finite(op):
+    # |S| in the hundreds: exp() of raw logits would overflow without the running-max bookkeeping
+    n, h, w = 1, 16, 16
+    v_a, v_b = orc.synthetic_features(41, n, h, w, 4.0)
+    W, g, b = orc.synthetic_weights(42, bias=False)
+    ref = orc.coattention(v_a, v_b, W, g, b)
+    cat_a, cat_b, z, lse = run(op, v_a, v_b, W, g, b)
+    assert np.isfinite(cat_a).all() and np.isfinite(cat_b).all() and np.isfinite(lse).all()
+    # near one-hot softmax: attended features must stay inside the convex hull of the values
+    zb = z[1].reshape(n, C, h * w)
+    A = v_a.reshape(n, C, -1)
+    assert (zb <= A.max(axis=2, keepdims=True) + 1e-2).all() and (zb >= A.min(axis=2, keepdims=True) - 1e-2).all()
+    assert np.abs(lse[0] - ref["lse_a"]).max() < 0.5
+
+
+def test_bf16_headline_shape(op):
+    n, h, w = 1, 60, 60
+    v_a, v_b = orc.synthetic_features(61, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(62, bias=False)
+    ref = orc.coattention(v_a, v_b, W, g, b, dtype=np.float32)
+    cat_a, cat_b, _, _ = run(op, v_a, v_b, W, g, b, bf16=True)
+    assert rel_l2(cat_a, ref["cat_a"]) < TOL      # bf16 does meet 1e-3 at the headline shape (L = 3600, S std ~ 2)
+    assert rel_l2(cat_b, ref["cat_b"]) < TOL
+
+
+def test_deterministic_and_batch_invariant(op):
+    n, h, w = 3, 20, 20
+    v_a, v_b = orc.synthetic_features(51, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(52, bias=True)
+    first = run(op, v_a, v_b, W, g, b)
+    again = run(op, v_a, v_b, W, g, b)
+    for x, y in zip(first, again):
+        assert np.array_equal(x, y)
+    # a sample's result does not depend on what else is in the batch
+    solo = run(op, v_a[1:2], v_b[1:2], W, g, b)
+    assert np.array_equal(solo[0][0], first[0][1]) and np.array_equal(solo[1][0], first[1][1])
+
+
+def test_full_size_properties_batch32(op):
+    """BASELINE cfg 2 size (batch 32, 60x60): size-independent properties instead of an O(L^2) oracle."""
+    dev = torch.device("cuda:0")
+    n, h, w = 32, 60, 60
+    L = h * w
+    gen = torch.Generator(device=dev); gen.manual_seed(1234)
+    x = torch.randn((2, n, C, h, w), generator=gen, device=dev)
+    feats = torch.where(x >= 0, x, 0.25 * x) * 0.66
+    v_a, v_b = feats[0].contiguous(), feats[1].contiguous()
+    v_b[:, 7] = 1.0            # a constant value channel must be reproduced exactly by any softmax average
+    v_a[:, 9] = -2.0
+    W, g, b = (torch.from_numpy(t).to(dev) for t in orc.synthetic_weights(5, bias=True))
+    cat_a, cat_b, z, lse = op(v_a, v_b, W, g, b)
+    torch.cuda.synchronize()
+    assert torch.isfinite(cat_a).all() and torch.isfinite(cat_b).all()
+    assert (z[0][:, 7] - 1.0).abs().max() < 2e-3      # sum_j P_a[i, j] == 1
+    assert (z[1][:, 9] + 2.0).abs().max() < 4e-3      # sum_i P_b[i, j] == 1
+    # convex-hull property on every channel
+    zmax, zmin = z[0].amax(dim=2), z[0].amin(dim=2)
+    vb = v_b.view(n, C, L)
+    assert (zmax <= vb.amax(dim=2) + 1e-2).all() and (zmin >= vb.amin(dim=2) - 1e-2).all()
+    # gate: cat[:, :C] = z * sigmoid(g.z + b), checked with torch on the kernel's own z
+    za = z[0].view(n, C, h, w)
+    mask = torch.sigmoid((za * g.view(1, C, 1, 1)).sum(1, keepdim=True) + b)
+    assert (cat_a[:, :C] - za * mask).abs().max() < 1e-5
+    assert torch.equal(cat_a[:, C:], v_a) and torch.equal(cat_b[:, C:], v_b)
+    # batch invariance at full size: sample 17 alone reproduces its slice bit for bit
+    solo = op(v_a[17:18].contiguous(), v_b[17:18].contiguous(), W, g, b)
+    torch.cuda.synchronize()
+    assert torch.equal(solo[0][0], cat_a[17]) and torch.equal(solo[1][0], cat_b[17])
+    # spot-check 3 samples against the oracle restricted to a handful of query rows (O(L) per row)
+    for s in (0, 13, 31):
+        A = v_a[s].view(C, L).double().cpu().numpy(); B = v_b[s].view(C, L).double().cpu().numpy()
+        Wd = W.double().cpu().numpy()
+        rows = np.array([0, 1, 127, 128, 2047, 3599])
+        q = (Wd @ A[:, rows]).T                       # [rows, C]
+        srow = q @ B                                   # [rows, L]
+        p = orc.softmax(srow, axis=1)
+        ref = (B @ p.T)                                # [C, rows]
+        got = z[0][s][:, rows].double().cpu().numpy()
+        assert rel_l2(got, ref) < 5e-3
+
+
+def test_argument_checks(op):
+    dev = torch.device("cuda:0")
+    x = torch.zeros(1, 256, 4, 4, device=dev)
+    with pytest.raises(ValueError):
+        op(x, torch.zeros(1, 256, 4, 5, device=dev), torch.zeros(256, 256, device=dev), torch.zeros(256, device=dev))
+    with pytest.raises(TypeError):
+        op(x.half(), x.half(), torch.zeros(256, 256, device=dev), torch.zeros(256, device=dev))
+    with pytest.raises(ValueError):
+        y = torch.zeros(1, 128, 4, 4, device=dev)
+        op(y, y, torch.zeros(256, 256, device=dev), torch.zeros(128, device=dev))
