@@ -243,8 +243,8 @@ def run_ours(args):
     g_dep = torch.randn((C,), generator=g, device=dev) * 0.01
     b_dep = (torch.rand((1,), generator=g, device=dev) * 2 - 1) * k
     cat = [torch.empty((n, 2 * C, H, W), device=dev) for _ in range(4)]
-    z = torch.empty((2, n, C, L), device=dev)
     lse = torch.empty((2, n, L), device=dev)
+    mask = torch.empty((2, n, L), device=dev)
     nbytes = workspace_bytes(n, C, H, W)
     ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
     wsp = (ws.data_ptr() + 1023) // 1024 * 1024
@@ -260,12 +260,13 @@ def run_ours(args):
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-        _lib.check(lib.coattn_stage_attend(z.data_ptr(), lse.data_ptr(), wsp, nbytes, n, C, H, W, FLAGS, st), "attend")
+        _lib.check(lib.coattn_stage_attend_gate(ca.data_ptr(), cb.data_ptr(), None, lse.data_ptr(), mask.data_ptr(),
+                                                gw.data_ptr(), gbp, wsp, nbytes, n, C, H, W, FLAGS, st), "attend_gate")
         if record:
             e1.record(stream)
             attend_events.append((e0, e1))
-        _lib.check(lib.coattn_stage_gate(z.data_ptr(), va.data_ptr(), vb.data_ptr(), gw.data_ptr(), gbp,
-                                         ca.data_ptr(), cb.data_ptr(), n, C, H, W, st), "gate")
+        _lib.check(lib.coattn_stage_passthrough(va.data_ptr(), vb.data_ptr(), ca.data_ptr(), cb.data_ptr(), n, C, H, W, st),
+                   "passthrough")
 
     def step(record=False):
         modality(v_a, v_b, w_rgb, g_rgb, None, cat[0], cat[1], record)

@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcoattn_b200.so")
+LIB_PATH = os.environ.get("COATTN_B200_LIB", os.path.join(_HERE, "lib", "libcoattn_b200.so"))
 ABI_VERSION = 1
 
 _lock = threading.Lock()
@@ -18,6 +18,7 @@ _lib = None
 _vp, _i, _i64, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint
 
 FLAG_BF16 = 1  # COATTN_FLAG_BF16
+FLAG_UNFUSED_GATE = 2  # COATTN_FLAG_UNFUSED_GATE
 
 # name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
 SIGNATURES = {
@@ -25,7 +26,9 @@ SIGNATURES = {
     "coattn_b200_strerror": (ctypes.c_char_p, [_i]),
     "coattn_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "coattn_workspace_segment": (_i, [ctypes.c_char_p, _i, _i, _i, _i, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
-    "coattn_forward": (_i, [_vp] * 10 + [_i64, _i, _i, _i, _i, _u, _vp]),
+    "coattn_forward": (_i, [_vp] * 11 + [_i64, _i, _i, _i, _i, _u, _vp]),
+    "coattn_stage_attend_gate": (_i, [_vp] * 8 + [_i64, _i, _i, _i, _i, _u, _vp]),
+    "coattn_stage_passthrough": (_i, [_vp] * 4 + [_i, _i, _i, _i, _vp]),
     "coattn_stage_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_project": (_i, [_vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_attend": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),

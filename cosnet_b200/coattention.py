@@ -56,8 +56,10 @@ def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
     return n, c, h, w
 
 
-def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False):
-    """Runs the four CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L].
+def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False,
+                            unfused_gate=False, want_mask=False, want_z=True):
+    """Runs the CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L]
+    (plus mask [2,N,L] when want_mask=True; fused path only).
 
     bf16_operands=False (default): fp16 tensor-core operands with fp32 accumulation (COATTN_FLAG_BF16 unset);
     True: bf16 operands (see include/coattn_b200.h for the trade-off).
@@ -73,22 +75,27 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         gb = None if gate_bias is None else gate_bias.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
         cat_a = torch.empty((n, 2 * c, h, w), dtype=torch.float32, device=dev)
         cat_b = torch.empty((n, 2 * c, h, w), dtype=torch.float32, device=dev)
-        z = torch.empty((2, n, c, h * w), dtype=torch.float32, device=dev)
+        z = torch.empty((2, n, c, h * w), dtype=torch.float32, device=dev) if (want_z or unfused_gate) else None
         lse = torch.empty((2, n, h * w), dtype=torch.float32, device=dev)
         nbytes = workspace_bytes(n, c, h, w)
         ws = _workspace(dev, nbytes)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        mask = torch.empty((2, n, h * w), dtype=torch.float32, device=dev) if want_mask else None
+        flags = (_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)
         code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
                                   None if gb is None else gb.data_ptr(), cat_a.data_ptr(), cat_b.data_ptr(),
-                                  z.data_ptr(), lse.data_ptr(), _aligned_ptr(ws), nbytes, n, c, h, w,
-                                  _lib.FLAG_BF16 if bf16_operands else 0, stream)
+                                  None if z is None else z.data_ptr(), lse.data_ptr(),
+                                  None if mask is None else mask.data_ptr(),
+                                  _aligned_ptr(ws), nbytes, n, c, h, w, flags, stream)
         _lib.check(code, "coattn_forward")
+    if want_mask:
+        return cat_a, cat_b, z, lse, mask
     return cat_a, cat_b, z, lse
 
 
 def coattention(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False):
     """Drop-in for rgbd_segmentation_RAA.py:150-187: returns (cat_a, cat_b), each [N, 2C, H, W]."""
-    cat_a, cat_b, _, _ = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands)
+    cat_a, cat_b, _, _ = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands, want_z=False)
     return cat_a, cat_b
 
 
@@ -144,7 +151,7 @@ class HostPipeline:
                 code = self.lib.coattn_forward(
                     s["va"].data_ptr(), s["vb"].data_ptr(), weight.data_ptr(), gw.data_ptr(),
                     None if gate_bias is None else gate_bias.data_ptr(), s["ca"].data_ptr(), s["cb"].data_ptr(),
-                    None, None, _aligned_ptr(s["ws"]), s["nbytes"], m, c, h, w, self.flags, st.cuda_stream)
+                    None, None, None, _aligned_ptr(s["ws"]), s["nbytes"], m, c, h, w, self.flags, st.cuda_stream)
                 _lib.check(code, "coattn_forward")
                 out_a[lo:hi].copy_(s["ca"][:m], non_blocking=True)
                 out_b[lo:hi].copy_(s["cb"][:m], non_blocking=True)

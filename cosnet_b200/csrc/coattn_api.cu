@@ -2,6 +2,8 @@
 // TMA descriptor encoding and kernel launches.  No torch types, no global mutable state.
 #include "../../include/coattn_b200.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -158,11 +160,15 @@ int coattn_stage_prep(const float* v_a, const float* v_b, const float* w, void* 
   p.Lp = ly.Lp;
   unsigned short* w16 = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16));
   const dim3 grid(ly.Lp / kPrepTileL, 2 * n);
+  const bool vec = (ly.L % 4 == 0) &&
+                   (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   if (flags & COATTN_FLAG_BF16) {
-    prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(p);
+    if (vec) prep_kernel_vec4<true><<<grid, kPrepThreads, 0, st>>>(p);
+    else prep_kernel<true><<<grid, kPrepThreads, 0, st>>>(p);
     cast_w_kernel<true><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
   } else {
-    prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(p);
+    if (vec) prep_kernel_vec4<false><<<grid, kPrepThreads, 0, st>>>(p);
+    else prep_kernel<false><<<grid, kPrepThreads, 0, st>>>(p);
     cast_w_kernel<false><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
   }
   return (int)cudaGetLastError();
@@ -191,8 +197,9 @@ int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c,
   return (int)cudaGetLastError();
 }
 
-int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace_bytes, int n, int c, int h,
-                        int w_, unsigned flags, void* stream) {
+static int launch_attend(float* cat_a, float* cat_b, float* z, float* lse, float* mask, const float* gate_w,
+                         const float* gate_b, void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
+                         unsigned flags, void* stream) {
   const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
@@ -208,8 +215,13 @@ int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace
   if (int e = make_tmap(enc, &tm_v, seg(workspace, ly.off_vv), (uint64_t)2 * n * kC, ly.Lp, kC, bf16)) return e;
   AttendParams p;
   p.t = reinterpret_cast<const unsigned short*>(seg(workspace, ly.off_t));
-  p.z = z ? z : reinterpret_cast<float*>(seg(workspace, ly.off_z));
+  p.z = z;
   p.lse = lse ? lse : reinterpret_cast<float*>(seg(workspace, ly.off_lse));
+  p.cat_a = cat_a;
+  p.cat_b = cat_b;
+  p.mask = mask;
+  p.gate_w = gate_w;
+  p.gate_b = gate_b;
   p.N = n;
   p.L = ly.L;
   p.Lp = ly.Lp;
@@ -219,8 +231,70 @@ int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace
   auto kern = bf16 ? attend_kernel<true> : attend_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttendSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  const int grid = p.num_items < sms ? p.num_items : sms;
+  int grid = p.num_items < sms ? p.num_items : sms;
+#ifdef COATTN_EXPERIMENT
+  if (const char* g = getenv("COATTN_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }
+#endif
+  p.trace = nullptr;
+#ifdef COATTN_TRACE
+  static long long* dtrace = nullptr;
+  if (!dtrace) cudaMalloc(&dtrace, 96 * 8 * sizeof(long long));
+  cudaMemsetAsync(dtrace, 0, 96 * 8 * sizeof(long long), st);
+  p.trace = dtrace;
+#endif
   kern<<<grid, kAttendThreads, kAttendSmemBytes, st>>>(tm_k, tm_v, p);
+#ifdef COATTN_TRACE
+  {
+    static int calls = 0;
+    if (++calls == 3) {
+      long long hbuf[96 * 8];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hbuf, dtrace, sizeof(hbuf), cudaMemcpyDeviceToHost);
+      const long long t0 = hbuf[0];
+      for (int i = 0; i < 40; ++i)
+        printf("tile %2d: loop+%6lld | S_issued +%5lld | p_full +%5lld | v_full +%5lld | PV_issued +%5lld || softmax saw S(j) at +%6lld\n", i,
+               hbuf[i * 8 + 0] - t0, hbuf[i * 8 + 1] - hbuf[i * 8 + 0], hbuf[i * 8 + 2] - hbuf[i * 8 + 1],
+               hbuf[i * 8 + 3] - hbuf[i * 8 + 2], hbuf[i * 8 + 4] - hbuf[i * 8 + 3], hbuf[i * 8 + 5] - t0);
+    }
+  }
+#endif
+  return (int)cudaGetLastError();
+}
+
+int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace_bytes, int n, int c, int h,
+                        int w_, unsigned flags, void* stream) {
+  if (int e = check_dims(n, c, h, w_)) return e;
+  if (!workspace) return COATTN_E_NULL;
+  float* zbuf = z ? z : reinterpret_cast<float*>(seg(workspace, make_layout(n, h, w_).off_z));
+  return launch_attend(nullptr, nullptr, zbuf, lse, nullptr, nullptr, nullptr, workspace, workspace_bytes, n, c, h, w_,
+                       flags, stream);
+}
+
+int coattn_stage_attend_gate(float* cat_a, float* cat_b, float* z, float* lse, float* mask, const float* gate_w,
+                             const float* gate_b, void* workspace, int64_t workspace_bytes, int n, int c, int h,
+                             int w_, unsigned flags, void* stream) {
+  if (!cat_a || !cat_b || !gate_w) return COATTN_E_NULL;
+  return launch_attend(cat_a, cat_b, z, lse, mask, gate_w, gate_b, workspace, workspace_bytes, n, c, h, w_, flags,
+                       stream);
+}
+
+int coattn_stage_passthrough(const float* v_a, const float* v_b, float* cat_a, float* cat_b, int n, int c, int h,
+                             int w_, void* stream) {
+  if (!v_a || !v_b || !cat_a || !cat_b) return COATTN_E_NULL;
+  if (int e = check_dims(n, c, h, w_)) return e;
+  if (int e = check_arch(nullptr)) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PassParams p;
+  p.v_a = v_a; p.v_b = v_b; p.cat_a = cat_a; p.cat_b = cat_b; p.N = n;
+  p.plane = (size_t)kC * h * w_;
+  const uintptr_t ptrs = reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b) |
+                         reinterpret_cast<uintptr_t>(cat_a) | reinterpret_cast<uintptr_t>(cat_b);
+  // ~16 float4 per thread
+  const size_t n4 = p.plane / 4;
+  int gx = (int)((n4 + 256 * 16 - 1) / (256 * 16));
+  if (gx < 1) gx = 1;
+  if ((p.plane % 4) == 0 && (ptrs & 15) == 0) passthrough_kernel<4><<<dim3(gx, 2 * n), 256, 0, st>>>(p);
+  else passthrough_kernel<1><<<dim3(gx, 2 * n), 256, 0, st>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -245,17 +319,23 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
 }
 
 int coattn_forward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* gate_b,
-                   float* cat_a, float* cat_b, float* z, float* lse, void* workspace, int64_t workspace_bytes,
-                   int n, int c, int h, int w_, unsigned flags, void* stream) {
+                   float* cat_a, float* cat_b, float* z, float* lse, float* mask, void* workspace,
+                   int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags, void* stream) {
   if (!v_a || !v_b || !w || !gate_w || !cat_a || !cat_b) return COATTN_E_NULL;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
   if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
-  float* zbuf = z ? z : reinterpret_cast<float*>(seg(workspace, ly.off_z));
   if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
   if (int e = coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
-  if (int e = coattn_stage_attend(zbuf, lse, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
-  return coattn_stage_gate(zbuf, v_a, v_b, gate_w, gate_b, cat_a, cat_b, n, c, h, w_, stream);
+  if (flags & COATTN_FLAG_UNFUSED_GATE) {
+    float* zbuf = z ? z : reinterpret_cast<float*>(seg(workspace, ly.off_z));
+    if (int e = coattn_stage_attend(zbuf, lse, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+    return coattn_stage_gate(zbuf, v_a, v_b, gate_w, gate_b, cat_a, cat_b, n, c, h, w_, stream);
+  }
+  if (int e = coattn_stage_attend_gate(cat_a, cat_b, z, lse, mask, gate_w, gate_b, workspace, workspace_bytes, n, c, h,
+                                       w_, flags, stream))
+    return e;
+  return coattn_stage_passthrough(v_a, v_b, cat_a, cat_b, n, c, h, w_, stream);
 }
 
 }  // extern "C"

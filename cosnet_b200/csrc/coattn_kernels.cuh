@@ -75,6 +75,47 @@ __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepParams p) {
   }
 }
 
+// Vectorised variant for L % 4 == 0 (and 16-byte aligned inputs): float4 loads, 8-byte / 16-byte stores.
+constexpr int kPrepStrideV = kC + 8;  // 16-bit elements; 528-byte rows keep 16-byte alignment for uint4 reads
+
+template <bool BF16>
+__global__ void __launch_bounds__(kPrepThreads) prep_kernel_vec4(PrepParams p) {
+  __shared__ __align__(16) unsigned short tile[kPrepTileL * kPrepStrideV];
+  const int n = blockIdx.y >> 1;
+  const int which = blockIdx.y & 1;  // 0: A, 1: B
+  const int l0 = blockIdx.x * kPrepTileL;
+  const float* src = (which ? p.vb : p.va) + (size_t)n * kC * p.L;
+  unsigned short* x16 = (which ? p.b16 : p.a16) + (size_t)n * kC * p.Lp;
+  unsigned short* xt = (which ? p.bt : p.at) + (size_t)n * p.Lp * kC;
+
+  const int col4 = threadIdx.x & 15;   // float4 column inside the 64-position tile
+  const int crow = threadIdx.x >> 4;   // 0..15
+  const int l = l0 + 4 * col4;
+  const bool valid = l < p.L;          // L % 4 == 0: a float4 is entirely inside or outside
+#pragma unroll 4
+  for (int k = 0; k < kC / 16; ++k) {
+    const int c = crow + 16 * k;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)c * p.L + l));
+    const uint32_t lo = pack16x2<BF16>(v.x, v.y), hi = pack16x2<BF16>(v.z, v.w);
+    *reinterpret_cast<uint2*>(x16 + (size_t)c * p.Lp + l) = make_uint2(lo, hi);
+    unsigned short* t = tile + (4 * col4) * kPrepStrideV + c;
+    t[0] = (unsigned short)(lo & 0xFFFFu);
+    t[kPrepStrideV] = (unsigned short)(lo >> 16);
+    t[2 * kPrepStrideV] = (unsigned short)(hi & 0xFFFFu);
+    t[3 * kPrepStrideV] = (unsigned short)(hi >> 16);
+  }
+  __syncthreads();
+  const int c8 = threadIdx.x & 31;   // group of 8 channels
+  const int r0 = threadIdx.x >> 5;   // 0..7
+#pragma unroll
+  for (int k = 0; k < kPrepTileL / 8; ++k) {
+    const int r = r0 + 8 * k;
+    const uint4 w = *reinterpret_cast<const uint4*>(&tile[r * kPrepStrideV + 8 * c8]);
+    *reinterpret_cast<uint4*>(xt + (size_t)(l0 + r) * kC + 8 * c8) = w;
+  }
+}
+
 // fp32 [C][C] -> 16-bit [C][C]
 template <bool BF16>
 __global__ void cast_w_kernel(const float* __restrict__ w, unsigned short* __restrict__ w16, int n) {
@@ -93,6 +134,17 @@ constexpr int kMmaWarp = 5;
 __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
   const uint32_t a = smem_u32(p);
   return p + ((1024u - (a & 1023u)) & 1023u);
+}
+
+// One lane polls the barrier, the warp reconverges behind it (4 pollers per CTA instead of 128).
+__device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t parity, int lane, int tag) {
+  if (lane == 0) mbar_wait(bar, parity, tag);
+  __syncwarp();
+}
+// Every lane has fenced its own tcgen05 traffic; one elected arrival per warp publishes it.
+__device__ __forceinline__ void warp_mbar_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
 }
 
 // ==============================================================================================
@@ -226,13 +278,29 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units: O is only rescaled whe
 
 struct AttendParams {
   const unsigned short* t;  // [2][N][Lp][C] 16-bit: t[0] = Bt, t[1] = Qt (queries of pass p are t[1-p])
-  float* z;     // [2][N][C][L]  raw attended features (pass 0: Z_a, pass 1: Z_b)
+  float* z;     // [2][N][C][L]  raw attended features (pass 0: Z_a, pass 1: Z_b); may be null when cat_* are set
   float* lse;   // [2][N][L]     log-sum-exp of each softmax row (natural log)
+  // fused gate epilogue (:177-184): when cat_a/cat_b are set the drain also writes Z * sigmoid(g.Z + b) into the
+  // first C channels of the concat tensors and the gate values into mask
+  float* cat_a;          // [N][2C][L] or null
+  float* cat_b;          // [N][2C][L] or null
+  float* mask;           // [2][N][L] or null
+  const float* gate_w;   // [C]
+  const float* gate_b;   // [1] or null
   int N, L, Lp;
   int q_tiles;   // ceil(L / 128)
   int kv_tiles;  // ceil(L / 64)
   int num_items; // 2 * N * q_tiles
+  long long* trace;  // debug only (COATTN_TRACE builds): clock64 stamps of block 0
 };
+
+#ifdef COATTN_TRACE
+#define TRACE_MMA(slot) do { if (blockIdx.x == 0 && lane == 0 && tcount < 96) p.trace[tcount * 8 + (slot)] = clock64(); } while (0)
+#define TRACE_SM(slot) do { if (blockIdx.x == 0 && warp == 0 && lane == 0 && scount < 96) p.trace[scount * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE_MMA(slot) do {} while (0)
+#define TRACE_SM(slot) do {} while (0)
+#endif
 
 template <bool BF16>
 __global__ void __launch_bounds__(kAttendThreads, 1)
@@ -244,7 +312,7 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
   uint8_t* sK = smem;
   uint8_t* sV = sK + kKStages * kKBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kVStages * kVBytes);
-  uint64_t* q_full = bars + 0;                 // query tile staged in TMEM (128 arrivals)
+  uint64_t* q_full = bars + 0;                 // query tile staged in TMEM (one arrival per softmax warp)
   uint64_t* k_full = bars + 1;                 // [kKStages]
   uint64_t* k_empty = k_full + kKStages;       // [kKStages]
   uint64_t* v_full = k_empty + kKStages;       // [kVStages]
@@ -252,8 +320,7 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
   uint64_t* s_full = v_empty + kVStages;       // [2]
   uint64_t* p_full = s_full + 2;               // [2]
   uint64_t* o_full = p_full + 2;               // one completion per PV step
-  uint64_t* o_free = o_full + 1;               // softmax warps drained O of the item
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -261,12 +328,11 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
   if (warp == kKProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 128);
+    mbar_init(q_full, 4);
     for (int s = 0; s < kKStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
     for (int s = 0; s < kVStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(p_full + b, 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(p_full + b, 4); }
     mbar_init(o_full, 1);
-    mbar_init(o_free, 128);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -289,10 +355,14 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
         for (int j = 0; j < T; ++j, ++cnt) {
           const uint32_t s = cnt % kKStages, ph = (cnt / kKStages) & 1;
           mbar_wait(k_empty + s, ph ^ 1, 2);
+#if defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 3
+          mbar_arrive(k_full + s);
+#else
           mbar_arrive_expect_tx(k_full + s, kKBytes);
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb)
             tma_load_2d(sK + s * kKBytes + kb * (kBN * 128), &tmap_k, k_full + s, kb * 64, krow0 + j * kBN);
+#endif
         }
       }
     }
@@ -306,58 +376,82 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
         for (int j = 0; j < T; ++j, ++cnt) {
           const uint32_t s = cnt % kVStages, ph = (cnt / kVStages) & 1;
           mbar_wait(v_empty + s, ph ^ 1, 3);
+#if defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 3
+          mbar_arrive(v_full + s);
+#else
           mbar_arrive_expect_tx(v_full + s, kVBytes);
           tma_load_2d(sV + s * kVBytes, &tmap_v, v_full + s, j * kBN, vrow0);
+#endif
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_16(kBM, kBN, BF16);
-      constexpr uint32_t idesc_o = make_idesc_16(kBM, kC, BF16);
-      uint32_t it = 0, kcnt = 0, vcnt = 0;
-      uint32_t pphase0 = 0, pphase1 = 0;
-      const uint32_t tO = tmem + kTmemColsO;
-      const uint32_t tQ = tmem + kTmemColsQ;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        auto issue_s = [&](int j) {
-          const uint32_t s = kcnt % kKStages, ph = (kcnt / kKStages) & 1;
-          mbar_wait(k_full + s, ph, 10);
-          tc_fence_after();
-          const uint32_t tS = tmem + kTmemColsS + (uint32_t)(j & 1) * kBN;
+    // ------------------------------------------------------------------ MMA issuer
+    // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers;
+    // only the tcgen05.mma / tcgen05.commit instructions themselves are issued by one elected lane.
+    constexpr uint32_t idesc_s = make_idesc_16(kBM, kBN, BF16);
+    constexpr uint32_t idesc_o = make_idesc_16(kBM, kC, BF16);
+    uint32_t it = 0, kcnt = 0, vcnt = 0;
+    uint32_t pphase0 = 0, pphase1 = 0;
+    int tcount = 0; (void)tcount;
+    const uint32_t tO = tmem + kTmemColsO;
+    const uint32_t tQ = tmem + kTmemColsQ;
+    const uint32_t sK_addr = smem_u32(sK);
+    const uint32_t sV_addr = smem_u32(sV);
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      auto issue_s = [&](int j) {
+        const uint32_t s = kcnt % kKStages, ph = (kcnt / kKStages) & 1;
+        warp_mbar_wait(k_full + s, ph, lane, 10);
+        tc_fence_after();
+        const uint32_t tS = tmem + kTmemColsS + (uint32_t)(j & 1) * kBN;
+        const uint64_t bd0 = make_sdesc_k_sw128(sK_addr + s * kKBytes);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kC / 16; ++kk) {
-            const uint64_t bd =
-                make_sdesc_k_sw128(smem_u32(sK + s * kKBytes + (kk >> 2) * (kBN * 128) + (kk & 3) * 32));
+            // k-block kk/4 is 8 KB further, the 16-element step inside a 128-byte row is 32 B (>>4 in the descriptor)
+            const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (kBN * 128) + (kk & 3) * 32) >> 4);
+#if !(defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 4)
             umma_ts(tS, tQ + kk * 8, bd, idesc_s, kk > 0);
+#endif
           }
           umma_commit(k_empty + s);
           umma_commit(s_full + (j & 1));
-          ++kcnt;
-        };
-        // q_full(it) also implies that the softmax warps finished draining O of the previous item
-        mbar_wait(q_full, it & 1, 11);
+        }
+        __syncwarp();
+        ++kcnt;
+      };
+      // q_full(it) also implies that the softmax warps finished draining O of the previous item
+      warp_mbar_wait(q_full, it & 1, lane, 11);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        TRACE_MMA(0);
+        if (j + 1 < T) issue_s(j + 1);
+        TRACE_MMA(1);
+        const int b = j & 1;
+        if (b == 0) { warp_mbar_wait(p_full + 0, pphase0, lane, 13); pphase0 ^= 1; }
+        else        { warp_mbar_wait(p_full + 1, pphase1, lane, 13); pphase1 ^= 1; }
+        TRACE_MMA(2);
+        const uint32_t s = vcnt % kVStages, ph = (vcnt / kVStages) & 1;
+        warp_mbar_wait(v_full + s, ph, lane, 14);
         tc_fence_after();
-        issue_s(0);
-        for (int j = 0; j < T; ++j) {
-          if (j + 1 < T) issue_s(j + 1);
-          const int b = j & 1;
-          if (b == 0) { mbar_wait(p_full + 0, pphase0, 13); pphase0 ^= 1; }
-          else        { mbar_wait(p_full + 1, pphase1, 13); pphase1 ^= 1; }
-          const uint32_t s = vcnt % kVStages, ph = (vcnt / kVStages) & 1;
-          mbar_wait(v_full + s, ph, 14);
-          tc_fence_after();
-          const uint32_t tP = tmem + kTmemColsS + (uint32_t)b * kBN;
+        TRACE_MMA(3);
+        const uint32_t tP = tmem + kTmemColsS + (uint32_t)b * kBN;
+        const uint64_t vd0 = make_sdesc_k_sw128(sV_addr + s * kVBytes);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kBN / 16; ++kk) {
-            const uint64_t bd = make_sdesc_k_sw128(smem_u32(sV + s * kVBytes + kk * 32));
-            umma_ts(tO, tP + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+#if !(defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 4)
+            umma_ts(tO, tP + kk * 8, vd0 + (uint64_t)((kk * 32) >> 4), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+#endif
           }
           umma_commit(v_empty + s);
           umma_commit(o_full);
-          ++vcnt;
         }
+        __syncwarp();
+        TRACE_MMA(4);
+        ++tcount;
+        ++vcnt;
       }
     }
   } else {
@@ -367,6 +461,7 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
     const uint32_t tQ = tmem + lane_base + kTmemColsQ;
     uint32_t sphase0 = 0, sphase1 = 0;
     uint32_t it = 0;
+    int scount = 0; (void)scount;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int qt = item % p.q_tiles;
       const int np = item / p.q_tiles;
@@ -391,19 +486,41 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(q_full);
+        warp_mbar_arrive(q_full, lane);
       }
       float m = -INFINITY, l = 0.0f;
       for (int j = 0; j < T; ++j) {
         const int b = j & 1;
         const uint32_t tS = tmem + lane_base + kTmemColsS + (uint32_t)b * kBN;
-        if (b == 0) { mbar_wait(s_full + 0, sphase0, 20); sphase0 ^= 1; }
-        else        { mbar_wait(s_full + 1, sphase1, 20); sphase1 ^= 1; }
+        if (b == 0) { warp_mbar_wait(s_full + 0, sphase0, lane, 20); sphase0 ^= 1; }
+        else        { warp_mbar_wait(s_full + 1, sphase1, lane, 20); sphase1 ^= 1; }
         tc_fence_after();
+        TRACE_SM(5);
+        ++scount;
+#if defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT >= 2
+        // experiment: no softmax work at all (measures the bare TMA + MMA pipeline)
+        tc_fence_before();
+        warp_mbar_arrive(p_full + b, lane);
+        continue;
+#endif
         uint32_t s0[32], s1[32];
         tmem_ld32(tS, s0);
         tmem_ld32(tS + 32, s1);
         tmem_ld_wait();
+#if defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 1
+        // experiment: TMEM traffic only, no exp/max math
+        {
+          uint32_t pk[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) pk[k] = s0[k] ^ s1[k];
+          tmem_st32(tS, pk);
+          tmem_st_wait();
+          tc_fence_before();
+          warp_mbar_arrive(p_full + b, lane);
+          l = 1.0f;
+          continue;
+        }
+#endif
         if (j == T - 1) {
           const int nvalid = p.L - j * kBN;  // >= 1
           if (nvalid < kBN) {
@@ -427,7 +544,7 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
             const float m_new = fmaxf(m, tmax);
             const float scale = fast_exp2((m - m_new) * kLog2e);
             // PV(j-2) is complete (s_full(j) was observed), so the barrier is in phase j-1 or later
-            mbar_wait(o_full, (pv_base + (uint32_t)j - 1u) & 1u, 21);
+            warp_mbar_wait(o_full, (pv_base + (uint32_t)j - 1u) & 1u, lane, 21);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < kC / 32; ++ch) {
@@ -466,26 +583,60 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
         tmem_st32(tS, pk);   // P (16-bit pairs) overlays the first 32 columns of the S buffer
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(p_full + b);
+        warp_mbar_arrive(p_full + b, lane);
       }
       // drain: Z[c][row] = O[row][c] / l
       // Phases are waited one by one: after s_full(T-1) only PV(T-3) is known complete, so the barrier may
       // still be in phase T-2; a parity wait for phase T-1 alone would alias and pass early.
-      if (T >= 2) mbar_wait(o_full, (pv_base + (uint32_t)T - 2u) & 1u, 23);
-      mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, 22);
+      if (T >= 2) warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 2u) & 1u, lane, 23);
+      warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, lane, 22);
       tc_fence_after();
       const float inv = 1.0f / l;
       const bool valid = row < p.L;
-      float* zcol = p.z + ((size_t)(pass * p.N + n) * kC) * p.L + row;
+      if (p.z != nullptr) {
+        float* zcol = p.z + ((size_t)(pass * p.N + n) * kC) * p.L + row;
 #pragma unroll 1
-      for (int ch = 0; ch < kC / 32; ++ch) {
-        uint32_t o[32];
-        tmem_ld32(tO + ch * 32, o);
-        tmem_ld_wait();
-        if (valid) {
+        for (int ch = 0; ch < kC / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) zcol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * inv;
+            for (int k = 0; k < 32; ++k) zcol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * inv;
+          }
         }
+      }
+      if (p.cat_a != nullptr) {
+        // gate logit of this position: g . Z[:, row] + b  (two passes over the accumulator, it stays in TMEM)
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < kC / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            d0 = fmaf(__ldg(p.gate_w + ch * 32 + k + 0), __uint_as_float(o[k + 0]), d0);
+            d1 = fmaf(__ldg(p.gate_w + ch * 32 + k + 1), __uint_as_float(o[k + 1]), d1);
+            d2 = fmaf(__ldg(p.gate_w + ch * 32 + k + 2), __uint_as_float(o[k + 2]), d2);
+            d3 = fmaf(__ldg(p.gate_w + ch * 32 + k + 3), __uint_as_float(o[k + 3]), d3);
+          }
+        }
+        const float logit = ((d0 + d1) + (d2 + d3)) * inv + (p.gate_b ? __ldg(p.gate_b) : 0.f);
+        const float gate = 1.0f / (1.0f + __expf(-logit));
+        const float sc = inv * gate;
+        float* ccol = (pass ? p.cat_b : p.cat_a) + (size_t)n * 2 * kC * p.L + row;
+#pragma unroll 1
+        for (int ch = 0; ch < kC / 32; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) ccol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * sc;
+          }
+        }
+        if (valid && p.mask != nullptr) p.mask[(size_t)(pass * p.N + n) * p.L + row] = gate;
       }
       if (valid) p.lse[(size_t)(pass * p.N + n) * p.L + row] = m + __logf(l);
     }
@@ -495,6 +646,42 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
+  }
+}
+
+// ==============================================================================================
+// passthrough: cat_x[n][C + c][:] = v_x[n][c][:]  (the second half of the concat, :186-187).  Pure HBM copy:
+// 8 L C bytes per (sample, side).  Per sample the source is one contiguous run of C*L floats.
+// ==============================================================================================
+struct PassParams {
+  const float* v_a;
+  const float* v_b;
+  float* cat_a;
+  float* cat_b;
+  int N;
+  size_t plane;   // C * L floats
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256) passthrough_kernel(PassParams p) {
+  const int side = blockIdx.y / p.N;
+  const int n = blockIdx.y - side * p.N;
+  const float* src = (side ? p.v_b : p.v_a) + (size_t)n * p.plane;
+  float* dst = (side ? p.cat_b : p.cat_a) + (size_t)n * 2 * p.plane + p.plane;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if constexpr (VEC == 4) {
+    const size_t n4 = p.plane / 4;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      const float4 a = __ldcs(s4 + i), b = __ldcs(s4 + i + stride), c = __ldcs(s4 + i + 2 * stride),
+                   d = __ldcs(s4 + i + 3 * stride);
+      __stcs(d4 + i, a); __stcs(d4 + i + stride, b); __stcs(d4 + i + 2 * stride, c); __stcs(d4 + i + 3 * stride, d);
+    }
+    for (; i < n4; i += stride) __stcs(d4 + i, __ldcs(s4 + i));
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.plane; i += stride) dst[i] = src[i];
   }
 }
 

@@ -23,6 +23,7 @@
  *   z          [2, N, 256, H*W]    raw attended features, z[0] = Z_a, z[1] = Z_b   (:169-170)
  *   lse        [2, N, H*W]         natural-log normalisers: lse[0][n][i] = log sum_j exp S[i,j]
  *                                  (softmax of :165), lse[1][n][j] = log sum_i exp S[i,j] (:164)
+ *   mask       [2, N, H*W]         sigmoid gate values, mask[0] = input_mask_a, mask[1] = input_mask_b (:180-182)
  */
 #ifndef COATTN_B200_H_
 #define COATTN_B200_H_
@@ -55,6 +56,12 @@ enum {
  *                          train-like logit scales).
  */
 #define COATTN_FLAG_BF16 1u
+/*
+ *   COATTN_FLAG_UNFUSED_GATE  run the gate / sigmoid / concat stage as its own HBM-bound kernel
+ *                          (coattn_stage_gate) instead of fusing it into the drain of the attend kernel.
+ *                          Same results to fp32 rounding; kept for per-kernel roofline measurements.
+ */
+#define COATTN_FLAG_UNFUSED_GATE 2u
 
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);
@@ -67,12 +74,13 @@ int64_t coattn_workspace_bytes(int n, int c, int h, int w);
 
 /*
  * Whole hot path for one modality (replaces :150-187 or :204-238):
- *   prep (16-bit cast/transposes) -> project (Q = W A) -> attend (both softmax axes) -> gate/concat.
- * z and lse are outputs kept for the backward pass; either may be NULL, in which case they live
- * in the workspace (z) or are dropped (lse is always computed; NULL routes it to the workspace).
+ *   prep (16-bit cast/transposes) -> project (Q = W A) -> attend (both softmax axes, gate + sigmoid + scale
+ *   fused into its drain) -> passthrough copy of the original features into the second half of the concat.
+ * z, lse and mask are optional outputs kept for the backward pass; each may be NULL (lse and, with
+ * COATTN_FLAG_UNFUSED_GATE, z are then routed to the workspace).
  */
 int coattn_forward(const float* v_a, const float* v_b, const float* w, const float* gate_w,
-                   const float* gate_b, float* cat_a, float* cat_b, float* z, float* lse,
+                   const float* gate_b, float* cat_a, float* cat_b, float* z, float* lse, float* mask,
                    void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
                    unsigned flags, void* stream);
 
@@ -88,7 +96,16 @@ int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c,
 /* stage 3 (:160-170): fused affinity / dual softmax / attend.  Writes z and lse. */
 int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace_bytes, int n,
                         int c, int h, int w_, unsigned flags, void* stream);
-/* stage 4 (:177-187): gate, sigmoid, scale, concat. */
+/* stages 3+4a fused (:160-184): as stage 3, and the drain also writes Z * sigmoid(gate(Z)) into channels
+ * [0, 256) of cat_a / cat_b and the gate values into mask.  z, lse (-> workspace) and mask may be NULL. */
+int coattn_stage_attend_gate(float* cat_a, float* cat_b, float* z, float* lse, float* mask,
+                             const float* gate_w, const float* gate_b, void* workspace,
+                             int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
+                             void* stream);
+/* stage 4b (:186-187): cat_x[:, 256:512] = v_x, the passthrough half of the concat. */
+int coattn_stage_passthrough(const float* v_a, const float* v_b, float* cat_a, float* cat_b, int n,
+                             int c, int h, int w_, void* stream);
+/* stage 4 (:177-187), stand-alone: gate, sigmoid, scale, concat (both halves). */
 int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const float* gate_w,
                       const float* gate_b, float* cat_a, float* cat_b, int n, int c, int h, int w_,
                       void* stream);

@@ -61,7 +61,7 @@ def test_workspace_size_and_shape_errors(lib):
 
 def test_argument_errors_before_any_cuda_work(lib):
     # NULL pointers and bad shapes are rejected on the host, before touching a device
-    assert lib.coattn_forward(None, None, None, None, None, None, None, None, None, None, 0, 1, 256, 4, 4, 0, None) == -1
+    assert lib.coattn_forward(None, None, None, None, None, None, None, None, None, None, None, 0, 1, 256, 4, 4, 0, None) == -1
     assert lib.coattn_stage_gate(None, None, None, None, None, None, None, 1, 256, 4, 4, None) == -1
     assert lib.coattn_stage_project(None, 0, 1, 64, 4, 4, 0, None) == -2
 

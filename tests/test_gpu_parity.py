@@ -136,6 +136,27 @@ def test_bf16_headline_shape(op):
     assert rel_l2(cat_b, ref["cat_b"]) < TOL
 
 
+def test_fused_and_unfused_gate_agree(op):
+    n, h, w = 2, 12, 11
+    v_a, v_b = orc.synthetic_features(71, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(72, bias=True)
+    dev = torch.device("cuda:0")
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    fused = op(t(v_a), t(v_b), t(W), t(g), t(b), False, False, True)          # + mask
+    unfused = op(t(v_a), t(v_b), t(W), t(g), t(b), False, True)
+    torch.cuda.synchronize()
+    assert (fused[0] - unfused[0]).abs().max() < 2e-6 and (fused[1] - unfused[1]).abs().max() < 2e-6
+    assert torch.equal(fused[2], unfused[2]) and torch.equal(fused[3], unfused[3])      # raw z and lse are identical
+    ref = orc.coattention(v_a, v_b, W, g, b)
+    mask = fused[4].cpu().numpy()
+    assert np.abs(mask[0] - ref["mask_a"].reshape(n, -1)).max() < 1e-4
+    assert np.abs(mask[1] - ref["mask_b"].reshape(n, -1)).max() < 1e-4
+    # without the optional z output the concat is unchanged
+    no_z = op(t(v_a), t(v_b), t(W), t(g), t(b), False, False, False, False)
+    torch.cuda.synchronize()
+    assert no_z[2] is None and torch.equal(no_z[0], fused[0]) and torch.equal(no_z[1], fused[1])
+
+
 def test_deterministic_and_batch_invariant(op):
     n, h, w = 3, 20, 20
     v_a, v_b = orc.synthetic_features(51, n, h, w, 0.66)
