@@ -1,0 +1,436 @@
+// attend2: the CTA-pair (cta_group::2) version of the fused affinity / softmax / attend kernel.
+//
+// One cluster of two CTAs owns a 256-row query tile (128 rows per CTA) of one (sample, pass) and sweeps all
+// key/value tiles of 128 positions.  tcgen05.mma.cta_group::2 runs M = 256 MMAs across both SMs:
+//   S(j)  = Q K(j)^T : M 256, N 128, K 256 -> 16 x (256x128x16); A = Q tile from shared memory (each CTA its own
+//           128 rows), B = key tile, each CTA stages HALF of the 128 key rows (64 x 256, 32 KB)
+//   O    += P(j) V(j): M 256, N 256, K 128 ->  8 x (256x256x16); A = P from TMEM, B = value tile, each CTA stages
+//           HALF of the 256 channels (128 x 128, 32 KB)
+// so every MMA runs at the full N >= 128 rate and each SM pulls half of each K/V tile from L2.
+//
+//   warps 0-7   softmax + drain, two warpgroups: warp w and w+4 own the same 32 query rows (TMEM lane quadrant
+//               w % 4); warpgroup 0 handles key columns [0,64) of each tile and channels [0,128) of the drain,
+//               warpgroup 1 the other halves.  Row max / row sum / gate dot are exchanged through shared memory.
+//   warp 8      TMA producer: query tile + key tiles          warp 10   TMA producer: value tiles
+//   warp 9      MMA issuer (leader CTA only) + TMEM allocator
+//
+//   TMEM columns (per CTA): [0,256) O accumulator | [256,384) S/P buffer 0 | [384,512) S/P buffer 1
+//   Barriers with a "(L)" are only used in the leader CTA and are signalled from both CTAs.
+#pragma once
+#include "coattn_kernels.cuh"
+
+namespace coattn {
+
+constexpr int k2BM = 128;           // query rows per CTA (256 per pair)
+constexpr int k2BN = 128;           // key/value positions per tile (pair wide)
+constexpr int k2KStages = 3;
+constexpr int k2VStages = 2;
+constexpr int k2QBytes = k2BM * kC * 2;          // 64 KB : 4 k-blocks x [128 rows x 128 B]
+constexpr int k2KBytes = (k2BN / 2) * kC * 2;    // 32 KB : 4 k-blocks x [ 64 rows x 128 B]   (this CTA's key rows)
+constexpr int k2VBytes = (kC / 2) * k2BN * 2;    // 32 KB : 2 k-blocks x [128 rows x 128 B]   (this CTA's channels)
+constexpr int k2Threads = 352;
+constexpr int k2SoftmaxWarps = 8;
+constexpr int k2KProducerWarp = 8;
+constexpr int k2MmaWarp = 9;
+constexpr int k2VProducerWarp = 10;
+constexpr int k2ScratchBytes = 2 * 2 * 128 * 4;  // exchange buffer [parity][warpgroup][row]
+constexpr int k2SmemBytes = k2QBytes + k2KStages * k2KBytes + k2VStages * k2VBytes + k2ScratchBytes + 256;
+constexpr uint32_t k2TmemO = 0;
+constexpr uint32_t k2TmemS = 256;
+
+static_assert(k2SmemBytes <= 232448, "attend2 shared memory exceeds the 227 KB per-CTA limit");
+
+struct Attend2Params {
+  float* z;     // [2][N][C][L] raw attended features or null
+  float* lse;   // [2][N][L]
+  float* cat_a; // [N][2C][L] or null: fused gate epilogue (see AttendParams)
+  float* cat_b;
+  float* mask;  // [2][N][L] or null
+  const float* gate_w;
+  const float* gate_b;
+  int N, L, Lp;
+  int q_pairs;   // ceil(L / 256)
+  int kv_tiles;  // ceil(L / 128)
+  int num_items; // 2 * N * q_pairs
+};
+
+// exchange one float between the two threads that own the same query row (warp w and warp w + 4)
+__device__ __forceinline__ float pair_exchange(float v, float* xbuf, uint32_t seq, int wg, int row, int quad) {
+  xbuf[((seq & 1u) * 2 + wg) * 128 + row] = v;
+  named_bar_sync(1 + quad, 64);
+  return xbuf[((seq & 1u) * 2 + (wg ^ 1)) * 128 + row];
+}
+
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  box {64, 128}
+               const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  box {64, 64}
+               const __grid_constant__ CUtensorMap tmap_v,  // VV [2*N*C][Lp],  box {64, 128}
+               Attend2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + k2QBytes;
+  uint8_t* sV = sK + k2KStages * k2KBytes;
+  float* xbuf = reinterpret_cast<float*>(sV + k2VStages * k2VBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xbuf) + k2ScratchBytes);
+  uint64_t* q_full = bars + 0;                  // (L) query tiles of both CTAs landed (tx bytes)
+  uint64_t* q_empty = bars + 1;                 // every affinity MMA of the item completed
+  uint64_t* k_full = bars + 2;                  // (L) [k2KStages] both halves of a key tile landed
+  uint64_t* k_empty = k_full + k2KStages;       // [k2KStages]
+  uint64_t* v_full = k_empty + k2KStages;       // (L) [k2VStages]
+  uint64_t* v_empty = v_full + k2VStages;       // [k2VStages]
+  uint64_t* s_full = v_empty + k2VStages;       // [2]
+  uint64_t* p_full = s_full + 2;                // (L) [2] 16 arrivals: 8 softmax warps of each CTA
+  uint64_t* o_full = p_full + 2;                // one completion per PV step
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("attend2: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == k2KProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < k2KStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
+    for (int s = 0; s < k2VStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(p_full + b, 2 * k2SoftmaxWarps); }
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == k2MmaWarp) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int T = p.kv_tiles;
+
+  if (warp == k2KProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer: query tile + key tiles
+    if (lane == 0) {
+      const uint32_t q_full_l = mapa_u32(smem_u32(q_full), 0);
+      uint32_t it = 0, cnt = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
+        const int qp = item % p.q_pairs;
+        const int np = item / p.q_pairs;
+        const int pass = np & 1;
+        const int n = np >> 1;
+        const int qrow0 = ((1 - pass) * p.N + n) * p.Lp + qp * (2 * k2BM) + (int)rank * k2BM;
+        const int krow0 = (pass * p.N + n) * p.Lp + (int)rank * (k2BN / 2);
+        mbar_wait(q_empty, (it & 1) ^ 1, 1);
+        if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * k2QBytes);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(sQ + kb * (k2BM * 128), &tmap_q, q_full_l, kb * 64, qrow0);
+        for (int j = 0; j < T; ++j, ++cnt) {
+          const uint32_t s = cnt % k2KStages, ph = (cnt / k2KStages) & 1;
+          mbar_wait(k_empty + s, ph ^ 1, 2);
+          if (rank == 0) mbar_arrive_expect_tx(k_full + s, 2 * k2KBytes);
+          const uint32_t full_l = mapa_u32(smem_u32(k_full + s), 0);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)
+            tma_load_2d_pair(sK + s * k2KBytes + kb * ((k2BN / 2) * 128), &tmap_k, full_l, kb * 64, krow0 + j * k2BN);
+        }
+      }
+    }
+  } else if (warp == k2VProducerWarp) {
+    // ------------------------------------------------------------------ TMA producer: value tiles
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        const int np = item / p.q_pairs;
+        const int vrow0 = ((np & 1) * p.N + (np >> 1)) * kC + (int)rank * (kC / 2);
+        for (int j = 0; j < T; ++j, ++cnt) {
+          const uint32_t s = cnt % k2VStages, ph = (cnt / k2VStages) & 1;
+          mbar_wait(v_empty + s, ph ^ 1, 3);
+          if (rank == 0) mbar_arrive_expect_tx(v_full + s, 2 * k2VBytes);
+          const uint32_t full_l = mapa_u32(smem_u32(v_full + s), 0);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+            tma_load_2d_pair(sV + s * k2VBytes + kb * ((kC / 2) * 128), &tmap_v, full_l, j * k2BN + kb * 64, vrow0);
+        }
+      }
+    }
+  } else if (warp == k2MmaWarp) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA; uniform control flow)
+    if (rank == 0) {
+      constexpr uint32_t idesc_s = make_idesc_16(2 * k2BM, k2BN, BF16);
+      constexpr uint32_t idesc_o = make_idesc_16(2 * k2BM, kC, BF16);
+      uint32_t it = 0, kcnt = 0, vcnt = 0;
+      uint32_t pphase0 = 0, pphase1 = 0;
+      const uint32_t tO = tmem + k2TmemO;
+      const uint64_t qd0 = make_sdesc_k_sw128(smem_u32(sQ));
+      const uint32_t sK_addr = smem_u32(sK);
+      const uint32_t sV_addr = smem_u32(sV);
+#ifdef COATTN_TRACE
+      long long tr[24][6]; int tc = 0;
+#define TR2(i) do { if (tc < 24) tr[tc][i] = clock64(); } while (0)
+#else
+#define TR2(i) do {} while (0)
+#endif
+      for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
+        auto issue_s = [&](int j) {
+          const uint32_t s = kcnt % k2KStages, ph = (kcnt / k2KStages) & 1;
+          warp_mbar_wait(k_full + s, ph, lane, 10);
+          TR2(1);
+          tc_fence_after();
+          const uint32_t tS = tmem + k2TmemS + (uint32_t)(j & 1) * k2BN;
+          const uint64_t kd0 = make_sdesc_k_sw128(sK_addr + s * k2KBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < kC / 16; ++kk) {
+              const uint64_t ad = qd0 + (uint64_t)(((kk >> 2) * (k2BM * 128) + (kk & 3) * 32) >> 4);
+              const uint64_t bd = kd0 + (uint64_t)(((kk >> 2) * ((k2BN / 2) * 128) + (kk & 3) * 32) >> 4);
+              umma2_ss(tS, ad, bd, idesc_s, kk > 0);
+            }
+            umma2_commit_mc(k_empty + s, 3);
+            umma2_commit_mc(s_full + (j & 1), 3);
+          }
+          __syncwarp();
+          ++kcnt;
+        };
+        warp_mbar_wait(q_full, it & 1, lane, 11);
+        tc_fence_after();
+        issue_s(0);
+        for (int j = 0; j < T; ++j) {
+          TR2(0);
+          if (j + 1 < T) {
+            issue_s(j + 1);
+            TR2(2);
+          } else {
+            if (elect_one()) umma2_commit_mc(q_empty, 3);   // the query tiles may be overwritten
+            __syncwarp();
+          }
+          const int b = j & 1;
+          // P(0) of an item is only produced after the previous item's O was drained, so no separate O barrier
+          if (b == 0) { warp_mbar_wait(p_full + 0, pphase0, lane, 13); pphase0 ^= 1; }
+          else        { warp_mbar_wait(p_full + 1, pphase1, lane, 13); pphase1 ^= 1; }
+          TR2(3);
+          const uint32_t s = vcnt % k2VStages, ph = (vcnt / k2VStages) & 1;
+          warp_mbar_wait(v_full + s, ph, lane, 14);
+          tc_fence_after();
+          TR2(4);
+          const uint32_t tP = tmem + k2TmemS + (uint32_t)b * k2BN;
+          const uint64_t vd0 = make_sdesc_k_sw128(sV_addr + s * k2VBytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < k2BN / 16; ++kk) {
+              const uint64_t bd = vd0 + (uint64_t)(((kk >> 2) * ((kC / 2) * 128) + (kk & 3) * 32) >> 4);
+              umma2_ts(tO, tP + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma2_commit_mc(v_empty + s, 3);
+            umma2_commit_mc(o_full, 3);
+          }
+          __syncwarp();
+          TR2(5);
+#ifdef COATTN_TRACE
+          ++tc;
+#endif
+          ++vcnt;
+        }
+      }
+#ifdef COATTN_TRACE
+      if (blockIdx.x == 0 && lane == 0)
+        for (int i = 2; i < 22; ++i)
+          printf("tile %2d: +%6lld | k_full %5lld | S_issue %5lld | p_full %5lld | v_full %5lld | PV_issue %5lld\n", i,
+                 tr[i][0] - tr[2][0], tr[i][1] - tr[i][0], tr[i][2] - tr[i][1], tr[i][3] - tr[i][2], tr[i][4] - tr[i][3],
+                 tr[i][5] - tr[i][4]);
+#endif
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + drain
+    const int wg = warp >> 2;            // 0: key columns [0,64) / channels [0,128);  1: the other halves
+    const int quad = warp & 3;           // TMEM lane quadrant
+    const int rloc = quad * 32 + lane;   // query row inside this CTA's 128-row tile
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const uint32_t tO = tmem + lane_base + k2TmemO + (uint32_t)wg * 128;   // this warpgroup's 128 channels
+    const uint32_t p_full_l0 = mapa_u32(smem_u32(p_full + 0), 0);
+    const uint32_t p_full_l1 = mapa_u32(smem_u32(p_full + 1), 0);
+    uint32_t sphase0 = 0, sphase1 = 0, it = 0, seq = 0;
+#ifdef COATTN_TRACE
+    long long ts[24][6]; int sc = 0;
+#define TS2(i) do { if (sc < 24) ts[sc][i] = clock64(); } while (0)
+#else
+#define TS2(i) do {} while (0)
+#endif
+    for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
+      const int qp = item % p.q_pairs;
+      const int np = item / p.q_pairs;
+      const int pass = np & 1;
+      const int n = np >> 1;
+      const int row = qp * (2 * k2BM) + (int)rank * k2BM + rloc;
+      const uint32_t pv_base = it * (uint32_t)T;
+      float m = -INFINITY, l = 0.0f;
+      for (int j = 0; j < T; ++j) {
+        const int b = j & 1;
+        const uint32_t tSb = tmem + lane_base + k2TmemS + (uint32_t)b * k2BN;
+        TS2(0);
+        if (b == 0) { warp_mbar_wait(s_full + 0, sphase0, lane, 20); sphase0 ^= 1; }
+        else        { warp_mbar_wait(s_full + 1, sphase1, lane, 20); sphase1 ^= 1; }
+        tc_fence_after();
+        TS2(1);
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tSb + wg * 64, s0);
+        tmem_ld32(tSb + wg * 64 + 32, s1);
+        tmem_ld_wait();
+        TS2(2);
+        if (j == T - 1) {
+          const int nvalid = p.L - j * k2BN - wg * 64;   // may be <= 0 for warpgroup 1: everything masked
+          if (nvalid < 64) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              if (k >= nvalid) s0[k] = 0xff800000u;        // -inf
+              if (32 + k >= nvalid) s1[k] = 0xff800000u;
+            }
+          }
+        }
+        float hmax = __uint_as_float(s0[0]);
+#pragma unroll
+        for (int k = 1; k < 32; ++k) hmax = fmaxf(hmax, __uint_as_float(s0[k]));
+#pragma unroll
+        for (int k = 0; k < 32; ++k) hmax = fmaxf(hmax, __uint_as_float(s1[k]));
+        // both halves of the row agree on the tile max; the exchange barrier also orders "both warpgroups have
+        // read their S columns" before either overwrites them with P (P of warpgroup 1 lands on S of warpgroup 0)
+        const float tmax = fmaxf(hmax, pair_exchange(hmax, xbuf, seq++, wg, rloc, quad));
+        TS2(3);
+        if (j == 0) {
+          m = tmax;
+        } else {
+          const bool need = (tmax - m) * kLog2e > kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = fmaxf(m, tmax);
+            const float scale = fast_exp2((m - m_new) * kLog2e);
+            // PV(j-2) is complete (s_full(j) was observed), so the barrier is in phase j-1 or later
+            warp_mbar_wait(o_full, (pv_base + (uint32_t)j - 1u) & 1u, lane, 21);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+              uint32_t o[32];
+              tmem_ld32(tO + ch * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * scale);
+              tmem_st32(tO + ch * 32, o);
+            }
+            tmem_st_wait();
+            l *= scale;
+            m = m_new;
+          }
+        }
+        const float neg_m = -m * kLog2e;
+        uint32_t pk[32];
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s0[2 * k]), kLog2e, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s0[2 * k + 1]), kLog2e, neg_m));
+          pk[k] = pack16x2<BF16>(p0, p1);
+          if constexpr (BF16) { l0 += bf16lo_to_f32(pk[k]); l1 += bf16hi_to_f32(pk[k]); }
+          else { l0 += p0; l1 += p1; }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s1[2 * k]), kLog2e, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s1[2 * k + 1]), kLog2e, neg_m));
+          pk[16 + k] = pack16x2<BF16>(p0, p1);
+          if constexpr (BF16) { l2 += bf16lo_to_f32(pk[16 + k]); l3 += bf16hi_to_f32(pk[16 + k]); }
+          else { l2 += p0; l3 += p1; }
+        }
+        l += (l0 + l1) + (l2 + l3);
+        TS2(4);
+        tmem_st32(tSb + wg * 32, pk);   // packed P: 64 keys of this warpgroup -> 32 columns
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(b == 0 ? p_full_l0 : p_full_l1);
+        TS2(5);
+#ifdef COATTN_TRACE
+        ++sc;
+#endif
+      }
+#ifdef COATTN_TRACE
+      if (blockIdx.x == 0 && threadIdx.x == 0 && it == 0)
+        for (int i = 2; i < 20; ++i)
+          printf("softmax tile %2d: +%6lld | wait S %5lld | ld %5lld | max+xchg %5lld | exp %5lld | st+arrive %5lld\n", i,
+                 ts[i][0] - ts[2][0], ts[i][1] - ts[i][0], ts[i][2] - ts[i][1], ts[i][3] - ts[i][2], ts[i][4] - ts[i][3],
+                 ts[i][5] - ts[i][4]);
+#endif
+      // ---- drain.  Wait the last two PV phases one by one (see attend_kernel for the aliasing argument).
+      if (T >= 2) warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 2u) & 1u, lane, 23);
+      warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, lane, 22);
+      tc_fence_after();
+      l += pair_exchange(l, xbuf, seq++, wg, rloc, quad);
+      const float inv = 1.0f / l;
+      const bool valid = row < p.L;
+      const int c0 = wg * 128;
+      if (p.z != nullptr) {
+        float* zcol = p.z + ((size_t)(pass * p.N + n) * kC + c0) * p.L + row;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) zcol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * inv;
+          }
+        }
+      }
+      if (p.cat_a != nullptr) {
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            d0 = fmaf(__ldg(p.gate_w + c0 + ch * 32 + k + 0), __uint_as_float(o[k + 0]), d0);
+            d1 = fmaf(__ldg(p.gate_w + c0 + ch * 32 + k + 1), __uint_as_float(o[k + 1]), d1);
+            d2 = fmaf(__ldg(p.gate_w + c0 + ch * 32 + k + 2), __uint_as_float(o[k + 2]), d2);
+            d3 = fmaf(__ldg(p.gate_w + c0 + ch * 32 + k + 3), __uint_as_float(o[k + 3]), d3);
+          }
+        }
+        float dot = (d0 + d1) + (d2 + d3);
+        const float other = pair_exchange(dot, xbuf, seq++, wg, rloc, quad);
+        dot = (wg == 0) ? (dot + other) : (other + dot);   // same summation order in both halves
+        const float logit = dot * inv + (p.gate_b ? __ldg(p.gate_b) : 0.f);
+        const float gate = 1.0f / (1.0f + __expf(-logit));
+        const float sc = inv * gate;
+        float* ccol = (pass ? p.cat_b : p.cat_a) + ((size_t)n * 2 * kC + c0) * p.L + row;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tO + ch * 32, o);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) ccol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * sc;
+          }
+        }
+        if (valid && wg == 0 && p.mask != nullptr) p.mask[(size_t)(pass * p.N + n) * p.L + row] = gate;
+      }
+      if (valid && wg == 0) p.lse[(size_t)(pass * p.N + n) * p.L + row] = m + __logf(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA may leave (or free TMEM) while its partner can still signal it
+  if (warp == k2MmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem, 512);
+  }
+}
+
+}  // namespace coattn

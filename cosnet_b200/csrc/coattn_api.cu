@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "coattn_kernels.cuh"
+#include "attend2_kernel.cuh"
 
 namespace {
 
@@ -213,6 +214,28 @@ static int launch_attend(float* cat_a, float* cat_b, float* z, float* lse, float
   const uint64_t t_rows = (uint64_t)2 * n * ly.Lp;
   if (int e = make_tmap(enc, &tm_k, seg(workspace, ly.off_t), t_rows, kC, kBN, bf16)) return e;
   if (int e = make_tmap(enc, &tm_v, seg(workspace, ly.off_vv), (uint64_t)2 * n * kC, ly.Lp, kC, bf16)) return e;
+  if (!(flags & COATTN_FLAG_SINGLE_CTA)) {
+    // default: CTA-pair kernel (cluster of 2, tcgen05 cta_group::2)
+    CUtensorMap tm_q, tm_k2, tm_v2;
+    if (int e = make_tmap(enc, &tm_q, seg(workspace, ly.off_t), t_rows, kC, k2BM, bf16)) return e;
+    if (int e = make_tmap(enc, &tm_k2, seg(workspace, ly.off_t), t_rows, kC, k2BN / 2, bf16)) return e;
+    if (int e = make_tmap(enc, &tm_v2, seg(workspace, ly.off_vv), (uint64_t)2 * n * kC, ly.Lp, kC / 2, bf16)) return e;
+    Attend2Params q;
+    q.z = z;
+    q.lse = lse ? lse : reinterpret_cast<float*>(seg(workspace, ly.off_lse));
+    q.cat_a = cat_a; q.cat_b = cat_b; q.mask = mask; q.gate_w = gate_w; q.gate_b = gate_b;
+    q.N = n; q.L = ly.L; q.Lp = ly.Lp;
+    q.q_pairs = (ly.L + 2 * k2BM - 1) / (2 * k2BM);
+    q.kv_tiles = (ly.L + k2BN - 1) / k2BN;
+    q.num_items = 2 * n * q.q_pairs;
+    auto kern2 = bf16 ? attend2_kernel<true> : attend2_kernel<false>;
+    cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+    if (e2 != cudaSuccess) return (int)e2;
+    int clusters = sms / 2;
+    if (q.num_items < clusters) clusters = q.num_items;
+    kern2<<<2 * clusters, k2Threads, k2SmemBytes, st>>>(tm_q, tm_k2, tm_v2, q);
+    return (int)cudaGetLastError();
+  }
   AttendParams p;
   p.t = reinterpret_cast<const unsigned short*>(seg(workspace, ly.off_t));
   p.z = z;

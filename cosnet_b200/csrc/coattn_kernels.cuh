@@ -16,7 +16,7 @@
 namespace coattn {
 
 constexpr int kC = 256;       // channels (all_channel of the reference ctor, :22)
-constexpr int kLPad = 128;    // spatial padding granule of the bf16 workspace
+constexpr int kLPad = 256;    // spatial padding granule of the 16-bit workspace (one CTA-pair query tile)
 
 // ==============================================================================================
 // prep: cast + transpose + pad

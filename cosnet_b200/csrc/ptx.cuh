@@ -223,6 +223,86 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// thread-block clusters / CTA pairs (cta_group::2)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier that lives in another CTA of the cluster (address from mapa_u32)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default .release.cta semantics, as CUTLASS' ClusterBarrier::arrive(cta_id): a cluster-scope release here
+  // costs ~1000 cycles per arrival (it drains/invalidates like a cluster fence)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-D TMA load issued by one CTA of a pair: data lands in the issuing CTA's shared memory, the byte count is
+// signalled on `mbar_cluster_addr`, which may belong to either CTA of the pair (here: always the leader's).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t mbar_cluster_addr, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 MMAs over a CTA pair: issued by one thread of the leader CTA; A rows / D rows split by CTA (128 each),
+// B rows (the N dimension) split by CTA (N/2 each); descriptors and TMEM addresses are CTA-relative.
+__device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread completed) on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+// named barrier among `nthreads` threads of the CTA (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // two fp32 -> packed bf16x2 (lo = a, hi = b), round-to-nearest-even
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   uint32_t r;

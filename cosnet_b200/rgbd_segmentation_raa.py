@@ -1,0 +1,144 @@
+"""Drop-in `RGBDSegmentation_RAA` (ResNet + ASPP + Add, RGB + depth siamese model).
+
+Same class name, constructor, `forward(rgbs_a, rgbs_b, depths_a, depths_b) -> (x1, x2, labels)`, `get_params`,
+`load_state` and state_dict keys as the reference (rgbd_segmentation_RAA.py:18-268), so config.yaml, train.py and
+test.py keep working; the two inline co-attention blocks (:150-187 and :204-238) are replaced by one call each
+into the sm_100a kernels (`cosnet_b200.coattention`).  Everything else (encoders, 3x3 reduce convs, BN,
+classifiers, upsampling) stays on cuDNN / ATen.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .backbone import DepthEncoder_ResNetASPP, Encoder, init_reference_style
+from .coattention import coattention
+
+# legacy checkpoint prefixes -> current names (rgbd_segmentation_RAA.py:114-133); first match wins,
+# "encoder.main_classifier" must be tested before the generic "encoder." rule
+_LEGACY_PREFIXES = (
+    ("encoder.layer5.", "encoder.aspp."),
+    ("encoder.main_classifier", "encoder.main_classifier"),
+    ("encoder.", "encoder.backbone."),
+    ("linear_e.", "rgb_similarity_weights."),
+    ("conv1.", "reduce_channels_A."),
+    ("conv2.", "reduce_channels_B."),
+    ("bn1.", "bn_A."),
+    ("bn2.", "bn_B."),
+    ("main_classifier1.", "segmentation_classifier_A."),
+    ("main_classifier2.", "segmentation_classifier_B."),
+)
+
+_PARAM_SUBSETS = {
+    # subset -> groups it contains (rgbd_segmentation_RAA.py:70-75)
+    "none": (),
+    "encoder": ("encoder",),
+    "rgb_attention": ("rgb_attention",),
+    "rgb": ("encoder", "rgb_attention"),
+    "depth": ("depth",),
+    "decoder": ("decoder",),
+    "all": ("encoder", "rgb_attention", "depth", "decoder"),
+}
+
+
+class RGBDSegmentation_RAA(nn.Module):
+    def __init__(self, block, num_blocks_of_layers_4_rgb, num_blocks_of_layers_4_depth, num_classes,
+                 all_channel=256, all_dim=60 * 60, no_grad_for_counterpart=True):
+        super().__init__()
+        c = all_channel
+        # RGB branch (:26-34)
+        self.encoder = Encoder(3, block, num_blocks_of_layers_4_rgb, num_classes)
+        self.rgb_similarity_weights = nn.Linear(c, c, bias=False)
+        self.gate = nn.Conv2d(c, 1, kernel_size=1, bias=False)
+        self.gate_s = nn.Sigmoid()
+        self.reduce_channels_A = nn.Conv2d(2 * c, c, kernel_size=3, padding=1, bias=False)
+        self.reduce_channels_B = nn.Conv2d(2 * c, c, kernel_size=3, padding=1, bias=False)
+        self.bn_A = nn.BatchNorm2d(c)
+        self.bn_B = nn.BatchNorm2d(c)
+        self.prelu = nn.ReLU(inplace=True)
+        # depth branch (:37-43)
+        self.depth_encoder = DepthEncoder_ResNetASPP(256, block, num_blocks_of_layers_4_depth, num_classes)
+        self.depth_similarity_weights = nn.Linear(c, c, bias=False)
+        self.depth_gate = nn.Conv2d(c, 1, kernel_size=1, bias=True)
+        self.depth_gate_s = nn.Sigmoid()
+        self.depth_reduce_channels = nn.Conv2d(2 * c, c, kernel_size=3, padding=1, bias=False)
+        self.depth_bn = nn.BatchNorm2d(c)
+        self.depth_weights = nn.Conv2d(c, c, kernel_size=1, bias=True)
+        # decoder (:47-49)
+        self.segmentation_classifier_A = nn.Conv2d(c, num_classes, kernel_size=1, bias=True)
+        self.segmentation_classifier_B = nn.Conv2d(c, num_classes, kernel_size=1, bias=True)
+        self.softmax = nn.Sigmoid()
+
+        self.no_grad_for_counterpart = no_grad_for_counterpart
+        # `all_dim` is accepted for signature compatibility and ignored, like in the reference (:153)
+        init_reference_style(self)   # :53-62 (nn.Linear keeps its default init)
+        # the operator that replaces :150-187 / :204-238; tests may swap it for the CPU oracle
+        self.coattention_impl = coattention
+
+    # ------------------------------------------------------------------ optimiser groups (:65-100)
+    def get_params(self, subset="none"):
+        groups = {
+            "encoder": [self.encoder],
+            "rgb_attention": [self.rgb_similarity_weights, self.gate, self.reduce_channels_A, self.reduce_channels_B,
+                              self.bn_A, self.bn_B],
+            "depth": self.depth_encoder.get_params() + [self.depth_gate, self.depth_similarity_weights,
+                                                        self.depth_reduce_channels, self.depth_bn, self.depth_weights],
+            "decoder": [self.segmentation_classifier_A, self.segmentation_classifier_B],
+        }
+        out = []
+        for g in _PARAM_SUBSETS.get(subset, ()):
+            out.extend(groups[g])
+        return out
+
+    # ------------------------------------------------------------------ checkpoints (:103-136)
+    @staticmethod
+    def _current_key(key: str) -> str:
+        if key.startswith("module."):      # saved from nn.DataParallel
+            key = key[len("module."):]
+        for old, new in _LEGACY_PREFIXES:
+            if key.startswith(old):
+                return new + key[len(old):]
+        return key
+
+    def load_state(self, state_dict):
+        merged = self.state_dict().copy()
+        for key, value in state_dict.items():
+            merged[self._current_key(key)] = value
+        self.load_state_dict(merged)
+
+    # ------------------------------------------------------------------ forward (:139-268)
+    def _encode_pair(self, enc, x_a, x_b, returns_tuple):
+        """Frame A with grad, frame B under no_grad when `no_grad_for_counterpart` (:143-148, :198-203)."""
+        out_a = enc(x_a)
+        if self.no_grad_for_counterpart:
+            with torch.no_grad():
+                out_b = enc(x_b)
+        else:
+            out_b = enc(x_b)
+        if returns_tuple:
+            return out_a[0], out_b[0], out_b[1]    # the auxiliary map that survives is frame B's (:143, :146/148)
+        return out_a, out_b, None
+
+    def forward(self, rgbs_a, rgbs_b, depths_a, depths_b):
+        input_size = rgbs_a.shape[2:]
+
+        v_a, v_b, labels = self._encode_pair(self.encoder, rgbs_a, rgbs_b, True)
+        cat_a, cat_b = self.coattention_impl(v_a, v_b, self.rgb_similarity_weights.weight, self.gate.weight, None)
+        z_a = self.bn_A(self.reduce_channels_A(cat_a))          # :188, :190
+        z_b = self.bn_B(self.reduce_channels_B(cat_b))          # :189, :191
+        del v_a, v_b, cat_a, cat_b
+
+        d_a, d_b, _ = self._encode_pair(self.depth_encoder, depths_a, depths_b, False)
+        dcat_a, dcat_b = self.coattention_impl(d_a, d_b, self.depth_similarity_weights.weight, self.depth_gate.weight,
+                                               self.depth_gate.bias)
+        dz_a = self.depth_weights(self.depth_bn(self.depth_reduce_channels(dcat_a)))       # :239, :242, :245
+        with torch.no_grad():                                                               # :240-247
+            dz_b = self.depth_weights(self.depth_bn(self.depth_reduce_channels(dcat_b)))
+        del d_a, d_b, dcat_a, dcat_b
+
+        z_a = self.prelu(z_a + dz_a)                            # :251, :256
+        z_b = self.prelu(z_b + dz_b)                            # :252, :257
+        x1 = self.softmax(F.interpolate(self.segmentation_classifier_A(z_a), input_size, mode="bilinear"))  # :260-265
+        x2 = self.softmax(F.interpolate(self.segmentation_classifier_B(z_b), input_size, mode="bilinear"))
+        return x1, x2, labels

@@ -62,6 +62,12 @@ enum {
  *                          Same results to fp32 rounding; kept for per-kernel roofline measurements.
  */
 #define COATTN_FLAG_UNFUSED_GATE 2u
+/*
+ *   COATTN_FLAG_SINGLE_CTA  run the attend stage with the single-CTA kernel (128-row query tiles, 64-position
+ *                          key tiles) instead of the default CTA-pair kernel (tcgen05 cta_group::2, 256-row
+ *                          query tiles, 128-position key tiles).  Same math; kept as a cross-check.
+ */
+#define COATTN_FLAG_SINGLE_CTA 4u
 
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);

@@ -50,12 +50,13 @@ def main():
     ap.add_argument("--bias", type=int, default=1)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--bf16", type=int, default=0)
+    ap.add_argument("--single", type=int, default=0)
     args = ap.parse_args()
     n, h, w, c = args.n, args.h, args.w, 256
-    FL = 1 if args.bf16 else 0
+    FL = (1 if args.bf16 else 0) | (4 if args.single else 0)
     odt = torch.bfloat16 if args.bf16 else torch.float16
     L = h * w
-    Lp = (L + 127) // 128 * 128
+    Lp = (L + 255) // 256 * 256
     lib = _lib.load()
     dev = torch.device("cuda:0")
     print(f"[diag] stage={args.stage} n={n} h={h} w={w} L={L} Lp={Lp} sigma={args.sigma} dev={torch.cuda.get_device_name(0)}", flush=True)
@@ -126,7 +127,7 @@ def main():
             ref = torch.cat([zs * torch.sigmoid(t), v], 1)
             print(f"[gate] side {side} max abs err:", float((cat - ref).abs().max()), " passthrough exact:", bool(torch.equal(cat[:, c:], v)), flush=True)
     if args.stage in ("forward", "time"):
-        cat_a, cat_b, z, lse = coattention_forward_raw(tva, tvb, tW, tg, tb, bool(args.bf16))
+        cat_a, cat_b, z, lse = coattention_forward_raw(tva, tvb, tW, tg, tb, bool(args.bf16), single_cta=bool(args.single))
         torch.cuda.synchronize()
         if args.stage == "forward":
             full = orc.coattention(v_a, v_b, W, g, b)

@@ -46,7 +46,7 @@ def test_version_and_errors(lib):
 def test_workspace_size_and_shape_errors(lib):
     # 60x60 -> Lp = 3712: five bf16 planes of N*Lp*C plus W16, z, lse
     n, c, h, w = 2, 256, 60, 60
-    lp = 3712
+    lp = 3840
     plane = n * lp * c * 2
     expect_min = 5 * plane + c * c * 2 + 2 * n * c * h * w * 4 + 2 * n * h * w * 4
     got = lib.coattn_workspace_bytes(n, c, h, w)

@@ -223,3 +223,57 @@ def test_argument_checks(op):
     with pytest.raises(ValueError):
         y = torch.zeros(1, 128, 4, 4, device=dev)
         op(y, y, torch.zeros(256, 256, device=dev), torch.zeros(128, device=dev))
+
+
+class _Stub(torch.nn.Module):
+    """Encoder stand-in that replays queued synthetic features (same trick as oracle/ref_harness.py)."""
+
+    def __init__(self, as_tuple):
+        super().__init__()
+        self.queue, self.as_tuple = [], as_tuple
+
+    def forward(self, x):
+        f = self.queue.pop(0)
+        return (f, x.new_zeros(1)) if self.as_tuple else f
+
+
+@pytest.mark.parametrize("sigma,hw", [(0.66, (60, 60)), (1.0, (30, 30))])
+def test_end_to_end_masks_agree_with_oracle_operator(op, sigma, hw):
+    """BASELINE.json: binarised masks must agree on >= 99.9 % of pixels.  The whole drop-in module (reduce convs,
+    BN, depth fusion, classifiers, x8 upsampling) runs twice on the same weights: once with the CUDA co-attention,
+    once with the CPU oracle injected as the operator."""
+    from cosnet_b200.backbone import Bottleneck
+    from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1234)
+    model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).eval()
+    model.encoder, model.depth_encoder = _Stub(True), _Stub(False)
+    model = model.to(dev)
+    n, (h, w) = 2, hw
+    feats = [torch.from_numpy(f).to(dev) for f in orc.synthetic_features(91, n, h, w, sigma, count=4)]
+    img = torch.zeros(n, 3, h * 8, w * 8, device=dev)
+    dimg = torch.zeros(n, 1, h * 8, w * 8, device=dev)
+
+    def run_model():
+        model.encoder.queue = [feats[0], feats[1]]
+        model.depth_encoder.queue = [feats[2], feats[3]]
+        with torch.no_grad():
+            return model(img, img, dimg, dimg)
+
+    x1, x2, _ = run_model()
+
+    def oracle_impl(v_a, v_b, weight, gate_weight, gate_bias):
+        out = orc.coattention(v_a.cpu().numpy(), v_b.cpu().numpy(), weight.detach().cpu().numpy(),
+                              gate_weight.detach().cpu().numpy(),
+                              None if gate_bias is None else gate_bias.detach().cpu().numpy(), dtype=np.float32)
+        return torch.from_numpy(out["cat_a"]).to(dev), torch.from_numpy(out["cat_b"]).to(dev)
+
+    model.coattention_impl = oracle_impl
+    r1, r2, _ = run_model()
+    for got, ref in ((x1, r1), (x2, r2)):
+        assert got.shape == (n, 1, h * 8, w * 8)
+        # the test is only meaningful if the maps straddle the threshold
+        assert float(ref.min()) < 0.5 < float(ref.max())
+        agree = ((got > 0.5) == (ref > 0.5)).float().mean().item()
+        assert agree >= 0.999, agree
+        assert (got - ref).abs().max().item() < 2e-3

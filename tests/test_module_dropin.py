@@ -1,0 +1,133 @@
+"""Drop-in boundary of the nn.Module: ctor, state_dict keys, get_params, load_state and the
+forward wiring, checked on CPU against the unmodified reference with the oracle injected as the co-attention
+operator (test-only injection; the product default refuses CPU tensors)."""
+import os
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from cosnet_b200.backbone import Bottleneck
+from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
+from oracle import coattn_oracle as orc
+from oracle import ref_harness
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_ref = pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree not present")
+
+
+def oracle_impl(v_a, v_b, weight, gate_weight, gate_bias):
+    out = orc.coattention(v_a.detach().numpy(), v_b.detach().numpy(), weight.detach().numpy(),
+                          gate_weight.detach().numpy(), None if gate_bias is None else gate_bias.detach().numpy(),
+                          dtype=np.float32)
+    return torch.from_numpy(out["cat_a"]), torch.from_numpy(out["cat_b"])
+
+
+def small_model(**kw):
+    return RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1, **kw)
+
+
+@needs_ref
+def test_state_dict_keys_match_reference():
+    RefRAA, RefBottleneck = ref_harness.import_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = RefRAA(RefBottleneck, [1, 2, 1, 1], [1, 1, 2, 1], num_classes=1)
+    mine = RGBDSegmentation_RAA(Bottleneck, [1, 2, 1, 1], [1, 1, 2, 1], num_classes=1)
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    assert all(rs[k].shape == ms[k].shape for k in rs)
+    # same set of trainable parameters (the projection-shortcut BN affines are frozen, residual_net.py:132-133)
+    assert [n for n, p in ref.named_parameters() if p.requires_grad] == [n for n, p in mine.named_parameters() if p.requires_grad]
+    for subset in ("none", "all", "encoder", "rgb_attention", "rgb", "depth", "decoder"):
+        r = [type(m).__name__ for m in ref.get_params(subset)]
+        m = [type(x).__name__ for x in mine.get_params(subset)]
+        assert r == m, subset
+        assert sum(p.numel() for mod in ref.get_params(subset) for p in mod.parameters()) == \
+            sum(p.numel() for mod in mine.get_params(subset) for p in mod.parameters())
+
+
+def test_full_size_constructor_signature_and_param_count():
+    m = RGBDSegmentation_RAA(Bottleneck, [3, 4, 23, 3], [3, 4, 6, 3], num_classes=1)   # train.py:379
+    assert sum(p.numel() for p in m.parameters()) == 142371334                       # SURVEY.md 2.1 [measured]
+    assert len(m.state_dict()) == 1059
+    assert m.rgb_similarity_weights.weight.shape == (256, 256) and m.gate.weight.shape == (1, 256, 1, 1)
+    assert m.depth_gate.bias.shape == (1,) and m.gate.bias is None
+
+
+@needs_ref
+@pytest.mark.parametrize("frozen", [True, False])
+def test_forward_matches_reference_with_oracle_operator(frozen):
+    RefRAA, RefBottleneck = ref_harness.import_reference()
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = RefRAA(RefBottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1, no_grad_for_counterpart=frozen).eval()
+    mine = small_model(no_grad_for_counterpart=frozen).eval()
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    mine.coattention_impl = oracle_impl
+    g = torch.Generator().manual_seed(1)
+    ra, rb = torch.randn(1, 3, 65, 57, generator=g), torch.randn(1, 3, 65, 57, generator=g)
+    da, db = torch.randn(1, 1, 65, 57, generator=g), torch.randn(1, 1, 65, 57, generator=g)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = ref(ra, rb, da, db)
+        got = mine(ra, rb, da, db)
+    for w, g_ in zip(want, got):
+        assert w.shape == g_.shape
+        assert (w - g_).abs().max() < 1e-5
+    # the third output is frame B's auxiliary map (rgbd_segmentation_RAA.py:143-148, :268)
+    assert torch.allclose(got[2], mine.encoder(rb)[1])
+
+
+def test_load_state_renames_legacy_keys():
+    m = small_model()
+    sd = m.state_dict()
+    legacy = {}
+    for k, v in sd.items():
+        new = k
+        if k.startswith("encoder.aspp."):
+            new = k.replace("encoder.aspp.", "encoder.layer5.")
+        elif k.startswith("encoder.backbone."):
+            new = k.replace("encoder.backbone.", "encoder.")
+        elif k.startswith("rgb_similarity_weights."):
+            new = k.replace("rgb_similarity_weights.", "linear_e.")
+        elif k.startswith("reduce_channels_A."):
+            new = k.replace("reduce_channels_A.", "conv1.")
+        elif k.startswith("reduce_channels_B."):
+            new = k.replace("reduce_channels_B.", "conv2.")
+        elif k.startswith("bn_A."):
+            new = k.replace("bn_A.", "bn1.")
+        elif k.startswith("bn_B."):
+            new = k.replace("bn_B.", "bn2.")
+        elif k.startswith("segmentation_classifier_A."):
+            new = k.replace("segmentation_classifier_A.", "main_classifier1.")
+        elif k.startswith("segmentation_classifier_B."):
+            new = k.replace("segmentation_classifier_B.", "main_classifier2.")
+        legacy["module." + new] = torch.full_like(v, 0.5) if v.is_floating_point() else v
+    fresh = small_model()
+    fresh.load_state(legacy)
+    for k, v in fresh.state_dict().items():
+        if v.is_floating_point():
+            assert torch.all(v == 0.5), k
+
+
+def test_default_operator_has_no_cpu_fallback():
+    from cosnet_b200._lib import CoattnError
+    m = small_model().eval()
+    x = torch.zeros(1, 3, 33, 33)
+    d = torch.zeros(1, 1, 33, 33)
+    with pytest.raises(CoattnError), torch.no_grad():
+        m(x, x, d, d)
+
+
+def test_dropin_import_paths():
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "dropin"), ROOT]))
+    code = ("from rgbd_segmentation_RAA import RGBDSegmentation_RAA; from deeplab.residual_net import Bottleneck; "
+            "m = RGBDSegmentation_RAA(Bottleneck, [1,1,1,1], [1,1,1,1], num_classes=1); print(type(m).__module__)")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "cosnet_b200.rgbd_segmentation_raa" in out.stdout
