@@ -28,7 +28,7 @@ SIGNATURES = {
     "coattn_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "coattn_workspace_segment": (_i, [ctypes.c_char_p, _i, _i, _i, _i, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "coattn_forward": (_i, [_vp] * 11 + [_i64, _i, _i, _i, _i, _u, _vp]),
-    "coattn_stage_attend_gate": (_i, [_vp] * 8 + [_i64, _i, _i, _i, _i, _u, _vp]),
+    "coattn_stage_attend_gate": (_i, [_vp] * 10 + [_i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_passthrough": (_i, [_vp] * 4 + [_i, _i, _i, _i, _vp]),
     "coattn_stage_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_project": (_i, [_vp, _i64, _i, _i, _i, _i, _u, _vp]),

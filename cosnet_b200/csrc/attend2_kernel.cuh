@@ -13,6 +13,8 @@
 //               warpgroup 1 the other halves.  Row max / row sum / gate dot are exchanged through shared memory.
 //   warp 8      TMA producer: query tile + key tiles          warp 10   TMA producer: value tiles
 //   warp 9      MMA issuer (leader CTA only) + TMEM allocator
+//   warp 11     copies this CTA's 128 positions of the original fp32 features into channels [256,512) of the
+//               concat (the passthrough half, :186-187) while the tensor pipe is busy -- ~3.5 B/clk per SM
 //
 //   TMEM columns (per CTA): [0,256) O accumulator | [256,384) S/P buffer 0 | [384,512) S/P buffer 1
 //   Barriers with a "(L)" are only used in the leader CTA and are signalled from both CTAs.
@@ -28,11 +30,12 @@ constexpr int k2VStages = 2;
 constexpr int k2QBytes = k2BM * kC * 2;          // 64 KB : 4 k-blocks x [128 rows x 128 B]
 constexpr int k2KBytes = (k2BN / 2) * kC * 2;    // 32 KB : 4 k-blocks x [ 64 rows x 128 B]   (this CTA's key rows)
 constexpr int k2VBytes = (kC / 2) * k2BN * 2;    // 32 KB : 2 k-blocks x [128 rows x 128 B]   (this CTA's channels)
-constexpr int k2Threads = 352;
+constexpr int k2Threads = 384;
 constexpr int k2SoftmaxWarps = 8;
 constexpr int k2KProducerWarp = 8;
 constexpr int k2MmaWarp = 9;
 constexpr int k2VProducerWarp = 10;
+constexpr int k2CopyWarp = 11;         // passthrough half of the concat: cat[:, C + c, rows] = v[:, c, rows]
 constexpr int k2ScratchBytes = 2 * 2 * 128 * 4;  // exchange buffer [parity][warpgroup][row]
 constexpr int k2SmemBytes = k2QBytes + k2KStages * k2KBytes + k2VStages * k2VBytes + k2ScratchBytes + 256;
 constexpr uint32_t k2TmemO = 0;
@@ -48,6 +51,8 @@ struct Attend2Params {
   float* mask;  // [2][N][L] or null
   const float* gate_w;
   const float* gate_b;
+  const float* v_a;   // [N][C][L] original fp32 features, or null: when set (together with cat_*), the copy warp also
+  const float* v_b;   //           writes the passthrough half of the concat (:186-187)
   int N, L, Lp;
   int q_pairs;   // ceil(L / 256)
   int kv_tiles;  // ceil(L / 128)
@@ -159,6 +164,50 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb)
             tma_load_2d_pair(sV + s * k2VBytes + kb * ((kC / 2) * 128), &tmap_v, full_l, j * k2BN + kb * 64, vrow0);
+        }
+      }
+    }
+  } else if (warp == k2CopyWarp) {
+    // ------------------------------------------------------------------ passthrough copy (fp32, bit exact)
+    if (p.v_a != nullptr && p.cat_a != nullptr) {
+      const bool vec = (p.L % 4 == 0) &&
+                       (((reinterpret_cast<uintptr_t>(p.v_a) | reinterpret_cast<uintptr_t>(p.v_b) |
+                          reinterpret_cast<uintptr_t>(p.cat_a) | reinterpret_cast<uintptr_t>(p.cat_b)) & 15) == 0);
+      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+        const int qp = item % p.q_pairs;
+        const int np = item / p.q_pairs;
+        const int pass = np & 1;
+        const int n = np >> 1;
+        const int row0 = qp * (2 * k2BM) + (int)rank * k2BM;
+        const float* src = (pass ? p.v_b : p.v_a) + (size_t)n * kC * p.L;
+        float* dst = (pass ? p.cat_b : p.cat_a) + ((size_t)n * 2 * kC + kC) * p.L;
+        if (vec) {
+          const int r = row0 + 4 * lane;
+          if (r < p.L) {
+#pragma unroll 1
+            for (int c = 0; c < kC; c += 8) {
+              float4 t[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) t[u] = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(c + u) * p.L + r));
+#pragma unroll
+              for (int u = 0; u < 8; ++u) __stcs(reinterpret_cast<float4*>(dst + (size_t)(c + u) * p.L + r), t[u]);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < kC; c += 2) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int r = row0 + (u & 3) * 32 + lane;
+              t[u] = (r < p.L) ? __ldcs(src + (size_t)(c + (u >> 2)) * p.L + r) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int r = row0 + (u & 3) * 32 + lane;
+              if (r < p.L) __stcs(dst + (size_t)(c + (u >> 2)) * p.L + r, t[u]);
+            }
+          }
         }
       }
     }

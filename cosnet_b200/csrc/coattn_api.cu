@@ -198,8 +198,8 @@ int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c,
   return (int)cudaGetLastError();
 }
 
-static int launch_attend(float* cat_a, float* cat_b, float* z, float* lse, float* mask, const float* gate_w,
-                         const float* gate_b, void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
+static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float* cat_b, float* z, float* lse,
+                         float* mask, const float* gate_w, const float* gate_b, void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
                          unsigned flags, void* stream) {
   const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
   if (int e = check_dims(n, c, h, w_)) return e;
@@ -224,6 +224,7 @@ static int launch_attend(float* cat_a, float* cat_b, float* z, float* lse, float
     q.z = z;
     q.lse = lse ? lse : reinterpret_cast<float*>(seg(workspace, ly.off_lse));
     q.cat_a = cat_a; q.cat_b = cat_b; q.mask = mask; q.gate_w = gate_w; q.gate_b = gate_b;
+    q.v_a = v_a; q.v_b = v_b;
     q.N = n; q.L = ly.L; q.Lp = ly.Lp;
     q.q_pairs = (ly.L + 2 * k2BM - 1) / (2 * k2BM);
     q.kv_tiles = (ly.L + k2BN - 1) / k2BN;
@@ -289,16 +290,21 @@ int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace
   if (int e = check_dims(n, c, h, w_)) return e;
   if (!workspace) return COATTN_E_NULL;
   float* zbuf = z ? z : reinterpret_cast<float*>(seg(workspace, make_layout(n, h, w_).off_z));
-  return launch_attend(nullptr, nullptr, zbuf, lse, nullptr, nullptr, nullptr, workspace, workspace_bytes, n, c, h, w_,
-                       flags, stream);
+  return launch_attend(nullptr, nullptr, nullptr, nullptr, zbuf, lse, nullptr, nullptr, nullptr, workspace,
+                       workspace_bytes, n, c, h, w_, flags, stream);
 }
 
-int coattn_stage_attend_gate(float* cat_a, float* cat_b, float* z, float* lse, float* mask, const float* gate_w,
-                             const float* gate_b, void* workspace, int64_t workspace_bytes, int n, int c, int h,
-                             int w_, unsigned flags, void* stream) {
+int coattn_stage_attend_gate(const float* v_a, const float* v_b, float* cat_a, float* cat_b, float* z, float* lse,
+                             float* mask, const float* gate_w, const float* gate_b, void* workspace,
+                             int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags, void* stream) {
   if (!cat_a || !cat_b || !gate_w) return COATTN_E_NULL;
-  return launch_attend(cat_a, cat_b, z, lse, mask, gate_w, gate_b, workspace, workspace_bytes, n, c, h, w_, flags,
-                       stream);
+  if ((v_a == nullptr) != (v_b == nullptr)) return COATTN_E_NULL;
+  const bool pair = !(flags & COATTN_FLAG_SINGLE_CTA);
+  if (int e = launch_attend(pair ? v_a : nullptr, pair ? v_b : nullptr, cat_a, cat_b, z, lse, mask, gate_w, gate_b,
+                            workspace, workspace_bytes, n, c, h, w_, flags, stream))
+    return e;
+  if (!pair && v_a) return coattn_stage_passthrough(v_a, v_b, cat_a, cat_b, n, c, h, w_, stream);
+  return COATTN_OK;
 }
 
 int coattn_stage_passthrough(const float* v_a, const float* v_b, float* cat_a, float* cat_b, int n, int c, int h,
@@ -355,10 +361,8 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
     if (int e = coattn_stage_attend(zbuf, lse, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
     return coattn_stage_gate(zbuf, v_a, v_b, gate_w, gate_b, cat_a, cat_b, n, c, h, w_, stream);
   }
-  if (int e = coattn_stage_attend_gate(cat_a, cat_b, z, lse, mask, gate_w, gate_b, workspace, workspace_bytes, n, c, h,
-                                       w_, flags, stream))
-    return e;
-  return coattn_stage_passthrough(v_a, v_b, cat_a, cat_b, n, c, h, w_, stream);
+  return coattn_stage_attend_gate(v_a, v_b, cat_a, cat_b, z, lse, mask, gate_w, gate_b, workspace, workspace_bytes, n, c,
+                                  h, w_, flags, stream);
 }
 
 }  // extern "C"

@@ -102,12 +102,14 @@ int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c,
 /* stage 3 (:160-170): fused affinity / dual softmax / attend.  Writes z and lse. */
 int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace_bytes, int n,
                         int c, int h, int w_, unsigned flags, void* stream);
-/* stages 3+4a fused (:160-184): as stage 3, and the drain also writes Z * sigmoid(gate(Z)) into channels
- * [0, 256) of cat_a / cat_b and the gate values into mask.  z, lse (-> workspace) and mask may be NULL. */
-int coattn_stage_attend_gate(float* cat_a, float* cat_b, float* z, float* lse, float* mask,
-                             const float* gate_w, const float* gate_b, void* workspace,
-                             int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
-                             void* stream);
+/* stages 3+4 fused (:160-187): as stage 3, and the drain also writes Z * sigmoid(gate(Z)) into channels
+ * [0, 256) of cat_a / cat_b and the gate values into mask.  If v_a / v_b are given (both or neither), the
+ * passthrough half cat_x[:, 256:512] = v_x is written too (by a spare warp of the attend kernel; by the
+ * passthrough kernel under COATTN_FLAG_SINGLE_CTA).  z, lse (-> workspace) and mask may be NULL. */
+int coattn_stage_attend_gate(const float* v_a, const float* v_b, float* cat_a, float* cat_b, float* z,
+                             float* lse, float* mask, const float* gate_w, const float* gate_b,
+                             void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
+                             unsigned flags, void* stream);
 /* stage 4b (:186-187): cat_x[:, 256:512] = v_x, the passthrough half of the concat. */
 int coattn_stage_passthrough(const float* v_a, const float* v_b, float* cat_a, float* cat_b, int n,
                              int c, int h, int w_, void* stream);

@@ -136,7 +136,7 @@ def main():
             print("[forward] max abs err lse_a:", float(np.abs(lse[0].cpu().numpy() - full["lse_a"]).max()),
                   " lse_b:", float(np.abs(lse[1].cpu().numpy() - full["lse_b"]).max()), flush=True)
         # per-stage timing with CUDA events (fused path: prep, project, attend+gate, passthrough; plus the stand-alone gate)
-        names = ["prep", "project", "attend", "passthru", "total", "gate(unfused)"]
+        names = ["prep", "project", "attend", "-", "total", "gate(unfused)"]
         acc = {k: [] for k in names}
         zt = torch.empty(2, n, c, L, device=dev); lt = torch.empty(2, n, L, device=dev); mk = torch.empty(2, n, L, device=dev)
         ca = torch.empty(n, 2 * c, h, w, device=dev); cb = torch.empty(n, 2 * c, h, w, device=dev)
@@ -146,8 +146,8 @@ def main():
             ev[0].record()
             _lib.check(lib.coattn_stage_prep(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "prep"); ev[1].record()
             _lib.check(lib.coattn_stage_project(wsp, nbytes, n, c, h, w, FL, st), "project"); ev[2].record()
-            _lib.check(lib.coattn_stage_attend_gate(ca.data_ptr(), cb.data_ptr(), None, lt.data_ptr(), mk.data_ptr(), tg.data_ptr(), bp, wsp, nbytes, n, c, h, w, FL, st), "attend_gate"); ev[3].record()
-            _lib.check(lib.coattn_stage_passthrough(tva.data_ptr(), tvb.data_ptr(), ca.data_ptr(), cb.data_ptr(), n, c, h, w, st), "passthrough"); ev[4].record()
+            _lib.check(lib.coattn_stage_attend_gate(tva.data_ptr(), tvb.data_ptr(), ca.data_ptr(), cb.data_ptr(), None, lt.data_ptr(), mk.data_ptr(), tg.data_ptr(), bp, wsp, nbytes, n, c, h, w, FL, st), "attend_gate"); ev[3].record()
+            ev[4].record()
             _lib.check(lib.coattn_stage_gate(zt.data_ptr(), tva.data_ptr(), tvb.data_ptr(), tg.data_ptr(), bp, ca.data_ptr(), cb.data_ptr(), n, c, h, w, st), "gate"); ev[5].record()
             torch.cuda.synchronize()
             if itn >= 3:
@@ -163,8 +163,6 @@ def main():
                 extra = f"  algorithmic {n * 6.0 * L * L * c / t / 1e9:.1f} TFLOP/s, executed {n * 8.0 * L * L * c / t / 1e9:.1f} TFLOP/s"
             if k == "gate(unfused)":
                 extra = f"  {2 * n * 16.0 * L * c / t / 1e6:.1f} GB/s"
-            if k == "passthru":
-                extra = f"  {2 * n * 8.0 * L * c / t / 1e6:.1f} GB/s"
             if k == "prep":
                 extra = f"  {(2 * n * 4.0 * L * c + 4 * n * 2.0 * Lp * c) / t / 1e6:.1f} GB/s"
             if k == "total":
