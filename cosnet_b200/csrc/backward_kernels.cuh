@@ -1,0 +1,370 @@
+// Backward of the co-attention block (what autograd does through rgbd_segmentation_RAA.py:158-187, train.py:599).
+//
+// The softmax matrices are NOT kept from the forward pass (the reference keeps S_row and S_column, 104 MB per
+// sample and modality at L = 3600): S is recomputed from the 16-bit operands and the saved log-sum-exp vectors.
+//
+//   bwd_prep      d_cat_a/b, Z, mask, g  ->  dZ_a, dZ_b (16-bit, both layouts), delta_a, delta_b, d_gate, dA init
+//   gemm_nt  x3   S = Qt Bt^T,  dP_a = dZa_t Bt^T,  dP_b = At dZb_t^T                 (fp32, [L, L])
+//   bwd_combine   dS = P_a (dP_a - delta_a) + P_b (dP_b - delta_b),  P_b              (bf16, [L, L], transient)
+//   gemm_nt  x4   dQ = dS B^T;  dA += P_b dZ_b^T;  dA += dQ W;  dW += dQ^T A^T
+//
+// with P_a[i,j] = exp(S[i,j] - lse_a[i]) (softmax over j, :165) and P_b[i,j] = exp(S[i,j] - lse_b[j]) (:164).
+// Gradient semantics follow the reference: the B-side gate mask is a constant (:178-182) and, with
+// no_grad_for_counterpart (:144-148), V_b receives no gradient.
+#pragma once
+#include "coattn_kernels.cuh"
+
+namespace coattn {
+
+// ==============================================================================================
+// gemm_nt: D[b][m][n] = sum_k A[b][m][k] * B[b][n][k]     (16-bit K-major operands, fp32 accumulate in TMEM)
+// one 128x128 output tile per CTA, K streamed in 64-element blocks through a 3-stage TMA ring; two CTAs per SM so
+// one tile's epilogue overlaps the other's main loop.
+// ==============================================================================================
+constexpr int kGemmStages = 3;
+constexpr int kGemmStageBytes = 2 * 128 * 128;   // A 16 KB + B 16 KB
+constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 1024 + 128;
+
+enum GemmMode : int {
+  kGemmStoreF32 = 0,        // out0[(b*rows0 + m)*ld0 + n] = d                               (m < m_valid)
+  kGemmStore16Both = 1,     // out0 (bf16 [m][n]) and out1 (bf16 transposed [n][m])
+  kGemmAddF32T = 2,         // out0[(b*rows0 + n)*ld0 + m] += d   transposed, m < m_valid       (dA contributions)
+  kGemmAtomicF32 = 3        // atomicAdd(out0[m*ld0 + n], d)      no batch offset               (dW, reduced over b)
+};
+
+struct GemmParams {
+  void* out0;
+  void* out1;
+  int64_t ld0, ld1;        // leading dimensions in elements
+  int64_t rows0, rows1;    // rows per batch entry of out0 / out1
+  int a_rows_per_batch;    // row offset between batch entries in the A / B tensor maps
+  int b_rows_per_batch;
+  int num_kb;              // K / 64
+  int m_valid;             // rows m >= m_valid are not stored
+  uint32_t idesc;          // instruction descriptor (M128 N128, operand formats)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kNumThreads, 2)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K], box {64, 128}
+               const __grid_constant__ CUtensorMap tmap_b,  // [batch*b_rows][K], box {64, 128}
+               GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kGemmStages;
+  uint64_t* d_full = empty + kGemmStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int n0 = blockIdx.y * 128;
+  const int b = blockIdx.z;
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kGemmStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      const int arow = b * p.a_rows_per_batch + m0;
+      const int brow = b * p.b_rows_per_batch + n0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int s = kb % kGemmStages;
+        const uint32_t ph = (kb / kGemmStages) & 1;
+        mbar_wait(empty + s, ph ^ 1, 30);
+        mbar_arrive_expect_tx(full + s, kGemmStageBytes);
+        tma_load_2d(smem + s * kGemmStageBytes, &tmap_a, full + s, kb * 64, arow);
+        tma_load_2d(smem + s * kGemmStageBytes + 16384, &tmap_b, full + s, kb * 64, brow);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    const uint32_t base = smem_u32(smem);
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int s = kb % kGemmStages;
+      const uint32_t ph = (kb / kGemmStages) & 1;
+      warp_mbar_wait(full + s, ph, lane, 31);
+      tc_fence_after();
+      const uint64_t ad0 = make_sdesc_k_sw128(base + s * kGemmStageBytes);
+      const uint64_t bd0 = make_sdesc_k_sw128(base + s * kGemmStageBytes + 16384);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem, ad0 + 2 * k, bd0 + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(empty + s);
+        if (kb == p.num_kb - 1) umma_commit(d_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    warp_mbar_wait(d_full, 0, lane, 32);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const bool valid = m < p.m_valid;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(taddr + ch * 32, v);
+      tmem_ld_wait();
+      const int n = n0 + ch * 32;
+      if constexpr (MODE == kGemmStoreF32) {
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out0) + ((int64_t)b * p.rows0 + m) * p.ld0 + n);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+        }
+      } else if constexpr (MODE == kGemmStore16Both) {
+        unsigned short* o0 = static_cast<unsigned short*>(p.out0) + ((int64_t)b * p.rows0 + m) * p.ld0 + n;
+        unsigned short* o1 = static_cast<unsigned short*>(p.out1) + ((int64_t)b * p.rows1 + n) * p.ld1 + m;
+        uint32_t pk[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+        uint4* d4 = reinterpret_cast<uint4*>(o0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d4[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          o1[(int64_t)k * p.ld1] = (unsigned short)((k & 1) ? (pk[k >> 1] >> 16) : (pk[k >> 1] & 0xFFFFu));
+      } else if constexpr (MODE == kGemmAddF32T) {
+        if (valid) {
+          float* o = static_cast<float*>(p.out0) + ((int64_t)b * p.rows0 + n) * p.ld0 + m;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[(int64_t)k * p.ld0] += __uint_as_float(v[k]);
+        }
+      } else {
+        float* o = static_cast<float*>(p.out0) + (int64_t)m * p.ld0 + n;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) atomicAdd(o + k, __uint_as_float(v[k]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// ==============================================================================================
+// bwd_prep: everything that is per position (no L x L work).  One block = 64 positions x 256 channels.
+//   d_ta   = (sum_c dZag Z_a) m_a (1 - m_a)          gate logit gradient, A side only (:177-182)
+//   dZ_a   = dZag m_a + g d_ta                        dZ_b = dZbg m_b
+//   delta  = sum_c dZ_x Z_x
+//   d_gate_w += sum_i d_ta[i] Z_a[:, i]               d_gate_b += sum_i d_ta[i]
+//   dA      = d_cat_a[:, C:2C]                        (passthrough half of the concat, :186)
+// ==============================================================================================
+struct BwdPrepParams {
+  const float* d_cat_a;   // [N][2C][L]
+  const float* d_cat_b;   // [N][2C][L] or null (depth: the B branch is gradient dead)
+  const float* z;         // [2][N][C][L]
+  const float* mask;      // [2][N][L]
+  const float* gate_w;    // [C]
+  unsigned short* dza_t;  // [N][Lp][C] bf16
+  unsigned short* dzb_t;  // [N][Lp][C] bf16
+  unsigned short* dzb16;  // [N][C][Lp] bf16
+  float* delta;           // [2][N][L]
+  float* d_gate_w;        // [C]   (accumulated with atomics; caller zeroes)
+  float* d_gate_b;        // [1] or null
+  float* d_va;            // [N][C][L]  initialised with the passthrough gradient
+  int N, L, Lp;
+};
+
+constexpr int kBwdPrepThreads = 256;
+constexpr int kBwdStride = kC + 8;
+
+__global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams p) {
+  __shared__ __align__(16) unsigned short tile[64 * kBwdStride];
+  __shared__ float red[4][64];
+  __shared__ float s_dta[64], s_ma[64], s_mb[64];
+  __shared__ float s_gw[kC];
+  const int n = blockIdx.y;
+  const int l0 = blockIdx.x * 64;
+  const int pos = threadIdx.x & 63;
+  const int cg = threadIdx.x >> 6;     // 4 channel groups of 64
+  const int l = l0 + pos;
+  const bool valid = l < p.L;
+  s_gw[threadIdx.x] = p.gate_w[threadIdx.x];
+  const float* dca = p.d_cat_a + (size_t)n * 2 * kC * p.L;
+  const float* za = p.z + (size_t)n * kC * p.L;
+  const float* zb = p.z + (size_t)(p.N + n) * kC * p.L;
+  const bool has_b = p.d_cat_b != nullptr;
+  const float* dcb = has_b ? p.d_cat_b + (size_t)n * 2 * kC * p.L : nullptr;
+  if (threadIdx.x < 64) {
+    const int ll = l0 + threadIdx.x;
+    s_ma[threadIdx.x] = ll < p.L ? p.mask[(size_t)n * p.L + ll] : 0.f;
+    s_mb[threadIdx.x] = ll < p.L ? p.mask[(size_t)(p.N + n) * p.L + ll] : 0.f;
+  }
+  // ---- pass 1: dot1 = sum_c dZag * Z_a
+  float acc = 0.f;
+  if (valid) {
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) {
+      const int c = cg * 64 + k;
+      acc = fmaf(__ldg(dca + (size_t)c * p.L + l), __ldg(za + (size_t)c * p.L + l), acc);
+    }
+  }
+  red[cg][pos] = acc;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const float dot1 = red[0][pos] + red[1][pos] + red[2][pos] + red[3][pos];
+    const float m = s_ma[pos];
+    s_dta[pos] = dot1 * m * (1.f - m);
+  }
+  __syncthreads();
+  // ---- pass 2 (A side): dZ_a, delta_a, d_gate_w partials, transposed tile
+  const float dta = s_dta[pos], ma = s_ma[pos];
+  float dl = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < 64; ++k) {
+    const int c = cg * 64 + k;
+    float dz = 0.f, zz = 0.f;
+    if (valid) {
+      zz = __ldg(za + (size_t)c * p.L + l);
+      dz = fmaf(s_gw[c], dta, __ldg(dca + (size_t)c * p.L + l) * ma);
+      // passthrough half of the concat -> gradient of V_a
+      p.d_va[((size_t)n * kC + c) * p.L + l] = __ldg(dca + (size_t)(kC + c) * p.L + l);
+    }
+    dl = fmaf(dz, zz, dl);
+    tile[pos * kBwdStride + c] = cvt16<true>(dz);
+    // d_gate_w[c] += sum over the 64 positions of d_ta * Z_a  (warp reduce over positions, then one atomic per warp)
+    float gsum = dta * zz;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(p.d_gate_w + c, gsum);
+  }
+  red[cg][pos] = dl;
+  __syncthreads();
+  if (threadIdx.x < 64 && l0 + threadIdx.x < p.L) {
+    p.delta[(size_t)n * p.L + l0 + threadIdx.x] = red[0][pos] + red[1][pos] + red[2][pos] + red[3][pos];
+  }
+  if (p.d_gate_b != nullptr && threadIdx.x < 32) {
+    float t = s_dta[threadIdx.x] + s_dta[threadIdx.x + 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (threadIdx.x == 0) atomicAdd(p.d_gate_b, t);
+  }
+  // transposed store: dza_t[l0 + r][c]
+  {
+    const int c8 = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+    unsigned short* dst = p.dza_t + ((size_t)n * p.Lp + l0) * kC;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = r0 + 8 * k;
+      *reinterpret_cast<uint4*>(dst + (size_t)r * kC + 8 * c8) = *reinterpret_cast<const uint4*>(&tile[r * kBwdStride + 8 * c8]);
+    }
+  }
+  __syncthreads();
+  // ---- pass 3 (B side): dZ_b = dZbg * m_b (mask is a constant), delta_b; both layouts
+  const float mb = s_mb[pos];
+  dl = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < 64; ++k) {
+    const int c = cg * 64 + k;
+    float dz = 0.f, zz = 0.f;
+    if (valid && has_b) {
+      zz = __ldg(zb + (size_t)c * p.L + l);
+      dz = __ldg(dcb + (size_t)c * p.L + l) * mb;
+    }
+    dl = fmaf(dz, zz, dl);
+    const unsigned short h = cvt16<true>(dz);
+    tile[pos * kBwdStride + c] = h;
+    p.dzb16[((size_t)n * kC + c) * p.Lp + l] = h;
+  }
+  red[cg][pos] = dl;
+  __syncthreads();
+  if (threadIdx.x < 64 && l0 + threadIdx.x < p.L) {
+    p.delta[(size_t)(p.N + n) * p.L + l0 + threadIdx.x] = red[0][pos] + red[1][pos] + red[2][pos] + red[3][pos];
+  }
+  {
+    const int c8 = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+    unsigned short* dst = p.dzb_t + ((size_t)n * p.Lp + l0) * kC;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = r0 + 8 * k;
+      *reinterpret_cast<uint4*>(dst + (size_t)r * kC + 8 * c8) = *reinterpret_cast<const uint4*>(&tile[r * kBwdStride + 8 * c8]);
+    }
+  }
+}
+
+// ==============================================================================================
+// bwd_combine: elementwise over the [Lp, Lp] matrices of one sample.
+// ==============================================================================================
+struct BwdCombineParams {
+  const float* s;      // [N][Lp][Lp]
+  const float* dpa;    // [N][Lp][Lp]
+  const float* dpb;    // [N][Lp][Lp] or null (no B-side gradient)
+  const float* lse;    // [2][N][L]
+  const float* delta;  // [2][N][L]
+  unsigned short* ds;  // [N][Lp][Lp] bf16
+  unsigned short* pb;  // [N][Lp][Lp] bf16 (only written when dpb != null)
+  int N, L, Lp;
+};
+
+__global__ void __launch_bounds__(256) bwd_combine_kernel(BwdCombineParams p) {
+  const int n = blockIdx.z;
+  const int i = blockIdx.y;
+  const int j = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (j >= p.Lp) return;
+  const size_t off = ((size_t)n * p.Lp + i) * p.Lp + j;
+  uint2 ods = make_uint2(0u, 0u), opb = make_uint2(0u, 0u);
+  if (i < p.L && j < p.L) {
+    const float lse_a = __ldg(p.lse + (size_t)n * p.L + i);
+    const float del_a = __ldg(p.delta + (size_t)n * p.L + i);
+    const float4 s4 = __ldcs(reinterpret_cast<const float4*>(p.s + off));
+    const float4 a4 = __ldcs(reinterpret_cast<const float4*>(p.dpa + off));
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.dpb) b4 = __ldcs(reinterpret_cast<const float4*>(p.dpb + off));
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    float dsv[4], pbv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int jj = j + e;
+      if (jj < p.L) {
+        const float pa = __expf(sv[e] - lse_a);
+        float d = pa * (av[e] - del_a);
+        float pbe = 0.f;
+        if (p.dpb) {
+          pbe = __expf(sv[e] - __ldg(p.lse + (size_t)(p.N + n) * p.L + jj));
+          d = fmaf(pbe, bv[e] - __ldg(p.delta + (size_t)(p.N + n) * p.L + jj), d);
+        }
+        dsv[e] = d;
+        pbv[e] = pbe;
+      } else {
+        dsv[e] = 0.f;
+        pbv[e] = 0.f;
+      }
+    }
+    ods = make_uint2(pack_bf16x2(dsv[0], dsv[1]), pack_bf16x2(dsv[2], dsv[3]));
+    opb = make_uint2(pack_bf16x2(pbv[0], pbv[1]), pack_bf16x2(pbv[2], pbv[3]));
+  }
+  *reinterpret_cast<uint2*>(p.ds + off) = ods;
+  if (p.dpb) *reinterpret_cast<uint2*>(p.pb + off) = opb;
+}
+
+// W [C_out][C_in] fp32 -> Wt [C_in][C_out] bf16 (B operand of dA += dQ W: dA[i][c] = sum_d dQt[i][d] Wt[c][d])
+__global__ void transpose_w_kernel(const float* __restrict__ w, unsigned short* __restrict__ wt) {
+  const int c = blockIdx.x;       // C_in
+  const int d = threadIdx.x;      // C_out
+  wt[c * kC + d] = cvt16<true>(w[d * kC + c]);
+}
+
+}  // namespace coattn

@@ -10,6 +10,7 @@
 
 #include "coattn_kernels.cuh"
 #include "attend2_kernel.cuh"
+#include "backward_kernels.cuh"
 
 namespace {
 
@@ -115,6 +116,7 @@ const char* coattn_b200_strerror(int code) {
     case COATTN_E_ARCH: return "device is not sm_100 class (B200); there is no fallback path";
     case COATTN_E_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
     case COATTN_E_ALIGN: return "tensor pointer not 16-byte aligned";
+    case COATTN_E_UNSUPPORTED: return "not implemented: gradients for the counterpart frame (no_grad_for_counterpart=False)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
   }
 }
@@ -363,6 +365,162 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
   }
   return coattn_stage_attend_gate(v_a, v_b, cat_a, cat_b, z, lse, mask, gate_w, gate_b, workspace, workspace_bytes, n, c,
                                   h, w_, flags, stream);
+}
+
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- backward
+namespace {
+struct BwdLayout {
+  Layout fwd;
+  int64_t off_g;   // second copy of the forward operand segments, always bf16 (operands of the gradient GEMMs)
+  int64_t off_dza_t, off_dzb_t, off_dzb16, off_delta, off_s, off_dpa, off_dpb, off_ds, off_pb, off_dqt, off_dq16,
+      off_wt, total;
+};
+BwdLayout make_bwd_layout(int n, int h, int w) {
+  BwdLayout b{};
+  b.fwd = make_layout(n, h, w);
+  const int64_t Lp = b.fwd.Lp, L = b.fwd.L;
+  const int64_t plane = (int64_t)n * Lp * kC * 2;
+  const int64_t mat32 = (int64_t)n * Lp * Lp * 4, mat16 = (int64_t)n * Lp * Lp * 2;
+  int64_t off = b.fwd.total;
+  auto take = [&](int64_t bytes) { const int64_t o = off; off = round_up(off + bytes, kAlign); return o; };
+  b.off_g = take(b.fwd.total);
+  b.off_dza_t = take(plane); b.off_dzb_t = take(plane); b.off_dzb16 = take(plane);
+  b.off_delta = take((int64_t)2 * n * L * 4);
+  b.off_s = take(mat32); b.off_dpa = take(mat32); b.off_dpb = take(mat32);
+  b.off_ds = take(mat16); b.off_pb = take(mat16);
+  b.off_dqt = take(plane); b.off_dq16 = take(plane);
+  b.off_wt = take((int64_t)kC * kC * 2);
+  b.total = off;
+  return b;
+}
+
+template <int MODE>
+int launch_gemm(EncodeTiledFn enc, cudaStream_t st, const void* a, uint64_t a_rows, bool a_bf16, const void* b,
+                uint64_t b_rows, bool b_bf16, uint64_t k, int m_tiles, int n_tiles, int batch, GemmParams gp) {
+  CUtensorMap ta, tb;
+  if (int e = make_tmap(enc, &ta, a, a_rows, k, 128, a_bf16)) return e;
+  if (int e = make_tmap(enc, &tb, b, b_rows, k, 128, b_bf16)) return e;
+  gp.num_kb = (int)(k / 64);
+  gp.idesc = (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+  auto kern = gemm_nt_kernel<MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<dim3(m_tiles, n_tiles, batch), kNumThreads, kGemmSmemBytes, st>>>(ta, tb, gp);
+  return (int)cudaGetLastError();
+}
+}  // namespace
+
+extern "C" {
+
+int64_t coattn_backward_workspace_bytes(int n, int c, int h, int w) {
+  if (check_dims(n, c, h, w) != COATTN_OK) return COATTN_E_SHAPE;
+  return make_bwd_layout(n, h, w).total;
+}
+
+int coattn_backward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* z,
+                    const float* lse, const float* mask, const float* d_cat_a, const float* d_cat_b, float* d_v_a,
+                    float* d_v_b, float* d_w, float* d_gate_w, float* d_gate_b, void* workspace,
+                    int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags, void* stream) {
+  if (!v_a || !v_b || !w || !gate_w || !z || !lse || !mask || !d_cat_a || !d_v_a || !d_w || !d_gate_w)
+    return COATTN_E_NULL;
+  if (d_v_b != nullptr) return COATTN_E_UNSUPPORTED;
+  if (int e = check_dims(n, c, h, w_)) return e;
+  const BwdLayout bl = make_bwd_layout(n, h, w_);
+  const Layout& ly = bl.fwd;
+  if (!workspace) return COATTN_E_NULL;
+  if ((reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) != 0 || workspace_bytes < bl.total) return COATTN_E_WORKSPACE;
+  if (int e = check_arch(nullptr)) return e;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return COATTN_E_DRIVER;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fbf16 = (flags & COATTN_FLAG_BF16) != 0;   // format of the forward operands (Qt, Bt, At, A16, B16)
+  const bool has_b = d_cat_b != nullptr;
+  const int L = ly.L, Lp = ly.Lp;
+  const int64_t plane_elems = ly.t_pass_elems();
+
+  // Operands of the forward pass are regenerated rather than kept alive between forward and backward.
+  // S must be recomputed from exactly the operands the forward used (format `flags`), so that exp(S - lse) is the
+  // forward's softmax; every other GEMM multiplies by a bf16 gradient operand, and tcgen05 kind::f16 requires both
+  // operands in the same format, so with an fp16 forward a second, bf16 set of operands is prepared.
+  if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+  if (int e = coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+  void* gws = workspace;
+  if (!fbf16) {
+    gws = seg(workspace, bl.off_g);
+    if (int e = coattn_stage_prep(v_a, v_b, w, gws, ly.total, n, c, h, w_, COATTN_FLAG_BF16, stream)) return e;
+  }
+  unsigned short* bt = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_t));       // forward format
+  unsigned short* qt = bt + plane_elems;                                                  // forward format
+  unsigned short* bt_g = reinterpret_cast<unsigned short*>(seg(gws, ly.off_t));           // bf16
+  unsigned short* at = reinterpret_cast<unsigned short*>(seg(gws, ly.off_at));            // bf16
+  unsigned short* b16 = reinterpret_cast<unsigned short*>(seg(gws, ly.off_vv));           // bf16
+  unsigned short* a16 = b16 + plane_elems;                                                // bf16
+  unsigned short* dza_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dza_t));
+  unsigned short* dzb_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb_t));
+  unsigned short* dzb16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb16));
+  float* delta = reinterpret_cast<float*>(seg(workspace, bl.off_delta));
+  float* smat = reinterpret_cast<float*>(seg(workspace, bl.off_s));
+  float* dpa = reinterpret_cast<float*>(seg(workspace, bl.off_dpa));
+  float* dpb = reinterpret_cast<float*>(seg(workspace, bl.off_dpb));
+  unsigned short* ds = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_ds));
+  unsigned short* pb = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pb));
+  unsigned short* dqt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dqt));
+  unsigned short* dq16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dq16));
+  unsigned short* wt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_wt));
+
+  cudaError_t ce;
+  if ((ce = cudaMemsetAsync(d_w, 0, (size_t)kC * kC * 4, st)) != cudaSuccess) return (int)ce;
+  if ((ce = cudaMemsetAsync(d_gate_w, 0, (size_t)kC * 4, st)) != cudaSuccess) return (int)ce;
+  if (d_gate_b && (ce = cudaMemsetAsync(d_gate_b, 0, 4, st)) != cudaSuccess) return (int)ce;
+
+  BwdPrepParams bp;
+  bp.d_cat_a = d_cat_a; bp.d_cat_b = d_cat_b; bp.z = z; bp.mask = mask; bp.gate_w = gate_w;
+  bp.dza_t = dza_t; bp.dzb_t = dzb_t; bp.dzb16 = dzb16; bp.delta = delta;
+  bp.d_gate_w = d_gate_w; bp.d_gate_b = d_gate_b; bp.d_va = d_v_a; bp.N = n; bp.L = L; bp.Lp = Lp;
+  bwd_prep_kernel<<<dim3(Lp / 64, n), kBwdPrepThreads, 0, st>>>(bp);
+  transpose_w_kernel<<<kC, kC, 0, st>>>(w, wt);
+  if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
+
+  const uint64_t rowsL = (uint64_t)n * Lp, rowsC = (uint64_t)n * kC;
+  const int lt = Lp / 128;
+  GemmParams gp{};
+  // S = Qt Bt^T, dP_a = dZa_t Bt^T, dP_b = At dZb_t^T      [N][Lp][Lp] fp32
+  gp.out1 = nullptr; gp.ld0 = Lp; gp.rows0 = Lp; gp.ld1 = 0; gp.rows1 = 0;
+  gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = Lp; gp.m_valid = Lp;
+  gp.out0 = smat;
+  if (int e = launch_gemm<kGemmStoreF32>(enc, st, qt, rowsL, fbf16, bt, rowsL, fbf16, kC, lt, lt, n, gp)) return e;
+  gp.out0 = dpa;
+  if (int e = launch_gemm<kGemmStoreF32>(enc, st, dza_t, rowsL, true, bt_g, rowsL, true, kC, lt, lt, n, gp)) return e;
+  if (has_b) {
+    gp.out0 = dpb;
+    if (int e = launch_gemm<kGemmStoreF32>(enc, st, at, rowsL, true, dzb_t, rowsL, true, kC, lt, lt, n, gp)) return e;
+  }
+  BwdCombineParams cp;
+  cp.s = smat; cp.dpa = dpa; cp.dpb = has_b ? dpb : nullptr; cp.lse = lse; cp.delta = delta; cp.ds = ds; cp.pb = pb;
+  cp.N = n; cp.L = L; cp.Lp = Lp;
+  bwd_combine_kernel<<<dim3((Lp / 4 + 255) / 256, Lp, n), 256, 0, st>>>(cp);
+  if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
+  // dQ[i][c] = sum_j dS[i][j] B16[c][j]   -> dQt [N][Lp][C] and dQ16 [N][C][Lp] (bf16)
+  gp.out0 = dqt; gp.ld0 = kC; gp.rows0 = Lp; gp.out1 = dq16; gp.ld1 = Lp; gp.rows1 = kC;
+  gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = kC; gp.m_valid = Lp;
+  if (int e = launch_gemm<kGemmStore16Both>(enc, st, ds, rowsL, true, b16, rowsC, true, Lp, lt, kC / 128, n, gp)) return e;
+  // dA[c][i] += sum_j P_b[i][j] dZ_b[c][j]
+  gp.out0 = d_v_a; gp.ld0 = L; gp.rows0 = kC; gp.out1 = nullptr; gp.m_valid = L;
+  if (has_b) {
+    gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = kC;
+    if (int e = launch_gemm<kGemmAddF32T>(enc, st, pb, rowsL, true, dzb16, rowsC, true, Lp, lt, kC / 128, n, gp)) return e;
+  }
+  // dA[c][i] += sum_d dQt[i][d] W[d][c]
+  gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = 0;
+  if (int e = launch_gemm<kGemmAddF32T>(enc, st, dqt, rowsL, true, wt, kC, true, kC, lt, kC / 128, n, gp)) return e;
+  // dW[d][c] += sum_n sum_i dQ16[n][d][i] A16[n][c][i]
+  gp.out0 = d_w; gp.ld0 = kC; gp.rows0 = 0; gp.m_valid = kC;
+  gp.a_rows_per_batch = kC; gp.b_rows_per_batch = kC;
+  if (int e = launch_gemm<kGemmAtomicF32>(enc, st, dq16, rowsC, true, a16, rowsC, true, Lp, kC / 128, kC / 128, n, gp)) return e;
+  return COATTN_OK;
 }
 
 }  // extern "C"

@@ -44,7 +44,8 @@ enum {
   COATTN_E_WORKSPACE = -3,   /* workspace too small or not 1024-byte aligned                */
   COATTN_E_ARCH = -4,        /* current device is not compute capability 10.x (no fallback) */
   COATTN_E_DRIVER = -5,      /* cuTensorMapEncodeTiled unavailable / failed                 */
-  COATTN_E_ALIGN = -6        /* a tensor pointer is not 16-byte aligned                     */
+  COATTN_E_ALIGN = -6,       /* a tensor pointer is not 16-byte aligned                     */
+  COATTN_E_UNSUPPORTED = -7  /* valid request the library does not implement (yet)          */
 };
 
 /*
@@ -117,6 +118,27 @@ int coattn_stage_passthrough(const float* v_a, const float* v_b, float* cat_a, f
 int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const float* gate_w,
                       const float* gate_b, float* cat_a, float* cat_b, int n, int c, int h, int w_,
                       void* stream);
+
+/*
+ * Backward of `coattn_forward` for one modality: what autograd computes through :158-187 (train.py:599), with
+ * the reference's semantics -- the B-side gate mask is a constant (:178-182) and V_b is a constant
+ * (no_grad_for_counterpart, :144-148).  S is recomputed from the 16-bit operands and the saved `lse`; the
+ * softmax matrices of the forward pass are not stored.
+ *
+ *   inputs   v_a, v_b, w, gate_w           as in coattn_forward
+ *            z [2,N,256,L], lse [2,N,L], mask [2,N,L]      saved outputs of coattn_forward
+ *            d_cat_a, d_cat_b [N,512,H,W]  gradients w.r.t. the two concat tensors; d_cat_b may be NULL
+ *                                          (depth modality: the B branch is gradient dead, :240-247)
+ *   outputs  d_v_a [N,256,H,W], d_w [256,256], d_gate_w [256], d_gate_b [1] (may be NULL); all overwritten
+ *            d_v_b must be NULL: gradients for the counterpart frame (no_grad_for_counterpart=False) are not
+ *            implemented -> COATTN_E_UNSUPPORTED.
+ */
+int64_t coattn_backward_workspace_bytes(int n, int c, int h, int w);
+int coattn_backward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* z,
+                    const float* lse, const float* mask, const float* d_cat_a, const float* d_cat_b,
+                    float* d_v_a, float* d_v_b, float* d_w, float* d_gate_w, float* d_gate_b,
+                    void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
+                    void* stream);
 
 /*
  * Debug/test view of the workspace: byte offset and byte size of a named segment
