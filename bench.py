@@ -344,12 +344,12 @@ def run_ours(args):
             "flops_per_frame_pair": 2 * FLOPS_PER_PAIR_MODALITY,
         },
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * pipe.h2d_bytes,
-                "d2h_bytes_per_step": 2 * pipe.d2h_bytes, "steps": e2e_steps, "matches_resident_path": same,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * pipe.h2d_bytes * world,
+                "d2h_bytes_per_step": 2 * pipe.d2h_bytes * world, "steps": e2e_steps, "matches_resident_path": same,
                 "api": "cosnet_b200.coattention.HostPipeline (pinned host in/out, 3 streams x chunks of 4 pairs)"},
         "gpu_launches": 8 * args.steps,   # per modality call: prep, cast_w, project, attend(+gate+concat)
         "roofline": {
-            "kernel": "attend_kernel", "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"],
+            "kernel": "attend2_kernel", "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"],
             "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": None,
             "peak_kind": f"{peaks['source']} burst bf16 (sustained {peaks['bf16_tflops_sustained']})",
             "ms_per_launch": attend_ms, "algorithmic_flops_per_launch": n * FLOPS_ATTEND_PER_PAIR_MODALITY,

@@ -20,6 +20,7 @@ _vp, _i, _i64, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint
 FLAG_BF16 = 1  # COATTN_FLAG_BF16
 FLAG_UNFUSED_GATE = 2  # COATTN_FLAG_UNFUSED_GATE
 FLAG_SINGLE_CTA = 4  # COATTN_FLAG_SINGLE_CTA
+FLAG_A_ONLY = 8  # COATTN_FLAG_A_ONLY
 
 # name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
 SIGNATURES = {

@@ -57,7 +57,7 @@ def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
 
 
 def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False,
-                            unfused_gate=False, want_mask=False, want_z=True, single_cta=False):
+                            unfused_gate=False, want_mask=False, want_z=True, single_cta=False, a_only=False):
     """Runs the CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L]
     (plus mask [2,N,L] when want_mask=True; fused path only).
 
@@ -74,7 +74,7 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         gw = gate_weight.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
         gb = None if gate_bias is None else gate_bias.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
         cat_a = torch.empty((n, 2 * c, h, w), dtype=torch.float32, device=dev)
-        cat_b = torch.empty((n, 2 * c, h, w), dtype=torch.float32, device=dev)
+        cat_b = None if a_only else torch.empty((n, 2 * c, h, w), dtype=torch.float32, device=dev)
         z = torch.empty((2, n, c, h * w), dtype=torch.float32, device=dev) if (want_z or unfused_gate) else None
         lse = torch.empty((2, n, h * w), dtype=torch.float32, device=dev)
         nbytes = workspace_bytes(n, c, h, w)
@@ -82,9 +82,10 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         stream = torch.cuda.current_stream(dev).cuda_stream
         mask = torch.empty((2, n, h * w), dtype=torch.float32, device=dev) if want_mask else None
         flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)
-                 | (_lib.FLAG_SINGLE_CTA if single_cta else 0))
+                 | (_lib.FLAG_SINGLE_CTA if single_cta else 0) | (_lib.FLAG_A_ONLY if a_only else 0))
         code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
-                                  None if gb is None else gb.data_ptr(), cat_a.data_ptr(), cat_b.data_ptr(),
+                                  None if gb is None else gb.data_ptr(), cat_a.data_ptr(),
+                                  None if cat_b is None else cat_b.data_ptr(),
                                   None if z is None else z.data_ptr(), lse.data_ptr(),
                                   None if mask is None else mask.data_ptr(),
                                   _aligned_ptr(ws), nbytes, n, c, h, w, flags, stream)

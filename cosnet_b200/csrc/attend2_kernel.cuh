@@ -56,7 +56,8 @@ struct Attend2Params {
   int N, L, Lp;
   int q_pairs;   // ceil(L / 256)
   int kv_tiles;  // ceil(L / 128)
-  int num_items; // 2 * N * q_pairs
+  int num_items; // passes * N * q_pairs
+  int passes;    // 2, or 1 = frame-A outputs only (pass 0; test.py averages x1 only, test.py:301)
 };
 
 // exchange one float between the two threads that own the same query row (warp w and warp w + 4)
@@ -130,8 +131,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
       for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
         const int qp = item % p.q_pairs;
         const int np = item / p.q_pairs;
-        const int pass = np & 1;
-        const int n = np >> 1;
+        const int pass = (p.passes == 2) ? (np & 1) : 0;
+        const int n = (p.passes == 2) ? (np >> 1) : np;
         const int qrow0 = ((1 - pass) * p.N + n) * p.Lp + qp * (2 * k2BM) + (int)rank * k2BM;
         const int krow0 = (pass * p.N + n) * p.Lp + (int)rank * (k2BN / 2);
         mbar_wait(q_empty, (it & 1) ^ 1, 1);
@@ -155,7 +156,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
       uint32_t cnt = 0;
       for (int item = cluster_id; item < p.num_items; item += num_clusters) {
         const int np = item / p.q_pairs;
-        const int vrow0 = ((np & 1) * p.N + (np >> 1)) * kC + (int)rank * (kC / 2);
+        const int vpass = (p.passes == 2) ? (np & 1) : 0;
+        const int vn = (p.passes == 2) ? (np >> 1) : np;
+        const int vrow0 = (vpass * p.N + vn) * kC + (int)rank * (kC / 2);
         for (int j = 0; j < T; ++j, ++cnt) {
           const uint32_t s = cnt % k2VStages, ph = (cnt / k2VStages) & 1;
           mbar_wait(v_empty + s, ph ^ 1, 3);
@@ -176,8 +179,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
       for (int item = cluster_id; item < p.num_items; item += num_clusters) {
         const int qp = item % p.q_pairs;
         const int np = item / p.q_pairs;
-        const int pass = np & 1;
-        const int n = np >> 1;
+        const int pass = (p.passes == 2) ? (np & 1) : 0;
+        const int n = (p.passes == 2) ? (np >> 1) : np;
         const int row0 = qp * (2 * k2BM) + (int)rank * k2BM;
         const float* src = (pass ? p.v_b : p.v_a) + (size_t)n * kC * p.L;
         float* dst = (pass ? p.cat_b : p.cat_a) + ((size_t)n * 2 * kC + kC) * p.L;
@@ -316,8 +319,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
     for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
       const int qp = item % p.q_pairs;
       const int np = item / p.q_pairs;
-      const int pass = np & 1;
-      const int n = np >> 1;
+      const int pass = (p.passes == 2) ? (np & 1) : 0;
+      const int n = (p.passes == 2) ? (np >> 1) : np;
       const int row = qp * (2 * k2BM) + (int)rank * k2BM + rloc;
       const uint32_t pv_base = it * (uint32_t)T;
       float m = -INFINITY, l = 0.0f;

@@ -116,7 +116,7 @@ const char* coattn_b200_strerror(int code) {
     case COATTN_E_ARCH: return "device is not sm_100 class (B200); there is no fallback path";
     case COATTN_E_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
     case COATTN_E_ALIGN: return "tensor pointer not 16-byte aligned";
-    case COATTN_E_UNSUPPORTED: return "not implemented: gradients for the counterpart frame (no_grad_for_counterpart=False)";
+    case COATTN_E_UNSUPPORTED: return "valid request that is not implemented (counterpart-frame gradients, or a flag combination)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
   }
 }
@@ -230,7 +230,8 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     q.N = n; q.L = ly.L; q.Lp = ly.Lp;
     q.q_pairs = (ly.L + 2 * k2BM - 1) / (2 * k2BM);
     q.kv_tiles = (ly.L + k2BN - 1) / k2BN;
-    q.num_items = 2 * n * q.q_pairs;
+    q.passes = (flags & COATTN_FLAG_A_ONLY) ? 1 : 2;
+    q.num_items = q.passes * n * q.q_pairs;
     auto kern2 = bf16 ? attend2_kernel<true> : attend2_kernel<false>;
     cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
     if (e2 != cudaSuccess) return (int)e2;
@@ -239,6 +240,7 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     kern2<<<2 * clusters, k2Threads, k2SmemBytes, st>>>(tm_q, tm_k2, tm_v2, q);
     return (int)cudaGetLastError();
   }
+  if (flags & COATTN_FLAG_A_ONLY) return COATTN_E_UNSUPPORTED;   // single-CTA cross-check kernel: both passes only
   AttendParams p;
   p.t = reinterpret_cast<const unsigned short*>(seg(workspace, ly.off_t));
   p.z = z;
@@ -299,7 +301,8 @@ int coattn_stage_attend(float* z, float* lse, void* workspace, int64_t workspace
 int coattn_stage_attend_gate(const float* v_a, const float* v_b, float* cat_a, float* cat_b, float* z, float* lse,
                              float* mask, const float* gate_w, const float* gate_b, void* workspace,
                              int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags, void* stream) {
-  if (!cat_a || !cat_b || !gate_w) return COATTN_E_NULL;
+  if (!cat_a || !gate_w) return COATTN_E_NULL;
+  if (!cat_b && !(flags & COATTN_FLAG_A_ONLY)) return COATTN_E_NULL;
   if ((v_a == nullptr) != (v_b == nullptr)) return COATTN_E_NULL;
   const bool pair = !(flags & COATTN_FLAG_SINGLE_CTA);
   if (int e = launch_attend(pair ? v_a : nullptr, pair ? v_b : nullptr, cat_a, cat_b, z, lse, mask, gate_w, gate_b,
@@ -352,7 +355,9 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
 int coattn_forward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* gate_b,
                    float* cat_a, float* cat_b, float* z, float* lse, float* mask, void* workspace,
                    int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags, void* stream) {
-  if (!v_a || !v_b || !w || !gate_w || !cat_a || !cat_b) return COATTN_E_NULL;
+  if (!v_a || !v_b || !w || !gate_w || !cat_a) return COATTN_E_NULL;
+  if (!cat_b && !(flags & COATTN_FLAG_A_ONLY)) return COATTN_E_NULL;
+  if ((flags & COATTN_FLAG_A_ONLY) && (flags & (COATTN_FLAG_UNFUSED_GATE | COATTN_FLAG_SINGLE_CTA))) return COATTN_E_UNSUPPORTED;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
   if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;

@@ -69,6 +69,12 @@ enum {
  *                          query tiles, 128-position key tiles).  Same math; kept as a cross-check.
  */
 #define COATTN_FLAG_SINGLE_CTA 4u
+/*
+ *   COATTN_FLAG_A_ONLY     compute only the frame-A outputs (cat_a, lse[0], mask[0], z[0]); cat_b is not written.
+ *                          For test.py-style inference, which only averages x1 over the reference frames
+ *                          (test.py:301-305): halves the attend work.  CTA-pair kernel only.
+ */
+#define COATTN_FLAG_A_ONLY 8u
 
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);

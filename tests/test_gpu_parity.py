@@ -277,3 +277,39 @@ def test_end_to_end_masks_agree_with_oracle_operator(op, sigma, hw):
         agree = ((got > 0.5) == (ref > 0.5)).float().mean().item()
         assert agree >= 0.999, agree
         assert (got - ref).abs().max().item() < 2e-3
+
+
+def test_frame_a_only_matches_full(op):
+    n, h, w = 3, 12, 11
+    v_a, v_b = orc.synthetic_features(81, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(82, bias=True)
+    dev = torch.device("cuda:0")
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    full = op(t(v_a), t(v_b), t(W), t(g), t(b))
+    a_only = op(t(v_a), t(v_b), t(W), t(g), t(b), False, False, False, True, False, True)
+    torch.cuda.synchronize()
+    assert a_only[1] is None
+    assert torch.equal(a_only[0], full[0])
+    assert torch.equal(a_only[2][0], full[2][0]) and torch.equal(a_only[3][0], full[3][0])
+
+
+def test_multi_reference_inference_matches_pairwise_loop():
+    """test.py:278-305: mean over references of the frame-A mask; the batched, query-hoisted path must equal running the
+    drop-in module once per (query, reference) pair."""
+    from cosnet_b200.backbone import Bottleneck
+    from cosnet_b200.inference import segment_with_references
+    from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).to(dev).eval()
+    q, r, hw = 2, 3, 97
+    tgt, tgt_d = torch.randn(q, 3, hw, hw, device=dev), torch.randn(q, 1, hw, hw, device=dev)
+    refs, refs_d = torch.randn(q, r, 3, hw, hw, device=dev), torch.randn(q, r, 1, hw, hw, device=dev)
+    got = segment_with_references(model, tgt, tgt_d, refs, refs_d)
+    want = torch.zeros_like(got)
+    with torch.no_grad():
+        for i in range(r):                                       # the reference's loop (test.py:287-301)
+            want += model(tgt, refs[:, i], tgt_d, refs_d[:, i])[0]
+    want /= r
+    assert got.shape == (q, 1, hw, hw)
+    assert (got - want).abs().max().item() < 1e-5
