@@ -254,25 +254,25 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
         };
         warp_mbar_wait(q_full, it & 1, lane, 11);
         tc_fence_after();
+        // Tensor-pipe order per item: S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ... | PV(T-1).  S(j+2) reuses the buffer
+        // of P(j) and is issued right behind PV(j) (in-order execution).  The waits for TMA tiles are hoisted to
+        // just after the long PV MMAs were queued, so only the wait for P(j) sits between two issue bursts.
         issue_s(0);
+        if (T > 1) issue_s(1);
+        if (T <= 2) { if (elect_one()) umma2_commit_mc(q_empty, 3); __syncwarp(); }
+        {
+          const uint32_t s = vcnt % k2VStages, ph = (vcnt / k2VStages) & 1;
+          warp_mbar_wait(v_full + s, ph, lane, 14);
+        }
         for (int j = 0; j < T; ++j) {
           TR2(0);
-          if (j + 1 < T) {
-            issue_s(j + 1);
-            TR2(2);
-          } else {
-            if (elect_one()) umma2_commit_mc(q_empty, 3);   // the query tiles may be overwritten
-            __syncwarp();
-          }
           const int b = j & 1;
           // P(0) of an item is only produced after the previous item's O was drained, so no separate O barrier
           if (b == 0) { warp_mbar_wait(p_full + 0, pphase0, lane, 13); pphase0 ^= 1; }
           else        { warp_mbar_wait(p_full + 1, pphase1, lane, 13); pphase1 ^= 1; }
-          TR2(3);
-          const uint32_t s = vcnt % k2VStages, ph = (vcnt / k2VStages) & 1;
-          warp_mbar_wait(v_full + s, ph, lane, 14);
           tc_fence_after();
-          TR2(4);
+          TR2(3);
+          const uint32_t s = vcnt % k2VStages;
           const uint32_t tP = tmem + k2TmemS + (uint32_t)b * k2BN;
           const uint64_t vd0 = make_sdesc_k_sw128(sV_addr + s * k2VBytes);
           if (elect_one()) {
@@ -285,11 +285,20 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
             umma2_commit_mc(o_full, 3);
           }
           __syncwarp();
+          ++vcnt;
+          TR2(4);
+          if (j + 1 < T) {   // value tile of the next step: waited while PV(j) executes
+            const uint32_t s1 = vcnt % k2VStages, ph1 = (vcnt / k2VStages) & 1;
+            warp_mbar_wait(v_full + s1, ph1, lane, 14);
+          }
+          if (j + 2 < T) {
+            issue_s(j + 2);
+            if (j + 3 == T) { if (elect_one()) umma2_commit_mc(q_empty, 3); __syncwarp(); }   // last S of the item issued
+          }
           TR2(5);
 #ifdef COATTN_TRACE
           ++tc;
 #endif
-          ++vcnt;
         }
       }
 #ifdef COATTN_TRACE
@@ -385,16 +394,20 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s0[2 * k]), kLog2e, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s0[2 * k + 1]), kLog2e, neg_m));
+          const float x0 = fmaf(__uint_as_float(s0[2 * k]), kLog2e, neg_m);
+          const float x1 = fmaf(__uint_as_float(s0[2 * k + 1]), kLog2e, neg_m);
+          const float p0 = fast_exp2(x0);
+          const float p1 = fast_exp2(x1);
           pk[k] = pack16x2<BF16>(p0, p1);
           if constexpr (BF16) { l0 += bf16lo_to_f32(pk[k]); l1 += bf16hi_to_f32(pk[k]); }
           else { l0 += p0; l1 += p1; }
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s1[2 * k]), kLog2e, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s1[2 * k + 1]), kLog2e, neg_m));
+          const float x0 = fmaf(__uint_as_float(s1[2 * k]), kLog2e, neg_m);
+          const float x1 = fmaf(__uint_as_float(s1[2 * k + 1]), kLog2e, neg_m);
+          const float p0 = fast_exp2(x0);
+          const float p1 = fast_exp2(x1);
           pk[16 + k] = pack16x2<BF16>(p0, p1);
           if constexpr (BF16) { l2 += bf16lo_to_f32(pk[16 + k]); l3 += bf16hi_to_f32(pk[16 + k]); }
           else { l2 += p0; l3 += p1; }

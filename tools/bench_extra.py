@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Secondary workloads of BASELINE.json (configs 3-5) on the co-attention hot path, synthetic features.
+
+    python tools/bench_extra.py --workload {hd|inference|train} [--steps K --warmup W]
+    torchrun --nproc-per-node N tools/bench_extra.py --workload ...        (pair / query sharded, weak scaling)
+
+  hd         cfg 3: 480x854 input -> 61x107x256 features (what the reference really produces), batch 16 per GPU
+  inference  cfg 4: test.py-style, each query co-attended with 5 reference frames (frame-A outputs only),
+             480x640 input -> 61x81x256 features, 8 queries (40 pairs) per GPU
+  train      cfg 5: forward + hand-written backward of both modalities, 8 pairs per GPU, NCCL all-reduce of the
+             hot-path gradients (W, gate: 131 585 floats per step)
+Prints one JSON line (rank 0).  Times are CUDA events, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.nn.functional as F
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", required=True, choices=["hd", "inference", "train"])
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from cosnet_b200 import coattention
+    from cosnet_b200.coattention import coattention_forward_raw
+    C = 256
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+
+    def feats(n, h, w, grad=False):
+        x = torch.randn((n, C, h, w), generator=g, device=dev)
+        x = F.prelu(x, torch.tensor([0.25], device=dev)) * 0.66
+        return x.requires_grad_(grad)
+    k = 1.0 / 16
+    W = [((torch.rand((C, C), generator=g, device=dev) * 2 - 1) * k) for _ in range(2)]
+    G = [torch.randn((C,), generator=g, device=dev) * 0.01 for _ in range(2)]
+    Bd = (torch.rand((1,), generator=g, device=dev) * 2 - 1) * k
+
+    if args.workload == "hd":
+        n, h, w = 16, 61, 107
+        va, vb, da, db = (feats(n, h, w) for _ in range(4))
+        def step():
+            coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False)
+            coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False)
+        pairs = n
+        desc = "co-attention at 480x854 input (61x107x256 features), batch 16 per GPU"
+    elif args.workload == "inference":
+        qn, r, h, w = 8, 5, 61, 81
+        va, da = feats(qn, h, w), feats(qn, h, w)
+        vb, db = feats(qn * r, h, w), feats(qn * r, h, w)
+        def step():
+            a = va.repeat_interleave(r, 0); d = da.repeat_interleave(r, 0)
+            coattention_forward_raw(a, vb, W[0], G[0], None, want_z=False, a_only=True)
+            coattention_forward_raw(d, db, W[1], G[1], Bd, want_z=False, a_only=True)
+        pairs = qn * r
+        desc = "test.py-style inference: 8 queries x 5 references per GPU, 61x81x256 features, frame-A outputs only"
+    else:
+        n, h, w = 8, 60, 60
+        va, da = feats(n, h, w, True), feats(n, h, w, True)
+        vb, db = feats(n, h, w), feats(n, h, w)
+        params = [W[0].requires_grad_(True), G[0].requires_grad_(True), W[1].requires_grad_(True), G[1].requires_grad_(True), Bd.requires_grad_(True)]
+        ra = torch.randn((n, 2 * C, h, w), generator=g, device=dev); rb = torch.randn((n, 2 * C, h, w), generator=g, device=dev)
+        def step():
+            for p in params + [va, da]:
+                p.grad = None
+            ca, cb = coattention(va, vb, params[0], params[1], None)
+            dca, dcb = coattention(da, db, params[2], params[3], params[4])
+            # depth: the B branch is gradient dead in the reference (:240-247) -> only cat_a carries gradient
+            loss = (ca * ra).sum() + (cb * rb).sum() + (dca * ra).sum()
+            loss.backward()
+            if world > 1:
+                flat = torch.cat([p.grad.reshape(-1) for p in params])
+                dist.all_reduce(flat)
+        pairs = n
+        desc = "train step on the hot path: forward + backward (RGB full, depth A-branch), 8 pairs per GPU, NCCL all-reduce of hot-path grads"
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": "co-attn frame-pairs/sec", "workload": args.workload, "config": desc, "value": pairs * world * args.steps / (ms * 1e-3),
+                          "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "scaling": "weak",
+                          "includes": "tensor allocations of the Python operator (caching allocator), all kernels of both modalities"}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
