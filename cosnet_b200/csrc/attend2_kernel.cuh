@@ -122,6 +122,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int T = p.kv_tiles;
+  // keys the MMAs touch in the last (ragged) tile: valid keys rounded up to the MMA's N granule of 16
+  const int n_last = ((p.L - (T - 1) * k2BN) + 15) & ~15;
 
   if (warp == k2KProducerWarp) {
     // ------------------------------------------------------------------ TMA producer: query tile + key tiles
@@ -134,7 +136,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
         const int pass = (p.passes == 2) ? (np & 1) : 0;
         const int n = (p.passes == 2) ? (np >> 1) : np;
         const int qrow0 = ((1 - pass) * p.N + n) * p.Lp + qp * (2 * k2BM) + (int)rank * k2BM;
-        const int krow0 = (pass * p.N + n) * p.Lp + (int)rank * (k2BN / 2);
+        const int krow_base = (pass * p.N + n) * p.Lp;
+        const int krow0 = krow_base + (int)rank * (k2BN / 2);
         mbar_wait(q_empty, (it & 1) ^ 1, 1);
         if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * k2QBytes);
 #pragma unroll
@@ -144,9 +147,11 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
           mbar_wait(k_empty + s, ph ^ 1, 2);
           if (rank == 0) mbar_arrive_expect_tx(k_full + s, 2 * k2KBytes);
           const uint32_t full_l = mapa_u32(smem_u32(k_full + s), 0);
+          // ragged last tile: the MMA only uses n_last (multiple of 16) keys, CTA r supplies keys [r, r+1) * n_last/2
+          const int krow = (j == T - 1) ? krow_base + j * k2BN + (int)rank * (n_last / 2) : krow0 + j * k2BN;
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb)
-            tma_load_2d_pair(sK + s * k2KBytes + kb * ((k2BN / 2) * 128), &tmap_k, full_l, kb * 64, krow0 + j * k2BN);
+            tma_load_2d_pair(sK + s * k2KBytes + kb * ((k2BN / 2) * 128), &tmap_k, full_l, kb * 64, krow);
         }
       }
     }
@@ -219,6 +224,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
     if (rank == 0) {
       constexpr uint32_t idesc_s = make_idesc_16(2 * k2BM, k2BN, BF16);
       constexpr uint32_t idesc_o = make_idesc_16(2 * k2BM, kC, BF16);
+      const uint32_t idesc_s_last = make_idesc_16(2 * k2BM, (uint32_t)n_last, BF16);
+      const int ksteps_last = n_last / 16;
       uint32_t it = 0, kcnt = 0, vcnt = 0;
       uint32_t pphase0 = 0, pphase1 = 0;
       const uint32_t tO = tmem + k2TmemO;
@@ -239,12 +246,13 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
           tc_fence_after();
           const uint32_t tS = tmem + k2TmemS + (uint32_t)(j & 1) * k2BN;
           const uint64_t kd0 = make_sdesc_k_sw128(sK_addr + s * k2KBytes);
+          const uint32_t idesc = (j == T - 1) ? idesc_s_last : idesc_s;
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < kC / 16; ++kk) {
               const uint64_t ad = qd0 + (uint64_t)(((kk >> 2) * (k2BM * 128) + (kk & 3) * 32) >> 4);
               const uint64_t bd = kd0 + (uint64_t)(((kk >> 2) * ((k2BN / 2) * 128) + (kk & 3) * 32) >> 4);
-              umma2_ss(tS, ad, bd, idesc_s, kk > 0);
+              umma2_ss(tS, ad, bd, idesc, kk > 0);
             }
             umma2_commit_mc(k_empty + s, 3);
             umma2_commit_mc(s_full + (j & 1), 3);
@@ -275,11 +283,14 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
           const uint32_t s = vcnt % k2VStages;
           const uint32_t tP = tmem + k2TmemS + (uint32_t)b * k2BN;
           const uint64_t vd0 = make_sdesc_k_sw128(sV_addr + s * k2VBytes);
+          const int ksteps = (j == T - 1) ? ksteps_last : k2BN / 16;
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < k2BN / 16; ++kk) {
-              const uint64_t bd = vd0 + (uint64_t)(((kk >> 2) * ((kC / 2) * 128) + (kk & 3) * 32) >> 4);
-              umma2_ts(tO, tP + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+              if (kk < ksteps) {
+                const uint64_t bd = vd0 + (uint64_t)(((kk >> 2) * ((kC / 2) * 128) + (kk & 3) * 32) >> 4);
+                umma2_ts(tO, tP + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+              }
             }
             umma2_commit_mc(v_empty + s, 3);
             umma2_commit_mc(o_full, 3);
