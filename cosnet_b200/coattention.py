@@ -95,8 +95,8 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
     return cat_a, cat_b, z, lse
 
 
-def backward_workspace_bytes(n: int, c: int, h: int, w: int) -> int:
-    r = _lib.load().coattn_backward_workspace_bytes(n, c, h, w)
+def backward_workspace_bytes(n: int, c: int, h: int, w: int, counterpart: bool = False) -> int:
+    r = _lib.load().coattn_backward_workspace_bytes(n, c, h, w, 1 if counterpart else 0)
     if r < 0:
         _lib.check(int(r), "coattn_backward_workspace_bytes")
     return int(r)
@@ -106,8 +106,8 @@ class _CoAttentionFn(torch.autograd.Function):
     """Autograd bridge: forward = coattn_forward (keeps z, lse, mask), backward = coattn_backward.
 
     Gradient semantics of the reference: the B-side gate mask is a constant (rgbd_segmentation_RAA.py:178-182), so the
-    gate parameters only receive gradient through cat_a; gradients for the counterpart features v_b
-    (no_grad_for_counterpart=False) are not implemented.
+    gate parameters only receive gradient through cat_a; the gradient for the counterpart features v_b is only
+    computed when v_b requires grad (no_grad_for_counterpart=False, :147-148).
     """
 
     @staticmethod
@@ -123,10 +123,6 @@ class _CoAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_cat_a, d_cat_b):
-        if ctx.v_b_needs_grad:
-            raise NotImplementedError(
-                "coattention backward w.r.t. the counterpart features (no_grad_for_counterpart=False) is not implemented; "
-                "the reference's training script only uses no_grad_for_counterpart=True (train.py:379)")
         v_a, v_b, weight, gate_weight, z, lse, mask = ctx.saved_tensors
         n, c, h, w = v_a.shape
         dev = v_a.device
@@ -142,16 +138,17 @@ class _CoAttentionFn(torch.autograd.Function):
             d_w = torch.empty((c, c), dtype=torch.float32, device=dev)
             d_gw = torch.empty((c,), dtype=torch.float32, device=dev)
             d_gb = torch.empty((1,), dtype=torch.float32, device=dev) if ctx.has_bias else None
-            nbytes = backward_workspace_bytes(n, c, h, w)
+            d_v_b = torch.empty_like(v_b) if ctx.v_b_needs_grad else None
+            nbytes = backward_workspace_bytes(n, c, h, w, ctx.v_b_needs_grad)
             ws = _workspace(dev, nbytes)
             stream = torch.cuda.current_stream(dev).cuda_stream
             code = lib.coattn_backward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(), z.data_ptr(),
                                        lse.data_ptr(), mask.data_ptr(), d_cat_a.data_ptr(),
-                                       None if d_cat_b is None else d_cat_b.data_ptr(), d_v_a.data_ptr(), None,
-                                       d_w.data_ptr(), d_gw.data_ptr(), None if d_gb is None else d_gb.data_ptr(),
+                                       None if d_cat_b is None else d_cat_b.data_ptr(), d_v_a.data_ptr(),
+                                       None if d_v_b is None else d_v_b.data_ptr(), d_w.data_ptr(), d_gw.data_ptr(), None if d_gb is None else d_gb.data_ptr(),
                                        _aligned_ptr(ws), nbytes, n, c, h, w, _lib.FLAG_BF16 if ctx.bf16 else 0, stream)
             _lib.check(code, "coattn_backward")
-        return d_v_a, None, d_w.to(weight.dtype), d_gw.view_as(gate_weight).to(gate_weight.dtype), d_gb, None
+        return d_v_a, d_v_b, d_w.to(weight.dtype), d_gw.view_as(gate_weight).to(gate_weight.dtype), d_gb, None
 
 
 def coattention(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False):

@@ -29,7 +29,8 @@ enum GemmMode : int {
   kGemmStoreF32 = 0,        // out0[(b*rows0 + m)*ld0 + n] = d                               (m < m_valid)
   kGemmStore16Both = 1,     // out0 (bf16 [m][n]) and out1 (bf16 transposed [n][m])
   kGemmAddF32T = 2,         // out0[(b*rows0 + n)*ld0 + m] += d   transposed, m < m_valid       (dA contributions)
-  kGemmAtomicF32 = 3        // atomicAdd(out0[m*ld0 + n], d)      no batch offset               (dW, reduced over b)
+  kGemmAtomicF32 = 3,       // atomicAdd(out0[m*ld0 + n], d)      no batch offset               (dW, reduced over b)
+  kGemmStore16 = 4          // out0 (bf16 [m][n]) only
 };
 
 struct GemmParams {
@@ -129,6 +130,15 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K]
             dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
                                  __uint_as_float(v[4 * q + 3]));
         }
+      } else if constexpr (MODE == kGemmStore16) {
+        unsigned short* o0 = static_cast<unsigned short*>(p.out0) + ((int64_t)b * p.rows0 + m) * p.ld0 + n;
+        uint4* d4 = reinterpret_cast<uint4*>(o0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          d4[q] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
+                             pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                             pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+                             pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
       } else if constexpr (MODE == kGemmStore16Both) {
         unsigned short* o0 = static_cast<unsigned short*>(p.out0) + ((int64_t)b * p.rows0 + m) * p.ld0 + n;
         unsigned short* o1 = static_cast<unsigned short*>(p.out1) + ((int64_t)b * p.rows1 + n) * p.ld1 + m;
@@ -179,6 +189,8 @@ struct BwdPrepParams {
   unsigned short* dza_t;  // [N][Lp][C] bf16
   unsigned short* dzb_t;  // [N][Lp][C] bf16
   unsigned short* dzb16;  // [N][C][Lp] bf16
+  unsigned short* dza16;  // [N][C][Lp] bf16 or null (only needed for counterpart gradients)
+  float* d_vb;            // [N][C][L] or null: initialised with the passthrough gradient d_cat_b[:, C:2C]
   float* delta;           // [2][N][L]
   float* d_gate_w;        // [C]   (accumulated with atomics; caller zeroes)
   float* d_gate_b;        // [1] or null
@@ -194,6 +206,7 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
   __shared__ float red[4][64];
   __shared__ float s_dta[64], s_ma[64], s_mb[64];
   __shared__ float s_gw[kC];
+  __shared__ float s_gacc[kC];
   const int n = blockIdx.y;
   const int l0 = blockIdx.x * 64;
   const int pos = threadIdx.x & 63;
@@ -201,6 +214,7 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
   const int l = l0 + pos;
   const bool valid = l < p.L;
   s_gw[threadIdx.x] = p.gate_w[threadIdx.x];
+  s_gacc[threadIdx.x] = 0.f;
   const float* dca = p.d_cat_a + (size_t)n * 2 * kC * p.L;
   const float* za = p.z + (size_t)n * kC * p.L;
   const float* zb = p.z + (size_t)(p.N + n) * kC * p.L;
@@ -242,15 +256,18 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
       p.d_va[((size_t)n * kC + c) * p.L + l] = __ldg(dca + (size_t)(kC + c) * p.L + l);
     }
     dl = fmaf(dz, zz, dl);
-    tile[pos * kBwdStride + c] = cvt16<true>(dz);
-    // d_gate_w[c] += sum over the 64 positions of d_ta * Z_a  (warp reduce over positions, then one atomic per warp)
+    const unsigned short hz = cvt16<true>(dz);
+    tile[pos * kBwdStride + c] = hz;
+    if (p.dza16 != nullptr) p.dza16[((size_t)n * kC + c) * p.Lp + l] = hz;
+    // d_gate_w[c] += sum over the 64 positions of d_ta * Z_a  (warp reduce over positions, block total in shared memory)
     float gsum = dta * zz;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
-    if ((threadIdx.x & 31) == 0) atomicAdd(p.d_gate_w + c, gsum);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_gacc[c], gsum);
   }
   red[cg][pos] = dl;
   __syncthreads();
+  atomicAdd(p.d_gate_w + threadIdx.x, s_gacc[threadIdx.x]);   // one global atomic per channel and block
   if (threadIdx.x < 64 && l0 + threadIdx.x < p.L) {
     p.delta[(size_t)n * p.L + l0 + threadIdx.x] = red[0][pos] + red[1][pos] + red[2][pos] + red[3][pos];
   }
@@ -281,6 +298,9 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
     if (valid && has_b) {
       zz = __ldg(zb + (size_t)c * p.L + l);
       dz = __ldg(dcb + (size_t)c * p.L + l) * mb;
+      if (p.d_vb != nullptr) p.d_vb[((size_t)n * kC + c) * p.L + l] = __ldg(dcb + (size_t)(kC + c) * p.L + l);
+    } else if (valid && p.d_vb != nullptr) {
+      p.d_vb[((size_t)n * kC + c) * p.L + l] = 0.f;
     }
     dl = fmaf(dz, zz, dl);
     const unsigned short h = cvt16<true>(dz);
@@ -314,6 +334,7 @@ struct BwdCombineParams {
   const float* delta;  // [2][N][L]
   unsigned short* ds;  // [N][Lp][Lp] bf16
   unsigned short* pb;  // [N][Lp][Lp] bf16 (only written when dpb != null)
+  unsigned short* pa;  // [N][Lp][Lp] bf16 or null (counterpart gradients only)
   int N, L, Lp;
 };
 
@@ -323,7 +344,7 @@ __global__ void __launch_bounds__(256) bwd_combine_kernel(BwdCombineParams p) {
   const int j = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (j >= p.Lp) return;
   const size_t off = ((size_t)n * p.Lp + i) * p.Lp + j;
-  uint2 ods = make_uint2(0u, 0u), opb = make_uint2(0u, 0u);
+  uint2 ods = make_uint2(0u, 0u), opb = make_uint2(0u, 0u), opa = make_uint2(0u, 0u);
   if (i < p.L && j < p.L) {
     const float lse_a = __ldg(p.lse + (size_t)n * p.L + i);
     const float del_a = __ldg(p.delta + (size_t)n * p.L + i);
@@ -334,7 +355,7 @@ __global__ void __launch_bounds__(256) bwd_combine_kernel(BwdCombineParams p) {
     const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
     const float av[4] = {a4.x, a4.y, a4.z, a4.w};
     const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
-    float dsv[4], pbv[4];
+    float dsv[4], pbv[4], pav[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int jj = j + e;
@@ -348,16 +369,36 @@ __global__ void __launch_bounds__(256) bwd_combine_kernel(BwdCombineParams p) {
         }
         dsv[e] = d;
         pbv[e] = pbe;
+        pav[e] = pa;
       } else {
         dsv[e] = 0.f;
         pbv[e] = 0.f;
+        pav[e] = 0.f;
       }
     }
     ods = make_uint2(pack_bf16x2(dsv[0], dsv[1]), pack_bf16x2(dsv[2], dsv[3]));
     opb = make_uint2(pack_bf16x2(pbv[0], pbv[1]), pack_bf16x2(pbv[2], pbv[3]));
+    opa = make_uint2(pack_bf16x2(pav[0], pav[1]), pack_bf16x2(pav[2], pav[3]));
   }
   *reinterpret_cast<uint2*>(p.ds + off) = ods;
   if (p.dpb) *reinterpret_cast<uint2*>(p.pb + off) = opb;
+  if (p.pa) *reinterpret_cast<uint2*>(p.pa + off) = opa;
+}
+
+// 16-bit [N][Lp][Lp] -> transposed per sample (32x32 tiles through shared memory); counterpart gradients only
+__global__ void __launch_bounds__(256) transpose16_kernel(const unsigned short* __restrict__ src,
+                                                          unsigned short* __restrict__ dst, int Lp) {
+  __shared__ unsigned short t[32][34];
+  const size_t base = (size_t)blockIdx.z * Lp * Lp;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y0 = blockIdx.y * 32 + (threadIdx.x >> 5);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[(threadIdx.x >> 5) + 8 * k][threadIdx.x & 31] = src[base + (size_t)(y0 + 8 * k) * Lp + x];
+  __syncthreads();
+  const int xo = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int yo0 = blockIdx.x * 32 + (threadIdx.x >> 5);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dst[base + (size_t)(yo0 + 8 * k) * Lp + xo] = t[threadIdx.x & 31][(threadIdx.x >> 5) + 8 * k];
 }
 
 // W [C_out][C_in] fp32 -> Wt [C_in][C_out] bf16 (B operand of dA += dQ W: dA[i][c] = sum_d dQt[i][d] Wt[c][d])

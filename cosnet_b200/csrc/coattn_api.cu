@@ -382,6 +382,8 @@ struct BwdLayout {
   int64_t off_g;   // second copy of the forward operand segments, always bf16 (operands of the gradient GEMMs)
   int64_t off_dza_t, off_dzb_t, off_dzb16, off_delta, off_s, off_dpa, off_dpb, off_ds, off_pb, off_dqt, off_dq16,
       off_wt, total;
+  // counterpart gradients only (d_v_b requested): dZ_a in [C][Lp], P_a, dS^T, P_a^T, Q in [C][Lp]
+  int64_t off_dza16, off_pa, off_ds_t, off_pa_t, off_q16, total_counterpart;
 };
 BwdLayout make_bwd_layout(int n, int h, int w) {
   BwdLayout b{};
@@ -399,6 +401,9 @@ BwdLayout make_bwd_layout(int n, int h, int w) {
   b.off_dqt = take(plane); b.off_dq16 = take(plane);
   b.off_wt = take((int64_t)kC * kC * 2);
   b.total = off;
+  b.off_dza16 = take(plane); b.off_pa = take(mat16); b.off_ds_t = take(mat16); b.off_pa_t = take(mat16);
+  b.off_q16 = take(plane);
+  b.total_counterpart = off;
   return b;
 }
 
@@ -420,9 +425,10 @@ int launch_gemm(EncodeTiledFn enc, cudaStream_t st, const void* a, uint64_t a_ro
 
 extern "C" {
 
-int64_t coattn_backward_workspace_bytes(int n, int c, int h, int w) {
+int64_t coattn_backward_workspace_bytes(int n, int c, int h, int w, int counterpart) {
   if (check_dims(n, c, h, w) != COATTN_OK) return COATTN_E_SHAPE;
-  return make_bwd_layout(n, h, w).total;
+  const BwdLayout bl = make_bwd_layout(n, h, w);
+  return counterpart ? bl.total_counterpart : bl.total;
 }
 
 int coattn_backward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* z,
@@ -431,12 +437,14 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
                     int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags, void* stream) {
   if (!v_a || !v_b || !w || !gate_w || !z || !lse || !mask || !d_cat_a || !d_v_a || !d_w || !d_gate_w)
     return COATTN_E_NULL;
-  if (d_v_b != nullptr) return COATTN_E_UNSUPPORTED;
+  const bool counterpart = d_v_b != nullptr;
   if (int e = check_dims(n, c, h, w_)) return e;
   const BwdLayout bl = make_bwd_layout(n, h, w_);
   const Layout& ly = bl.fwd;
   if (!workspace) return COATTN_E_NULL;
-  if ((reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) != 0 || workspace_bytes < bl.total) return COATTN_E_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) != 0 ||
+      workspace_bytes < (counterpart ? bl.total_counterpart : bl.total))
+    return COATTN_E_WORKSPACE;
   if (int e = check_arch(nullptr)) return e;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return COATTN_E_DRIVER;
@@ -483,6 +491,13 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
 
   BwdPrepParams bp;
   bp.d_cat_a = d_cat_a; bp.d_cat_b = d_cat_b; bp.z = z; bp.mask = mask; bp.gate_w = gate_w;
+  unsigned short* dza16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dza16));
+  unsigned short* pa = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa));
+  unsigned short* ds_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_ds_t));
+  unsigned short* pa_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa_t));
+  unsigned short* q16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_q16));
+  bp.dza16 = counterpart ? dza16 : nullptr;
+  bp.d_vb = d_v_b;
   bp.dza_t = dza_t; bp.dzb_t = dzb_t; bp.dzb16 = dzb16; bp.delta = delta;
   bp.d_gate_w = d_gate_w; bp.d_gate_b = d_gate_b; bp.d_va = d_v_a; bp.N = n; bp.L = L; bp.Lp = Lp;
   bwd_prep_kernel<<<dim3(Lp / 64, n), kBwdPrepThreads, 0, st>>>(bp);
@@ -505,6 +520,7 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   }
   BwdCombineParams cp;
   cp.s = smat; cp.dpa = dpa; cp.dpb = has_b ? dpb : nullptr; cp.lse = lse; cp.delta = delta; cp.ds = ds; cp.pb = pb;
+  cp.pa = counterpart ? pa : nullptr;
   cp.N = n; cp.L = L; cp.Lp = Lp;
   bwd_combine_kernel<<<dim3((Lp / 4 + 255) / 256, Lp, n), 256, 0, st>>>(cp);
   if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
@@ -525,6 +541,21 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   gp.out0 = d_w; gp.ld0 = kC; gp.rows0 = 0; gp.m_valid = kC;
   gp.a_rows_per_batch = kC; gp.b_rows_per_batch = kC;
   if (int e = launch_gemm<kGemmAtomicF32>(enc, st, dq16, rowsC, true, a16, rowsC, true, Lp, kC / 128, kC / 128, n, gp)) return e;
+  if (counterpart) {
+    // dB[c][j] = sum_i Q[c][i] dS[i][j] + sum_i dZ_a[c][i] P_a[i][j]   (+ passthrough, written by bwd_prep)
+    transpose16_kernel<<<dim3(Lp / 32, Lp / 32, n), 256, 0, st>>>(ds, ds_t, Lp);
+    transpose16_kernel<<<dim3(Lp / 32, Lp / 32, n), 256, 0, st>>>(pa, pa_t, Lp);
+    if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
+    // Q16[c][i] = sum_d W[c][d] A[d][i]  (bf16, channel-major): A operand W16 (bf16 copy in the gradient operand set)
+    unsigned short* w16g = reinterpret_cast<unsigned short*>(seg(gws, ly.off_w16));
+    gp.out0 = q16; gp.ld0 = Lp; gp.rows0 = kC; gp.out1 = nullptr; gp.m_valid = kC;
+    gp.a_rows_per_batch = 0; gp.b_rows_per_batch = Lp;
+    if (int e = launch_gemm<kGemmStore16>(enc, st, w16g, kC, true, at, rowsL, true, kC, kC / 128, lt, n, gp)) return e;
+    gp.out0 = d_v_b; gp.ld0 = L; gp.rows0 = kC; gp.m_valid = L;
+    gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = kC;
+    if (int e = launch_gemm<kGemmAddF32T>(enc, st, ds_t, rowsL, true, q16, rowsC, true, Lp, lt, kC / 128, n, gp)) return e;
+    if (int e = launch_gemm<kGemmAddF32T>(enc, st, pa_t, rowsL, true, dza16, rowsC, true, Lp, lt, kC / 128, n, gp)) return e;
+  }
   return COATTN_OK;
 }
 

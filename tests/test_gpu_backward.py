@@ -72,15 +72,48 @@ def test_gradients_against_oracle(coattention, n, h, w, bias, with_b):
     assert np.isfinite(got["d_v_a"]).all()
 
 
-def test_counterpart_gradients_are_refused(coattention):
+@pytest.mark.parametrize("n,h,w,bias", [(1, 4, 5, False), (2, 12, 11, True)])
+def test_counterpart_gradients(coattention, n, h, w, bias):
+    """no_grad_for_counterpart=False (:147-148): V_b receives gradient too."""
+    v_a, v_b = orc.synthetic_features(400 + h * w, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(401 + h * w, bias=bias)
+    rng = np.random.default_rng(6)
+    r_a = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    r_b = rng.standard_normal((n, 512, h, w), dtype=np.float32)
     dev = torch.device("cuda:0")
-    v_a = torch.randn(1, 256, 4, 4, device=dev, requires_grad=True)
-    v_b = torch.randn(1, 256, 4, 4, device=dev, requires_grad=True)
-    W = torch.randn(256, 256, device=dev) * 0.05
-    g = torch.randn(256, device=dev) * 0.01
-    cat_a, cat_b = coattention(v_a, v_b, W, g, None)
-    with pytest.raises(NotImplementedError):
-        (cat_a.sum() + cat_b.sum()).backward()
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    va, vb = t(v_a).requires_grad_(True), t(v_b).requires_grad_(True)
+    w_ = t(W).requires_grad_(True)
+    gw = t(g).requires_grad_(True)
+    gb = None if b is None else t(b).requires_grad_(True)
+    cat_a, cat_b = coattention(va, vb, w_, gw, gb)
+    ((cat_a * t(r_a)).sum() + (cat_b * t(r_b)).sum()).backward()
+    torch.cuda.synchronize()
+    ref = orc.coattention_grads(v_a, v_b, W, g, b, r_a, r_b, counterpart_grad=True)
+    assert rel_l2(vb.grad.cpu().numpy(), ref["d_v_b"]) < GRAD_TOL, rel_l2(vb.grad.cpu().numpy(), ref["d_v_b"])
+    assert rel_l2(va.grad.cpu().numpy(), ref["d_v_a"]) < GRAD_TOL
+    assert rel_l2(w_.grad.cpu().numpy(), ref["d_w"]) < GRAD_TOL
+
+
+def test_counterpart_golden_gradients_of_the_reference(coattention):
+    fx = load_golden("bwd_n1_4x5_s066_both")
+    inp = golden_inputs(fx)
+    n, h, w, seed = int(fx["n"]), int(fx["h"]), int(fx["w"]), int(fx["seed"])
+    rng = np.random.default_rng(seed + 7)
+    r_a = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    r_b = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    dev = torch.device("cuda:0")
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    va, vb = t(inp["v_a"]).requires_grad_(True), t(inp["v_b"]).requires_grad_(True)
+    w_ = t(inp["w_rgb"]).requires_grad_(True)
+    gw = t(inp["g_rgb"]).requires_grad_(True)
+    cat_a, cat_b = coattention(va, vb, w_, gw, None)
+    ((cat_a * t(r_a)).sum() + (cat_b * t(r_b)).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel_l2(vb.grad.cpu().numpy(), fx["d_v_b"]) < GRAD_TOL
+    assert rel_l2(va.grad.cpu().numpy(), fx["d_v_a"]) < GRAD_TOL
+    assert rel_l2(w_.grad.cpu().numpy(), fx["d_w"]) < GRAD_TOL
+    assert rel_l2(gw.grad.cpu().numpy(), fx["d_gate_w"]) < GRAD_TOL
 
 
 def test_module_backward_runs(coattention):
