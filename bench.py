@@ -306,7 +306,9 @@ def run_ours(args):
 
     def e2e_step():
         pipe(hin[0], hin[1], w_rgb, g_rgb, None, hout[0], hout[1])
+        pipe.wait_host()
         pipe(hin[2], hin[3], w_dep, g_dep, b_dep, hout[2], hout[3])
+        pipe.wait_host()
     e2e_step()
     torch.cuda.synchronize()
     barrier()
