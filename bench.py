@@ -255,8 +255,8 @@ def run_ours(args):
 
     def modality(va, vb, wt, gw, gb, ca, cb, record):
         gbp = None if gb is None else gb.data_ptr()
-        _lib.check(lib.coattn_stage_prep(va.data_ptr(), vb.data_ptr(), wt.data_ptr(), wsp, nbytes, n, C, H, W, FLAGS, st), "prep")
-        _lib.check(lib.coattn_stage_project(wsp, nbytes, n, C, H, W, FLAGS, st), "project")
+        _lib.check(lib.coattn_stage_prep_project(va.data_ptr(), vb.data_ptr(), wt.data_ptr(), wsp, nbytes, n, C, H, W, FLAGS, st),
+                   "prep_project")
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -349,7 +349,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * pipe.h2d_bytes * world,
                 "d2h_bytes_per_step": 2 * pipe.d2h_bytes * world, "steps": e2e_steps, "matches_resident_path": same,
                 "api": "cosnet_b200.coattention.HostPipeline (pinned host in/out, 3 streams x chunks of 4 pairs)"},
-        "gpu_launches": 8 * args.steps,   # per modality call: prep, cast_w, project, attend(+gate+concat)
+        "gpu_launches": 8 * args.steps,   # per modality call: prep(V_b), cast_w, project_fused(V_a), attend2(+gate+concat)
         "roofline": {
             "kernel": "attend2_kernel", "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"],
             "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"], "traffic": None,

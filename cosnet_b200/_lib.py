@@ -21,6 +21,7 @@ FLAG_BF16 = 1  # COATTN_FLAG_BF16
 FLAG_UNFUSED_GATE = 2  # COATTN_FLAG_UNFUSED_GATE
 FLAG_SINGLE_CTA = 4  # COATTN_FLAG_SINGLE_CTA
 FLAG_A_ONLY = 8  # COATTN_FLAG_A_ONLY
+FLAG_UNFUSED_PREP = 16  # COATTN_FLAG_UNFUSED_PREP
 
 # name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
 SIGNATURES = {
@@ -33,6 +34,7 @@ SIGNATURES = {
     "coattn_stage_passthrough": (_i, [_vp] * 4 + [_i, _i, _i, _i, _vp]),
     "coattn_stage_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_project": (_i, [_vp, _i64, _i, _i, _i, _i, _u, _vp]),
+    "coattn_stage_prep_project": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_attend": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_gate": (_i, [_vp] * 7 + [_i, _i, _i, _i, _vp]),
     "coattn_backward_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),

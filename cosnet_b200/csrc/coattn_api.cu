@@ -17,6 +17,7 @@ namespace {
 using namespace coattn;
 
 constexpr int64_t kAlign = 1024;
+constexpr unsigned kInternalPrepOnlyB = 1u << 30;   // internal: prep converts V_b only (V_a goes through project_fused)
 inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
@@ -161,8 +162,9 @@ int coattn_stage_prep(const float* v_a, const float* v_b, const float* w, void* 
   p.a16 = p.b16 + plane_elems;
   p.L = ly.L;
   p.Lp = ly.Lp;
+  p.only_b = (flags & kInternalPrepOnlyB) ? 1 : 0;
   unsigned short* w16 = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16));
-  const dim3 grid(ly.Lp / kPrepTileL, 2 * n);
+  const dim3 grid(ly.Lp / kPrepTileL, p.only_b ? n : 2 * n);
   const bool vec = (ly.L % 4 == 0) &&
                    (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   if (flags & COATTN_FLAG_BF16) {
@@ -198,6 +200,43 @@ int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c,
   if (e != cudaSuccess) return (int)e;
   kern<<<dim3(ly.Lp / 128, n), kNumThreads, kProjSmemBytes, st>>>(tm_at, tm_w, p);
   return (int)cudaGetLastError();
+}
+
+// prep (V_b only) + fused A-side prep/projection: the default forward path
+static int prep_and_project_fused(const float* v_a, const float* v_b, const float* w, void* workspace,
+                                  int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags, void* stream) {
+  if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags | kInternalPrepOnlyB, stream))
+    return e;
+  const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
+  const Layout ly = make_layout(n, h, w_);
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return COATTN_E_DRIVER;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tm_w;
+  if (int e = make_tmap(enc, &tm_w, seg(workspace, ly.off_w16), kC, kC, 256, bf16)) return e;
+  ProjectFusedParams p;
+  p.va = v_a;
+  p.a16 = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)) + ly.t_pass_elems();
+  p.qt = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_t)) + ly.t_pass_elems();
+  p.L = ly.L;
+  p.Lp = ly.Lp;
+  auto kern = bf16 ? project_fused_kernel<true> : project_fused_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<dim3(ly.Lp / 128, n), kNumThreads, kProjSmemBytes, st>>>(tm_w, p);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int coattn_stage_prep_project(const float* v_a, const float* v_b, const float* w, void* workspace,
+                                        int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
+                                        void* stream) {
+  if (!v_a || !v_b || !w) return COATTN_E_NULL;
+  if (int e = check_dims(n, c, h, w_)) return e;
+  if (((h * w_) % 2 != 0) || (reinterpret_cast<uintptr_t>(v_a) & 7) != 0) {   // odd L: separate kernels
+    if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+    return coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, flags, stream);
+  }
+  return prep_and_project_fused(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream);
 }
 
 static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float* cat_b, float* z, float* lse,
@@ -361,8 +400,14 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
   if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
-  if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
-  if (int e = coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+  // the fused kernel reads the features with float2 loads: needs even L and 8-byte aligned rows
+  const bool can_fuse = (ly.L % 2 == 0) && ((reinterpret_cast<uintptr_t>(v_a) & 7) == 0);
+  if ((flags & COATTN_FLAG_UNFUSED_PREP) || !can_fuse) {
+    if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+    if (int e = coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+  } else {
+    if (int e = prep_and_project_fused(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+  }
   if (flags & COATTN_FLAG_UNFUSED_GATE) {
     float* zbuf = z ? z : reinterpret_cast<float*>(seg(workspace, ly.off_z));
     if (int e = coattn_stage_attend(zbuf, lse, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;

@@ -36,13 +36,14 @@ struct PrepParams {
   unsigned short* a16;  // [N][C][Lp]
   unsigned short* b16;  // [N][C][Lp]
   int L, Lp;
+  int only_b;            // 1: blockIdx.y indexes samples of V_b only (V_a is handled by project_fused_kernel)
 };
 
 template <bool BF16>
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel(PrepParams p) {
   __shared__ __align__(16) unsigned short tile[kPrepTileL * kPrepStride];
-  const int n = blockIdx.y >> 1;
-  const int which = blockIdx.y & 1;  // 0: A, 1: B
+  const int n = p.only_b ? blockIdx.y : (blockIdx.y >> 1);
+  const int which = p.only_b ? 1 : (blockIdx.y & 1);  // 0: A, 1: B
   const int l0 = blockIdx.x * kPrepTileL;
   const float* src = (which ? p.vb : p.va) + (size_t)n * kC * p.L;
   unsigned short* x16 = (which ? p.b16 : p.a16) + (size_t)n * kC * p.Lp;
@@ -81,8 +82,8 @@ constexpr int kPrepStrideV = kC + 8;  // 16-bit elements; 528-byte rows keep 16-
 template <bool BF16>
 __global__ void __launch_bounds__(kPrepThreads) prep_kernel_vec4(PrepParams p) {
   __shared__ __align__(16) unsigned short tile[kPrepTileL * kPrepStrideV];
-  const int n = blockIdx.y >> 1;
-  const int which = blockIdx.y & 1;  // 0: A, 1: B
+  const int n = p.only_b ? blockIdx.y : (blockIdx.y >> 1);
+  const int which = p.only_b ? 1 : (blockIdx.y & 1);  // 0: A, 1: B
   const int l0 = blockIdx.x * kPrepTileL;
   const float* src = (which ? p.vb : p.va) + (size_t)n * kC * p.L;
   unsigned short* x16 = (which ? p.b16 : p.a16) + (size_t)n * kC * p.Lp;
@@ -221,6 +222,145 @@ project_kernel(const __grid_constant__ CUtensorMap tmap_at,  // [N*Lp][C], box {
     tc_fence_after();
     const int row = warp * 32 + lane;
     unsigned short* dst = p.qt + (size_t)(row0 + row) * kC;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t v[32];
+      tmem_ld32(taddr + ch * 32, v);
+      tmem_ld_wait();
+      uint4* d4 = reinterpret_cast<uint4*>(dst + ch * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack16x2<BF16>(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+        o.y = pack16x2<BF16>(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+        o.z = pack16x2<BF16>(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+        o.w = pack16x2<BF16>(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+        d4[q] = o;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ==============================================================================================
+// project_fused: the A side of prep and the W projection in one kernel (L % 4 == 0 not required, but the
+// launcher only uses it when the fp32 rows are 4-byte aligned, i.e. always).  Per 128-position tile:
+//   warps 0-3 read the fp32 features [256 ch][128 pos] (thread = position, coalesced per channel row), convert to
+//   16 bit, write A16 [C][Lp] (values operand of pass 1) and build the At tile directly in shared memory in the
+//   K-major / 128-byte-swizzle layout the UMMA descriptor expects (16-byte chunk index XOR row % 8) -- At never
+//   exists in HBM; W16 arrives by TMA; 16 x tcgen05.mma; the same warps drain TMEM into Qt [Lp][C].
+// ==============================================================================================
+struct ProjectFusedParams {
+  const float* va;        // [N][C][L]
+  unsigned short* a16;    // [N][C][Lp]
+  unsigned short* qt;     // [N][Lp][C]
+  int L, Lp;
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(kNumThreads, 1)
+project_fused_kernel(const __grid_constant__ CUtensorMap tmap_w,   // [C][C], box {64, 256}
+                     ProjectFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint8_t* sA = smem;               // 4 k-blocks x [128 rows x 128 B], written by the threads
+  uint8_t* sW = smem + 64 * 1024;   // 4 k-blocks x [256 rows x 128 B], TMA
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 192 * 1024);
+  uint64_t* w_full = bars + 0;
+  uint64_t* a_full = bars + 1;      // 4 arrivals (one per converting warp)
+  uint64_t* d_full = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.y;
+  const int l0 = blockIdx.x * 128;
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 4);
+    mbar_init(d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, 128 * 1024);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(sW + kb * 32768, &tmap_w, w_full, kb * 64, 0);
+    }
+  } else if (warp == kMmaWarp) {
+    warp_mbar_wait(w_full, 0, lane, 100);
+    warp_mbar_wait(a_full, 0, lane, 102);
+    tc_fence_after();
+    const uint64_t ad0 = make_sdesc_k_sw128(smem_u32(sA));
+    const uint64_t bd0 = make_sdesc_k_sw128(smem_u32(sW));
+    constexpr uint32_t idesc = make_idesc_16(128, 256, BF16);
+    if (elect_one()) {
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk)
+        umma_ss(tmem, ad0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                bd0 + (uint64_t)(((kk >> 2) * 32768 + (kk & 3) * 32) >> 4), idesc, kk > 0);
+      umma_commit(d_full);
+    }
+    __syncwarp();
+  } else {
+    // ---- convert: thread = two neighbouring positions (rows 2q, 2q+1 of the At tile) x 128 channels.
+    // Requires L even (float2 loads); the launcher falls back to the unfused kernels otherwise.
+    const int q2 = (warp & 1) * 32 + lane;      // position pair 0..63
+    const int chalf = warp >> 1;                // channels [128 * chalf, 128 * chalf + 128)
+    const int r0 = 2 * q2;
+    const int lpos = l0 + r0;
+    const bool valid2 = lpos < p.L;             // L even: both positions valid or both padding
+    const float* src = p.va + (size_t)n * kC * p.L + lpos;
+    unsigned short* a16 = p.a16 + (size_t)n * kC * p.Lp + lpos;
+#pragma unroll 1
+    for (int gb = 0; gb < 4; ++gb) {            // 4 batches of 32 channels
+      float2 v[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const int c = chalf * 128 + gb * 32 + u;
+        v[u] = valid2 ? __ldcs(reinterpret_cast<const float2*>(src + (size_t)c * p.L)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {             // 8 channels = one 16-byte chunk of a row
+        const int c0 = chalf * 128 + gb * 32 + g * 8;
+        const int kb = c0 >> 6, chunk = (c0 & 63) >> 3;
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          lo[t] = pack16x2<BF16>(v[g * 8 + 2 * t].x, v[g * 8 + 2 * t + 1].x);   // position r0,   channels c0+2t, c0+2t+1
+          hi[t] = pack16x2<BF16>(v[g * 8 + 2 * t].y, v[g * 8 + 2 * t + 1].y);   // position r0+1
+        }
+        *reinterpret_cast<uint4*>(sA + kb * 16384 + r0 * 128 + ((chunk ^ (r0 & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(sA + kb * 16384 + (r0 + 1) * 128 + ((chunk ^ ((r0 + 1) & 7)) << 4)) =
+            make_uint4(hi[0], hi[1], hi[2], hi[3]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)     // A16[c][lpos .. lpos+1]: 4-byte stores, 128 contiguous bytes per warp
+          *reinterpret_cast<uint32_t*>(a16 + (size_t)(c0 + u) * p.Lp) = pack16x2<BF16>(v[g * 8 + u].x, v[g * 8 + u].y);
+      }
+    }
+    fence_proxy_async_smem();     // generic-proxy stores to sA -> visible to the tensor core (async proxy)
+    warp_mbar_arrive(a_full, lane);
+    // ---- epilogue: thread = one output row of Qt
+    warp_mbar_wait(d_full, 0, lane, 101);
+    tc_fence_after();
+    unsigned short* dst = p.qt + ((size_t)n * p.Lp + l0 + warp * 32 + lane) * kC;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int ch = 0; ch < 8; ++ch) {

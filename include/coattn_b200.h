@@ -75,6 +75,11 @@ enum {
  *                          (test.py:301-305): halves the attend work.  CTA-pair kernel only.
  */
 #define COATTN_FLAG_A_ONLY 8u
+/*
+ *   COATTN_FLAG_UNFUSED_PREP  run prep (both frames) and project as separate kernels with the At operand
+ *                          round-tripping through HBM, instead of the fused A-side prep + projection kernel.
+ */
+#define COATTN_FLAG_UNFUSED_PREP 16u
 
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);
@@ -103,6 +108,11 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
 int coattn_stage_prep(const float* v_a, const float* v_b, const float* w, void* workspace,
                       int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
                       void* stream);
+/* stages 1+2 fused (default path of coattn_forward): V_b through the prep kernel; V_a is converted, written as A16
+ * and projected (Qt = (W A)^T) by one kernel, At never reaches HBM.  Fills Bt, B16, A16, W16, Qt. */
+int coattn_stage_prep_project(const float* v_a, const float* v_b, const float* w, void* workspace,
+                              int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
+                              void* stream);
 /* stage 2 (:159): Qt = At W^T on the tensor cores. */
 int coattn_stage_project(void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
                          unsigned flags, void* stream);

@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--bf16", type=int, default=0)
     ap.add_argument("--single", type=int, default=0)
+    ap.add_argument("--unfused-prep", type=int, default=0)
     args = ap.parse_args()
     n, h, w, c = args.n, args.h, args.w, 256
     FL = (1 if args.bf16 else 0) | (4 if args.single else 0)
@@ -144,8 +145,12 @@ def main():
         for itn in range(args.iters + 3):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
             ev[0].record()
-            _lib.check(lib.coattn_stage_prep(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "prep"); ev[1].record()
-            _lib.check(lib.coattn_stage_project(wsp, nbytes, n, c, h, w, FL, st), "project"); ev[2].record()
+            if args.unfused_prep:
+                _lib.check(lib.coattn_stage_prep(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "prep"); ev[1].record()
+                _lib.check(lib.coattn_stage_project(wsp, nbytes, n, c, h, w, FL, st), "project"); ev[2].record()
+            else:
+                ev[1].record()
+                _lib.check(lib.coattn_stage_prep_project(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "prep_project"); ev[2].record()
             _lib.check(lib.coattn_stage_attend_gate(tva.data_ptr(), tvb.data_ptr(), ca.data_ptr(), cb.data_ptr(), None, lt.data_ptr(), mk.data_ptr(), tg.data_ptr(), bp, wsp, nbytes, n, c, h, w, FL, st), "attend_gate"); ev[3].record()
             ev[4].record()
             _lib.check(lib.coattn_stage_gate(zt.data_ptr(), tva.data_ptr(), tvb.data_ptr(), tg.data_ptr(), bp, ca.data_ptr(), cb.data_ptr(), n, c, h, w, st), "gate"); ev[5].record()

@@ -279,6 +279,19 @@ def test_end_to_end_masks_agree_with_oracle_operator(op, sigma, hw):
         assert (got - ref).abs().max().item() < 2e-3
 
 
+def test_fused_and_unfused_prep_agree(op):
+    for (n, h, w) in ((2, 12, 11), (1, 31, 41), (1, 60, 60)):
+        v_a, v_b = orc.synthetic_features(85, n, h, w, 0.66)
+        W, g, b = orc.synthetic_weights(86, bias=True)
+        dev = torch.device("cuda:0")
+        t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+        fused = op(t(v_a), t(v_b), t(W), t(g), t(b))
+        unfused = op(t(v_a), t(v_b), t(W), t(g), t(b), unfused_prep=True)
+        torch.cuda.synchronize()
+        for x, y in zip(fused, unfused):
+            assert torch.equal(x, y)      # same conversions, same MMAs: bit-identical
+
+
 def test_frame_a_only_matches_full(op):
     n, h, w = 3, 12, 11
     v_a, v_b = orc.synthetic_features(81, n, h, w, 0.66)
