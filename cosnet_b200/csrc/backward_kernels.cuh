@@ -4,8 +4,8 @@
 // sample and modality at L = 3600): S is recomputed from the 16-bit operands and the saved log-sum-exp vectors.
 //
 //   bwd_prep      d_cat_a/b, Z, mask, g  ->  dZ_a, dZ_b (16-bit, both layouts), delta_a, delta_b, d_gate, dA init
-//   gemm_nt  x3   S = Qt Bt^T,  dP_a = dZa_t Bt^T,  dP_b = At dZb_t^T                 (fp32, [L, L])
-//   bwd_combine   dS = P_a (dP_a - delta_a) + P_b (dP_b - delta_b),  P_b              (bf16, [L, L], transient)
+//   bwd_tile      per 128x128 tile: S = Qt Bt^T, dP_a = dZa_t Bt^T, dP_b = At dZb_t^T in TMEM, combined on the fly into
+//                 dS = P_a (dP_a - delta_a) + P_b (dP_b - delta_b) and P_b            (bf16, [L, L], transient)
 //   gemm_nt  x4   dQ = dS B^T;  dA += P_b dZ_b^T;  dA += dQ W;  dW += dQ^T A^T
 //
 // with P_a[i,j] = exp(S[i,j] - lse_a[i]) (softmax over j, :165) and P_b[i,j] = exp(S[i,j] - lse_b[j]) (:164).
@@ -324,65 +324,179 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
 }
 
 // ==============================================================================================
-// bwd_combine: elementwise over the [Lp, Lp] matrices of one sample.
+// bwd_tile: the three [L, L] products of the backward and their elementwise combination in ONE kernel, one
+// 128 x 128 tile (i-tile, j-tile) of one sample per CTA -- nothing of size L x L is ever written in fp32:
+//   S    = Qt[i] Bt[j]^T      (forward operand format, so that exp(S - lse) is exactly the forward's softmax)
+//   dP_a = dZa_t[i] Bt[j]^T   (bf16)
+//   dP_b = At[i] dZb_t[j]^T   (bf16; HAS_B only)
+//   dS = P_a (dP_a - delta_a[i]) + P_b (dP_b - delta_b[j]),   P_a = exp(S - lse_a[i]),  P_b = exp(S - lse_b[j])
+// written as bf16: dS, P_b (HAS_B) and P_a (counterpart gradients only).  TMEM: three 128-column accumulators.
 // ==============================================================================================
-struct BwdCombineParams {
-  const float* s;      // [N][Lp][Lp]
-  const float* dpa;    // [N][Lp][Lp]
-  const float* dpb;    // [N][Lp][Lp] or null (no B-side gradient)
-  const float* lse;    // [2][N][L]
-  const float* delta;  // [2][N][L]
-  unsigned short* ds;  // [N][Lp][Lp] bf16
-  unsigned short* pb;  // [N][Lp][Lp] bf16 (only written when dpb != null)
-  unsigned short* pa;  // [N][Lp][Lp] bf16 or null (counterpart gradients only)
+constexpr int kTileStageBytes = 6 * 16384;   // Qt, Bt | dZa_t, Bt(bf16) | At(bf16), dZb_t   (128 rows x 64 ch each)
+constexpr int kTileStages = 2;
+constexpr int kTileSmemBytes = kTileStages * kTileStageBytes + 1024 /*align*/ + 1024 /*column vectors*/ + 128;
+
+struct BwdTileParams {
+  const float* lse;      // [2][N][L]
+  const float* delta;    // [2][N][L]
+  unsigned short* ds;    // [N][Lp][Lp] bf16
+  unsigned short* pb;    // [N][Lp][Lp] bf16 (HAS_B)
+  unsigned short* pa;    // [N][Lp][Lp] bf16 or null
   int N, L, Lp;
+  uint32_t idesc_fwd;    // M128 N128, forward operand format
+  uint32_t idesc_bf16;   // M128 N128, bf16 x bf16
 };
 
-__global__ void __launch_bounds__(256) bwd_combine_kernel(BwdCombineParams p) {
+template <bool HAS_B>
+__global__ void __launch_bounds__(kNumThreads, 1)
+bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant__ CUtensorMap tm_bt,
+                const __grid_constant__ CUtensorMap tm_dza, const __grid_constant__ CUtensorMap tm_btg,
+                const __grid_constant__ CUtensorMap tm_atg, const __grid_constant__ CUtensorMap tm_dzb,
+                BwdTileParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  float* colv = reinterpret_cast<float*>(smem + kTileStages * kTileStageBytes);   // [0,128) lse_b, [128,256) delta_b
+  uint64_t* bars = reinterpret_cast<uint64_t*>(colv + 256);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kTileStages;
+  uint64_t* d_full = empty + kTileStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * 128;
+  const int j0 = blockIdx.y * 128;
   const int n = blockIdx.z;
-  const int i = blockIdx.y;
-  const int j = (blockIdx.x * 256 + threadIdx.x) * 4;
-  if (j >= p.Lp) return;
-  const size_t off = ((size_t)n * p.Lp + i) * p.Lp + j;
-  uint2 ods = make_uint2(0u, 0u), opb = make_uint2(0u, 0u), opa = make_uint2(0u, 0u);
-  if (i < p.L && j < p.L) {
-    const float lse_a = __ldg(p.lse + (size_t)n * p.L + i);
-    const float del_a = __ldg(p.delta + (size_t)n * p.L + i);
-    const float4 s4 = __ldcs(reinterpret_cast<const float4*>(p.s + off));
-    const float4 a4 = __ldcs(reinterpret_cast<const float4*>(p.dpa + off));
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.dpb) b4 = __ldcs(reinterpret_cast<const float4*>(p.dpb + off));
-    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
-    float dsv[4], pbv[4], pav[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int jj = j + e;
-      if (jj < p.L) {
-        const float pa = __expf(sv[e] - lse_a);
-        float d = pa * (av[e] - del_a);
-        float pbe = 0.f;
-        if (p.dpb) {
-          pbe = __expf(sv[e] - __ldg(p.lse + (size_t)(p.N + n) * p.L + jj));
-          d = fmaf(pbe, bv[e] - __ldg(p.delta + (size_t)(p.N + n) * p.L + jj), d);
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_bt); tma_prefetch_desc(&tm_dza);
+    tma_prefetch_desc(&tm_btg); tma_prefetch_desc(&tm_atg); tma_prefetch_desc(&tm_dzb);
+    for (int s = 0; s < kTileStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(d_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x < 128) {   // per-column normalisers of this j-tile
+    const int j = j0 + threadIdx.x;
+    const bool ok = HAS_B && j < p.L;
+    colv[threadIdx.x] = ok ? p.lse[(size_t)(p.N + n) * p.L + j] : 0.f;
+    colv[128 + threadIdx.x] = ok ? p.delta[(size_t)(p.N + n) * p.L + j] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr int kNumKb = kC / 64;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      const int irow = n * p.Lp + i0, jrow = n * p.Lp + j0;
+      for (int kb = 0; kb < kNumKb; ++kb) {
+        const int s = kb % kTileStages;
+        const uint32_t ph = (kb / kTileStages) & 1;
+        mbar_wait(empty + s, ph ^ 1, 40);
+        mbar_arrive_expect_tx(full + s, HAS_B ? kTileStageBytes : 4 * 16384);
+        uint8_t* st = smem + s * kTileStageBytes;
+        tma_load_2d(st + 0 * 16384, &tm_qt, full + s, kb * 64, irow);
+        tma_load_2d(st + 1 * 16384, &tm_bt, full + s, kb * 64, jrow);
+        tma_load_2d(st + 2 * 16384, &tm_dza, full + s, kb * 64, irow);
+        tma_load_2d(st + 3 * 16384, &tm_btg, full + s, kb * 64, jrow);
+        if (HAS_B) {
+          tma_load_2d(st + 4 * 16384, &tm_atg, full + s, kb * 64, irow);
+          tma_load_2d(st + 5 * 16384, &tm_dzb, full + s, kb * 64, jrow);
         }
-        dsv[e] = d;
-        pbv[e] = pbe;
-        pav[e] = pa;
-      } else {
-        dsv[e] = 0.f;
-        pbv[e] = 0.f;
-        pav[e] = 0.f;
       }
     }
-    ods = make_uint2(pack_bf16x2(dsv[0], dsv[1]), pack_bf16x2(dsv[2], dsv[3]));
-    opb = make_uint2(pack_bf16x2(pbv[0], pbv[1]), pack_bf16x2(pbv[2], pbv[3]));
-    opa = make_uint2(pack_bf16x2(pav[0], pav[1]), pack_bf16x2(pav[2], pav[3]));
+  } else if (warp == kMmaWarp) {
+    const uint32_t base = smem_u32(smem);
+    for (int kb = 0; kb < kNumKb; ++kb) {
+      const int s = kb % kTileStages;
+      const uint32_t ph = (kb / kTileStages) & 1;
+      warp_mbar_wait(full + s, ph, lane, 41);
+      tc_fence_after();
+      const uint32_t sb = base + s * kTileStageBytes;
+      const uint64_t d0 = make_sdesc_k_sw128(sb), d1 = make_sdesc_k_sw128(sb + 16384), d2 = make_sdesc_k_sw128(sb + 2 * 16384),
+                     d3 = make_sdesc_k_sw128(sb + 3 * 16384), d4 = make_sdesc_k_sw128(sb + 4 * 16384),
+                     d5 = make_sdesc_k_sw128(sb + 5 * 16384);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem, d0 + 2 * k, d1 + 2 * k, p.idesc_fwd, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem + 128, d2 + 2 * k, d3 + 2 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+        if (HAS_B) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem + 256, d4 + 2 * k, d5 + 2 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty + s);
+        if (kb == kNumKb - 1) umma_commit(d_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    warp_mbar_wait(d_full, 0, lane, 42);
+    tc_fence_after();
+    const int i = i0 + warp * 32 + lane;
+    const bool vi = i < p.L;
+    const float lse_a = vi ? __ldg(p.lse + (size_t)n * p.L + i) : 0.f;
+    const float del_a = vi ? __ldg(p.delta + (size_t)n * p.L + i) : 0.f;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const size_t rowoff = ((size_t)n * p.Lp + i) * p.Lp + j0;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t sv[32], av[32], bv[32];
+      tmem_ld32(taddr + ch * 32, sv);
+      tmem_ld32(taddr + 128 + ch * 32, av);
+      if (HAS_B) tmem_ld32(taddr + 256 + ch * 32, bv);
+      tmem_ld_wait();
+      uint32_t ods[16], opb[16], opa[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        float d[2], pbv[2], pav[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = 2 * q + e;
+          const int jl = ch * 32 + k;
+          const bool ok = vi && (j0 + jl) < p.L;
+          const float sx = __uint_as_float(sv[k]);
+          const float pa = ok ? __expf(sx - lse_a) : 0.f;
+          float dd = pa * (__uint_as_float(av[k]) - del_a);
+          float pb = 0.f;
+          if (HAS_B) {
+            pb = ok ? __expf(sx - colv[jl]) : 0.f;
+            dd = fmaf(pb, __uint_as_float(bv[k]) - colv[128 + jl], dd);
+          }
+          d[e] = ok ? dd : 0.f;
+          pbv[e] = pb;
+          pav[e] = pa;
+        }
+        ods[q] = pack_bf16x2(d[0], d[1]);
+        opb[q] = pack_bf16x2(pbv[0], pbv[1]);
+        opa[q] = pack_bf16x2(pav[0], pav[1]);
+      }
+      uint4* o = reinterpret_cast<uint4*>(p.ds + rowoff + ch * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = make_uint4(ods[4 * q], ods[4 * q + 1], ods[4 * q + 2], ods[4 * q + 3]);
+      if (HAS_B) {
+        uint4* ob = reinterpret_cast<uint4*>(p.pb + rowoff + ch * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ob[q] = make_uint4(opb[4 * q], opb[4 * q + 1], opb[4 * q + 2], opb[4 * q + 3]);
+      }
+      if (p.pa != nullptr) {
+        uint4* oa = reinterpret_cast<uint4*>(p.pa + rowoff + ch * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) oa[q] = make_uint4(opa[4 * q], opa[4 * q + 1], opa[4 * q + 2], opa[4 * q + 3]);
+      }
+    }
+    tc_fence_before();
   }
-  *reinterpret_cast<uint2*>(p.ds + off) = ods;
-  if (p.dpb) *reinterpret_cast<uint2*>(p.pb + off) = opb;
-  if (p.pa) *reinterpret_cast<uint2*>(p.pa + off) = opa;
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
 }
 
 // 16-bit [N][Lp][Lp] -> transposed per sample (32x32 tiles through shared memory); counterpart gradients only

@@ -425,8 +425,7 @@ namespace {
 struct BwdLayout {
   Layout fwd;
   int64_t off_g;   // second copy of the forward operand segments, always bf16 (operands of the gradient GEMMs)
-  int64_t off_dza_t, off_dzb_t, off_dzb16, off_delta, off_s, off_dpa, off_dpb, off_ds, off_pb, off_dqt, off_dq16,
-      off_wt, total;
+  int64_t off_dza_t, off_dzb_t, off_dzb16, off_delta, off_ds, off_pb, off_dqt, off_dq16, off_wt, total;
   // counterpart gradients only (d_v_b requested): dZ_a in [C][Lp], P_a, dS^T, P_a^T, Q in [C][Lp]
   int64_t off_dza16, off_pa, off_ds_t, off_pa_t, off_q16, total_counterpart;
 };
@@ -435,13 +434,12 @@ BwdLayout make_bwd_layout(int n, int h, int w) {
   b.fwd = make_layout(n, h, w);
   const int64_t Lp = b.fwd.Lp, L = b.fwd.L;
   const int64_t plane = (int64_t)n * Lp * kC * 2;
-  const int64_t mat32 = (int64_t)n * Lp * Lp * 4, mat16 = (int64_t)n * Lp * Lp * 2;
+  const int64_t mat16 = (int64_t)n * Lp * Lp * 2;
   int64_t off = b.fwd.total;
   auto take = [&](int64_t bytes) { const int64_t o = off; off = round_up(off + bytes, kAlign); return o; };
   b.off_g = take(b.fwd.total);
   b.off_dza_t = take(plane); b.off_dzb_t = take(plane); b.off_dzb16 = take(plane);
   b.off_delta = take((int64_t)2 * n * L * 4);
-  b.off_s = take(mat32); b.off_dpa = take(mat32); b.off_dpb = take(mat32);
   b.off_ds = take(mat16); b.off_pb = take(mat16);
   b.off_dqt = take(plane); b.off_dq16 = take(plane);
   b.off_wt = take((int64_t)kC * kC * 2);
@@ -520,9 +518,6 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   unsigned short* dzb_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb_t));
   unsigned short* dzb16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb16));
   float* delta = reinterpret_cast<float*>(seg(workspace, bl.off_delta));
-  float* smat = reinterpret_cast<float*>(seg(workspace, bl.off_s));
-  float* dpa = reinterpret_cast<float*>(seg(workspace, bl.off_dpa));
-  float* dpb = reinterpret_cast<float*>(seg(workspace, bl.off_dpb));
   unsigned short* ds = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_ds));
   unsigned short* pb = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pb));
   unsigned short* dqt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dqt));
@@ -552,23 +547,28 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   const uint64_t rowsL = (uint64_t)n * Lp, rowsC = (uint64_t)n * kC;
   const int lt = Lp / 128;
   GemmParams gp{};
-  // S = Qt Bt^T, dP_a = dZa_t Bt^T, dP_b = At dZb_t^T      [N][Lp][Lp] fp32
-  gp.out1 = nullptr; gp.ld0 = Lp; gp.rows0 = Lp; gp.ld1 = 0; gp.rows1 = 0;
-  gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = Lp; gp.m_valid = Lp;
-  gp.out0 = smat;
-  if (int e = launch_gemm<kGemmStoreF32>(enc, st, qt, rowsL, fbf16, bt, rowsL, fbf16, kC, lt, lt, n, gp)) return e;
-  gp.out0 = dpa;
-  if (int e = launch_gemm<kGemmStoreF32>(enc, st, dza_t, rowsL, true, bt_g, rowsL, true, kC, lt, lt, n, gp)) return e;
-  if (has_b) {
-    gp.out0 = dpb;
-    if (int e = launch_gemm<kGemmStoreF32>(enc, st, at, rowsL, true, dzb_t, rowsL, true, kC, lt, lt, n, gp)) return e;
+  {
+    // S, dP_a, dP_b and their combination: one kernel, one 128 x 128 tile per CTA, outputs bf16 dS / P_b (/ P_a)
+    CUtensorMap t_qt, t_bt, t_dza, t_btg, t_atg, t_dzb;
+    if (int e = make_tmap(enc, &t_qt, qt, rowsL, kC, 128, fbf16)) return e;
+    if (int e = make_tmap(enc, &t_bt, bt, rowsL, kC, 128, fbf16)) return e;
+    if (int e = make_tmap(enc, &t_dza, dza_t, rowsL, kC, 128, true)) return e;
+    if (int e = make_tmap(enc, &t_btg, bt_g, rowsL, kC, 128, true)) return e;
+    if (int e = make_tmap(enc, &t_atg, at, rowsL, kC, 128, true)) return e;
+    if (int e = make_tmap(enc, &t_dzb, dzb_t, rowsL, kC, 128, true)) return e;
+    BwdTileParams tp;
+    tp.lse = lse; tp.delta = delta; tp.ds = ds; tp.pb = pb;
+    tp.pa = counterpart ? reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa)) : nullptr;
+    tp.N = n; tp.L = L; tp.Lp = Lp;
+    const uint32_t f = fbf16 ? 1u : 0u;
+    tp.idesc_fwd = (1u << 4) | (f << 7) | (f << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    tp.idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    auto kern = has_b ? bwd_tile_kernel<true> : bwd_tile_kernel<false>;
+    if ((ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes)) != cudaSuccess)
+      return (int)ce;
+    kern<<<dim3(lt, lt, n), kNumThreads, kTileSmemBytes, st>>>(t_qt, t_bt, t_dza, t_btg, t_atg, t_dzb, tp);
+    if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
   }
-  BwdCombineParams cp;
-  cp.s = smat; cp.dpa = dpa; cp.dpb = has_b ? dpb : nullptr; cp.lse = lse; cp.delta = delta; cp.ds = ds; cp.pb = pb;
-  cp.pa = counterpart ? pa : nullptr;
-  cp.N = n; cp.L = L; cp.Lp = Lp;
-  bwd_combine_kernel<<<dim3((Lp / 4 + 255) / 256, Lp, n), 256, 0, st>>>(cp);
-  if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
   // dQ[i][c] = sum_j dS[i][j] B16[c][j]   -> dQt [N][Lp][C] and dQ16 [N][C][Lp] (bf16)
   gp.out0 = dqt; gp.ld0 = kC; gp.rows0 = Lp; gp.out1 = dq16; gp.ld1 = Lp; gp.rows1 = kC;
   gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = kC; gp.m_valid = Lp;
