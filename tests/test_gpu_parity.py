@@ -292,6 +292,23 @@ def test_fused_and_unfused_prep_agree(op):
             assert torch.equal(x, y)      # same conversions, same MMAs: bit-identical
 
 
+@pytest.mark.parametrize("n,h,w", [(2, 12, 11), (1, 40, 40)])
+def test_single_cta_cross_check_kernel(op, n, h, w):
+    """COATTN_FLAG_SINGLE_CTA: the earlier single-CTA attend kernel + stand-alone passthrough kernel (different tiling,
+    same math) must agree with the oracle and with the CTA-pair kernel."""
+    v_a, v_b = orc.synthetic_features(87, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(88, bias=True)
+    dev = torch.device("cuda:0")
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    pair = op(t(v_a), t(v_b), t(W), t(g), t(b))
+    single = op(t(v_a), t(v_b), t(W), t(g), t(b), single_cta=True)
+    torch.cuda.synchronize()
+    ref = orc.coattention(v_a, v_b, W, g, b)
+    assert rel_l2(single[0].cpu().numpy(), ref["cat_a"]) < TOL and rel_l2(single[1].cpu().numpy(), ref["cat_b"]) < TOL
+    assert (single[0] - pair[0]).abs().max() < 5e-3 and (single[1] - pair[1]).abs().max() < 5e-3
+    assert torch.equal(single[0][:, C:], t(v_a)) and torch.equal(single[1][:, C:], t(v_b))
+
+
 def test_frame_a_only_matches_full(op):
     n, h, w = 3, 12, 11
     v_a, v_b = orc.synthetic_features(81, n, h, w, 0.66)
