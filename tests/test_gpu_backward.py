@@ -133,3 +133,26 @@ def test_module_backward_runs(coattention):
         grad = dict(model.named_parameters())[name].grad
         assert grad is not None and torch.isfinite(grad).all(), name
     assert model.rgb_similarity_weights.weight.grad.abs().sum() > 0
+
+
+def test_train_step_harness_updates_hot_path_parameters(coattention):
+    """Two optimiser steps of the reference's loop body (train.py:582-602) through the drop-in model."""
+    from cosnet_b200.backbone import Bottleneck
+    from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
+    from cosnet_b200.train_step import TrainStep
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).to(dev).train()
+    step = TrainStep(model, learning_rate=1e-2, max_iter=10)
+    before = {k: v.detach().clone() for k, v in model.named_parameters() if k in
+              ("rgb_similarity_weights.weight", "gate.weight", "depth_similarity_weights.weight", "depth_gate.bias")}
+    g = torch.Generator(device=dev).manual_seed(2)
+    rgb = torch.randn(2, 3, 97, 97, device=dev, generator=g)
+    dep = torch.randn(2, 1, 97, 97, device=dev, generator=g)
+    gt = (torch.rand(2, 1, 97, 97, device=dev, generator=g) > 0.6).float()
+    losses = [float(step(rgb, rgb.flip(0), dep, dep.flip(0), gt, gt.flip(0))) for _ in range(2)]
+    assert all(np.isfinite(l) for l in losses)
+    after = dict(model.named_parameters())
+    for k, v in before.items():
+        assert not torch.equal(v, after[k].detach()), k
+        assert torch.isfinite(after[k]).all()
