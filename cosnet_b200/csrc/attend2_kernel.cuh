@@ -343,10 +343,29 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
       const int n = (p.passes == 2) ? (np >> 1) : np;
       const int row = qp * (2 * k2BM) + (int)rank * k2BM + rloc;
       const uint32_t pv_base = it * (uint32_t)T;
+      // rows of this warp that lie entirely in the padding of the last query tile: no softmax math, P = 0
+      // (zero MMA operands also draw less power, and this kernel runs against the power cap)
+      const bool warp_is_padding = (qp * (2 * k2BM) + (int)rank * k2BM + quad * 32) >= p.L;
       float m = -INFINITY, l = 0.0f;
       for (int j = 0; j < T; ++j) {
         const int b = j & 1;
         const uint32_t tSb = tmem + lane_base + k2TmemS + (uint32_t)b * k2BN;
+        if (warp_is_padding) {
+          if (b == 0) { warp_mbar_wait(s_full + 0, sphase0, lane, 20); sphase0 ^= 1; }
+          else        { warp_mbar_wait(s_full + 1, sphase1, lane, 20); sphase1 ^= 1; }
+          tc_fence_after();
+          // the partner warp (same rows) takes the same branch; the exchange barrier still orders its S reads
+          (void)pair_exchange(0.f, xbuf, seq++, wg, rloc, quad);
+          uint32_t zero[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) zero[k] = 0u;
+          tmem_st32(tSb + wg * 32, zero);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(b == 0 ? p_full_l0 : p_full_l1);
+          continue;
+        }
         TS2(0);
         if (b == 0) { warp_mbar_wait(s_full + 0, sphase0, lane, 20); sphase0 ^= 1; }
         else        { warp_mbar_wait(s_full + 1, sphase1, lane, 20); sphase1 ^= 1; }
@@ -447,6 +466,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
       warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, lane, 22);
       tc_fence_after();
       l += pair_exchange(l, xbuf, seq++, wg, rloc, quad);
+      if (warp_is_padding) {     // nothing to store; keep the exchange sequence of the gate dot in step
+        if (p.cat_a != nullptr) (void)pair_exchange(0.f, xbuf, seq++, wg, rloc, quad);
+        continue;
+      }
       const float inv = 1.0f / l;
       const bool valid = row < p.L;
       const int c0 = wg * 128;
