@@ -221,9 +221,9 @@ static int prep_and_project_fused(const float* v_a, const float* v_b, const floa
   p.L = ly.L;
   p.Lp = ly.Lp;
   auto kern = bf16 ? project_fused_kernel<true> : project_fused_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjFusedSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  kern<<<dim3(ly.Lp / 128, n), kNumThreads, kProjSmemBytes, st>>>(tm_w, p);
+  kern<<<dim3(ly.Lp / 128, n), kNumThreads, kProjFusedSmemBytes, st>>>(tm_w, p);
   return (int)cudaGetLastError();
 }
 

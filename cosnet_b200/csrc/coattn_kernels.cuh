@@ -263,19 +263,24 @@ struct ProjectFusedParams {
   int L, Lp;
 };
 
+constexpr int kPFStages = 2;
+constexpr int kPFStageBytes = 16384 + 32768;   // At k-block [128 pos x 64 ch] + W k-block [256 out x 64 in]
+constexpr int kProjFusedSmemBytes = kPFStages * kPFStageBytes + 1024 + 128;
+
+// K (input channels) is streamed in four 64-channel blocks through a 2-stage ring, so that the conversion of block
+// kb+1 overlaps the MMAs of block kb and two CTAs fit on an SM (96 KB shared memory, 256 TMEM columns each).
 template <bool BF16>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, 2)
 project_fused_kernel(const __grid_constant__ CUtensorMap tmap_w,   // [C][C], box {64, 256}
                      ProjectFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
-  uint8_t* sA = smem;               // 4 k-blocks x [128 rows x 128 B], written by the threads
-  uint8_t* sW = smem + 64 * 1024;   // 4 k-blocks x [256 rows x 128 B], TMA
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 192 * 1024);
-  uint64_t* w_full = bars + 0;
-  uint64_t* a_full = bars + 1;      // 4 arrivals (one per converting warp)
-  uint64_t* d_full = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPFStages * kPFStageBytes);
+  uint64_t* w_full = bars + 0;              // [2] TMA bytes of a W k-block
+  uint64_t* a_full = bars + kPFStages;      // [2] 4 arrivals (one per converting warp)
+  uint64_t* empty = bars + 2 * kPFStages;   // [2] MMAs of the stage completed
+  uint64_t* d_full = bars + 3 * kPFStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -284,8 +289,7 @@ project_fused_kernel(const __grid_constant__ CUtensorMap tmap_w,   // [C][C], bo
 
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_w);
-    mbar_init(w_full, 1);
-    mbar_init(a_full, 4);
+    for (int s = 0; s < kPFStages; ++s) { mbar_init(w_full + s, 1); mbar_init(a_full + s, 4); mbar_init(empty + s, 1); }
     mbar_init(d_full, 1);
     fence_mbar_init();
   }
@@ -300,63 +304,73 @@ project_fused_kernel(const __grid_constant__ CUtensorMap tmap_w,   // [C][C], bo
 
   if (warp == kProducerWarp) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, 128 * 1024);
-#pragma unroll
-      for (int kb = 0; kb < 4; ++kb) tma_load_2d(sW + kb * 32768, &tmap_w, w_full, kb * 64, 0);
+      for (int kb = 0; kb < 4; ++kb) {
+        const int s = kb & 1;
+        mbar_wait(empty + s, ((kb >> 1) & 1) ^ 1, 103);
+        mbar_arrive_expect_tx(w_full + s, 32768);
+        tma_load_2d(smem + s * kPFStageBytes + 16384, &tmap_w, w_full + s, kb * 64, 0);
+      }
     }
   } else if (warp == kMmaWarp) {
-    warp_mbar_wait(w_full, 0, lane, 100);
-    warp_mbar_wait(a_full, 0, lane, 102);
-    tc_fence_after();
-    const uint64_t ad0 = make_sdesc_k_sw128(smem_u32(sA));
-    const uint64_t bd0 = make_sdesc_k_sw128(smem_u32(sW));
     constexpr uint32_t idesc = make_idesc_16(128, 256, BF16);
-    if (elect_one()) {
+    const uint32_t base = smem_u32(smem);
+    for (int kb = 0; kb < 4; ++kb) {
+      const int s = kb & 1;
+      const uint32_t ph = (kb >> 1) & 1;
+      warp_mbar_wait(w_full + s, ph, lane, 100);
+      warp_mbar_wait(a_full + s, ph, lane, 102);
+      tc_fence_after();
+      const uint64_t ad0 = make_sdesc_k_sw128(base + s * kPFStageBytes);
+      const uint64_t bd0 = make_sdesc_k_sw128(base + s * kPFStageBytes + 16384);
+      if (elect_one()) {
 #pragma unroll
-      for (int kk = 0; kk < 16; ++kk)
-        umma_ss(tmem, ad0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
-                bd0 + (uint64_t)(((kk >> 2) * 32768 + (kk & 3) * 32) >> 4), idesc, kk > 0);
-      umma_commit(d_full);
+        for (int k = 0; k < 4; ++k) umma_ss(tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(empty + s);
+        if (kb == 3) umma_commit(d_full);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
-    // ---- convert: thread = two neighbouring positions (rows 2q, 2q+1 of the At tile) x 128 channels.
+    // ---- convert: thread = two neighbouring positions (rows 2q, 2q+1 of the At tile) x 32 channels of the k-block.
     // Requires L even (float2 loads); the launcher falls back to the unfused kernels otherwise.
     const int q2 = (warp & 1) * 32 + lane;      // position pair 0..63
-    const int chalf = warp >> 1;                // channels [128 * chalf, 128 * chalf + 128)
+    const int chalf = warp >> 1;                // channels [32 * chalf, 32 * chalf + 32) of the k-block
     const int r0 = 2 * q2;
     const int lpos = l0 + r0;
     const bool valid2 = lpos < p.L;             // L even: both positions valid or both padding
     const float* src = p.va + (size_t)n * kC * p.L + lpos;
     unsigned short* a16 = p.a16 + (size_t)n * kC * p.Lp + lpos;
 #pragma unroll 1
-    for (int gb = 0; gb < 4; ++gb) {            // 4 batches of 32 channels
+    for (int kb = 0; kb < 4; ++kb) {
+      const int s = kb & 1;
+      uint8_t* sA = smem + s * kPFStageBytes;
       float2 v[32];
 #pragma unroll
       for (int u = 0; u < 32; ++u) {
-        const int c = chalf * 128 + gb * 32 + u;
+        const int c = kb * 64 + chalf * 32 + u;
         v[u] = valid2 ? __ldcs(reinterpret_cast<const float2*>(src + (size_t)c * p.L)) : make_float2(0.f, 0.f);
       }
+      warp_mbar_wait(empty + s, ((kb >> 1) & 1) ^ 1, lane, 104);   // the MMAs that read this stage two blocks ago are done
 #pragma unroll
       for (int g = 0; g < 4; ++g) {             // 8 channels = one 16-byte chunk of a row
-        const int c0 = chalf * 128 + gb * 32 + g * 8;
-        const int kb = c0 >> 6, chunk = (c0 & 63) >> 3;
+        const int cl = chalf * 32 + g * 8;      // channel inside the k-block
+        const int chunk = cl >> 3;
         uint32_t lo[4], hi[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          lo[t] = pack16x2<BF16>(v[g * 8 + 2 * t].x, v[g * 8 + 2 * t + 1].x);   // position r0,   channels c0+2t, c0+2t+1
-          hi[t] = pack16x2<BF16>(v[g * 8 + 2 * t].y, v[g * 8 + 2 * t + 1].y);   // position r0+1
+          lo[t] = pack16x2<BF16>(v[g * 8 + 2 * t].x, v[g * 8 + 2 * t + 1].x);   // position r0
+          hi[t] = pack16x2<BF16>(v[g * 8 + 2 * t].y, v[g * 8 + 2 * t + 1].y);   // position r0 + 1
         }
-        *reinterpret_cast<uint4*>(sA + kb * 16384 + r0 * 128 + ((chunk ^ (r0 & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(sA + kb * 16384 + (r0 + 1) * 128 + ((chunk ^ ((r0 + 1) & 7)) << 4)) =
+        *reinterpret_cast<uint4*>(sA + r0 * 128 + ((chunk ^ (r0 & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(sA + (r0 + 1) * 128 + ((chunk ^ ((r0 + 1) & 7)) << 4)) =
             make_uint4(hi[0], hi[1], hi[2], hi[3]);
 #pragma unroll
         for (int u = 0; u < 8; ++u)     // A16[c][lpos .. lpos+1]: 4-byte stores, 128 contiguous bytes per warp
-          *reinterpret_cast<uint32_t*>(a16 + (size_t)(c0 + u) * p.Lp) = pack16x2<BF16>(v[g * 8 + u].x, v[g * 8 + u].y);
+          *reinterpret_cast<uint32_t*>(a16 + (size_t)(kb * 64 + cl + u) * p.Lp) = pack16x2<BF16>(v[g * 8 + u].x, v[g * 8 + u].y);
       }
+      fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core (async proxy)
+      warp_mbar_arrive(a_full + s, lane);
     }
-    fence_proxy_async_smem();     // generic-proxy stores to sA -> visible to the tensor core (async proxy)
-    warp_mbar_arrive(a_full, lane);
     // ---- epilogue: thread = one output row of Qt
     warp_mbar_wait(d_full, 0, lane, 101);
     tc_fence_after();
