@@ -260,8 +260,14 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
           __syncwarp();
           ++kcnt;
         };
+#ifdef COATTN_TRACE
+        long long ti0 = clock64();
+#endif
         warp_mbar_wait(q_full, it & 1, lane, 11);
         tc_fence_after();
+#ifdef COATTN_TRACE
+        long long ti1 = clock64(), ti2 = 0;
+#endif
         // Tensor-pipe order per item: S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ... | PV(T-1).  S(j+2) reuses the buffer
         // of P(j) and is issued right behind PV(j) (in-order execution).  The waits for TMA tiles are hoisted to
         // just after the long PV MMAs were queued, so only the wait for P(j) sits between two issue bursts.
@@ -280,6 +286,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
           else        { warp_mbar_wait(p_full + 1, pphase1, lane, 13); pphase1 ^= 1; }
           tc_fence_after();
           TR2(3);
+#ifdef COATTN_TRACE
+          if (j == 0) ti2 = clock64();
+#endif
           const uint32_t s = vcnt % k2VStages;
           const uint32_t tP = tmem + k2TmemS + (uint32_t)b * k2BN;
           const uint64_t vd0 = make_sdesc_k_sw128(sV_addr + s * k2VBytes);
@@ -311,6 +320,11 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
           ++tc;
 #endif
         }
+#ifdef COATTN_TRACE
+        if (blockIdx.x == 0 && lane == 0 && it < 6)
+          printf("MMA item %u: q_full wait %lld | first P wait (incl. S0,S1 issue) %lld | rest of item %lld | total %lld\n", it,
+                 ti1 - ti0, ti2 - ti1, clock64() - ti2, clock64() - ti0);
+#endif
       }
 #ifdef COATTN_TRACE
       if (blockIdx.x == 0 && lane == 0)
@@ -461,6 +475,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
                  ts[i][0] - ts[2][0], ts[i][1] - ts[i][0], ts[i][2] - ts[i][1], ts[i][3] - ts[i][2], ts[i][4] - ts[i][3],
                  ts[i][5] - ts[i][4]);
 #endif
+#ifdef COATTN_TRACE
+      long long td0 = clock64();
+#endif
       // ---- drain.  Wait the last two PV phases one by one (see attend_kernel for the aliasing argument).
       if (T >= 2) warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 2u) & 1u, lane, 23);
       warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, lane, 22);
@@ -521,6 +538,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
         if (valid && wg == 0 && p.mask != nullptr) p.mask[(size_t)(pass * p.N + n) * p.L + row] = gate;
       }
       if (valid && wg == 0) p.lse[(size_t)(pass * p.N + n) * p.L + row] = m + __logf(l);
+#ifdef COATTN_TRACE
+      if (blockIdx.x == 0 && threadIdx.x == 0 && it < 6) printf("softmax item %u: drain (from last P arrive to end) %lld cycles\n", it, clock64() - td0);
+#endif
     }
   }
   tc_fence_before();

@@ -299,9 +299,6 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttendSmemBytes);
   if (e != cudaSuccess) return (int)e;
   int grid = p.num_items < sms ? p.num_items : sms;
-#ifdef COATTN_EXPERIMENT
-  if (const char* g = getenv("COATTN_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }
-#endif
   p.trace = nullptr;
 #ifdef COATTN_TRACE
   static long long* dtrace = nullptr;

@@ -509,14 +509,10 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
         for (int j = 0; j < T; ++j, ++cnt) {
           const uint32_t s = cnt % kKStages, ph = (cnt / kKStages) & 1;
           mbar_wait(k_empty + s, ph ^ 1, 2);
-#if defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 3
-          mbar_arrive(k_full + s);
-#else
           mbar_arrive_expect_tx(k_full + s, kKBytes);
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb)
             tma_load_2d(sK + s * kKBytes + kb * (kBN * 128), &tmap_k, k_full + s, kb * 64, krow0 + j * kBN);
-#endif
         }
       }
     }
@@ -530,12 +526,8 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
         for (int j = 0; j < T; ++j, ++cnt) {
           const uint32_t s = cnt % kVStages, ph = (cnt / kVStages) & 1;
           mbar_wait(v_empty + s, ph ^ 1, 3);
-#if defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 3
-          mbar_arrive(v_full + s);
-#else
           mbar_arrive_expect_tx(v_full + s, kVBytes);
           tma_load_2d(sV + s * kVBytes, &tmap_v, v_full + s, j * kBN, vrow0);
-#endif
         }
       }
     }
@@ -564,9 +556,7 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
           for (int kk = 0; kk < kC / 16; ++kk) {
             // k-block kk/4 is 8 KB further, the 16-element step inside a 128-byte row is 32 B (>>4 in the descriptor)
             const uint64_t bd = bd0 + (uint64_t)(((kk >> 2) * (kBN * 128) + (kk & 3) * 32) >> 4);
-#if !(defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 4)
             umma_ts(tS, tQ + kk * 8, bd, idesc_s, kk > 0);
-#endif
           }
           umma_commit(k_empty + s);
           umma_commit(s_full + (j & 1));
@@ -595,9 +585,7 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < kBN / 16; ++kk) {
-#if !(defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 4)
             umma_ts(tO, tP + kk * 8, vd0 + (uint64_t)((kk * 32) >> 4), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-#endif
           }
           umma_commit(v_empty + s);
           umma_commit(o_full);
@@ -651,30 +639,10 @@ attend_kernel(const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  b
         tc_fence_after();
         TRACE_SM(5);
         ++scount;
-#if defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT >= 2
-        // experiment: no softmax work at all (measures the bare TMA + MMA pipeline)
-        tc_fence_before();
-        warp_mbar_arrive(p_full + b, lane);
-        continue;
-#endif
         uint32_t s0[32], s1[32];
         tmem_ld32(tS, s0);
         tmem_ld32(tS + 32, s1);
         tmem_ld_wait();
-#if defined(COATTN_EXPERIMENT) && COATTN_EXPERIMENT == 1
-        // experiment: TMEM traffic only, no exp/max math
-        {
-          uint32_t pk[32];
-#pragma unroll
-          for (int k = 0; k < 32; ++k) pk[k] = s0[k] ^ s1[k];
-          tmem_st32(tS, pk);
-          tmem_st_wait();
-          tc_fence_before();
-          warp_mbar_arrive(p_full + b, lane);
-          l = 1.0f;
-          continue;
-        }
-#endif
         if (j == T - 1) {
           const int nvalid = p.L - j * kBN;  // >= 1
           if (nvalid < kBN) {
