@@ -22,6 +22,7 @@ FLAG_UNFUSED_GATE = 2  # COATTN_FLAG_UNFUSED_GATE
 FLAG_SINGLE_CTA = 4  # COATTN_FLAG_SINGLE_CTA
 FLAG_A_ONLY = 8  # COATTN_FLAG_A_ONLY
 FLAG_UNFUSED_PREP = 16  # COATTN_FLAG_UNFUSED_PREP
+FLAG_GATED_ONLY = 32  # COATTN_FLAG_GATED_ONLY
 
 # name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
 SIGNATURES = {

@@ -57,7 +57,7 @@ def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
 
 
 def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False,
-                            unfused_gate=False, want_mask=False, want_z=True, single_cta=False, a_only=False, unfused_prep=False):
+                            unfused_gate=False, want_mask=False, want_z=True, single_cta=False, a_only=False, unfused_prep=False, gated_only=False):
     """Runs the CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L]
     (plus mask [2,N,L] when want_mask=True; fused path only).
 
@@ -73,8 +73,9 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         wt = weight.detach().to(device=dev, dtype=torch.float32).contiguous()
         gw = gate_weight.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
         gb = None if gate_bias is None else gate_bias.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
-        cat_a = torch.empty((n, 2 * c, h, w), dtype=torch.float32, device=dev)
-        cat_b = None if a_only else torch.empty((n, 2 * c, h, w), dtype=torch.float32, device=dev)
+        oc = c if gated_only else 2 * c
+        cat_a = torch.empty((n, oc, h, w), dtype=torch.float32, device=dev)
+        cat_b = None if a_only else torch.empty((n, oc, h, w), dtype=torch.float32, device=dev)
         z = torch.empty((2, n, c, h * w), dtype=torch.float32, device=dev) if (want_z or unfused_gate) else None
         lse = torch.empty((2, n, h * w), dtype=torch.float32, device=dev)
         nbytes = workspace_bytes(n, c, h, w)
@@ -83,7 +84,7 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         mask = torch.empty((2, n, h * w), dtype=torch.float32, device=dev) if want_mask else None
         flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)
                  | (_lib.FLAG_SINGLE_CTA if single_cta else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
-                 | (_lib.FLAG_UNFUSED_PREP if unfused_prep else 0))
+                 | (_lib.FLAG_UNFUSED_PREP if unfused_prep else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0))
         code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
                                   None if gb is None else gb.data_ptr(), cat_a.data_ptr(),
                                   None if cat_b is None else cat_b.data_ptr(),
@@ -112,9 +113,10 @@ class _CoAttentionFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, v_a, v_b, weight, gate_weight, gate_bias, bf16_operands):
+    def forward(ctx, v_a, v_b, weight, gate_weight, gate_bias, bf16_operands, gated_only=False):
         cat_a, cat_b, z, lse, mask = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands,
-                                                             want_mask=True, want_z=True)
+                                                             want_mask=True, want_z=True, gated_only=gated_only)
+        ctx.gated_only = gated_only
         ctx.save_for_backward(v_a, v_b, weight, gate_weight, z, lse, mask)
         ctx.has_bias = gate_bias is not None
         ctx.bf16 = bool(bf16_operands)
@@ -131,6 +133,10 @@ class _CoAttentionFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             if d_cat_a is None:
                 d_cat_a = torch.zeros((n, 2 * c, h, w), dtype=torch.float32, device=dev)
+            elif ctx.gated_only:      # the C ABI takes concat-shaped cotangents; the passthrough half has no gradient here
+                d_cat_a = torch.cat([d_cat_a.float(), torch.zeros_like(d_cat_a, dtype=torch.float32)], 1)
+            if d_cat_b is not None and ctx.gated_only:
+                d_cat_b = torch.cat([d_cat_b.float(), torch.zeros_like(d_cat_b, dtype=torch.float32)], 1)
             d_cat_a = d_cat_a.contiguous().float()
             d_cat_b = None if d_cat_b is None else d_cat_b.contiguous().float()
             wt = weight.detach().float().contiguous()
@@ -149,17 +155,21 @@ class _CoAttentionFn(torch.autograd.Function):
                                        None if d_v_b is None else d_v_b.data_ptr(), d_w.data_ptr(), d_gw.data_ptr(), None if d_gb is None else d_gb.data_ptr(),
                                        _aligned_ptr(ws), nbytes, n, c, h, w, _lib.FLAG_BF16 if ctx.bf16 else 0, stream)
             _lib.check(code, "coattn_backward")
-        return d_v_a, d_v_b, d_w.to(weight.dtype), d_gw.view_as(gate_weight).to(gate_weight.dtype), d_gb, None
+        return d_v_a, d_v_b, d_w.to(weight.dtype), d_gw.view_as(gate_weight).to(gate_weight.dtype), d_gb, None, None
 
 
-def coattention(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False):
+def coattention(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False, gated_only=False):
     """Drop-in for rgbd_segmentation_RAA.py:150-187: returns (cat_a, cat_b), each [N, 2C, H, W].  Differentiable
-    w.r.t. v_a, weight, gate_weight and gate_bias (hand-written CUDA backward)."""
+    w.r.t. v_a, v_b, weight, gate_weight and gate_bias (hand-written CUDA backward).
+
+    gated_only=True returns only the gated attended features Z * sigmoid(gate(Z)), [N, C, H, W] each (the first half of
+    the concat), for consumers that apply the reduce conv in two halves and never need the concat itself."""
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (v_a, v_b, weight, gate_weight, gate_bias))
     if needs_grad:
-        return _CoAttentionFn.apply(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands)
-    cat_a, cat_b, _, _ = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands, want_z=False)
+        return _CoAttentionFn.apply(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands, gated_only)
+    cat_a, cat_b, _, _ = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands, want_z=False,
+                                                 gated_only=gated_only)
     return cat_a, cat_b
 
 

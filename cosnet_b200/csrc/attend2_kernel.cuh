@@ -53,6 +53,7 @@ struct Attend2Params {
   const float* gate_b;
   const float* v_a;   // [N][C][L] original fp32 features, or null: when set (together with cat_*), the copy warp also
   const float* v_b;   //           writes the passthrough half of the concat (:186-187)
+  int out_channels;   // channels per sample of cat_*: 2C (concat layout) or C (gated half only, no passthrough)
   int N, L, Lp;
   int q_pairs;   // ceil(L / 256)
   int kv_tiles;  // ceil(L / 128)
@@ -524,7 +525,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
         const float logit = dot * inv + (p.gate_b ? __ldg(p.gate_b) : 0.f);
         const float gate = 1.0f / (1.0f + __expf(-logit));
         const float sc = inv * gate;
-        float* ccol = (pass ? p.cat_b : p.cat_a) + ((size_t)n * 2 * kC + c0) * p.L + row;
+        float* ccol = (pass ? p.cat_b : p.cat_a) + ((size_t)n * p.out_channels + c0) * p.L + row;
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           uint32_t o[32];

@@ -265,7 +265,9 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     q.z = z;
     q.lse = lse ? lse : reinterpret_cast<float*>(seg(workspace, ly.off_lse));
     q.cat_a = cat_a; q.cat_b = cat_b; q.mask = mask; q.gate_w = gate_w; q.gate_b = gate_b;
-    q.v_a = v_a; q.v_b = v_b;
+    q.v_a = (flags & COATTN_FLAG_GATED_ONLY) ? nullptr : v_a;
+    q.v_b = (flags & COATTN_FLAG_GATED_ONLY) ? nullptr : v_b;
+    q.out_channels = (flags & COATTN_FLAG_GATED_ONLY) ? kC : 2 * kC;
     q.N = n; q.L = ly.L; q.Lp = ly.Lp;
     q.q_pairs = (ly.L + 2 * k2BM - 1) / (2 * k2BM);
     q.kv_tiles = (ly.L + k2BN - 1) / k2BN;
@@ -279,7 +281,7 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     kern2<<<2 * clusters, k2Threads, k2SmemBytes, st>>>(tm_q, tm_k2, tm_v2, q);
     return (int)cudaGetLastError();
   }
-  if (flags & COATTN_FLAG_A_ONLY) return COATTN_E_UNSUPPORTED;   // single-CTA cross-check kernel: both passes only
+  if (flags & (COATTN_FLAG_A_ONLY | COATTN_FLAG_GATED_ONLY)) return COATTN_E_UNSUPPORTED;   // cross-check kernel: full concat only
   AttendParams p;
   p.t = reinterpret_cast<const unsigned short*>(seg(workspace, ly.off_t));
   p.z = z;
@@ -393,7 +395,8 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
                    int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags, void* stream) {
   if (!v_a || !v_b || !w || !gate_w || !cat_a) return COATTN_E_NULL;
   if (!cat_b && !(flags & COATTN_FLAG_A_ONLY)) return COATTN_E_NULL;
-  if ((flags & COATTN_FLAG_A_ONLY) && (flags & (COATTN_FLAG_UNFUSED_GATE | COATTN_FLAG_SINGLE_CTA))) return COATTN_E_UNSUPPORTED;
+  if ((flags & (COATTN_FLAG_A_ONLY | COATTN_FLAG_GATED_ONLY)) && (flags & (COATTN_FLAG_UNFUSED_GATE | COATTN_FLAG_SINGLE_CTA)))
+    return COATTN_E_UNSUPPORTED;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
   if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;

@@ -75,6 +75,9 @@ class RGBDSegmentation_RAA(nn.Module):
         init_reference_style(self)   # :53-62 (nn.Linear keeps its default init)
         # the operator that replaces :150-187 / :204-238; tests may swap it for the CPU oracle
         self.coattention_impl = coattention
+        # True: never materialise the concat -- conv(cat([Zg, V]), W) is evaluated as conv(Zg, W[:, :C]) + conv(V, W[:, C:])
+        # (same parameters and state_dict; fp32 summation order differs by ~1e-6).  SURVEY.md 8f, row N3.
+        self.split_reduce_conv = False
 
     # ------------------------------------------------------------------ optimiser groups (:65-100)
     def get_params(self, subset="none"):
@@ -120,22 +123,47 @@ class RGBDSegmentation_RAA(nn.Module):
             return out_a[0], out_b[0], out_b[1]    # the auxiliary map that survives is frame B's (:143, :146/148)
         return out_a, out_b, None
 
+    @staticmethod
+    def _split_conv(conv, gated, passthrough):
+        """conv(cat([gated, passthrough], 1)) without the concat: the 3x3 weight [C, 2C, 3, 3] is applied in two halves."""
+        c = gated.shape[1]
+        w = conv.weight
+        return (F.conv2d(gated, w[:, :c], None, conv.stride, conv.padding, conv.dilation) +
+                F.conv2d(passthrough, w[:, c:], conv.bias, conv.stride, conv.padding, conv.dilation))
+
     def forward(self, rgbs_a, rgbs_b, depths_a, depths_b):
         input_size = rgbs_a.shape[2:]
 
         v_a, v_b, labels = self._encode_pair(self.encoder, rgbs_a, rgbs_b, True)
-        cat_a, cat_b = self.coattention_impl(v_a, v_b, self.rgb_similarity_weights.weight, self.gate.weight, None)
-        z_a = self.bn_A(self.reduce_channels_A(cat_a))          # :188, :190
-        z_b = self.bn_B(self.reduce_channels_B(cat_b))          # :189, :191
-        del v_a, v_b, cat_a, cat_b
+        if self.split_reduce_conv:
+            g_a, g_b = self.coattention_impl(v_a, v_b, self.rgb_similarity_weights.weight, self.gate.weight, None,
+                                             gated_only=True)
+            z_a = self.bn_A(self._split_conv(self.reduce_channels_A, g_a, v_a))
+            z_b = self.bn_B(self._split_conv(self.reduce_channels_B, g_b, v_b))
+            del g_a, g_b
+        else:
+            cat_a, cat_b = self.coattention_impl(v_a, v_b, self.rgb_similarity_weights.weight, self.gate.weight, None)
+            z_a = self.bn_A(self.reduce_channels_A(cat_a))          # :188, :190
+            z_b = self.bn_B(self.reduce_channels_B(cat_b))          # :189, :191
+            del cat_a, cat_b
+        del v_a, v_b
 
         d_a, d_b, _ = self._encode_pair(self.depth_encoder, depths_a, depths_b, False)
-        dcat_a, dcat_b = self.coattention_impl(d_a, d_b, self.depth_similarity_weights.weight, self.depth_gate.weight,
-                                               self.depth_gate.bias)
-        dz_a = self.depth_weights(self.depth_bn(self.depth_reduce_channels(dcat_a)))       # :239, :242, :245
-        with torch.no_grad():                                                               # :240-247
-            dz_b = self.depth_weights(self.depth_bn(self.depth_reduce_channels(dcat_b)))
-        del d_a, d_b, dcat_a, dcat_b
+        if self.split_reduce_conv:
+            g_a, g_b = self.coattention_impl(d_a, d_b, self.depth_similarity_weights.weight, self.depth_gate.weight,
+                                             self.depth_gate.bias, gated_only=True)
+            dz_a = self.depth_weights(self.depth_bn(self._split_conv(self.depth_reduce_channels, g_a, d_a)))
+            with torch.no_grad():
+                dz_b = self.depth_weights(self.depth_bn(self._split_conv(self.depth_reduce_channels, g_b, d_b)))
+            del g_a, g_b
+        else:
+            dcat_a, dcat_b = self.coattention_impl(d_a, d_b, self.depth_similarity_weights.weight, self.depth_gate.weight,
+                                                   self.depth_gate.bias)
+            dz_a = self.depth_weights(self.depth_bn(self.depth_reduce_channels(dcat_a)))       # :239, :242, :245
+            with torch.no_grad():                                                               # :240-247
+                dz_b = self.depth_weights(self.depth_bn(self.depth_reduce_channels(dcat_b)))
+            del dcat_a, dcat_b
+        del d_a, d_b
 
         z_a = self.prelu(z_a + dz_a)                            # :251, :256
         z_b = self.prelu(z_b + dz_b)                            # :252, :257

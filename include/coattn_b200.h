@@ -80,6 +80,13 @@ enum {
  *                          round-tripping through HBM, instead of the fused A-side prep + projection kernel.
  */
 #define COATTN_FLAG_UNFUSED_PREP 16u
+/*
+ *   COATTN_FLAG_GATED_ONLY  cat_a / cat_b are [N, 256, H, W]: only Z * sigmoid(gate(Z)) is produced, the passthrough
+ *                          half of the concat is not materialised.  For consumers that split the 3x3 reduce conv
+ *                          (:188-189) into its two 256-channel halves, conv(cat, W) = conv(Zg, W[:, :256]) +
+ *                          conv(V, W[:, 256:]), so the concat never exists.  CTA-pair kernel, fused gate only.
+ */
+#define COATTN_FLAG_GATED_ONLY 32u
 
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);

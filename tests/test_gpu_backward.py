@@ -156,3 +156,32 @@ def test_train_step_harness_updates_hot_path_parameters(coattention):
     for k, v in before.items():
         assert not torch.equal(v, after[k].detach()), k
         assert torch.isfinite(after[k]).all()
+
+
+def test_split_reduce_conv_module_forward_and_backward(coattention):
+    """The drop-in module with split_reduce_conv=True (gated-only operator output, no concat) matches the concat path in
+    the forward and in the gradients of the hot-path parameters."""
+    from cosnet_b200.backbone import Bottleneck
+    from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).to(dev).train()
+    x = torch.randn(2, 3, 97, 97, device=dev); d = torch.randn(2, 1, 97, 97, device=dev)
+    grads = {}
+    outs = {}
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    for split in (False, True):
+        model.load_state_dict(state)          # identical BN running stats for both runs
+        model.split_reduce_conv = split
+        model.zero_grad(set_to_none=True)
+        x1, x2, _ = model(x, x.flip(0), d, d.flip(0))
+        (x1.square().mean() + x2.mean()).backward()
+        outs[split] = (x1.detach().clone(), x2.detach().clone())
+        grads[split] = {k: p.grad.detach().clone() for k, p in model.named_parameters()
+                        if k in ("rgb_similarity_weights.weight", "gate.weight", "depth_similarity_weights.weight",
+                                 "depth_gate.weight", "reduce_channels_A.weight")}
+    for a, b in zip(outs[False], outs[True]):
+        assert (a - b).abs().max() < 1e-5
+    for k in grads[False]:
+        ref = grads[False][k]
+        assert (grads[True][k] - ref).norm() <= 5e-3 * ref.norm() + 1e-12, k   # bf16 rounding flips on ~1e-6 input differences

@@ -309,6 +309,19 @@ def test_single_cta_cross_check_kernel(op, n, h, w):
     assert torch.equal(single[0][:, C:], t(v_a)) and torch.equal(single[1][:, C:], t(v_b))
 
 
+def test_gated_only_output(op):
+    n, h, w = 2, 12, 11
+    v_a, v_b = orc.synthetic_features(91, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(92, bias=True)
+    dev = torch.device("cuda:0")
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    full = op(t(v_a), t(v_b), t(W), t(g), t(b))
+    gated = op(t(v_a), t(v_b), t(W), t(g), t(b), gated_only=True)
+    torch.cuda.synchronize()
+    assert gated[0].shape == (n, C, h, w) and gated[1].shape == (n, C, h, w)
+    assert torch.equal(gated[0], full[0][:, :C]) and torch.equal(gated[1], full[1][:, :C])
+
+
 def test_frame_a_only_matches_full(op):
     n, h, w = 3, 12, 11
     v_a, v_b = orc.synthetic_features(81, n, h, w, 0.66)

@@ -19,11 +19,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 needs_ref = pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree not present")
 
 
-def oracle_impl(v_a, v_b, weight, gate_weight, gate_bias):
+def oracle_impl(v_a, v_b, weight, gate_weight, gate_bias, gated_only=False):
     out = orc.coattention(v_a.detach().numpy(), v_b.detach().numpy(), weight.detach().numpy(),
                           gate_weight.detach().numpy(), None if gate_bias is None else gate_bias.detach().numpy(),
                           dtype=np.float32)
-    return torch.from_numpy(out["cat_a"]), torch.from_numpy(out["cat_b"])
+    cat_a, cat_b = torch.from_numpy(out["cat_a"]), torch.from_numpy(out["cat_b"])
+    if gated_only:
+        c = v_a.shape[1]
+        return cat_a[:, :c].contiguous(), cat_b[:, :c].contiguous()
+    return cat_a, cat_b
 
 
 def small_model(**kw):
@@ -81,6 +85,23 @@ def test_forward_matches_reference_with_oracle_operator(frozen):
         assert (w - g_).abs().max() < 1e-5
     # the third output is frame B's auxiliary map (rgbd_segmentation_RAA.py:143-148, :268)
     assert torch.allclose(got[2], mine.encoder(rb)[1])
+
+
+def test_split_reduce_conv_equals_concat_path():
+    """conv(cat([Zg, V]), W) == conv(Zg, W[:, :C]) + conv(V, W[:, C:]) -- the concat is never built."""
+    torch.manual_seed(5)
+    m = small_model().eval()
+    m.coattention_impl = oracle_impl
+    g = torch.Generator().manual_seed(6)
+    ra, rb = torch.randn(1, 3, 49, 57, generator=g), torch.randn(1, 3, 49, 57, generator=g)
+    da, db = torch.randn(1, 1, 49, 57, generator=g), torch.randn(1, 1, 49, 57, generator=g)
+    with torch.no_grad():
+        want = m(ra, rb, da, db)
+        m.split_reduce_conv = True
+        got = m(ra, rb, da, db)
+    for w_, g_ in zip(want, got):
+        assert (w_ - g_).abs().max() < 1e-5
+    assert list(m.state_dict().keys()) == list(small_model().state_dict().keys())
 
 
 def test_load_state_renames_legacy_keys():
