@@ -23,6 +23,7 @@ FLAG_SINGLE_CTA = 4  # COATTN_FLAG_SINGLE_CTA
 FLAG_A_ONLY = 8  # COATTN_FLAG_A_ONLY
 FLAG_UNFUSED_PREP = 16  # COATTN_FLAG_UNFUSED_PREP
 FLAG_GATED_ONLY = 32  # COATTN_FLAG_GATED_ONLY
+FLAG_KMAJOR = 64  # COATTN_FLAG_KMAJOR
 
 # name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
 SIGNATURES = {

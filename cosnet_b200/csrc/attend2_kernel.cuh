@@ -68,10 +68,13 @@ __device__ __forceinline__ float pair_exchange(float v, float* xbuf, uint32_t se
   return xbuf[((seq & 1u) * 2 + (wg ^ 1)) * 128 + row];
 }
 
-template <bool BF16>
+// MN = false: queries / keys come from the position-major arrays T = [Bt, Qt] ([Lp][C], K-major operands).
+// MN = true : queries / keys come from the channel-major arrays X = [B16, A16, Q16] ([C][Lp], the NCHW orientation)
+//             as MN-major UMMA operands -- no transposed copies of the features exist at all.
+template <bool BF16, bool MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
-attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  box {64, 128}
-               const __grid_constant__ CUtensorMap tmap_k,  // T  [2*N*Lp][C],  box {64, 64}
+attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C], box {64, 128};  MN: X [3*N*C][Lp], box {64, 256}
+               const __grid_constant__ CUtensorMap tmap_k,  // !MN: T [2*N*Lp][C], box {64, 64};   MN: same map as tmap_q
                const __grid_constant__ CUtensorMap tmap_v,  // VV [2*N*C][Lp],  box {64, 128}
                Attend2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -136,23 +139,42 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
         const int np = item / p.q_pairs;
         const int pass = (p.passes == 2) ? (np & 1) : 0;
         const int n = (p.passes == 2) ? (np >> 1) : np;
-        const int qrow0 = ((1 - pass) * p.N + n) * p.Lp + qp * (2 * k2BM) + (int)rank * k2BM;
-        const int krow_base = (pass * p.N + n) * p.Lp;
-        const int krow0 = krow_base + (int)rank * (k2BN / 2);
         mbar_wait(q_empty, (it & 1) ^ 1, 1);
         if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * k2QBytes);
+        if constexpr (MN) {
+          // X planes: 0 = B16, 1 = A16, 2 = Q16.  pass 0: queries Q16, keys B16;  pass 1: queries B16, keys Q16
+          const int qplane = pass ? 0 : 2, kplane = pass ? 2 : 0;
+          const int qch0 = (qplane * p.N + n) * kC, kch0 = (kplane * p.N + n) * kC;
+          const int qpos0 = qp * (2 * k2BM) + (int)rank * k2BM;
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(sQ + kb * (k2BM * 128), &tmap_q, q_full_l, kb * 64, qrow0);
-        for (int j = 0; j < T; ++j, ++cnt) {
-          const uint32_t s = cnt % k2KStages, ph = (cnt / k2KStages) & 1;
-          mbar_wait(k_empty + s, ph ^ 1, 2);
-          if (rank == 0) mbar_arrive_expect_tx(k_full + s, 2 * k2KBytes);
-          const uint32_t full_l = mapa_u32(smem_u32(k_full + s), 0);
-          // ragged last tile: the MMA only uses n_last (multiple of 16) keys, CTA r supplies keys [r, r+1) * n_last/2
-          const int krow = (j == T - 1) ? krow_base + j * k2BN + (int)rank * (n_last / 2) : krow0 + j * k2BN;
+          for (int mc = 0; mc < 2; ++mc)     // two 64-position chunks x 256 channel rows
+            tma_load_2d_pair(sQ + mc * 32768, &tmap_q, q_full_l, qpos0 + mc * 64, qch0);
+          for (int j = 0; j < T; ++j, ++cnt) {
+            const uint32_t s = cnt % k2KStages, ph = (cnt / k2KStages) & 1;
+            mbar_wait(k_empty + s, ph ^ 1, 2);
+            if (rank == 0) mbar_arrive_expect_tx(k_full + s, 2 * k2KBytes);
+            const uint32_t full_l = mapa_u32(smem_u32(k_full + s), 0);
+            // this CTA's half of the keys: 64 positions (n_last / 2 in the ragged last tile) x 256 channel rows
+            const int kpos = j * k2BN + (int)rank * ((j == T - 1) ? (n_last / 2) : (k2BN / 2));
+            tma_load_2d_pair(sK + s * k2KBytes, &tmap_k, full_l, kpos, kch0);
+          }
+        } else {
+          const int qrow0 = ((1 - pass) * p.N + n) * p.Lp + qp * (2 * k2BM) + (int)rank * k2BM;
+          const int krow_base = (pass * p.N + n) * p.Lp;
+          const int krow0 = krow_base + (int)rank * (k2BN / 2);
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb)
-            tma_load_2d_pair(sK + s * k2KBytes + kb * ((k2BN / 2) * 128), &tmap_k, full_l, kb * 64, krow);
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(sQ + kb * (k2BM * 128), &tmap_q, q_full_l, kb * 64, qrow0);
+          for (int j = 0; j < T; ++j, ++cnt) {
+            const uint32_t s = cnt % k2KStages, ph = (cnt / k2KStages) & 1;
+            mbar_wait(k_empty + s, ph ^ 1, 2);
+            if (rank == 0) mbar_arrive_expect_tx(k_full + s, 2 * k2KBytes);
+            const uint32_t full_l = mapa_u32(smem_u32(k_full + s), 0);
+            // ragged last tile: the MMA only uses n_last (multiple of 16) keys, CTA r supplies keys [r, r+1) * n_last/2
+            const int krow = (j == T - 1) ? krow_base + j * k2BN + (int)rank * (n_last / 2) : krow0 + j * k2BN;
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb)
+              tma_load_2d_pair(sK + s * k2KBytes + kb * ((k2BN / 2) * 128), &tmap_k, full_l, kb * 64, krow);
+          }
         }
       }
     }
@@ -223,14 +245,14 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
   } else if (warp == k2MmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA; uniform control flow)
     if (rank == 0) {
-      constexpr uint32_t idesc_s = make_idesc_16(2 * k2BM, k2BN, BF16);
+      constexpr uint32_t idesc_s = make_idesc_16_major(2 * k2BM, k2BN, BF16, MN, MN);
       constexpr uint32_t idesc_o = make_idesc_16(2 * k2BM, kC, BF16);
-      const uint32_t idesc_s_last = make_idesc_16(2 * k2BM, (uint32_t)n_last, BF16);
+      const uint32_t idesc_s_last = make_idesc_16_major(2 * k2BM, (uint32_t)n_last, BF16, MN, MN);
       const int ksteps_last = n_last / 16;
       uint32_t it = 0, kcnt = 0, vcnt = 0;
       uint32_t pphase0 = 0, pphase1 = 0;
       const uint32_t tO = tmem + k2TmemO;
-      const uint64_t qd0 = make_sdesc_k_sw128(smem_u32(sQ));
+      const uint64_t qd0 = MN ? make_sdesc_mn_sw128(smem_u32(sQ), 32768, 1024) : make_sdesc_k_sw128(smem_u32(sQ));
       const uint32_t sK_addr = smem_u32(sK);
       const uint32_t sV_addr = smem_u32(sV);
 #ifdef COATTN_TRACE
@@ -246,13 +268,14 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // T  [2*N*Lp][C],  
           TR2(1);
           tc_fence_after();
           const uint32_t tS = tmem + k2TmemS + (uint32_t)(j & 1) * k2BN;
-          const uint64_t kd0 = make_sdesc_k_sw128(sK_addr + s * k2KBytes);
+          const uint64_t kd0 = MN ? make_sdesc_mn_sw128(sK_addr + s * k2KBytes, 32768, 1024) : make_sdesc_k_sw128(sK_addr + s * k2KBytes);
           const uint32_t idesc = (j == T - 1) ? idesc_s_last : idesc_s;
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < kC / 16; ++kk) {
-              const uint64_t ad = qd0 + (uint64_t)(((kk >> 2) * (k2BM * 128) + (kk & 3) * 32) >> 4);
-              const uint64_t bd = kd0 + (uint64_t)(((kk >> 2) * ((k2BN / 2) * 128) + (kk & 3) * 32) >> 4);
+              // K-major: k-block kk/4 + 32 B per 16 channels inside the 128-byte row;  MN-major: 16 channel rows = 2048 B
+              const uint64_t ad = qd0 + (uint64_t)((MN ? kk * 2048 : ((kk >> 2) * (k2BM * 128) + (kk & 3) * 32)) >> 4);
+              const uint64_t bd = kd0 + (uint64_t)((MN ? kk * 2048 : ((kk >> 2) * ((k2BN / 2) * 128) + (kk & 3) * 32)) >> 4);
               umma2_ss(tS, ad, bd, idesc, kk > 0);
             }
             umma2_commit_mc(k_empty + s, 3);

@@ -37,7 +37,7 @@ Layout make_layout(int n, int h, int w) {
   int64_t off = 0;
   ly.off_t = off;   ly.bytes_t = 2 * plane;   off = round_up(off + ly.bytes_t, kAlign);
   ly.off_at = off;  ly.bytes_at = plane;      off = round_up(off + ly.bytes_at, kAlign);
-  ly.off_vv = off;  ly.bytes_vv = 2 * plane;  off = round_up(off + ly.bytes_vv, kAlign);
+  ly.off_vv = off;  ly.bytes_vv = 3 * plane;  off = round_up(off + ly.bytes_vv, kAlign);   // B16, A16, Q16 ([C][Lp] each)
   ly.off_w16 = off; ly.bytes_w16 = (int64_t)kC * kC * 2; off = round_up(off + ly.bytes_w16, kAlign);
   ly.off_z = off;   ly.bytes_z = (int64_t)2 * n * kC * ly.L * 4; off = round_up(off + ly.bytes_z, kAlign);
   ly.off_lse = off; ly.bytes_lse = (int64_t)2 * n * ly.L * 4;    off = round_up(off + ly.bytes_lse, kAlign);
@@ -227,11 +227,55 @@ static int prep_and_project_fused(const float* v_a, const float* v_b, const floa
   return (int)cudaGetLastError();
 }
 
+// MN-major path: cast both frames (no transposes) + channel-major projection
+static int cast_and_project_mn(const float* v_a, const float* v_b, const float* w, void* workspace, int64_t workspace_bytes,
+                               int n, int c, int h, int w_, unsigned flags, void* stream) {
+  if (int e = check_dims(n, c, h, w_)) return e;
+  const Layout ly = make_layout(n, h, w_);
+  if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
+  if (int e = check_arch(nullptr)) return e;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return COATTN_E_DRIVER;
+  const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned short* x = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv));
+  unsigned short* w16 = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16));
+  CastParams cp;
+  cp.va = v_a; cp.vb = v_b; cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp;
+  const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
+  const dim3 cgrid(n * kC, 2);
+  if (bf16) {
+    if (vec) cast_kernel<true, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<true, 1><<<cgrid, 256, 0, st>>>(cp);
+    cast_w_kernel<true><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+  } else {
+    if (vec) cast_kernel<false, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<false, 1><<<cgrid, 256, 0, st>>>(cp);
+    cast_w_kernel<false><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+  }
+  CUtensorMap tm_w, tm_x;
+  if (int e = make_tmap(enc, &tm_w, w16, kC, kC, 128, bf16)) return e;
+  if (int e = make_tmap(enc, &tm_x, x, (uint64_t)3 * n * kC, ly.Lp, 256, bf16)) return e;
+  int sms = 148;
+  if (int e = check_arch(&sms)) return e;
+  ProjectMnParams pp;
+  pp.q16 = x + 2 * ly.t_pass_elems();
+  pp.Lp = ly.Lp;
+  pp.tiles_per_sample = ly.Lp / kProjMnTile;
+  pp.num_tiles = n * pp.tiles_per_sample;
+  pp.a_row0_base = n * kC;
+  auto kern = bf16 ? project_mn_kernel<true> : project_mn_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjMnSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<pp.num_tiles < sms ? pp.num_tiles : sms, kNumThreads, kProjMnSmemBytes, st>>>(tm_w, tm_x, pp);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int coattn_stage_prep_project(const float* v_a, const float* v_b, const float* w, void* workspace,
                                         int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
                                         void* stream) {
   if (!v_a || !v_b || !w) return COATTN_E_NULL;
   if (int e = check_dims(n, c, h, w_)) return e;
+  if (!(flags & (COATTN_FLAG_KMAJOR | COATTN_FLAG_SINGLE_CTA | COATTN_FLAG_UNFUSED_PREP)))
+    return cast_and_project_mn(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream);
   if (((h * w_) % 2 != 0) || (reinterpret_cast<uintptr_t>(v_a) & 7) != 0) {   // odd L: separate kernels
     if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
     return coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, flags, stream);
@@ -257,10 +301,17 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
   if (int e = make_tmap(enc, &tm_v, seg(workspace, ly.off_vv), (uint64_t)2 * n * kC, ly.Lp, kC, bf16)) return e;
   if (!(flags & COATTN_FLAG_SINGLE_CTA)) {
     // default: CTA-pair kernel (cluster of 2, tcgen05 cta_group::2)
+    const bool mn = !(flags & (COATTN_FLAG_KMAJOR | COATTN_FLAG_UNFUSED_PREP));
     CUtensorMap tm_q, tm_k2, tm_v2;
-    if (int e = make_tmap(enc, &tm_q, seg(workspace, ly.off_t), t_rows, kC, k2BM, bf16)) return e;
-    if (int e = make_tmap(enc, &tm_k2, seg(workspace, ly.off_t), t_rows, kC, k2BN / 2, bf16)) return e;
-    if (int e = make_tmap(enc, &tm_v2, seg(workspace, ly.off_vv), (uint64_t)2 * n * kC, ly.Lp, kC / 2, bf16)) return e;
+    if (mn) {
+      // queries and keys straight from the channel-major planes X = [B16, A16, Q16]
+      if (int e = make_tmap(enc, &tm_q, seg(workspace, ly.off_vv), (uint64_t)3 * n * kC, ly.Lp, kC, bf16)) return e;
+      tm_k2 = tm_q;
+    } else {
+      if (int e = make_tmap(enc, &tm_q, seg(workspace, ly.off_t), t_rows, kC, k2BM, bf16)) return e;
+      if (int e = make_tmap(enc, &tm_k2, seg(workspace, ly.off_t), t_rows, kC, k2BN / 2, bf16)) return e;
+    }
+    if (int e = make_tmap(enc, &tm_v2, seg(workspace, ly.off_vv), (uint64_t)3 * n * kC, ly.Lp, kC / 2, bf16)) return e;
     Attend2Params q;
     q.z = z;
     q.lse = lse ? lse : reinterpret_cast<float*>(seg(workspace, ly.off_lse));
@@ -273,7 +324,8 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     q.kv_tiles = (ly.L + k2BN - 1) / k2BN;
     q.passes = (flags & COATTN_FLAG_A_ONLY) ? 1 : 2;
     q.num_items = q.passes * n * q.q_pairs;
-    auto kern2 = bf16 ? attend2_kernel<true> : attend2_kernel<false>;
+    auto kern2 = mn ? (bf16 ? attend2_kernel<true, true> : attend2_kernel<false, true>)
+                    : (bf16 ? attend2_kernel<true, false> : attend2_kernel<false, false>);
     cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
     if (e2 != cudaSuccess) return (int)e2;
     int clusters = sms / 2;
@@ -400,13 +452,12 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
   if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
-  // the fused kernel reads the features with float2 loads: needs even L and 8-byte aligned rows
-  const bool can_fuse = (ly.L % 2 == 0) && ((reinterpret_cast<uintptr_t>(v_a) & 7) == 0);
-  if ((flags & COATTN_FLAG_UNFUSED_PREP) || !can_fuse) {
+  if (flags & COATTN_FLAG_SINGLE_CTA) flags |= COATTN_FLAG_KMAJOR;   // the cross-check kernel only knows K-major operands
+  if (flags & COATTN_FLAG_UNFUSED_PREP) {
     if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
     if (int e = coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
   } else {
-    if (int e = prep_and_project_fused(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+    if (int e = coattn_stage_prep_project(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
   }
   if (flags & COATTN_FLAG_UNFUSED_GATE) {
     float* zbuf = z ? z : reinterpret_cast<float*>(seg(workspace, ly.off_z));

@@ -402,6 +402,178 @@ project_fused_kernel(const __grid_constant__ CUtensorMap tmap_w,   // [C][C], bo
 }
 
 // ==============================================================================================
+// MN-major path (default forward): the features are only CAST, never transposed.
+//   cast_kernel        fp32 [N][C][L] -> 16-bit X[plane][N][C][Lp] (plane 0 = V_b, plane 1 = V_a), zero padded
+//   project_mn_kernel  Q16[n][co][i] = sum_ci W[co][ci] A16[n][ci][i]  -> X plane 2, channel-major like its input:
+//                      A operand = W16 (K-major), B operand = the A16 tile as an MN-major operand (positions contiguous)
+// ==============================================================================================
+struct CastParams {
+  const float* va;
+  const float* vb;
+  unsigned short* x;   // [3][N][C][Lp]; planes 0 (V_b) and 1 (V_a) are written here
+  int N, L, Lp;
+};
+
+template <bool BF16, int VEC>
+__global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
+  const int row = blockIdx.x;                 // n * C + c
+  const int plane = blockIdx.y;               // 0: V_b, 1: V_a
+  const float* src = (plane ? p.va : p.vb) + (size_t)row * p.L;
+  unsigned short* dst = p.x + ((size_t)plane * p.N * kC + row) * p.Lp;
+  if constexpr (VEC == 4) {
+    for (int i = threadIdx.x * 4; i < p.Lp; i += 256 * 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < p.L) v = __ldcs(reinterpret_cast<const float4*>(src + i));     // L % 4 == 0
+      *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack16x2<BF16>(v.x, v.y), pack16x2<BF16>(v.z, v.w));
+    }
+  } else {
+    for (int i = threadIdx.x * 2; i < p.Lp; i += 256 * 2) {
+      const float a = (i < p.L) ? __ldcs(src + i) : 0.f;
+      const float b = (i + 1 < p.L) ? __ldcs(src + i + 1) : 0.f;
+      *reinterpret_cast<uint32_t*>(dst + i) = pack16x2<BF16>(a, b);
+    }
+  }
+}
+
+constexpr int kProjMnTile = 64;            // positions per tile
+constexpr int kProjMnXStages = 2;
+constexpr int kProjMnSmemBytes = 128 * 1024 + kProjMnXStages * 32 * 1024 + 1024 + 128;
+
+struct ProjectMnParams {
+  unsigned short* q16;   // X plane 2: [N][C][Lp]
+  int Lp;
+  int tiles_per_sample;  // Lp / 64
+  int num_tiles;         // N * Lp / 64
+  int a_row0_base;       // first row of plane A16 in the X tensor map (= 1 * N * C)
+};
+
+// Persistent: W16 (128 KB) is loaded once per CTA and stays in shared memory; 64-position tiles of A16 stream through
+// a 2-stage ring; two TMEM accumulator sets let the drain of tile t overlap the MMAs of tile t+1.
+template <bool BF16>
+__global__ void __launch_bounds__(kNumThreads, 1)
+project_mn_kernel(const __grid_constant__ CUtensorMap tmap_w,   // W16 [C][C], box {64, 128}
+                  const __grid_constant__ CUtensorMap tmap_x,   // X [3*N*C][Lp], box {64, 256}
+                  ProjectMnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_1024(smem_raw);
+  uint8_t* sW = smem;                 // 2 m-tiles x 4 k-blocks x [128 rows x 128 B] = 128 KB
+  uint8_t* sX = smem + 128 * 1024;    // stages x [256 channel rows x 128 B (64 positions)]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + kProjMnXStages * 32768);
+  uint64_t* w_full = bars + 0;
+  uint64_t* x_full = bars + 1;                      // [2]
+  uint64_t* x_empty = x_full + kProjMnXStages;      // [2]
+  uint64_t* d_full = x_empty + kProjMnXStages;      // [2]
+  uint64_t* d_empty = d_full + 2;                   // [2] 4 arrivals (epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+    mbar_init(w_full, 1);
+    for (int s = 0; s < kProjMnXStages; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(d_full + b, 1); mbar_init(d_empty + b, 4); }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, 128 * 1024);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sW + (mt * 4 + kb) * 16384, &tmap_w, w_full, kb * 64, mt * 128);
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++cnt) {
+        const int n = t / p.tiles_per_sample;
+        const int i0 = (t - n * p.tiles_per_sample) * kProjMnTile;
+        const uint32_t s = cnt % kProjMnXStages, ph = (cnt / kProjMnXStages) & 1;
+        mbar_wait(x_empty + s, ph ^ 1, 110);
+        mbar_arrive_expect_tx(x_full + s, 32768);
+        tma_load_2d(sX + s * 32768, &tmap_x, x_full + s, i0, p.a_row0_base + n * kC);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    constexpr uint32_t idesc = make_idesc_16_major(128, kProjMnTile, BF16, false, true);
+    const uint32_t wbase = smem_u32(sW);
+    const uint32_t xbase = smem_u32(sX);
+    warp_mbar_wait(w_full, 0, lane, 100);
+    uint32_t cnt = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++cnt) {
+      const uint32_t s = cnt % kProjMnXStages, ph = (cnt / kProjMnXStages) & 1;
+      const uint32_t b = cnt & 1, dph = (cnt >> 1) & 1;
+      warp_mbar_wait(x_full + s, ph, lane, 111);
+      warp_mbar_wait(d_empty + b, dph ^ 1, lane, 112);
+      tc_fence_after();
+      const uint64_t xd0 = make_sdesc_mn_sw128(xbase + s * 32768, 32768, 1024);
+      if (elect_one()) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) {
+            const uint64_t ad = make_sdesc_k_sw128(wbase + (mt * 4 + (kk >> 2)) * 16384 + (kk & 3) * 32);
+            umma_ss(tmem + b * 128 + mt * 64, ad, xd0 + (uint64_t)((kk * 2048) >> 4), idesc, kk > 0);
+          }
+        }
+        umma_commit(x_empty + s);
+        umma_commit(d_full + b);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue: thread = output channels (warp*32 + lane) and 128 + that; 64 positions each = 128 contiguous bytes
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t cnt = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++cnt) {
+      const int n = t / p.tiles_per_sample;
+      const int i0 = (t - n * p.tiles_per_sample) * kProjMnTile;
+      const uint32_t b = cnt & 1, dph = (cnt >> 1) & 1;
+      warp_mbar_wait(d_full + b, dph, lane, 101);
+      tc_fence_after();
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int co = mt * 128 + warp * 32 + lane;
+        uint4* d4 = reinterpret_cast<uint4*>(p.q16 + ((size_t)n * kC + co) * p.Lp + i0);
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr + b * 128 + mt * 64, v0);
+        tmem_ld32(taddr + b * 128 + mt * 64 + 32, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          d4[q] = make_uint4(pack16x2<BF16>(__uint_as_float(v0[8 * q + 0]), __uint_as_float(v0[8 * q + 1])),
+                             pack16x2<BF16>(__uint_as_float(v0[8 * q + 2]), __uint_as_float(v0[8 * q + 3])),
+                             pack16x2<BF16>(__uint_as_float(v0[8 * q + 4]), __uint_as_float(v0[8 * q + 5])),
+                             pack16x2<BF16>(__uint_as_float(v0[8 * q + 6]), __uint_as_float(v0[8 * q + 7])));
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          d4[4 + q] = make_uint4(pack16x2<BF16>(__uint_as_float(v1[8 * q + 0]), __uint_as_float(v1[8 * q + 1])),
+                                 pack16x2<BF16>(__uint_as_float(v1[8 * q + 2]), __uint_as_float(v1[8 * q + 3])),
+                                 pack16x2<BF16>(__uint_as_float(v1[8 * q + 4]), __uint_as_float(v1[8 * q + 5])),
+                                 pack16x2<BF16>(__uint_as_float(v1[8 * q + 6]), __uint_as_float(v1[8 * q + 7])));
+      }
+      tc_fence_before();
+      warp_mbar_arrive(d_empty + b, lane);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ==============================================================================================
 // attend: persistent flash-style kernel over work items (sample n, pass p, 128-row query tile)
 //
 //   warps 0-3  softmax + drain: thread r owns query row r (TMEM lane r); they also stage the query tile:

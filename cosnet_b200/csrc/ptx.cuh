@@ -150,6 +150,26 @@ __device__ __forceinline__ uint64_t make_sdesc_k_sw128(uint32_t smem_addr_bytes)
   return d;
 }
 
+// MN-major operand tile (the M or N index is contiguous in memory, e.g. NCHW features [channel][position] used with
+// position as M/N and channel as K), 128-byte swizzle: rows of 128 B hold 64 consecutive MN elements of one K index,
+// 8 K-rows form a 1024-byte swizzle atom; SBO = distance between 8-row K groups (1024 B when K rows are contiguous),
+// LBO = distance between 64-element MN chunks.  Stepping K by 16 adds 16 rows = 2048 B to the start address.
+// (validated against a host reference in tools/mn_major_test.cu)
+__device__ __forceinline__ uint64_t make_sdesc_mn_sw128(uint32_t smem_addr_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr_bytes & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// instruction descriptor with explicit operand majors (bit 15: A is MN-major, bit 16: B is MN-major)
+__host__ __device__ constexpr uint32_t make_idesc_16_major(uint32_t M, uint32_t N, bool bf16, bool a_mn, bool b_mn) {
+  return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: MMA issue (one thread) + commit
 // ----------------------------------------------------------------------------------------------

@@ -87,6 +87,13 @@ enum {
  *                          conv(V, W[:, 256:]), so the concat never exists.  CTA-pair kernel, fused gate only.
  */
 #define COATTN_FLAG_GATED_ONLY 32u
+/*
+ *   COATTN_FLAG_KMAJOR     use the position-major (transposed, [L][C]) copies of the features as K-major tensor-core
+ *                          operands for the affinity GEMM, as in the first version of the kernels.  Default: the
+ *                          features stay channel-major ([C][L], their NCHW orientation) and are consumed as MN-major
+ *                          operands, so the prep stage is a pure cast.  Same arithmetic, bit-identical results.
+ */
+#define COATTN_FLAG_KMAJOR 64u
 
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);
@@ -115,8 +122,9 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
 int coattn_stage_prep(const float* v_a, const float* v_b, const float* w, void* workspace,
                       int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
                       void* stream);
-/* stages 1+2 fused (default path of coattn_forward): V_b through the prep kernel; V_a is converted, written as A16
- * and projected (Qt = (W A)^T) by one kernel, At never reaches HBM.  Fills Bt, B16, A16, W16, Qt. */
+/* stages 1+2 of coattn_forward.  Default: cast both frames to 16 bit (channel-major, no transposes: B16, A16) and
+ * project Q16 = W A16 with the A16 tile as an MN-major tensor-core operand.  With COATTN_FLAG_KMAJOR: V_b through the
+ * transposing prep kernel, V_a through the fused convert + projection kernel (fills Bt, B16, A16, W16, Qt). */
 int coattn_stage_prep_project(const float* v_a, const float* v_b, const float* w, void* workspace,
                               int64_t workspace_bytes, int n, int c, int h, int w_, unsigned flags,
                               void* stream);

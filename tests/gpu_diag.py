@@ -52,9 +52,10 @@ def main():
     ap.add_argument("--bf16", type=int, default=0)
     ap.add_argument("--single", type=int, default=0)
     ap.add_argument("--unfused-prep", type=int, default=0)
+    ap.add_argument("--kmajor", type=int, default=0)
     args = ap.parse_args()
     n, h, w, c = args.n, args.h, args.w, 256
-    FL = (1 if args.bf16 else 0) | (4 if args.single else 0)
+    FL = (1 if args.bf16 else 0) | (4 if args.single else 0) | (64 if args.kmajor else 0)
     odt = torch.bfloat16 if args.bf16 else torch.float16
     L = h * w
     Lp = (L + 255) // 256 * 256
@@ -100,7 +101,7 @@ def main():
     if args.stage == "attend":
         z = torch.zeros(2, n, c, L, device=dev)
         lse = torch.zeros(2, n, L, device=dev)
-        _lib.check(lib.coattn_stage_attend(z.data_ptr(), lse.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "attend")
+        _lib.check(lib.coattn_stage_attend(z.data_ptr(), lse.data_ptr(), wsp, nbytes, n, c, h, w, FL | 64, st), "attend")   # K-major operands from stage_prep/project
         torch.cuda.synchronize()
         z = z.cpu().numpy(); lse = lse.cpu().numpy()
         # reference on the SAME bf16 operands (isolates kernel logic from quantisation)
@@ -148,6 +149,7 @@ def main():
             if args.unfused_prep:
                 _lib.check(lib.coattn_stage_prep(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "prep"); ev[1].record()
                 _lib.check(lib.coattn_stage_project(wsp, nbytes, n, c, h, w, FL, st), "project"); ev[2].record()
+                FL |= 64
             else:
                 ev[1].record()
                 _lib.check(lib.coattn_stage_prep_project(tva.data_ptr(), tvb.data_ptr(), tW.data_ptr(), wsp, nbytes, n, c, h, w, FL, st), "prep_project"); ev[2].record()

@@ -44,11 +44,11 @@ def test_version_and_errors(lib):
 
 
 def test_workspace_size_and_shape_errors(lib):
-    # 60x60 -> Lp = 3712: five bf16 planes of N*Lp*C plus W16, z, lse
+    # 60x60 -> Lp = 3840: six 16-bit planes of N*Lp*C (Bt, Qt, At, B16, A16, Q16) plus W16, z, lse
     n, c, h, w = 2, 256, 60, 60
     lp = 3840
     plane = n * lp * c * 2
-    expect_min = 5 * plane + c * c * 2 + 2 * n * c * h * w * 4 + 2 * n * h * w * 4
+    expect_min = 6 * plane + c * c * 2 + 2 * n * c * h * w * 4 + 2 * n * h * w * 4
     got = lib.coattn_workspace_bytes(n, c, h, w)
     assert expect_min <= got <= expect_min + 8 * 1024
     assert lib.coattn_workspace_bytes(n, 128, h, w) == -2      # C must be 256

@@ -285,11 +285,14 @@ def test_fused_and_unfused_prep_agree(op):
         W, g, b = orc.synthetic_weights(86, bias=True)
         dev = torch.device("cuda:0")
         t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
-        fused = op(t(v_a), t(v_b), t(W), t(g), t(b))
+        mn = op(t(v_a), t(v_b), t(W), t(g), t(b))                       # default: channel-major (MN-major) operands
+        kmajor = op(t(v_a), t(v_b), t(W), t(g), t(b), kmajor=True)      # transposing prep + fused convert/projection
         unfused = op(t(v_a), t(v_b), t(W), t(g), t(b), unfused_prep=True)
         torch.cuda.synchronize()
-        for x, y in zip(fused, unfused):
+        for x, y in zip(kmajor, unfused):
             assert torch.equal(x, y)      # same conversions, same MMAs: bit-identical
+        for x, y in zip(mn, unfused):     # same operand values, different operand layout
+            assert (x - y).abs().max() < 1e-5
 
 
 @pytest.mark.parametrize("n,h,w", [(2, 12, 11), (1, 40, 40)])
