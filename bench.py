@@ -354,8 +354,8 @@ def run_ours(args):
             "kernel": "attend2_kernel", "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"],
             "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"],
             # dram__bytes_read.sum + dram__bytes_write.sum of one attend2 launch at this shape, from the committed
-            # `ncu --set full` capture (profiles/r1_ncu_kernels.txt): 510.1 MB + 436.9 MB
-            "traffic": 947.1e6 if (n == PAIRS_PER_GPU and FLAGS == 0) else None,
+            # `ncu --set full` capture (profiles/r1_ncu_kernels.txt): 441.1 MB read + 431.3 MB written
+            "traffic": 872.4e6 if (n == PAIRS_PER_GPU and FLAGS == 0) else None,
             "peak_kind": f"{peaks['source']} burst bf16 (sustained {peaks['bf16_tflops_sustained']})",
             "ms_per_launch": attend_ms, "algorithmic_flops_per_launch": n * FLOPS_ATTEND_PER_PAIR_MODALITY,
             "whole_step_frac": (2 * n * FLOPS_PER_PAIR_MODALITY / (elapsed_ms / args.steps * 1e-3) / 1e12) / peaks["bf16_tflops"],
