@@ -359,3 +359,24 @@ def test_multi_reference_inference_matches_pairwise_loop():
     want /= r
     assert got.shape == (q, 1, hw, hw)
     assert (got - want).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("host_passthrough", [False, True])
+def test_host_pipeline_matches_resident_path(op, host_passthrough):
+    """The host-buffer entry point (pinned host in/out, chunks rotating over three streams) reproduces the resident
+    path bit for bit, with the device or the host writing the passthrough half."""
+    from cosnet_b200.coattention import HostPipeline
+    dev = torch.device("cuda:0")
+    n, c, h, w = 7, 256, 12, 11          # 7 pairs in chunks of 3: a ragged last chunk
+    v_a, v_b = (torch.from_numpy(x) for x in orc.synthetic_features(95, n, h, w, 0.66))
+    W, g, b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_weights(96, bias=True))
+    want = op(v_a.to(dev), v_b.to(dev), W, g, b)
+    pipe = HostPipeline(n, c, h, w, chunk=3, slots=3, device=dev, host_passthrough=host_passthrough)
+    out_a = torch.empty(n, 2 * c, h, w).pin_memory()
+    out_b = torch.empty(n, 2 * c, h, w).pin_memory()
+    for _ in range(2):                   # second call reuses the slots
+        out_a.zero_(); out_b.zero_()
+        pipe(v_a.pin_memory(), v_b.pin_memory(), W, g, b, out_a, out_b)
+        torch.cuda.synchronize()
+        pipe.wait_host()
+        assert torch.equal(out_a, want[0].cpu()) and torch.equal(out_b, want[1].cpu())
