@@ -12,6 +12,8 @@
 // Gradient semantics follow the reference: the B-side gate mask is a constant (:178-182) and, with
 // no_grad_for_counterpart (:144-148), V_b receives no gradient.
 #pragma once
+#include <type_traits>
+
 #include "coattn_kernels.cuh"
 
 namespace coattn {
@@ -153,9 +155,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K]
           o1[(int64_t)k * p.ld1] = (unsigned short)((k & 1) ? (pk[k >> 1] >> 16) : (pk[k >> 1] & 0xFFFFu));
       } else if constexpr (MODE == kGemmAddF32T) {
         if (valid) {
+          // all 32 loads first: with a run-time stride the compiler cannot prove the 32 addresses distinct and would
+          // otherwise serialise load -> add -> store (32 dependent memory round trips per chunk)
           float* o = static_cast<float*>(p.out0) + ((int64_t)b * p.rows0 + n) * p.ld0 + m;
+          float old[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) o[(int64_t)k * p.ld0] += __uint_as_float(v[k]);
+          for (int k = 0; k < 32; ++k) old[k] = o[(int64_t)k * p.ld0];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[(int64_t)k * p.ld0] = old[k] + __uint_as_float(v[k]);
         }
       } else {
         float* o = static_cast<float*>(p.out0) + (int64_t)m * p.ld0 + n;
@@ -324,17 +331,22 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
 }
 
 // ==============================================================================================
-// bwd_tile: the three [L, L] products of the backward and their elementwise combination in ONE kernel, one
-// 128 x 128 tile (i-tile, j-tile) of one sample per CTA -- nothing of size L x L is ever written in fp32:
+// bwd_tile: the three [L, L] products of the backward and their elementwise combination in ONE persistent kernel.
+// Work item = one 128 x 128 tile (i-tile, j-tile) of one sample; nothing of size L x L is ever written in fp32:
 //   S    = Qt[i] Bt[j]^T      (forward operand format, so that exp(S - lse) is exactly the forward's softmax)
 //   dP_a = dZa_t[i] Bt[j]^T   (bf16)
 //   dP_b = At[i] dZb_t[j]^T   (bf16; HAS_B only)
 //   dS = P_a (dP_a - delta_a[i]) + P_b (dP_b - delta_b[j]),   P_a = exp(S - lse_a[i]),  P_b = exp(S - lse_b[j])
 // written as bf16: dS, P_b (HAS_B) and P_a (counterpart gradients only).  TMEM: three 128-column accumulators.
+// One CTA per SM walks the tiles (i fastest, so the CTAs running together share a handful of j-tiles in L2); the TMA
+// ring runs continuously across tiles, so the 384 KB of operand tiles of the next item stream in while the eight
+// epilogue warps (two per TMEM lane quadrant, 64 columns each) are still combining the current one.
 // ==============================================================================================
-constexpr int kTileStageBytes = 6 * 16384;   // Qt, Bt | dZa_t, Bt(bf16) | At(bf16), dZb_t   (128 rows x 64 ch each)
-constexpr int kTileStages = 2;
-constexpr int kTileSmemBytes = kTileStages * kTileStageBytes + 1024 /*align*/ + 1024 /*column vectors*/ + 128;
+constexpr int kTileThreads = 320;            // warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
+constexpr int kTileProducerWarp = 8;
+constexpr int kTileMmaWarp = 9;
+constexpr int kTileRingBytes = 12 * 16384;   // HAS_B: 2 stages x 6 operand blocks;  otherwise 3 stages x 4 blocks
+constexpr int kTileSmemBytes = kTileRingBytes + 8 * 2048 /*store staging*/ + 1024 /*align*/ + 2048 /*column vectors x2*/ + 128;
 
 struct BwdTileParams {
   const float* lse;      // [2][N][L]
@@ -343,157 +355,249 @@ struct BwdTileParams {
   unsigned short* pb;    // [N][Lp][Lp] bf16 (HAS_B)
   unsigned short* pa;    // [N][Lp][Lp] bf16 or null
   int N, L, Lp;
+  int tiles_1d;          // Lp / 128
+  int num_tiles;         // N * tiles_1d^2
   uint32_t idesc_fwd;    // M128 N128, forward operand format
   uint32_t idesc_bf16;   // M128 N128, bf16 x bf16
 };
 
+// clock64 accounting of one CTA (debug builds only): where the producer, the MMA issuer and epilogue warp 0 spend time
+#ifdef COATTN_TRACE_BWD
+#define BT_T0() long long bt_t0 = clock64()
+#define BT_ACC(i) do { const long long bt_now = clock64(); bt_acc[i] += bt_now - bt_t0; bt_t0 = bt_now; } while (0)
+#define BT_REPORT()                                                                                                   \
+  do {                                                                                                                \
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kTileProducerWarp || warp == kTileMmaWarp))              \
+      printf("bwd_tile<%d> warp %d: empty-wait %lld | d_empty-wait %lld | full-wait %lld | prologue %lld | d_full-wait %lld | " \
+             "combine+store %lld | total %lld cycles\n", (int)HAS_B, warp, bt_acc[0], bt_acc[1], bt_acc[2], bt_acc[3],  \
+             bt_acc[4], bt_acc[5], clock64() - bt_start);                                                              \
+  } while (0)
+#else
+#define BT_T0() do {} while (0)
+#define BT_ACC(i) do {} while (0)
+#define BT_REPORT() do {} while (0)
+#endif
+
 template <bool HAS_B>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kTileThreads, 1)
 bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant__ CUtensorMap tm_bt,
                 const __grid_constant__ CUtensorMap tm_dza, const __grid_constant__ CUtensorMap tm_btg,
                 const __grid_constant__ CUtensorMap tm_atg, const __grid_constant__ CUtensorMap tm_dzb,
                 BwdTileParams p) {
   extern __shared__ uint8_t smem_raw[];
+  // operand blocks per stage: Qt, Bt | dZa_t, Bt(bf16) | At(bf16), dZb_t   (128 rows x 64 channels = 16 KB each)
+  constexpr int kTileStages = HAS_B ? 2 : 3;
+  constexpr int kTileStageBytes = (HAS_B ? 6 : 4) * 16384;
   uint8_t* smem = align_1024(smem_raw);
-  float* colv = reinterpret_cast<float*>(smem + kTileStages * kTileStageBytes);   // [0,128) lse_b, [128,256) delta_b
-  uint64_t* bars = reinterpret_cast<uint64_t*>(colv + 256);
+  uint8_t* stage_out = smem + kTileRingBytes;                                      // 8 warps x 2 KB
+  float* colv = reinterpret_cast<float*>(stage_out + 8 * 2048);                    // 2 x ([0,128) lse_b, [128,256) delta_b)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(colv + 512);
   uint64_t* full = bars;
   uint64_t* empty = bars + kTileStages;
   uint64_t* d_full = empty + kTileStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+  uint64_t* d_empty = d_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * 128;
-  const int j0 = blockIdx.y * 128;
-  const int n = blockIdx.z;
+#ifdef COATTN_TRACE_BWD
+  long long bt_acc[6] = {0, 0, 0, 0, 0, 0};
+  const long long bt_start = clock64();
+#endif
 
-  if (warp == kProducerWarp && lane == 0) {
+  if (warp == kTileProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_bt); tma_prefetch_desc(&tm_dza);
     tma_prefetch_desc(&tm_btg); tma_prefetch_desc(&tm_atg); tma_prefetch_desc(&tm_dzb);
     for (int s = 0; s < kTileStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(d_full, 1);
+    mbar_init(d_empty, 8);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) {
+  if (warp == kTileMmaWarp) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
-  }
-  if (threadIdx.x < 128) {   // per-column normalisers of this j-tile
-    const int j = j0 + threadIdx.x;
-    const bool ok = HAS_B && j < p.L;
-    colv[threadIdx.x] = ok ? p.lse[(size_t)(p.N + n) * p.L + j] : 0.f;
-    colv[128 + threadIdx.x] = ok ? p.delta[(size_t)(p.N + n) * p.L + j] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   constexpr int kNumKb = kC / 64;
+  const int per_sample = p.tiles_1d * p.tiles_1d;
 
-  if (warp == kProducerWarp) {
+  if (warp == kTileProducerWarp) {
     if (lane == 0) {
-      const int irow = n * p.Lp + i0, jrow = n * p.Lp + j0;
-      for (int kb = 0; kb < kNumKb; ++kb) {
-        const int s = kb % kTileStages;
-        const uint32_t ph = (kb / kTileStages) & 1;
-        mbar_wait(empty + s, ph ^ 1, 40);
-        mbar_arrive_expect_tx(full + s, HAS_B ? kTileStageBytes : 4 * 16384);
-        uint8_t* st = smem + s * kTileStageBytes;
-        tma_load_2d(st + 0 * 16384, &tm_qt, full + s, kb * 64, irow);
-        tma_load_2d(st + 1 * 16384, &tm_bt, full + s, kb * 64, jrow);
-        tma_load_2d(st + 2 * 16384, &tm_dza, full + s, kb * 64, irow);
-        tma_load_2d(st + 3 * 16384, &tm_btg, full + s, kb * 64, jrow);
-        if (HAS_B) {
-          tma_load_2d(st + 4 * 16384, &tm_atg, full + s, kb * 64, irow);
-          tma_load_2d(st + 5 * 16384, &tm_dzb, full + s, kb * 64, jrow);
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int n = t / per_sample, r = t - n * per_sample;
+        const int irow = n * p.Lp + (r % p.tiles_1d) * 128, jrow = n * p.Lp + (r / p.tiles_1d) * 128;
+        for (int kb = 0; kb < kNumKb; ++kb, ++cnt) {
+          const uint32_t s = cnt % kTileStages, ph = (cnt / kTileStages) & 1;
+          BT_T0();
+          mbar_wait(empty + s, ph ^ 1, 40);
+          BT_ACC(0);
+          mbar_arrive_expect_tx(full + s, kTileStageBytes);
+          uint8_t* st = smem + s * kTileStageBytes;
+          tma_load_2d(st + 0 * 16384, &tm_qt, full + s, kb * 64, irow);
+          tma_load_2d(st + 1 * 16384, &tm_bt, full + s, kb * 64, jrow);
+          tma_load_2d(st + 2 * 16384, &tm_dza, full + s, kb * 64, irow);
+          tma_load_2d(st + 3 * 16384, &tm_btg, full + s, kb * 64, jrow);
+          if (HAS_B) {
+            tma_load_2d(st + 4 * 16384, &tm_atg, full + s, kb * 64, irow);
+            tma_load_2d(st + 5 * 16384, &tm_dzb, full + s, kb * 64, jrow);
+          }
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kTileMmaWarp) {
     const uint32_t base = smem_u32(smem);
-    for (int kb = 0; kb < kNumKb; ++kb) {
-      const int s = kb % kTileStages;
-      const uint32_t ph = (kb / kTileStages) & 1;
-      warp_mbar_wait(full + s, ph, lane, 41);
+    uint32_t cnt = 0, it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      BT_T0();
+      warp_mbar_wait(d_empty, (it & 1) ^ 1, lane, 43);   // the epilogue has read the previous tile's accumulators
+      BT_ACC(1);
       tc_fence_after();
-      const uint32_t sb = base + s * kTileStageBytes;
-      const uint64_t d0 = make_sdesc_k_sw128(sb), d1 = make_sdesc_k_sw128(sb + 16384), d2 = make_sdesc_k_sw128(sb + 2 * 16384),
-                     d3 = make_sdesc_k_sw128(sb + 3 * 16384), d4 = make_sdesc_k_sw128(sb + 4 * 16384),
-                     d5 = make_sdesc_k_sw128(sb + 5 * 16384);
-      if (elect_one()) {
+      for (int kb = 0; kb < kNumKb; ++kb, ++cnt) {
+        const uint32_t s = cnt % kTileStages, ph = (cnt / kTileStages) & 1;
+        BT_T0();
+        warp_mbar_wait(full + s, ph, lane, 41);
+        BT_ACC(2);
+        tc_fence_after();
+        const uint32_t sb = base + s * kTileStageBytes;
+        const uint64_t d0 = make_sdesc_k_sw128(sb), d1 = make_sdesc_k_sw128(sb + 16384), d2 = make_sdesc_k_sw128(sb + 2 * 16384),
+                       d3 = make_sdesc_k_sw128(sb + 3 * 16384), d4 = make_sdesc_k_sw128(sb + 4 * 16384),
+                       d5 = make_sdesc_k_sw128(sb + 5 * 16384);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem, d0 + 2 * k, d1 + 2 * k, p.idesc_fwd, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_ss(tmem, d0 + 2 * k, d1 + 2 * k, p.idesc_fwd, (kb > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem + 128, d2 + 2 * k, d3 + 2 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
-        if (HAS_B) {
+          for (int k = 0; k < 4; ++k) umma_ss(tmem + 128, d2 + 2 * k, d3 + 2 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+          if (HAS_B) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem + 256, d4 + 2 * k, d5 + 2 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_ss(tmem + 256, d4 + 2 * k, d5 + 2 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty + s);
+          if (kb == kNumKb - 1) umma_commit(d_full);
         }
-        umma_commit(empty + s);
-        if (kb == kNumKb - 1) umma_commit(d_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    warp_mbar_wait(d_full, 0, lane, 42);
-    tc_fence_after();
-    const int i = i0 + warp * 32 + lane;
-    const bool vi = i < p.L;
-    const float lse_a = vi ? __ldg(p.lse + (size_t)n * p.L + i) : 0.f;
-    const float del_a = vi ? __ldg(p.delta + (size_t)n * p.L + i) : 0.f;
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    const size_t rowoff = ((size_t)n * p.Lp + i) * p.Lp + j0;
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      uint32_t sv[32], av[32], bv[32];
-      tmem_ld32(taddr + ch * 32, sv);
-      tmem_ld32(taddr + 128 + ch * 32, av);
-      if (HAS_B) tmem_ld32(taddr + 256 + ch * 32, bv);
-      tmem_ld_wait();
-      uint32_t ods[16], opb[16], opa[16];
+    const int quad = warp & 3;            // TMEM lane quadrant
+    const int half = warp >> 2;           // columns [64 half, 64 half + 64) of the tile
+    const int et = threadIdx.x;           // 0..255
+    uint8_t* stg = stage_out + warp * 2048;   // this warp's 32 rows x 64 B staging block
+    // staging block addressing: 16-byte chunk c of row r sits at r*64 + ((c ^ ((r >> 1) & 3)) * 16) -- conflict-free both
+    // for the row-per-lane writes and for the 8-rows-per-instruction reads that feed coalesced global stores
+    const uint32_t wr_row = (uint32_t)lane * 64, wr_x = ((uint32_t)lane >> 1) & 3;
+    const int rd_r = lane >> 2, rd_c = lane & 3;
+    auto flush = [&](unsigned short* base, size_t tile_off, const uint32_t* pk) {
+      // pk: this lane's row, 32 columns as 16 packed pairs
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        float d[2], pbv[2], pav[2];
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(stg + wr_row + ((c ^ wr_x) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      __syncwarp();
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int k = 2 * q + e;
-          const int jl = ch * 32 + k;
-          const bool ok = vi && (j0 + jl) < p.L;
-          const float sx = __uint_as_float(sv[k]);
-          const float pa = ok ? __expf(sx - lse_a) : 0.f;
-          float dd = pa * (__uint_as_float(av[k]) - del_a);
-          float pb = 0.f;
-          if (HAS_B) {
-            pb = ok ? __expf(sx - colv[jl]) : 0.f;
-            dd = fmaf(pb, __uint_as_float(bv[k]) - colv[128 + jl], dd);
-          }
-          d[e] = ok ? dd : 0.f;
-          pbv[e] = pb;
-          pav[e] = pa;
-        }
-        ods[q] = pack_bf16x2(d[0], d[1]);
-        opb[q] = pack_bf16x2(pbv[0], pbv[1]);
-        opa[q] = pack_bf16x2(pav[0], pav[1]);
+      for (int k = 0; k < 4; ++k) {
+        const int r = rd_r + 8 * k;
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 64 + ((rd_c ^ ((r >> 1) & 3)) << 4));
+        *reinterpret_cast<uint4*>(base + tile_off + (size_t)r * p.Lp + rd_c * 8) = v;
       }
-      uint4* o = reinterpret_cast<uint4*>(p.ds + rowoff + ch * 32);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) o[q] = make_uint4(ods[4 * q], ods[4 * q + 1], ods[4 * q + 2], ods[4 * q + 3]);
+      __syncwarp();
+    };
+    // per-tile vectors are fetched one tile ahead so that their latency hides behind the previous tile's combine
+    auto fetch = [&](int t, float& x, float& la, float& da) {
+      const int n = t / per_sample, r = t - n * per_sample;
+      const int i = (r % p.tiles_1d) * 128 + quad * 32 + lane;
+      const int j = (r / p.tiles_1d) * 128 + (et & 127);
+      x = (HAS_B && j < p.L) ? __ldg((et < 128 ? p.lse : p.delta) + (size_t)(p.N + n) * p.L + j) : 0.f;
+      la = (i < p.L) ? __ldg(p.lse + (size_t)n * p.L + i) : 0.f;
+      da = (i < p.L) ? __ldg(p.delta + (size_t)n * p.L + i) : 0.f;
+    };
+    float nx = 0.f, nla = 0.f, nda = 0.f;
+    if ((int)blockIdx.x < p.num_tiles) fetch(blockIdx.x, nx, nla, nda);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int n = t / per_sample, r = t - n * per_sample;
+      const int i0 = (r % p.tiles_1d) * 128, j0 = (r / p.tiles_1d) * 128;
+      float* cv = colv + (it & 1) * 256;
+      BT_T0();
       if (HAS_B) {
-        uint4* ob = reinterpret_cast<uint4*>(p.pb + rowoff + ch * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) ob[q] = make_uint4(opb[4 * q], opb[4 * q + 1], opb[4 * q + 2], opb[4 * q + 3]);
+        // per-column normalisers of this j-tile: -lse_b log2(e) (so that P_b = exp2(fma(S, log2e, .))) and delta_b.
+        // Double buffered by tile parity; the named barrier also keeps a fast warp from overwriting the buffer two
+        // tiles ahead while a slow one still reads it.
+        cv[et] = (et < 128) ? -nx * kLog2e : nx;
+        named_bar_sync(1, 256);
       }
-      if (p.pa != nullptr) {
-        uint4* oa = reinterpret_cast<uint4*>(p.pa + rowoff + ch * 32);
+      const int i = i0 + quad * 32 + lane;
+      const bool vi = i < p.L;
+      const float nlse_a = -nla * kLog2e;
+      const float del_a = nda;
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 64;
+      // element offset of (first row of this warp, first column of this warp's half) in the [N][Lp][Lp] outputs
+      const size_t tile_off = ((size_t)n * p.Lp + i0 + quad * 32) * p.Lp + j0 + half * 64;
+      const bool ragged = (i0 + 128 > p.L) || (j0 + 128 > p.L);   // tile-uniform: interior tiles need no masking
+      if (t + (int)gridDim.x < p.num_tiles) fetch(t + gridDim.x, nx, nla, nda);
+      BT_ACC(3);
+      warp_mbar_wait(d_full, it & 1, lane, 42);
+      BT_ACC(4);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t sv[32], av[32], bv[32];
+        tmem_ld32(taddr + ch * 32, sv);
+        tmem_ld32(taddr + 128 + ch * 32, av);
+        if (HAS_B) tmem_ld32(taddr + 256 + ch * 32, bv);
+        tmem_ld_wait();
+        if (ch == 1) {   // everything this warp needs from TMEM is in registers: release the accumulators early
+          tc_fence_before();
+          warp_mbar_arrive(d_empty, lane);
+        }
+        const int jl0 = half * 64 + ch * 32;
+        auto combine = [&](auto masked_tag) {
+          constexpr bool MASKED = decltype(masked_tag)::value;
+          // in place: sv <- P_a pairs (low half) ... the three results are packed into av (dS), bv (P_b), sv (P_a)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) oa[q] = make_uint4(opa[4 * q], opa[4 * q + 1], opa[4 * q + 2], opa[4 * q + 3]);
+          for (int g = 0; g < 8; ++g) {          // 4 columns per step
+            float4 nl = make_float4(0.f, 0.f, 0.f, 0.f), db = nl;
+            if (HAS_B) {
+              nl = *reinterpret_cast<const float4*>(cv + jl0 + 4 * g);
+              db = *reinterpret_cast<const float4*>(cv + 128 + jl0 + 4 * g);
+            }
+            const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, dbv[4] = {db.x, db.y, db.z, db.w};
+            float d[4], pa[4], pb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k = 4 * g + e;
+              const float sx = __uint_as_float(sv[k]);
+              float a = fast_exp2(fmaf(sx, kLog2e, nlse_a));
+              float b = HAS_B ? fast_exp2(fmaf(sx, kLog2e, nlv[e])) : 0.f;
+              if (MASKED) {
+                const bool ok = vi && (j0 + jl0 + k) < p.L;
+                a = ok ? a : 0.f;
+                b = ok ? b : 0.f;
+              }
+              float dd = a * (__uint_as_float(av[k]) - del_a);
+              if (HAS_B) dd = fmaf(b, __uint_as_float(bv[k]) - dbv[e], dd);
+              d[e] = dd; pa[e] = a; pb[e] = b;
+            }
+            // columns 4g..4g+3 are consumed: reuse the first half of the arrays for the packed results
+            av[2 * g] = pack_bf16x2(d[0], d[1]);  av[2 * g + 1] = pack_bf16x2(d[2], d[3]);
+            sv[2 * g] = pack_bf16x2(pa[0], pa[1]); sv[2 * g + 1] = pack_bf16x2(pa[2], pa[3]);
+            if (HAS_B) { bv[2 * g] = pack_bf16x2(pb[0], pb[1]); bv[2 * g + 1] = pack_bf16x2(pb[2], pb[3]); }
+          }
+        };
+        if (ragged) combine(std::true_type{}); else combine(std::false_type{});
+        flush(p.ds, tile_off + ch * 32, av);
+        if (HAS_B) flush(p.pb, tile_off + ch * 32, bv);
+        if (p.pa != nullptr) flush(p.pa, tile_off + ch * 32, sv);
       }
+      BT_ACC(5);
     }
-    tc_fence_before();
   }
+  BT_REPORT();
+  tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kTileMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

@@ -539,7 +539,8 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   if ((reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) != 0 ||
       workspace_bytes < (counterpart ? bl.total_counterpart : bl.total))
     return COATTN_E_WORKSPACE;
-  if (int e = check_arch(nullptr)) return e;
+  int sms = 148;
+  if (int e = check_arch(&sms)) return e;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return COATTN_E_DRIVER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -611,13 +612,14 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
     tp.lse = lse; tp.delta = delta; tp.ds = ds; tp.pb = pb;
     tp.pa = counterpart ? reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa)) : nullptr;
     tp.N = n; tp.L = L; tp.Lp = Lp;
+    tp.tiles_1d = lt; tp.num_tiles = n * lt * lt;
     const uint32_t f = fbf16 ? 1u : 0u;
     tp.idesc_fwd = (1u << 4) | (f << 7) | (f << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
     tp.idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
     auto kern = has_b ? bwd_tile_kernel<true> : bwd_tile_kernel<false>;
     if ((ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes)) != cudaSuccess)
       return (int)ce;
-    kern<<<dim3(lt, lt, n), kNumThreads, kTileSmemBytes, st>>>(t_qt, t_bt, t_dza, t_btg, t_atg, t_dzb, tp);
+    kern<<<tp.num_tiles < sms ? tp.num_tiles : sms, kTileThreads, kTileSmemBytes, st>>>(t_qt, t_bt, t_dza, t_btg, t_atg, t_dzb, tp);
     if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
   }
   // dQ[i][c] = sum_j dS[i][j] B16[c][j]   -> dQt [N][Lp][C] and dQ16 [N][C][Lp] (bf16)
