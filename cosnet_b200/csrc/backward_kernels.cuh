@@ -180,12 +180,15 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K]
 }
 
 // ==============================================================================================
-// bwd_prep: everything that is per position (no L x L work).  One block = 64 positions x 256 channels.
+// bwd_prep: everything that is per position (no L x L work).  One block = 32 positions x 256 channels
+// (warp = 32 channels, lane = position, so every global access is a coalesced 128-byte row segment).
 //   d_ta   = (sum_c dZag Z_a) m_a (1 - m_a)          gate logit gradient, A side only (:177-182)
 //   dZ_a   = dZag m_a + g d_ta                        dZ_b = dZbg m_b
 //   delta  = sum_c dZ_x Z_x
 //   d_gate_w += sum_i d_ta[i] Z_a[:, i]               d_gate_b += sum_i d_ta[i]
 //   dA      = d_cat_a[:, C:2C]                        (passthrough half of the concat, :186)
+// dZ_a / dZ_b leave as bf16 planes [N][C][Lp] -- the orientation every consumer takes (MN-major operands of the
+// tile kernel, K-major operands of the position-contracting GEMMs).
 // ==============================================================================================
 struct BwdPrepParams {
   const float* d_cat_a;   // [N][2C][L]
@@ -193,10 +196,8 @@ struct BwdPrepParams {
   const float* z;         // [2][N][C][L]
   const float* mask;      // [2][N][L]
   const float* gate_w;    // [C]
-  unsigned short* dza_t;  // [N][Lp][C] bf16
-  unsigned short* dzb_t;  // [N][Lp][C] bf16
+  unsigned short* dza16;  // [N][C][Lp] bf16
   unsigned short* dzb16;  // [N][C][Lp] bf16
-  unsigned short* dza16;  // [N][C][Lp] bf16 or null (only needed for counterpart gradients)
   float* d_vb;            // [N][C][L] or null: initialised with the passthrough gradient d_cat_b[:, C:2C]
   float* delta;           // [2][N][L]
   float* d_gate_w;        // [C]   (accumulated with atomics; caller zeroes)
@@ -206,136 +207,165 @@ struct BwdPrepParams {
 };
 
 constexpr int kBwdPrepThreads = 256;
-constexpr int kBwdStride = kC + 8;
+constexpr int kBwdPrepPos = 32;
+
+// sum over the 32 lanes of v[k] for every k: after the five exchange steps lane l holds the total of element
+// k = bitreverse5(l) ... expressed here simply as "the element this lane ends up with"; 31 shuffles instead of 160
+__device__ __forceinline__ float warp_multi_reduce32(float (&v)[32], int lane, int& owner) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const bool up = lane & 16;
+    const float send = up ? v[k] : v[k + 16];
+    const float keep = up ? v[k + 16] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool up = lane & 8;
+    const float send = up ? v[k] : v[k + 8];
+    const float keep = up ? v[k + 8] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool up = lane & 4;
+    const float send = up ? v[k] : v[k + 4];
+    const float keep = up ? v[k + 4] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool up = lane & 2;
+    const float send = up ? v[k] : v[k + 2];
+    const float keep = up ? v[k + 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  // bit b of the lane selected the upper half at the step of width b: element index = the lane bits read as written
+  owner = (lane & 16) | (lane & 8) | (lane & 4) | (lane & 2) | (lane & 1);
+  return v[0];
+}
 
 __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams p) {
-  __shared__ __align__(16) unsigned short tile[64 * kBwdStride];
-  __shared__ float red[4][64];
-  __shared__ float s_dta[64], s_ma[64], s_mb[64];
-  __shared__ float s_gw[kC];
-  __shared__ float s_gacc[kC];
+  __shared__ float red[8][kBwdPrepPos];
   const int n = blockIdx.y;
-  const int l0 = blockIdx.x * 64;
-  const int pos = threadIdx.x & 63;
-  const int cg = threadIdx.x >> 6;     // 4 channel groups of 64
-  const int l = l0 + pos;
+  const int lane = threadIdx.x & 31;
+  const int wrp = threadIdx.x >> 5;      // channels [32 wrp, 32 wrp + 32)
+  const int l = blockIdx.x * kBwdPrepPos + lane;
   const bool valid = l < p.L;
-  s_gw[threadIdx.x] = p.gate_w[threadIdx.x];
-  s_gacc[threadIdx.x] = 0.f;
-  const float* dca = p.d_cat_a + (size_t)n * 2 * kC * p.L;
-  const float* za = p.z + (size_t)n * kC * p.L;
-  const float* zb = p.z + (size_t)(p.N + n) * kC * p.L;
+  const int c0 = wrp * 32;
+  const float* dca = p.d_cat_a + ((size_t)n * 2 * kC + c0) * p.L + l;
+  const float* za = p.z + ((size_t)n * kC + c0) * p.L + l;
   const bool has_b = p.d_cat_b != nullptr;
-  const float* dcb = has_b ? p.d_cat_b + (size_t)n * 2 * kC * p.L : nullptr;
-  if (threadIdx.x < 64) {
-    const int ll = l0 + threadIdx.x;
-    s_ma[threadIdx.x] = ll < p.L ? p.mask[(size_t)n * p.L + ll] : 0.f;
-    s_mb[threadIdx.x] = ll < p.L ? p.mask[(size_t)(p.N + n) * p.L + ll] : 0.f;
-  }
-  // ---- pass 1: dot1 = sum_c dZag * Z_a
+  const float ma = valid ? __ldg(p.mask + (size_t)n * p.L + l) : 0.f;
+  const float mb = (valid && has_b) ? __ldg(p.mask + (size_t)(p.N + n) * p.L + l) : 0.f;
+
+  // ---- A side, pass 1: this thread's 32 channels of dZag and Z_a stay in registers
+  float g[32], zz[32];
   float acc = 0.f;
-  if (valid) {
-#pragma unroll 8
-    for (int k = 0; k < 64; ++k) {
-      const int c = cg * 64 + k;
-      acc = fmaf(__ldg(dca + (size_t)c * p.L + l), __ldg(za + (size_t)c * p.L + l), acc);
-    }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    g[k] = valid ? __ldcs(dca + (size_t)k * p.L) : 0.f;
+    zz[k] = valid ? __ldcs(za + (size_t)k * p.L) : 0.f;
   }
-  red[cg][pos] = acc;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc = fmaf(g[k], zz[k], acc);
+  red[wrp][lane] = acc;
   __syncthreads();
-  if (threadIdx.x < 64) {
-    const float dot1 = red[0][pos] + red[1][pos] + red[2][pos] + red[3][pos];
-    const float m = s_ma[pos];
-    s_dta[pos] = dot1 * m * (1.f - m);
-  }
+  float dta = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) dta += red[w][lane];
+  dta *= ma * (1.f - ma);
   __syncthreads();
-  // ---- pass 2 (A side): dZ_a, delta_a, d_gate_w partials, transposed tile
-  const float dta = s_dta[pos], ma = s_ma[pos];
+  // ---- pass 2: dZ_a, delta_a partial, d_gate_w partials
   float dl = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < 64; ++k) {
-    const int c = cg * 64 + k;
-    float dz = 0.f, zz = 0.f;
+  unsigned short* dza = p.dza16 + ((size_t)n * kC + c0) * p.Lp + l;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float dz = fmaf(__ldg(p.gate_w + c0 + k), dta, g[k] * ma);
+    dl = fmaf(dz, zz[k], dl);
+    dza[(size_t)k * p.Lp] = cvt16<true>(dz);     // positions >= L get 0 (g = 0, dta = 0)
+    zz[k] *= dta;                                // d_gate_w contribution of this position
+  }
+  red[wrp][lane] = dl;
+  int owner;
+  const float gsum = warp_multi_reduce32(zz, lane, owner);
+  atomicAdd(p.d_gate_w + c0 + owner, gsum);
+  // passthrough half of the concat -> gradient of V_a
+  {
+    const float* src = p.d_cat_a + ((size_t)n * 2 * kC + kC + c0) * p.L + l;
+    float* dst = p.d_va + ((size_t)n * kC + c0) * p.L + l;
     if (valid) {
-      zz = __ldg(za + (size_t)c * p.L + l);
-      dz = fmaf(s_gw[c], dta, __ldg(dca + (size_t)c * p.L + l) * ma);
-      // passthrough half of the concat -> gradient of V_a
-      p.d_va[((size_t)n * kC + c) * p.L + l] = __ldg(dca + (size_t)(kC + c) * p.L + l);
-    }
-    dl = fmaf(dz, zz, dl);
-    const unsigned short hz = cvt16<true>(dz);
-    tile[pos * kBwdStride + c] = hz;
-    if (p.dza16 != nullptr) p.dza16[((size_t)n * kC + c) * p.Lp + l] = hz;
-    // d_gate_w[c] += sum over the 64 positions of d_ta * Z_a  (warp reduce over positions, block total in shared memory)
-    float gsum = dta * zz;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_gacc[c], gsum);
-  }
-  red[cg][pos] = dl;
-  __syncthreads();
-  atomicAdd(p.d_gate_w + threadIdx.x, s_gacc[threadIdx.x]);   // one global atomic per channel and block
-  if (threadIdx.x < 64 && l0 + threadIdx.x < p.L) {
-    p.delta[(size_t)n * p.L + l0 + threadIdx.x] = red[0][pos] + red[1][pos] + red[2][pos] + red[3][pos];
-  }
-  if (p.d_gate_b != nullptr && threadIdx.x < 32) {
-    float t = s_dta[threadIdx.x] + s_dta[threadIdx.x + 32];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-    if (threadIdx.x == 0) atomicAdd(p.d_gate_b, t);
-  }
-  // transposed store: dza_t[l0 + r][c]
-  {
-    const int c8 = threadIdx.x & 31, r0 = threadIdx.x >> 5;
-    unsigned short* dst = p.dza_t + ((size_t)n * p.Lp + l0) * kC;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int r = r0 + 8 * k;
-      *reinterpret_cast<uint4*>(dst + (size_t)r * kC + 8 * c8) = *reinterpret_cast<const uint4*>(&tile[r * kBwdStride + 8 * c8]);
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, __ldcs(src + (size_t)k * p.L));
     }
   }
   __syncthreads();
-  // ---- pass 3 (B side): dZ_b = dZbg * m_b (mask is a constant), delta_b; both layouts
-  const float mb = s_mb[pos];
+  if (wrp == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    if (valid) p.delta[(size_t)n * p.L + l] = t;
+    if (p.d_gate_b != nullptr) {
+      float s = dta;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) atomicAdd(p.d_gate_b, s);
+    }
+  }
+  __syncthreads();
+  // ---- B side: dZ_b = dZbg * m_b (the mask is a constant), delta_b
   dl = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < 64; ++k) {
-    const int c = cg * 64 + k;
-    float dz = 0.f, zz = 0.f;
-    if (valid && has_b) {
-      zz = __ldg(zb + (size_t)c * p.L + l);
-      dz = __ldg(dcb + (size_t)c * p.L + l) * mb;
-      if (p.d_vb != nullptr) p.d_vb[((size_t)n * kC + c) * p.L + l] = __ldg(dcb + (size_t)(kC + c) * p.L + l);
-    } else if (valid && p.d_vb != nullptr) {
-      p.d_vb[((size_t)n * kC + c) * p.L + l] = 0.f;
-    }
-    dl = fmaf(dz, zz, dl);
-    const unsigned short h = cvt16<true>(dz);
-    tile[pos * kBwdStride + c] = h;
-    p.dzb16[((size_t)n * kC + c) * p.Lp + l] = h;
-  }
-  red[cg][pos] = dl;
-  __syncthreads();
-  if (threadIdx.x < 64 && l0 + threadIdx.x < p.L) {
-    p.delta[(size_t)(p.N + n) * p.L + l0 + threadIdx.x] = red[0][pos] + red[1][pos] + red[2][pos] + red[3][pos];
-  }
-  {
-    const int c8 = threadIdx.x & 31, r0 = threadIdx.x >> 5;
-    unsigned short* dst = p.dzb_t + ((size_t)n * p.Lp + l0) * kC;
+  unsigned short* dzb = p.dzb16 + ((size_t)n * kC + c0) * p.Lp + l;
+  if (has_b) {
+    const float* dcb = p.d_cat_b + ((size_t)n * 2 * kC + c0) * p.L + l;
+    const float* zb = p.z + ((size_t)(p.N + n) * kC + c0) * p.L + l;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int r = r0 + 8 * k;
-      *reinterpret_cast<uint4*>(dst + (size_t)r * kC + 8 * c8) = *reinterpret_cast<const uint4*>(&tile[r * kBwdStride + 8 * c8]);
+    for (int k = 0; k < 32; ++k) { g[k] = valid ? __ldcs(dcb + (size_t)k * p.L) : 0.f; zz[k] = valid ? __ldcs(zb + (size_t)k * p.L) : 0.f; }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float dz = g[k] * mb;
+      dl = fmaf(dz, zz[k], dl);
+      dzb[(size_t)k * p.Lp] = cvt16<true>(dz);
     }
+    if (p.d_vb != nullptr && valid) {
+      const float* src = dcb + (size_t)kC * p.L;
+      float* dst = p.d_vb + ((size_t)n * kC + c0) * p.L + l;
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, __ldcs(src + (size_t)k * p.L));
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) dzb[(size_t)k * p.Lp] = 0;
+    if (p.d_vb != nullptr && valid) {
+      float* dst = p.d_vb + ((size_t)n * kC + c0) * p.L + l;
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) dst[(size_t)k * p.L] = 0.f;
+    }
+  }
+  red[wrp][lane] = dl;
+  __syncthreads();
+  if (wrp == 0 && valid) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    p.delta[(size_t)(p.N + n) * p.L + l] = t;
   }
 }
 
 // ==============================================================================================
 // bwd_tile: the three [L, L] products of the backward and their elementwise combination in ONE persistent kernel.
 // Work item = one 128 x 128 tile (i-tile, j-tile) of one sample; nothing of size L x L is ever written in fp32:
-//   S    = Qt[i] Bt[j]^T      (forward operand format, so that exp(S - lse) is exactly the forward's softmax)
-//   dP_a = dZa_t[i] Bt[j]^T   (bf16)
-//   dP_b = At[i] dZb_t[j]^T   (bf16; HAS_B only)
+//   S    = Q[:, i]^T B[:, j]      (forward operand format, so that exp(S - lse) is exactly the forward's softmax)
+//   dP_a = dZ_a[:, i]^T B[:, j]   (bf16)
+//   dP_b = A[:, i]^T dZ_b[:, j]   (bf16; HAS_B only)
+// All six operands are read as MN-major tiles straight from channel-major planes [N][C][Lp] (positions contiguous,
+// channels = K), the orientation the forward pass and bwd_prep produce -- nothing is transposed for this kernel.
 //   dS = P_a (dP_a - delta_a[i]) + P_b (dP_b - delta_b[j]),   P_a = exp(S - lse_a[i]),  P_b = exp(S - lse_b[j])
 // written as bf16: dS, P_b (HAS_B) and P_a (counterpart gradients only).  TMEM: three 128-column accumulators.
 // One CTA per SM walks the tiles (i fastest, so the CTAs running together share a handful of j-tiles in L2); the TMA
@@ -385,7 +415,8 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
                 const __grid_constant__ CUtensorMap tm_atg, const __grid_constant__ CUtensorMap tm_dzb,
                 BwdTileParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // operand blocks per stage: Qt, Bt | dZa_t, Bt(bf16) | At(bf16), dZb_t   (128 rows x 64 channels = 16 KB each)
+  // operand blocks per stage: Q, B | dZ_a, B(bf16) | A(bf16), dZ_b   (64 channels x 128 positions = 16 KB each, stored as
+  // two 64-position chunks of 64 channel rows x 128 B, 128-byte swizzle)
   constexpr int kTileStages = HAS_B ? 2 : 3;
   constexpr int kTileStageBytes = (HAS_B ? 6 : 4) * 16384;
   uint8_t* smem = align_1024(smem_raw);
@@ -429,7 +460,7 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
       uint32_t cnt = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int n = t / per_sample, r = t - n * per_sample;
-        const int irow = n * p.Lp + (r % p.tiles_1d) * 128, jrow = n * p.Lp + (r / p.tiles_1d) * 128;
+        const int ipos = (r % p.tiles_1d) * 128, jpos = (r / p.tiles_1d) * 128;
         for (int kb = 0; kb < kNumKb; ++kb, ++cnt) {
           const uint32_t s = cnt % kTileStages, ph = (cnt / kTileStages) & 1;
           BT_T0();
@@ -437,13 +468,17 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
           BT_ACC(0);
           mbar_arrive_expect_tx(full + s, kTileStageBytes);
           uint8_t* st = smem + s * kTileStageBytes;
-          tma_load_2d(st + 0 * 16384, &tm_qt, full + s, kb * 64, irow);
-          tma_load_2d(st + 1 * 16384, &tm_bt, full + s, kb * 64, jrow);
-          tma_load_2d(st + 2 * 16384, &tm_dza, full + s, kb * 64, irow);
-          tma_load_2d(st + 3 * 16384, &tm_btg, full + s, kb * 64, jrow);
-          if (HAS_B) {
-            tma_load_2d(st + 4 * 16384, &tm_atg, full + s, kb * 64, irow);
-            tma_load_2d(st + 5 * 16384, &tm_dzb, full + s, kb * 64, jrow);
+          const int crow = n * kC + kb * 64;     // channel row of this k-block in a [N*C][Lp] plane
+#pragma unroll
+          for (int mc = 0; mc < 2; ++mc) {
+            tma_load_2d(st + 0 * 16384 + mc * 8192, &tm_qt, full + s, ipos + mc * 64, crow);
+            tma_load_2d(st + 1 * 16384 + mc * 8192, &tm_bt, full + s, jpos + mc * 64, crow);
+            tma_load_2d(st + 2 * 16384 + mc * 8192, &tm_dza, full + s, ipos + mc * 64, crow);
+            tma_load_2d(st + 3 * 16384 + mc * 8192, &tm_btg, full + s, jpos + mc * 64, crow);
+            if (HAS_B) {
+              tma_load_2d(st + 4 * 16384 + mc * 8192, &tm_atg, full + s, ipos + mc * 64, crow);
+              tma_load_2d(st + 5 * 16384 + mc * 8192, &tm_dzb, full + s, jpos + mc * 64, crow);
+            }
           }
         }
       }
@@ -463,17 +498,18 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
         BT_ACC(2);
         tc_fence_after();
         const uint32_t sb = base + s * kTileStageBytes;
-        const uint64_t d0 = make_sdesc_k_sw128(sb), d1 = make_sdesc_k_sw128(sb + 16384), d2 = make_sdesc_k_sw128(sb + 2 * 16384),
-                       d3 = make_sdesc_k_sw128(sb + 3 * 16384), d4 = make_sdesc_k_sw128(sb + 4 * 16384),
-                       d5 = make_sdesc_k_sw128(sb + 5 * 16384);
+        // MN-major tiles: 64-position chunks 8192 B apart (LBO), 8-channel groups 1024 B apart (SBO); 16 channels = 2048 B
+        const uint64_t d0 = make_sdesc_mn_sw128(sb, 8192, 1024), d1 = make_sdesc_mn_sw128(sb + 16384, 8192, 1024),
+                       d2 = make_sdesc_mn_sw128(sb + 2 * 16384, 8192, 1024), d3 = make_sdesc_mn_sw128(sb + 3 * 16384, 8192, 1024),
+                       d4 = make_sdesc_mn_sw128(sb + 4 * 16384, 8192, 1024), d5 = make_sdesc_mn_sw128(sb + 5 * 16384, 8192, 1024);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem, d0 + 2 * k, d1 + 2 * k, p.idesc_fwd, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_ss(tmem, d0 + 128 * k, d1 + 128 * k, p.idesc_fwd, (kb > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem + 128, d2 + 2 * k, d3 + 2 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_ss(tmem + 128, d2 + 128 * k, d3 + 128 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
           if (HAS_B) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tmem + 256, d4 + 2 * k, d5 + 2 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_ss(tmem + 256, d4 + 128 * k, d5 + 128 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty + s);
           if (kb == kNumKb - 1) umma_commit(d_full);

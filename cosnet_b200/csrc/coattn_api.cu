@@ -227,30 +227,25 @@ static int prep_and_project_fused(const float* v_a, const float* v_b, const floa
   return (int)cudaGetLastError();
 }
 
-// MN-major path: cast both frames (no transposes) + channel-major projection
-static int cast_and_project_mn(const float* v_a, const float* v_b, const float* w, void* workspace, int64_t workspace_bytes,
-                               int n, int c, int h, int w_, unsigned flags, void* stream) {
-  if (int e = check_dims(n, c, h, w_)) return e;
-  const Layout ly = make_layout(n, h, w_);
-  if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
-  if (int e = check_arch(nullptr)) return e;
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return COATTN_E_DRIVER;
-  const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  unsigned short* x = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv));
-  unsigned short* w16 = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16));
+// MN-major path: cast both frames (no transposes) + channel-major projection.
+//   x   [3][N][C][Lp] 16-bit planes: 0 = V_b, 1 = V_a (written by the cast), 2 = Q = W V_a (written by the projection)
+//   w16 [C][C] 16-bit copy of W
+static int cast_project_core(const float* v_a, const float* v_b, const float* w, unsigned short* x, unsigned short* w16,
+                             int n, const Layout& ly, bool bf16, bool project, cudaStream_t st) {
   CastParams cp;
   cp.va = v_a; cp.vb = v_b; cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp;
   const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   const dim3 cgrid(n * kC, 2);
   if (bf16) {
     if (vec) cast_kernel<true, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<true, 1><<<cgrid, 256, 0, st>>>(cp);
-    cast_w_kernel<true><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
   } else {
     if (vec) cast_kernel<false, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<false, 1><<<cgrid, 256, 0, st>>>(cp);
-    cast_w_kernel<false><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
   }
+  if (!project) return (int)cudaGetLastError();
+  if (bf16) cast_w_kernel<true><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+  else cast_w_kernel<false><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return COATTN_E_DRIVER;
   CUtensorMap tm_w, tm_x;
   if (int e = make_tmap(enc, &tm_w, w16, kC, kC, 128, bf16)) return e;
   if (int e = make_tmap(enc, &tm_x, x, (uint64_t)3 * n * kC, ly.Lp, 256, bf16)) return e;
@@ -267,6 +262,17 @@ static int cast_and_project_mn(const float* v_a, const float* v_b, const float* 
   if (e != cudaSuccess) return (int)e;
   kern<<<pp.num_tiles < sms ? pp.num_tiles : sms, kNumThreads, kProjMnSmemBytes, st>>>(tm_w, tm_x, pp);
   return (int)cudaGetLastError();
+}
+
+static int cast_and_project_mn(const float* v_a, const float* v_b, const float* w, void* workspace, int64_t workspace_bytes,
+                               int n, int c, int h, int w_, unsigned flags, void* stream) {
+  if (int e = check_dims(n, c, h, w_)) return e;
+  const Layout ly = make_layout(n, h, w_);
+  if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
+  if (int e = check_arch(nullptr)) return e;
+  return cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
+                           reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
+                           (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int coattn_stage_prep_project(const float* v_a, const float* v_b, const float* w, void* workspace,
@@ -475,10 +481,10 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
 namespace {
 struct BwdLayout {
   Layout fwd;
-  int64_t off_g;   // second copy of the forward operand segments, always bf16 (operands of the gradient GEMMs)
-  int64_t off_dza_t, off_dzb_t, off_dzb16, off_delta, off_ds, off_pb, off_dqt, off_dq16, off_wt, total;
-  // counterpart gradients only (d_v_b requested): dZ_a in [C][Lp], P_a, dS^T, P_a^T, Q in [C][Lp]
-  int64_t off_dza16, off_pa, off_ds_t, off_pa_t, off_q16, total_counterpart;
+  int64_t off_g;   // bf16 copies of the channel-major planes [B16, A16, (Q16)] (operands of the gradient GEMMs)
+  int64_t off_w16g, off_dza16, off_dzb16, off_delta, off_ds, off_pb, off_dqt, off_dq16, off_wt, total;
+  // counterpart gradients only (d_v_b requested): P_a, dS^T, P_a^T
+  int64_t off_pa, off_ds_t, off_pa_t, total_counterpart;
 };
 BwdLayout make_bwd_layout(int n, int h, int w) {
   BwdLayout b{};
@@ -488,17 +494,22 @@ BwdLayout make_bwd_layout(int n, int h, int w) {
   const int64_t mat16 = (int64_t)n * Lp * Lp * 2;
   int64_t off = b.fwd.total;
   auto take = [&](int64_t bytes) { const int64_t o = off; off = round_up(off + bytes, kAlign); return o; };
-  b.off_g = take(b.fwd.total);
-  b.off_dza_t = take(plane); b.off_dzb_t = take(plane); b.off_dzb16 = take(plane);
+  b.off_g = take(3 * plane);
+  b.off_w16g = take((int64_t)kC * kC * 2);
+  b.off_dza16 = take(plane); b.off_dzb16 = take(plane);
   b.off_delta = take((int64_t)2 * n * L * 4);
   b.off_ds = take(mat16); b.off_pb = take(mat16);
   b.off_dqt = take(plane); b.off_dq16 = take(plane);
   b.off_wt = take((int64_t)kC * kC * 2);
   b.total = off;
-  b.off_dza16 = take(plane); b.off_pa = take(mat16); b.off_ds_t = take(mat16); b.off_pa_t = take(mat16);
-  b.off_q16 = take(plane);
+  b.off_pa = take(mat16); b.off_ds_t = take(mat16); b.off_pa_t = take(mat16);
   b.total_counterpart = off;
   return b;
+}
+
+// 16-bit tensor map over channel-major planes [rows][Lp] with a {64 positions, 64 channels} box (MN-major operand chunks)
+int make_plane_tmap(EncodeTiledFn enc, CUtensorMap* out, const void* base, uint64_t rows, uint64_t lp, bool bf16) {
+  return make_tmap(enc, out, base, rows, lp, 64, bf16);
 }
 
 template <int MODE>
@@ -549,25 +560,25 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   const int L = ly.L, Lp = ly.Lp;
   const int64_t plane_elems = ly.t_pass_elems();
 
-  // Operands of the forward pass are regenerated rather than kept alive between forward and backward.
-  // S must be recomputed from exactly the operands the forward used (format `flags`), so that exp(S - lse) is the
-  // forward's softmax; every other GEMM multiplies by a bf16 gradient operand, and tcgen05 kind::f16 requires both
-  // operands in the same format, so with an fp16 forward a second, bf16 set of operands is prepared.
-  if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
-  if (int e = coattn_stage_project(workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
-  void* gws = workspace;
+  // Operands of the forward pass are regenerated rather than kept alive between forward and backward: the 16-bit
+  // channel-major planes X = [B16, A16, Q16] in the forward's format (S must be recomputed from exactly the operands the
+  // forward used, so that exp(S - lse) is the forward's softmax).  Every other product multiplies by a bf16 gradient
+  // operand, and tcgen05 kind::f16 needs both operands in one format, so with an fp16 forward a second, bf16 copy of
+  // the planes is cast as well (its Q16 plane is only needed for counterpart gradients).
+  if (int e = cast_and_project_mn(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+  unsigned short* xf = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv));     // forward format
+  unsigned short* xg = xf;                                                                // bf16
   if (!fbf16) {
-    gws = seg(workspace, bl.off_g);
-    if (int e = coattn_stage_prep(v_a, v_b, w, gws, ly.total, n, c, h, w_, COATTN_FLAG_BF16, stream)) return e;
+    xg = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_g));
+    if (int e = cast_project_core(v_a, v_b, w, xg, reinterpret_cast<unsigned short*>(seg(workspace, bl.off_w16g)), n, ly, true,
+                                  counterpart, st))
+      return e;
   }
-  unsigned short* bt = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_t));       // forward format
-  unsigned short* qt = bt + plane_elems;                                                  // forward format
-  unsigned short* bt_g = reinterpret_cast<unsigned short*>(seg(gws, ly.off_t));           // bf16
-  unsigned short* at = reinterpret_cast<unsigned short*>(seg(gws, ly.off_at));            // bf16
-  unsigned short* b16 = reinterpret_cast<unsigned short*>(seg(gws, ly.off_vv));           // bf16
-  unsigned short* a16 = b16 + plane_elems;                                                // bf16
-  unsigned short* dza_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dza_t));
-  unsigned short* dzb_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb_t));
+  unsigned short* b16f = xf;                              // B, forward format
+  unsigned short* q16f = xf + 2 * plane_elems;            // Q, forward format
+  unsigned short* b16 = xg;                               // B, bf16
+  unsigned short* a16 = xg + plane_elems;                 // A, bf16
+  unsigned short* dza16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dza16));
   unsigned short* dzb16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb16));
   float* delta = reinterpret_cast<float*>(seg(workspace, bl.off_delta));
   unsigned short* ds = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_ds));
@@ -583,16 +594,13 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
 
   BwdPrepParams bp;
   bp.d_cat_a = d_cat_a; bp.d_cat_b = d_cat_b; bp.z = z; bp.mask = mask; bp.gate_w = gate_w;
-  unsigned short* dza16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dza16));
   unsigned short* pa = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa));
   unsigned short* ds_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_ds_t));
   unsigned short* pa_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa_t));
-  unsigned short* q16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_q16));
-  bp.dza16 = counterpart ? dza16 : nullptr;
   bp.d_vb = d_v_b;
-  bp.dza_t = dza_t; bp.dzb_t = dzb_t; bp.dzb16 = dzb16; bp.delta = delta;
+  bp.dza16 = dza16; bp.dzb16 = dzb16; bp.delta = delta;
   bp.d_gate_w = d_gate_w; bp.d_gate_b = d_gate_b; bp.d_va = d_v_a; bp.N = n; bp.L = L; bp.Lp = Lp;
-  bwd_prep_kernel<<<dim3(Lp / 64, n), kBwdPrepThreads, 0, st>>>(bp);
+  bwd_prep_kernel<<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
   transpose_w_kernel<<<kC, kC, 0, st>>>(w, wt);
   if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
 
@@ -602,20 +610,21 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   {
     // S, dP_a, dP_b and their combination: one kernel, one 128 x 128 tile per CTA, outputs bf16 dS / P_b (/ P_a)
     CUtensorMap t_qt, t_bt, t_dza, t_btg, t_atg, t_dzb;
-    if (int e = make_tmap(enc, &t_qt, qt, rowsL, kC, 128, fbf16)) return e;
-    if (int e = make_tmap(enc, &t_bt, bt, rowsL, kC, 128, fbf16)) return e;
-    if (int e = make_tmap(enc, &t_dza, dza_t, rowsL, kC, 128, true)) return e;
-    if (int e = make_tmap(enc, &t_btg, bt_g, rowsL, kC, 128, true)) return e;
-    if (int e = make_tmap(enc, &t_atg, at, rowsL, kC, 128, true)) return e;
-    if (int e = make_tmap(enc, &t_dzb, dzb_t, rowsL, kC, 128, true)) return e;
+    if (int e = make_plane_tmap(enc, &t_qt, q16f, rowsC, Lp, fbf16)) return e;
+    if (int e = make_plane_tmap(enc, &t_bt, b16f, rowsC, Lp, fbf16)) return e;
+    if (int e = make_plane_tmap(enc, &t_dza, dza16, rowsC, Lp, true)) return e;
+    if (int e = make_plane_tmap(enc, &t_btg, b16, rowsC, Lp, true)) return e;
+    if (int e = make_plane_tmap(enc, &t_atg, a16, rowsC, Lp, true)) return e;
+    if (int e = make_plane_tmap(enc, &t_dzb, dzb16, rowsC, Lp, true)) return e;
     BwdTileParams tp;
     tp.lse = lse; tp.delta = delta; tp.ds = ds; tp.pb = pb;
     tp.pa = counterpart ? reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa)) : nullptr;
     tp.N = n; tp.L = L; tp.Lp = Lp;
     tp.tiles_1d = lt; tp.num_tiles = n * lt * lt;
     const uint32_t f = fbf16 ? 1u : 0u;
-    tp.idesc_fwd = (1u << 4) | (f << 7) | (f << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-    tp.idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    (void)f;
+    tp.idesc_fwd = make_idesc_16_major(128, 128, fbf16, true, true);    // both operands MN-major
+    tp.idesc_bf16 = make_idesc_16_major(128, 128, true, true, true);
     auto kern = has_b ? bwd_tile_kernel<true> : bwd_tile_kernel<false>;
     if ((ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes)) != cudaSuccess)
       return (int)ce;
@@ -644,11 +653,8 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
     transpose16_kernel<<<dim3(Lp / 32, Lp / 32, n), 256, 0, st>>>(ds, ds_t, Lp);
     transpose16_kernel<<<dim3(Lp / 32, Lp / 32, n), 256, 0, st>>>(pa, pa_t, Lp);
     if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
-    // Q16[c][i] = sum_d W[c][d] A[d][i]  (bf16, channel-major): A operand W16 (bf16 copy in the gradient operand set)
-    unsigned short* w16g = reinterpret_cast<unsigned short*>(seg(gws, ly.off_w16));
-    gp.out0 = q16; gp.ld0 = Lp; gp.rows0 = kC; gp.out1 = nullptr; gp.m_valid = kC;
-    gp.a_rows_per_batch = 0; gp.b_rows_per_batch = Lp;
-    if (int e = launch_gemm<kGemmStore16>(enc, st, w16g, kC, true, at, rowsL, true, kC, kC / 128, lt, n, gp)) return e;
+    // Q in bf16, channel-major: plane 2 of the bf16 operand set (projected above when counterpart gradients are on)
+    unsigned short* q16 = xg + 2 * plane_elems;
     gp.out0 = d_v_b; gp.ld0 = L; gp.rows0 = kC; gp.m_valid = L;
     gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = kC;
     if (int e = launch_gemm<kGemmAddF32T>(enc, st, ds_t, rowsL, true, q16, rowsC, true, Lp, lt, kC / 128, n, gp)) return e;
