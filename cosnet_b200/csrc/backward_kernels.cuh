@@ -42,7 +42,8 @@ struct GemmParams {
   int64_t rows0, rows1;    // rows per batch entry of out0 / out1
   int a_rows_per_batch;    // row offset between batch entries in the A / B tensor maps
   int b_rows_per_batch;
-  int num_kb;              // K / 64
+  int num_kb;              // K / 64 handled by one CTA
+  int k_split;             // CTAs per batch entry along K (atomic mode only); blockIdx.z = b * k_split + slice
   int m_valid;             // rows m >= m_valid are not stored
   uint32_t idesc;          // instruction descriptor (M128 N128, operand formats)
 };
@@ -64,7 +65,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K]
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
   const int n0 = blockIdx.y * 128;
-  const int b = blockIdx.z;
+  const int b = blockIdx.z / p.k_split;
+  const int kb0 = (blockIdx.z % p.k_split) * p.num_kb;   // first 64-element k-block of this CTA's K slice
 
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -91,8 +93,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K]
         const uint32_t ph = (kb / kGemmStages) & 1;
         mbar_wait(empty + s, ph ^ 1, 30);
         mbar_arrive_expect_tx(full + s, kGemmStageBytes);
-        tma_load_2d(smem + s * kGemmStageBytes, &tmap_a, full + s, kb * 64, arow);
-        tma_load_2d(smem + s * kGemmStageBytes + 16384, &tmap_b, full + s, kb * 64, brow);
+        tma_load_2d(smem + s * kGemmStageBytes, &tmap_a, full + s, (kb0 + kb) * 64, arow);
+        tma_load_2d(smem + s * kGemmStageBytes + 16384, &tmap_b, full + s, (kb0 + kb) * 64, brow);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -165,9 +167,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K]
           for (int k = 0; k < 32; ++k) o[(int64_t)k * p.ld0] = old[k] + __uint_as_float(v[k]);
         }
       } else {
+        // vectorised reductions (4 floats per operation): the row of a thread is contiguous in the output
         float* o = static_cast<float*>(p.out0) + (int64_t)m * p.ld0 + n;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) atomicAdd(o + k, __uint_as_float(v[k]));
+        for (int k = 0; k < 32; k += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + k), "f"(__uint_as_float(v[k])),
+                       "f"(__uint_as_float(v[k + 1])), "f"(__uint_as_float(v[k + 2])), "f"(__uint_as_float(v[k + 3]))
+                       : "memory");
       }
     }
     tc_fence_before();
@@ -301,8 +307,11 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
     const float* src = p.d_cat_a + ((size_t)n * 2 * kC + kC + c0) * p.L + l;
     float* dst = p.d_va + ((size_t)n * kC + c0) * p.L + l;
     if (valid) {
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, __ldcs(src + (size_t)k * p.L));
+      float t[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) t[k] = __ldcs(src + (size_t)k * p.L);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, t[k]);
     }
   }
   __syncthreads();
@@ -336,18 +345,20 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
     if (p.d_vb != nullptr && valid) {
       const float* src = dcb + (size_t)kC * p.L;
       float* dst = p.d_vb + ((size_t)n * kC + c0) * p.L + l;
-#pragma unroll 8
-      for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, __ldcs(src + (size_t)k * p.L));
+#pragma unroll
+      for (int k = 0; k < 32; ++k) g[k] = __ldcs(src + (size_t)k * p.L);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, g[k]);
     }
   } else {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) dzb[(size_t)k * p.Lp] = 0;
+    // depth modality: the B branch is gradient dead, nothing reads dZ_b or delta_b
     if (p.d_vb != nullptr && valid) {
       float* dst = p.d_vb + ((size_t)n * kC + c0) * p.L + l;
 #pragma unroll 8
       for (int k = 0; k < 32; ++k) dst[(size_t)k * p.L] = 0.f;
     }
   }
+  if (!has_b) return;
   red[wrp][lane] = dl;
   __syncthreads();
   if (wrp == 0 && valid) {
@@ -425,9 +436,13 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(colv + 512);
   uint64_t* full = bars;
   uint64_t* empty = bars + kTileStages;
-  uint64_t* d_full = empty + kTileStages;
-  uint64_t* d_empty = d_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 1);
+  // accumulator sets in TMEM: S | dP_a | dP_b = 384 columns with the B branch (one set), 256 without (two sets, so
+  // the epilogue of one tile overlaps the MMAs of the next)
+  constexpr int kAccSets = HAS_B ? 1 : 2;
+  constexpr uint32_t kAccStride = 256;
+  uint64_t* d_full = empty + kTileStages;      // [2]
+  uint64_t* d_empty = d_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -440,8 +455,7 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
     tma_prefetch_desc(&tm_qt); tma_prefetch_desc(&tm_bt); tma_prefetch_desc(&tm_dza);
     tma_prefetch_desc(&tm_btg); tma_prefetch_desc(&tm_atg); tma_prefetch_desc(&tm_dzb);
     for (int s = 0; s < kTileStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    mbar_init(d_full, 1);
-    mbar_init(d_empty, 8);
+    for (int a = 0; a < 2; ++a) { mbar_init(d_full + a, 1); mbar_init(d_empty + a, 8); }
     fence_mbar_init();
   }
   if (warp == kTileMmaWarp) {
@@ -487,8 +501,10 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
     const uint32_t base = smem_u32(smem);
     uint32_t cnt = 0, it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const uint32_t acc = it % kAccSets, aph = (it / kAccSets) & 1;
+      const uint32_t tacc = tmem + acc * kAccStride;
       BT_T0();
-      warp_mbar_wait(d_empty, (it & 1) ^ 1, lane, 43);   // the epilogue has read the previous tile's accumulators
+      warp_mbar_wait(d_empty + acc, aph ^ 1, lane, 43);   // the epilogue has read this set's previous accumulators
       BT_ACC(1);
       tc_fence_after();
       for (int kb = 0; kb < kNumKb; ++kb, ++cnt) {
@@ -504,15 +520,15 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
                        d4 = make_sdesc_mn_sw128(sb + 4 * 16384, 8192, 1024), d5 = make_sdesc_mn_sw128(sb + 5 * 16384, 8192, 1024);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem, d0 + 128 * k, d1 + 128 * k, p.idesc_fwd, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_ss(tacc, d0 + 128 * k, d1 + 128 * k, p.idesc_fwd, (kb > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem + 128, d2 + 128 * k, d3 + 128 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_ss(tacc + 128, d2 + 128 * k, d3 + 128 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
           if (HAS_B) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tmem + 256, d4 + 128 * k, d5 + 128 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_ss(tacc + 256, d4 + 128 * k, d5 + 128 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty + s);
-          if (kb == kNumKb - 1) umma_commit(d_full);
+          if (kb == kNumKb - 1) umma_commit(d_full + acc);
         }
         __syncwarp();
       }
@@ -568,13 +584,14 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
       const bool vi = i < p.L;
       const float nlse_a = -nla * kLog2e;
       const float del_a = nda;
-      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 64;
+      const uint32_t acc = it % kAccSets, aph = (it / kAccSets) & 1;
+      const uint32_t taddr = tmem + acc * kAccStride + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * 64;
       // element offset of (first row of this warp, first column of this warp's half) in the [N][Lp][Lp] outputs
       const size_t tile_off = ((size_t)n * p.Lp + i0 + quad * 32) * p.Lp + j0 + half * 64;
       const bool ragged = (i0 + 128 > p.L) || (j0 + 128 > p.L);   // tile-uniform: interior tiles need no masking
       if (t + (int)gridDim.x < p.num_tiles) fetch(t + gridDim.x, nx, nla, nda);
       BT_ACC(3);
-      warp_mbar_wait(d_full, it & 1, lane, 42);
+      warp_mbar_wait(d_full + acc, aph, lane, 42);
       BT_ACC(4);
       tc_fence_after();
 #pragma unroll 1
@@ -586,7 +603,7 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
         tmem_ld_wait();
         if (ch == 1) {   // everything this warp needs from TMEM is in registers: release the accumulators early
           tc_fence_before();
-          warp_mbar_arrive(d_empty, lane);
+          warp_mbar_arrive(d_empty + acc, lane);
         }
         const int jl0 = half * 64 + ch * 32;
         auto combine = [&](auto masked_tag) {

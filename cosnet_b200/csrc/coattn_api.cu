@@ -514,16 +514,18 @@ int make_plane_tmap(EncodeTiledFn enc, CUtensorMap* out, const void* base, uint6
 
 template <int MODE>
 int launch_gemm(EncodeTiledFn enc, cudaStream_t st, const void* a, uint64_t a_rows, bool a_bf16, const void* b,
-                uint64_t b_rows, bool b_bf16, uint64_t k, int m_tiles, int n_tiles, int batch, GemmParams gp) {
+                uint64_t b_rows, bool b_bf16, uint64_t k, int m_tiles, int n_tiles, int batch, GemmParams gp,
+                int k_split = 1) {
   CUtensorMap ta, tb;
   if (int e = make_tmap(enc, &ta, a, a_rows, k, 128, a_bf16)) return e;
   if (int e = make_tmap(enc, &tb, b, b_rows, k, 128, b_bf16)) return e;
-  gp.num_kb = (int)(k / 64);
+  gp.num_kb = (int)(k / 64) / k_split;     // callers pick k_split as a divisor of K / 64
+  gp.k_split = k_split;
   gp.idesc = (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
   auto kern = gemm_nt_kernel<MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  kern<<<dim3(m_tiles, n_tiles, batch), kNumThreads, kGemmSmemBytes, st>>>(ta, tb, gp);
+  kern<<<dim3(m_tiles, n_tiles, batch * k_split), kNumThreads, kGemmSmemBytes, st>>>(ta, tb, gp);
   return (int)cudaGetLastError();
 }
 }  // namespace
@@ -647,7 +649,12 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   // dW[d][c] += sum_n sum_i dQ16[n][d][i] A16[n][c][i]
   gp.out0 = d_w; gp.ld0 = kC; gp.rows0 = 0; gp.m_valid = kC;
   gp.a_rows_per_batch = kC; gp.b_rows_per_batch = kC;
-  if (int e = launch_gemm<kGemmAtomicF32>(enc, st, dq16, rowsC, true, a16, rowsC, true, Lp, kC / 128, kC / 128, n, gp)) return e;
+  // only 4 output tiles per sample: split the position range over several CTAs (the atomics already reduce over n)
+  int dw_split = 1;
+  for (int cand = 2; cand <= 8; ++cand)
+    if ((Lp / 64) % cand == 0 && 4 * n * cand <= 2 * sms) dw_split = cand;
+  if (int e = launch_gemm<kGemmAtomicF32>(enc, st, dq16, rowsC, true, a16, rowsC, true, Lp, kC / 128, kC / 128, n, gp, dw_split))
+    return e;
   if (counterpart) {
     // dB[c][j] = sum_i Q[c][i] dS[i][j] + sum_i dZ_a[c][i] P_a[i][j]   (+ passthrough, written by bwd_prep)
     transpose16_kernel<<<dim3(Lp / 32, Lp / 32, n), 256, 0, st>>>(ds, ds_t, Lp);
