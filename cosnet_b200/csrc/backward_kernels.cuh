@@ -594,56 +594,62 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
       warp_mbar_wait(d_full + acc, aph, lane, 42);
       BT_ACC(4);
       tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t sv[32], av[32], bv[32];
-        tmem_ld32(taddr + ch * 32, sv);
-        tmem_ld32(taddr + 128 + ch * 32, av);
-        if (HAS_B) tmem_ld32(taddr + 256 + ch * 32, bv);
-        tmem_ld_wait();
-        if (ch == 1) {   // everything this warp needs from TMEM is in registers: release the accumulators early
-          tc_fence_before();
-          warp_mbar_arrive(d_empty + acc, lane);
-        }
-        const int jl0 = half * 64 + ch * 32;
-        auto combine = [&](auto masked_tag) {
-          constexpr bool MASKED = decltype(masked_tag)::value;
-          // in place: sv <- P_a pairs (low half) ... the three results are packed into av (dS), bv (P_b), sv (P_a)
+      // Chunk 0 (32 columns) is combined in place (its packed results fit in half of the registers it arrived in), then
+      // chunk 1 is pulled out of TMEM and the accumulators are released BEFORE anything is written to memory, so the
+      // next tile's MMAs overlap both flushes and the second combine.
+      auto combine = [&](uint32_t (&sv)[32], uint32_t (&av)[32], uint32_t (&bv)[32], int jl0, auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {          // 4 columns per step
-            float4 nl = make_float4(0.f, 0.f, 0.f, 0.f), db = nl;
-            if (HAS_B) {
-              nl = *reinterpret_cast<const float4*>(cv + jl0 + 4 * g);
-              db = *reinterpret_cast<const float4*>(cv + 128 + jl0 + 4 * g);
-            }
-            const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, dbv[4] = {db.x, db.y, db.z, db.w};
-            float d[4], pa[4], pb[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int k = 4 * g + e;
-              const float sx = __uint_as_float(sv[k]);
-              float a = fast_exp2(fmaf(sx, kLog2e, nlse_a));
-              float b = HAS_B ? fast_exp2(fmaf(sx, kLog2e, nlv[e])) : 0.f;
-              if (MASKED) {
-                const bool ok = vi && (j0 + jl0 + k) < p.L;
-                a = ok ? a : 0.f;
-                b = ok ? b : 0.f;
-              }
-              float dd = a * (__uint_as_float(av[k]) - del_a);
-              if (HAS_B) dd = fmaf(b, __uint_as_float(bv[k]) - dbv[e], dd);
-              d[e] = dd; pa[e] = a; pb[e] = b;
-            }
-            // columns 4g..4g+3 are consumed: reuse the first half of the arrays for the packed results
-            av[2 * g] = pack_bf16x2(d[0], d[1]);  av[2 * g + 1] = pack_bf16x2(d[2], d[3]);
-            sv[2 * g] = pack_bf16x2(pa[0], pa[1]); sv[2 * g + 1] = pack_bf16x2(pa[2], pa[3]);
-            if (HAS_B) { bv[2 * g] = pack_bf16x2(pb[0], pb[1]); bv[2 * g + 1] = pack_bf16x2(pb[2], pb[3]); }
+        for (int g = 0; g < 8; ++g) {          // 4 columns per step
+          float4 nl = make_float4(0.f, 0.f, 0.f, 0.f), db = nl;
+          if (HAS_B) {
+            nl = *reinterpret_cast<const float4*>(cv + jl0 + 4 * g);
+            db = *reinterpret_cast<const float4*>(cv + 128 + jl0 + 4 * g);
           }
-        };
-        if (ragged) combine(std::true_type{}); else combine(std::false_type{});
-        flush(p.ds, tile_off + ch * 32, av);
-        if (HAS_B) flush(p.pb, tile_off + ch * 32, bv);
-        if (p.pa != nullptr) flush(p.pa, tile_off + ch * 32, sv);
-      }
+          const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, dbv[4] = {db.x, db.y, db.z, db.w};
+          float d[4], pa[4], pb[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = 4 * g + e;
+            const float sx = __uint_as_float(sv[k]);
+            float a = fast_exp2(fmaf(sx, kLog2e, nlse_a));
+            float b = HAS_B ? fast_exp2(fmaf(sx, kLog2e, nlv[e])) : 0.f;
+            if (MASKED) {
+              const bool ok = vi && (j0 + jl0 + k) < p.L;
+              a = ok ? a : 0.f;
+              b = ok ? b : 0.f;
+            }
+            float dd = a * (__uint_as_float(av[k]) - del_a);
+            if (HAS_B) dd = fmaf(b, __uint_as_float(bv[k]) - dbv[e], dd);
+            d[e] = dd; pa[e] = a; pb[e] = b;
+          }
+          // columns 4g..4g+3 are consumed: the first half of each array receives the packed results
+          // (av <- dS, bv <- P_b, sv <- P_a)
+          av[2 * g] = pack_bf16x2(d[0], d[1]);  av[2 * g + 1] = pack_bf16x2(d[2], d[3]);
+          sv[2 * g] = pack_bf16x2(pa[0], pa[1]); sv[2 * g + 1] = pack_bf16x2(pa[2], pa[3]);
+          if (HAS_B) { bv[2 * g] = pack_bf16x2(pb[0], pb[1]); bv[2 * g + 1] = pack_bf16x2(pb[2], pb[3]); }
+        }
+      };
+      const int jl = half * 64;
+      uint32_t s0[32], a0[32], b0[32], s1[32], a1[32], b1[32];
+      tmem_ld32(taddr, s0);
+      tmem_ld32(taddr + 128, a0);
+      if (HAS_B) tmem_ld32(taddr + 256, b0);
+      tmem_ld_wait();
+      if (ragged) combine(s0, a0, b0, jl, std::true_type{}); else combine(s0, a0, b0, jl, std::false_type{});
+      tmem_ld32(taddr + 32, s1);
+      tmem_ld32(taddr + 128 + 32, a1);
+      if (HAS_B) tmem_ld32(taddr + 256 + 32, b1);
+      tmem_ld_wait();
+      tc_fence_before();
+      warp_mbar_arrive(d_empty + acc, lane);   // everything this warp needs from TMEM is in registers
+      flush(p.ds, tile_off, a0);
+      if (HAS_B) flush(p.pb, tile_off, b0);
+      if (p.pa != nullptr) flush(p.pa, tile_off, s0);
+      if (ragged) combine(s1, a1, b1, jl + 32, std::true_type{}); else combine(s1, a1, b1, jl + 32, std::false_type{});
+      flush(p.ds, tile_off + 32, a1);
+      if (HAS_B) flush(p.pb, tile_off + 32, b1);
+      if (p.pa != nullptr) flush(p.pa, tile_off + 32, s1);
       BT_ACC(5);
     }
   }

@@ -55,7 +55,10 @@ def test_golden_gradients_of_the_reference(coattention):
 
 
 @pytest.mark.parametrize("n,h,w,bias,with_b", [(1, 12, 11, False, True), (2, 12, 11, True, True), (1, 12, 11, True, False),
-                                               (2, 20, 20, True, True), (1, 31, 41, False, True)])
+                                               (2, 20, 20, True, True), (1, 31, 41, False, True),
+                                               # more 128 x 128 tiles than SMs: every CTA of the persistent tile kernel walks
+                                               # several tiles (ring and accumulator phases wrap); depth variant included
+                                               (2, 31, 41, False, True), (4, 31, 41, True, False), (1, 60, 60, False, True)])
 def test_gradients_against_oracle(coattention, n, h, w, bias, with_b):
     v_a, v_b = orc.synthetic_features(300 + h * w, n, h, w, 0.66)
     W, g, b = orc.synthetic_weights(301 + h * w, bias=bias)
