@@ -260,7 +260,7 @@ static int cast_project_core(const float* v_a, const float* v_b, const float* w,
   auto kern = bf16 ? project_mn_kernel<true> : project_mn_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjMnSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  kern<<<pp.num_tiles < sms ? pp.num_tiles : sms, kNumThreads, kProjMnSmemBytes, st>>>(tm_w, tm_x, pp);
+  kern<<<pp.num_tiles < sms ? pp.num_tiles : sms, kProjMnThreads, kProjMnSmemBytes, st>>>(tm_w, tm_x, pp);
   return (int)cudaGetLastError();
 }
 

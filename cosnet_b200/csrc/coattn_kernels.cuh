@@ -437,7 +437,10 @@ __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
 
 constexpr int kProjMnTile = 64;            // positions per tile
 constexpr int kProjMnXStages = 2;
-constexpr int kProjMnSmemBytes = 128 * 1024 + kProjMnXStages * 32 * 1024 + 1024 + 128;
+constexpr int kProjMnThreads = 320;          // warps 0-7 epilogue (TMEM lane quadrant x m-tile), 8 TMA producer, 9 MMA issuer
+constexpr int kProjMnProducerWarp = 8;
+constexpr int kProjMnMmaWarp = 9;
+constexpr int kProjMnSmemBytes = 128 * 1024 + kProjMnXStages * 32 * 1024 + 8 * 4096 /*store staging*/ + 1024 + 128;
 
 struct ProjectMnParams {
   unsigned short* q16;   // X plane 2: [N][C][Lp]
@@ -450,7 +453,7 @@ struct ProjectMnParams {
 // Persistent: W16 (128 KB) is loaded once per CTA and stays in shared memory; 64-position tiles of A16 stream through
 // a 2-stage ring; two TMEM accumulator sets let the drain of tile t overlap the MMAs of tile t+1.
 template <bool BF16>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kProjMnThreads, 1)
 project_mn_kernel(const __grid_constant__ CUtensorMap tmap_w,   // W16 [C][C], box {64, 128}
                   const __grid_constant__ CUtensorMap tmap_x,   // X [3*N*C][Lp], box {64, 256}
                   ProjectMnParams p) {
@@ -458,26 +461,27 @@ project_mn_kernel(const __grid_constant__ CUtensorMap tmap_w,   // W16 [C][C], b
   uint8_t* smem = align_1024(smem_raw);
   uint8_t* sW = smem;                 // 2 m-tiles x 4 k-blocks x [128 rows x 128 B] = 128 KB
   uint8_t* sX = smem + 128 * 1024;    // stages x [256 channel rows x 128 B (64 positions)]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + kProjMnXStages * 32768);
+  uint8_t* sOut = sX + kProjMnXStages * 32768;      // 8 warps x [32 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 8 * 4096);
   uint64_t* w_full = bars + 0;
   uint64_t* x_full = bars + 1;                      // [2]
   uint64_t* x_empty = x_full + kProjMnXStages;      // [2]
   uint64_t* d_full = x_empty + kProjMnXStages;      // [2]
-  uint64_t* d_empty = d_full + 2;                   // [2] 4 arrivals (epilogue warps)
+  uint64_t* d_empty = d_full + 2;                   // [2] 8 arrivals (epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == kProducerWarp && lane == 0) {
+  if (warp == kProjMnProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_x);
     mbar_init(w_full, 1);
     for (int s = 0; s < kProjMnXStages; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(d_full + b, 1); mbar_init(d_empty + b, 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(d_full + b, 1); mbar_init(d_empty + b, 8); }
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) {
+  if (warp == kProjMnMmaWarp) {
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
@@ -486,7 +490,7 @@ project_mn_kernel(const __grid_constant__ CUtensorMap tmap_w,   // W16 [C][C], b
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == kProducerWarp) {
+  if (warp == kProjMnProducerWarp) {
     if (lane == 0) {
       mbar_arrive_expect_tx(w_full, 128 * 1024);
 #pragma unroll
@@ -503,7 +507,7 @@ project_mn_kernel(const __grid_constant__ CUtensorMap tmap_w,   // W16 [C][C], b
         tma_load_2d(sX + s * 32768, &tmap_x, x_full + s, i0, p.a_row0_base + n * kC);
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kProjMnMmaWarp) {
     constexpr uint32_t idesc = make_idesc_16_major(128, kProjMnTile, BF16, false, true);
     const uint32_t wbase = smem_u32(sW);
     const uint32_t xbase = smem_u32(sX);
@@ -531,8 +535,12 @@ project_mn_kernel(const __grid_constant__ CUtensorMap tmap_w,   // W16 [C][C], b
       __syncwarp();
     }
   } else {
-    // epilogue: thread = output channels (warp*32 + lane) and 128 + that; 64 positions each = 128 contiguous bytes
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    // epilogue: warp = (TMEM lane quadrant, m-tile); thread = one output channel, 64 positions = 128 bytes, staged
+    // through a swizzled 4 KB block per warp so that every global store instruction writes 4 full 128-byte rows
+    const int quad = warp & 3, mt = warp >> 2;
+    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + mt * 64;
+    uint8_t* stg = sOut + warp * 4096;
+    const int rd_r = lane >> 3, rd_c = lane & 7;
     uint32_t cnt = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++cnt) {
       const int n = t / p.tiles_per_sample;
@@ -540,34 +548,39 @@ project_mn_kernel(const __grid_constant__ CUtensorMap tmap_w,   // W16 [C][C], b
       const uint32_t b = cnt & 1, dph = (cnt >> 1) & 1;
       warp_mbar_wait(d_full + b, dph, lane, 101);
       tc_fence_after();
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const int co = mt * 128 + warp * 32 + lane;
-        uint4* d4 = reinterpret_cast<uint4*>(p.q16 + ((size_t)n * kC + co) * p.Lp + i0);
-        uint32_t v0[32], v1[32];
-        tmem_ld32(taddr + b * 128 + mt * 64, v0);
-        tmem_ld32(taddr + b * 128 + mt * 64 + 32, v1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          d4[q] = make_uint4(pack16x2<BF16>(__uint_as_float(v0[8 * q + 0]), __uint_as_float(v0[8 * q + 1])),
-                             pack16x2<BF16>(__uint_as_float(v0[8 * q + 2]), __uint_as_float(v0[8 * q + 3])),
-                             pack16x2<BF16>(__uint_as_float(v0[8 * q + 4]), __uint_as_float(v0[8 * q + 5])),
-                             pack16x2<BF16>(__uint_as_float(v0[8 * q + 6]), __uint_as_float(v0[8 * q + 7])));
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          d4[4 + q] = make_uint4(pack16x2<BF16>(__uint_as_float(v1[8 * q + 0]), __uint_as_float(v1[8 * q + 1])),
-                                 pack16x2<BF16>(__uint_as_float(v1[8 * q + 2]), __uint_as_float(v1[8 * q + 3])),
-                                 pack16x2<BF16>(__uint_as_float(v1[8 * q + 4]), __uint_as_float(v1[8 * q + 5])),
-                                 pack16x2<BF16>(__uint_as_float(v1[8 * q + 6]), __uint_as_float(v1[8 * q + 7])));
-      }
+      uint32_t v0[32], v1[32];
+      tmem_ld32(taddr + b * 128, v0);
+      tmem_ld32(taddr + b * 128 + 32, v1);
+      tmem_ld_wait();
       tc_fence_before();
-      warp_mbar_arrive(d_empty + b, lane);
+      warp_mbar_arrive(d_empty + b, lane);      // accumulators are in registers: the next tile's MMAs may overwrite them
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+            make_uint4(pack16x2<BF16>(__uint_as_float(v0[8 * q + 0]), __uint_as_float(v0[8 * q + 1])),
+                       pack16x2<BF16>(__uint_as_float(v0[8 * q + 2]), __uint_as_float(v0[8 * q + 3])),
+                       pack16x2<BF16>(__uint_as_float(v0[8 * q + 4]), __uint_as_float(v0[8 * q + 5])),
+                       pack16x2<BF16>(__uint_as_float(v0[8 * q + 6]), __uint_as_float(v0[8 * q + 7])));
+        *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + q) ^ (lane & 7)) << 4)) =
+            make_uint4(pack16x2<BF16>(__uint_as_float(v1[8 * q + 0]), __uint_as_float(v1[8 * q + 1])),
+                       pack16x2<BF16>(__uint_as_float(v1[8 * q + 2]), __uint_as_float(v1[8 * q + 3])),
+                       pack16x2<BF16>(__uint_as_float(v1[8 * q + 4]), __uint_as_float(v1[8 * q + 5])),
+                       pack16x2<BF16>(__uint_as_float(v1[8 * q + 6]), __uint_as_float(v1[8 * q + 7])));
+      }
+      __syncwarp();
+      unsigned short* dst = p.q16 + ((size_t)n * kC + mt * 128 + quad * 32) * p.Lp + i0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = rd_r + 4 * k;
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 128 + ((rd_c ^ (r & 7)) << 4));
+        *reinterpret_cast<uint4*>(dst + (size_t)r * p.Lp + rd_c * 8) = v;
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) {
+  if (warp == kProjMnMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
