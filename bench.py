@@ -349,7 +349,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * pipe.h2d_bytes * world,
                 "d2h_bytes_per_step": 2 * pipe.d2h_bytes * world, "steps": e2e_steps, "matches_resident_path": same,
                 "api": "cosnet_b200.coattention.HostPipeline (pinned host in/out, 3 streams x chunks of 4 pairs)"},
-        "gpu_launches": 8 * args.steps,   # per modality call: prep(V_b), cast_w, project_fused(V_a), attend2(+gate+concat)
+        "gpu_launches": 8 * args.steps,   # per modality call: cast(V_a, V_b), cast_w, project_mn, attend2(+gate+concat)
         "roofline": {
             "kernel": "attend2_kernel", "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"],
             "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"],
