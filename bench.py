@@ -333,6 +333,26 @@ def run_ours(args):
         return
 
     achieved_tflops = n * FLOPS_ATTEND_PER_PAIR_MODALITY / (attend_ms * 1e-3) / 1e12
+    # Denominator: when the attend kernel is timed INSIDE a long step loop the GPU sits at its power cap (SM clock
+    # ~1.5 GHz, reason sw_power_cap) and the sustained bf16 peak of MEASURED_PEAKS.json applies; a short run that never
+    # left the boost clock is held against the burst peak.  The fraction of the burst peak is always kept beside it.
+    clk = clocks.summary()
+    capped = bool(clk.get("sm_mhz") and clk.get("sm_max_mhz") and clk["sm_mhz"] < 0.9 * clk["sm_max_mhz"])
+    sustained = (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]) if capped else peaks["bf16_tflops"]
+    roofline = {
+        "kernel": "attend2_kernel", "bound": "tensor", "achieved": achieved_tflops, "peak": sustained,
+        "unit": "TFLOP/s", "frac": achieved_tflops / sustained,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one attend2 launch at this shape, from the committed
+        # `ncu --set full` capture (profiles/r1_ncu_kernels.txt): 441.1 MB read + 431.3 MB written
+        "traffic": 872.4e6 if (n == PAIRS_PER_GPU and FLAGS == 0) else None,
+        "peak_kind": (f"{peaks['source']} sustained dense bf16 (kernel timed inside the {args.steps}-step loop, SM clock "
+                      f"{clk.get('sm_mhz')} MHz under the power cap); burst peak {peaks['bf16_tflops']}") if capped else
+                     f"{peaks['source']} burst dense bf16 (clocks stayed at boost)",
+        "frac_of_burst_peak": achieved_tflops / peaks["bf16_tflops"],
+        "ms_per_launch": attend_ms, "algorithmic_flops_per_launch": n * FLOPS_ATTEND_PER_PAIR_MODALITY,
+        "executed_flops_per_launch": n * FLOPS_ATTEND_PER_PAIR_MODALITY * 8.0 / 6.0,
+        "whole_step_frac": (2 * n * FLOPS_PER_PAIR_MODALITY / (elapsed_ms / args.steps * 1e-3) / 1e12) / sustained,
+    }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -345,21 +365,12 @@ def run_ours(args):
             "l2": f"inputs of one step ({4 * n * C * L * 4 / 1e6:.0f} MB) exceed the 126 MB L2; no explicit flush",
             "flops_per_frame_pair": 2 * FLOPS_PER_PAIR_MODALITY,
         },
-        "clocks": clocks.summary(),
+        "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * pipe.h2d_bytes * world,
                 "d2h_bytes_per_step": 2 * pipe.d2h_bytes * world, "steps": e2e_steps, "matches_resident_path": same,
                 "api": "cosnet_b200.coattention.HostPipeline (pinned host in/out, 3 streams x chunks of 4 pairs)"},
         "gpu_launches": 8 * args.steps,   # per modality call: cast(V_a, V_b), cast_w, project_mn, attend2(+gate+concat)
-        "roofline": {
-            "kernel": "attend2_kernel", "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops"],
-            "unit": "TFLOP/s", "frac": achieved_tflops / peaks["bf16_tflops"],
-            # dram__bytes_read.sum + dram__bytes_write.sum of one attend2 launch at this shape, from the committed
-            # `ncu --set full` capture (profiles/r1_ncu_kernels.txt): 441.1 MB read + 431.3 MB written
-            "traffic": 872.4e6 if (n == PAIRS_PER_GPU and FLAGS == 0) else None,
-            "peak_kind": f"{peaks['source']} burst bf16 (sustained {peaks['bf16_tflops_sustained']})",
-            "ms_per_launch": attend_ms, "algorithmic_flops_per_launch": n * FLOPS_ATTEND_PER_PAIR_MODALITY,
-            "whole_step_frac": (2 * n * FLOPS_PER_PAIR_MODALITY / (elapsed_ms / args.steps * 1e-3) / 1e12) / peaks["bf16_tflops"],
-        },
+        "roofline": roofline,
     }
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_budget)

@@ -380,3 +380,43 @@ def test_host_pipeline_matches_resident_path(op, host_passthrough):
         torch.cuda.synchronize()
         pipe.wait_host()
         assert torch.equal(out_a, want[0].cpu()) and torch.equal(out_b, want[1].cpu())
+
+
+def test_forward_is_cuda_graph_capturable(op):
+    """The whole modality call (4 launches, no host synchronisation, no allocation inside the library) can be captured
+    into a CUDA graph and replayed on new inputs -- the way to run launch-bound small shapes (test.py-style inference
+    on a few pairs)."""
+    from cosnet_b200 import _lib
+    from cosnet_b200.coattention import workspace_bytes
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    n, c, h, w = 2, 256, 12, 11
+    v_a = torch.empty(n, c, h, w, device=dev)
+    v_b = torch.empty_like(v_a)
+    W, g, b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_weights(71, bias=True))
+    cat_a = torch.empty(n, 2 * c, h, w, device=dev)
+    cat_b = torch.empty_like(cat_a)
+    nbytes = workspace_bytes(n, c, h, w)
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    wsp = (ws.data_ptr() + 1023) // 1024 * 1024
+
+    def call(stream):
+        _lib.check(lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), W.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                      cat_a.data_ptr(), cat_b.data_ptr(), None, None, None, wsp, nbytes, n, c, h, w, 0,
+                                      stream.cuda_stream), "coattn_forward")
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        call(side)                                  # warm-up outside the capture (function attributes, descriptors)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        call(torch.cuda.current_stream(dev))
+    for seed in (72, 73):
+        fa, fb = (torch.from_numpy(x).to(dev) for x in orc.synthetic_features(seed, n, h, w, 0.66))
+        v_a.copy_(fa); v_b.copy_(fb)
+        graph.replay()
+        torch.cuda.synchronize()
+        want = op(fa, fb, W, g, b)
+        assert torch.equal(cat_a, want[0]) and torch.equal(cat_b, want[1])
