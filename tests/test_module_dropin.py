@@ -152,3 +152,61 @@ def test_dropin_import_paths():
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert "cosnet_b200.rgbd_segmentation_raa" in out.stdout
+
+
+def torch_impl(v_a, v_b, weight, gate_weight, gate_bias, gated_only=False):
+    """Differentiable restatement of :154-187 (test-only), B-side mask under no_grad like :178-182."""
+    import torch.nn.functional as F
+    n, c, h, w = v_a.shape
+    a, b = v_a.reshape(n, c, h * w), v_b.reshape(n, c, h * w)
+    s = torch.bmm(F.linear(a.transpose(1, 2), weight), b)
+    z_b = torch.bmm(a, F.softmax(s, dim=1)).view(n, c, h, w)
+    z_a = torch.bmm(b, F.softmax(s, dim=2).transpose(1, 2)).view(n, c, h, w)
+    m_a = torch.sigmoid(F.conv2d(z_a, gate_weight, gate_bias))
+    with torch.no_grad():
+        m_b = torch.sigmoid(F.conv2d(z_b, gate_weight, gate_bias))
+    if gated_only:
+        return z_a * m_a, z_b * m_b
+    return torch.cat([z_a * m_a, v_a], 1), torch.cat([z_b * m_b, v_b], 1)
+
+
+@needs_ref
+@pytest.mark.parametrize("frozen", [True, False])
+def test_train_mode_forward_backward_matches_reference(frozen):
+    """Train-mode wiring around the operator: BatchNorm statistics (incl. the second, no-grad depth_bn update of
+    :240-247), which parameters receive gradient (counterpart frozen or not, B-side depth branch dead) and the
+    gradient values, against the unmodified reference."""
+    RefRAA, RefBottleneck = ref_harness.import_reference()
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = RefRAA(RefBottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1, no_grad_for_counterpart=frozen).train()
+    mine = small_model(no_grad_for_counterpart=frozen).train()
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    mine.coattention_impl = torch_impl
+    g = torch.Generator().manual_seed(2)
+    ra, rb = torch.randn(2, 3, 41, 49, generator=g), torch.randn(2, 3, 41, 49, generator=g)
+    da, db = torch.randn(2, 1, 41, 49, generator=g), torch.randn(2, 1, 41, 49, generator=g)
+    r = [torch.randn(2, 1, 41, 49, generator=g) for _ in range(3)]
+    outs = []
+    for model in (ref, mine):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = model(ra, rb, da, db)
+        sum((o * w).sum() for o, w in zip(out, r)).backward()
+        outs.append(out)
+    for w_, g_ in zip(*outs):
+        assert (w_ - g_).abs().max() < 1e-5
+    ref_buf, my_buf = dict(ref.named_buffers()), dict(mine.named_buffers())
+    assert ref_buf.keys() == my_buf.keys()
+    for k in ref_buf:
+        assert torch.allclose(ref_buf[k].float(), my_buf[k].float(), rtol=1e-4, atol=1e-6), k
+    ref_par, my_par = dict(ref.named_parameters()), dict(mine.named_parameters())
+    # biases in front of a BatchNorm have a mathematically zero gradient (pure rounding noise): compare every
+    # gradient against its own norm plus a floor tied to the largest gradient in the model
+    top = max(float(p_.grad.norm()) for p_ in ref_par.values() if p_.grad is not None)
+    for k, pr in ref_par.items():
+        pm = my_par[k]
+        assert (pr.grad is None) == (pm.grad is None), k
+        if pr.grad is not None:
+            assert float((pr.grad - pm.grad).norm()) <= 2e-3 * float(pr.grad.norm()) + 1e-5 * top, k
