@@ -326,6 +326,29 @@ def run_ours(args):
     # sanity: the pipelined host path must reproduce the resident path bit for bit
     same = bool(torch.equal(hout[0], cat[0].cpu()) and torch.equal(hout[3], cat[3].cpu()))
 
+    # the same through the gated-only contract (the consumer splits the reduce conv, so the passthrough
+    # half of the concat -- a copy of the inputs the host already holds -- is neither produced nor sent back)
+    gpipe = HostPipeline(n, C, H, W, chunk=4, slots=3, device=dev, bf16_operands=bool(FLAGS & _lib.FLAG_BF16), gated_only=True)
+    gout = [torch.empty((n, C, H, W), dtype=torch.float32).pin_memory() for _ in range(4)]
+
+    def e2e_gated_step():
+        gpipe(hin[0], hin[1], w_rgb, g_rgb, None, gout[0], gout[1])
+        gpipe(hin[2], hin[3], w_dep, g_dep, b_dep, gout[2], gout[3])
+    e2e_gated_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_gated_step()
+    torch.cuda.synchronize()
+    e2e_gated_s = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([e2e_gated_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_gated_s = float(t.item())
+    same_gated = bool(torch.equal(gout[0], cat[0][:, :C].cpu()) and torch.equal(gout[3], cat[3][:, :C].cpu()))
+
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -368,7 +391,11 @@ def run_ours(args):
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * pipe.h2d_bytes * world,
                 "d2h_bytes_per_step": 2 * pipe.d2h_bytes * world, "steps": e2e_steps, "matches_resident_path": same,
-                "api": "cosnet_b200.coattention.HostPipeline (pinned host in/out, 3 streams x chunks of 4 pairs)"},
+                "api": "cosnet_b200.coattention.HostPipeline (pinned host in/out, 3 streams x chunks of 4 pairs)",
+                "gated_only_contract": {"value": total_pairs * e2e_steps / e2e_gated_s, "unit": UNIT,
+                                        "d2h_bytes_per_step": 2 * gpipe.d2h_bytes * world, "matches_resident_path": same_gated,
+                                        "note": "outputs [n,256,h,w]: the concat's passthrough half (= the caller's own inputs) "
+                                                "is not sent back; for the split-reduce-conv consumer"}},
         "gpu_launches": 8 * args.steps,   # per modality call: cast(V_a, V_b), cast_w, project_mn, attend2(+gate+concat)
         "roofline": roofline,
     }

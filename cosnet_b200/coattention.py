@@ -188,9 +188,15 @@ class HostPipeline:
     """
 
     def __init__(self, n: int, c: int, h: int, w: int, chunk: int = 4, slots: int = 3, device="cuda:0",
-                 bf16_operands: bool = False, host_passthrough: bool = False):
+                 bf16_operands: bool = False, host_passthrough: bool = False, gated_only: bool = False):
         self.n, self.c, self.h, self.w = n, c, h, w
         self.flags = _lib.FLAG_BF16 if bf16_operands else 0
+        # gated_only: outputs are [n, C, h, w] (Z * sigmoid(gate) only) for a consumer that applies the reduce conv to the
+        # two halves separately (split_reduce_conv) -- the passthrough half never exists, on the device or on the wire
+        self.gated_only = gated_only
+        if gated_only:
+            self.flags |= _lib.FLAG_GATED_ONLY
+            host_passthrough = False
         self.chunk = max(1, min(chunk, n))
         self.device = torch.device(device)
         self.host_passthrough = host_passthrough
@@ -203,14 +209,14 @@ class HostPipeline:
                     "stream": torch.cuda.Stream(self.device),
                     "va": torch.empty((self.chunk, c, h, w), dtype=torch.float32, device=self.device),
                     "vb": torch.empty((self.chunk, c, h, w), dtype=torch.float32, device=self.device),
-                    "ca": torch.empty((self.chunk, 2 * c, h, w), dtype=torch.float32, device=self.device),
-                    "cb": torch.empty((self.chunk, 2 * c, h, w), dtype=torch.float32, device=self.device),
+                    "ca": torch.empty((self.chunk, (c if gated_only else 2 * c), h, w), dtype=torch.float32, device=self.device),
+                    "cb": torch.empty((self.chunk, (c if gated_only else 2 * c), h, w), dtype=torch.float32, device=self.device),
                     "ws": torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device),
                     "nbytes": nbytes,
                 }
                 self.slots.append(s)
         self.h2d_bytes = 2 * n * c * h * w * 4
-        self.d2h_bytes = 2 * n * (c if host_passthrough else 2 * c) * h * w * 4
+        self.d2h_bytes = 2 * n * (c if (host_passthrough or gated_only) else 2 * c) * h * w * 4
         self.launches_per_call = 4 * ((n + self.chunk - 1) // self.chunk)
         self._worker = None
 
@@ -244,8 +250,9 @@ class HostPipeline:
             with torch.cuda.stream(st):
                 s["va"][:m].copy_(v_a[lo:hi], non_blocking=True)
                 s["vb"][:m].copy_(v_b[lo:hi], non_blocking=True)
-                pass_a = None if self.host_passthrough else s["va"].data_ptr()
-                pass_b = None if self.host_passthrough else s["vb"].data_ptr()
+                no_pass = self.host_passthrough or self.gated_only
+                pass_a = None if no_pass else s["va"].data_ptr()
+                pass_b = None if no_pass else s["vb"].data_ptr()
                 nb = s["nbytes"]
                 wsp = _aligned_ptr(s["ws"])
                 _lib.check(self.lib.coattn_stage_prep_project(s["va"].data_ptr(), s["vb"].data_ptr(), weight.data_ptr(), wsp,
