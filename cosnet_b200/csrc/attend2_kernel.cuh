@@ -43,6 +43,20 @@ constexpr uint32_t k2TmemS = 256;
 
 static_assert(k2SmemBytes <= 232448, "attend2 shared memory exceeds the 227 KB per-CTA limit");
 
+// Debug builds (-DCOATTN_TRACE2): per-item clock64 stamps of CTA 0 (MMA issuer: slots 0-4, softmax warp 0: slots 8-12),
+// dumped by the host after the third launch.  No device printf -- it perturbs the pipeline it is meant to observe.
+#ifdef COATTN_TRACE2
+__device__ long long g_attend2_trace[16 * 16];
+#define TRG(slot) do { if (blockIdx.x == 0 && lane == 0 && it < 16) g_attend2_trace[it * 16 + (slot)] = clock64(); } while (0)
+// per-tile stamps of item 3 (warm): MMA issuer slots 0-3, softmax warp 0 slots 4-7
+__device__ long long g_attend2_tiles[32 * 8];
+__device__ long long g_attend2_warps[2 * 32 * 8];   // [saw S | arrived P][tile][softmax warp] of item 3, CTA 0
+#define TRT(j, slot) do { if (blockIdx.x == 0 && lane == 0 && it == 3 && (j) < 32) g_attend2_tiles[(j) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TRG(slot) do {} while (0)
+#define TRT(j, slot) do {} while (0)
+#endif
+
 struct Attend2Params {
   float* z;     // [2][N][C][L] raw attended features or null
   float* lse;   // [2][N][L]
@@ -287,8 +301,13 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
 #ifdef COATTN_TRACE
         long long ti0 = clock64();
 #endif
+        TRG(0);
+#ifdef COATTN_EXP_DELAY_S
+        if (it > 0) { const long long tw = clock64(); while (clock64() - tw < COATTN_EXP_DELAY_S) {} }
+#endif
         warp_mbar_wait(q_full, it & 1, lane, 11);
         tc_fence_after();
+        TRG(1);
 #ifdef COATTN_TRACE
         long long ti1 = clock64(), ti2 = 0;
 #endif
@@ -298,6 +317,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         issue_s(0);
         if (T > 1) issue_s(1);
         if (T <= 2) { if (elect_one()) umma2_commit_mc(q_empty, 3); __syncwarp(); }
+        TRG(2);
         {
           const uint32_t s = vcnt % k2VStages, ph = (vcnt / k2VStages) & 1;
           warp_mbar_wait(v_full + s, ph, lane, 14);
@@ -310,6 +330,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           else        { warp_mbar_wait(p_full + 1, pphase1, lane, 13); pphase1 ^= 1; }
           tc_fence_after();
           TR2(3);
+          if (j == 0) TRG(3);
+          TRT(j, 0);
 #ifdef COATTN_TRACE
           if (j == 0) ti2 = clock64();
 #endif
@@ -331,15 +353,19 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           __syncwarp();
           ++vcnt;
           TR2(4);
+          if (j == T - 1) TRG(4);
+          TRT(j, 1);
           if (j + 1 < T) {   // value tile of the next step: waited while PV(j) executes
             const uint32_t s1 = vcnt % k2VStages, ph1 = (vcnt / k2VStages) & 1;
             warp_mbar_wait(v_full + s1, ph1, lane, 14);
           }
+          TRT(j, 2);
           if (j + 2 < T) {
             issue_s(j + 2);
             if (j + 3 == T) { if (elect_one()) umma2_commit_mc(q_empty, 3); __syncwarp(); }   // last S of the item issued
           }
           TR2(5);
+          TRT(j, 3);
 #ifdef COATTN_TRACE
           ++tc;
 #endif
@@ -368,6 +394,11 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     const uint32_t p_full_l0 = mapa_u32(smem_u32(p_full + 0), 0);
     const uint32_t p_full_l1 = mapa_u32(smem_u32(p_full + 1), 0);
     uint32_t sphase0 = 0, sphase1 = 0, it = 0, seq = 0;
+    float greg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.cat_a != nullptr) {
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) greg[ch] = __ldg(p.gate_w + wg * 128 + ch * 32 + lane);
+    }
 #ifdef COATTN_TRACE
     long long ts[24][6]; int sc = 0;
 #define TS2(i) do { if (sc < 24) ts[sc][i] = clock64(); } while (0)
@@ -385,6 +416,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       // (zero MMA operands also draw less power, and this kernel runs against the power cap)
       const bool warp_is_padding = (qp * (2 * k2BM) + (int)rank * k2BM + quad * 32) >= p.L;
       float m = -INFINITY, l = 0.0f;
+      if (warp == 0) TRG(8);
       for (int j = 0; j < T; ++j) {
         const int b = j & 1;
         const uint32_t tSb = tmem + lane_base + k2TmemS + (uint32_t)b * k2BN;
@@ -409,6 +441,11 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         else        { warp_mbar_wait(s_full + 1, sphase1, lane, 20); sphase1 ^= 1; }
         tc_fence_after();
         TS2(1);
+        if (warp == 0 && j == 0) TRG(9);
+        if (warp == 0) TRT(j, 4);
+#ifdef COATTN_TRACE2
+        if (blockIdx.x == 0 && lane == 0 && it == 3 && j < 32) g_attend2_warps[j * 8 + warp] = clock64();
+#endif
         uint32_t s0[32], s1[32];
         tmem_ld32(tSb + wg * 64, s0);
         tmem_ld32(tSb + wg * 64 + 32, s1);
@@ -424,11 +461,19 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             }
           }
         }
-        float hmax = __uint_as_float(s0[0]);
+        // four independent chains (a single 64-deep chain of dependent max operations costs ~250 cycles of latency)
+        float h0 = __uint_as_float(s0[0]), h1 = __uint_as_float(s0[1]), h2 = __uint_as_float(s0[2]), h3 = __uint_as_float(s0[3]);
 #pragma unroll
-        for (int k = 1; k < 32; ++k) hmax = fmaxf(hmax, __uint_as_float(s0[k]));
+        for (int k = 4; k < 32; k += 4) {
+          h0 = fmaxf(h0, __uint_as_float(s0[k]));     h1 = fmaxf(h1, __uint_as_float(s0[k + 1]));
+          h2 = fmaxf(h2, __uint_as_float(s0[k + 2])); h3 = fmaxf(h3, __uint_as_float(s0[k + 3]));
+        }
 #pragma unroll
-        for (int k = 0; k < 32; ++k) hmax = fmaxf(hmax, __uint_as_float(s1[k]));
+        for (int k = 0; k < 32; k += 4) {
+          h0 = fmaxf(h0, __uint_as_float(s1[k]));     h1 = fmaxf(h1, __uint_as_float(s1[k + 1]));
+          h2 = fmaxf(h2, __uint_as_float(s1[k + 2])); h3 = fmaxf(h3, __uint_as_float(s1[k + 3]));
+        }
+        const float hmax = fmaxf(fmaxf(h0, h1), fmaxf(h2, h3));
         // both halves of the row agree on the tile max; the exchange barrier also orders "both warpgroups have
         // read their S columns" before either overwrites them with P (P of warpgroup 1 lands on S of warpgroup 0)
         const float tmax = fmaxf(hmax, pair_exchange(hmax, xbuf, seq++, wg, rloc, quad));
@@ -436,7 +481,12 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         if (j == 0) {
           m = tmax;
         } else {
-          const bool need = (tmax - m) * kLog2e > kRescaleThreshold;
+          // lazy rescale: the reference max only moves when the row max jumps by more than 2^13 (fp16 P stays below
+          // 8192 < 65504 and keeps its 11-bit precision at any magnitude; bf16 has the range for 2^24).  The slow
+          // path costs ~3 k cycles and stalls the whole CTA pair, and `__any_sync` takes it for all 32 rows of a warp, so
+          // with the usual 2^8 threshold spiky features (logit sigma ~ 6 in log2 units) hit it on most early tiles.
+          constexpr float kThreshold = BF16 ? 24.0f : 13.0f;
+          const bool need = (tmax - m) * kLog2e > kThreshold;
           if (__any_sync(0xffffffffu, need)) {
             const float m_new = fmaxf(m, tmax);
             const float scale = fast_exp2((m - m_new) * kLog2e);
@@ -488,6 +538,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(b == 0 ? p_full_l0 : p_full_l1);
         TS2(5);
+        if (warp == 0) TRT(j, 5);
+#ifdef COATTN_TRACE2
+        if (blockIdx.x == 0 && lane == 0 && it == 3 && j < 32) g_attend2_warps[256 + j * 8 + warp] = clock64();
+#endif
 #ifdef COATTN_TRACE
         ++sc;
 #endif
@@ -502,11 +556,23 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
 #ifdef COATTN_TRACE
       long long td0 = clock64();
 #endif
+      if (warp == 0) TRG(10);
       // ---- drain.  Wait the last two PV phases one by one (see attend_kernel for the aliasing argument).
       if (T >= 2) warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 2u) & 1u, lane, 23);
       warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, lane, 22);
       tc_fence_after();
+      if (warp == 0) TRG(11);
+#ifdef COATTN_EXP_EARLY_LD
+      {
+        uint32_t tmp[32];
+        tmem_ld32(tmem + lane_base + k2TmemS + COATTN_EXP_EARLY_LD, tmp);   // probe: a load right behind the last PV
+        tmem_ld_wait();
+        if (tmp[0] == 0x7fc12345u) l += 1.0f;
+        if (warp == 0) TRG(15);
+      }
+#endif
       l += pair_exchange(l, xbuf, seq++, wg, rloc, quad);
+      if (warp == 0) TRG(5);
       if (warp_is_padding) {     // nothing to store; keep the exchange sequence of the gate dot in step
         if (p.cat_a != nullptr) (void)pair_exchange(0.f, xbuf, seq++, wg, rloc, quad);
         continue;
@@ -528,40 +594,60 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         }
       }
       if (p.cat_a != nullptr) {
+        // gate weights of this warpgroup's 128 channels live in registers, one value per lane and 32-channel chunk
+        // (greg, loaded once per kernel) and are broadcast by shuffles: 128 global loads per item used to queue behind
+        // the copy warp's traffic in the LSU and made this pass the longest part of the drain
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t o[32];
-          tmem_ld32(tO + ch * 32, o);
+        {
+          uint32_t oa[32], ob[32];
+          tmem_ld32(tO, oa);
           tmem_ld_wait();
+          if (warp == 0) TRG(6);
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            d0 = fmaf(__ldg(p.gate_w + c0 + ch * 32 + k + 0), __uint_as_float(o[k + 0]), d0);
-            d1 = fmaf(__ldg(p.gate_w + c0 + ch * 32 + k + 1), __uint_as_float(o[k + 1]), d1);
-            d2 = fmaf(__ldg(p.gate_w + c0 + ch * 32 + k + 2), __uint_as_float(o[k + 2]), d2);
-            d3 = fmaf(__ldg(p.gate_w + c0 + ch * 32 + k + 3), __uint_as_float(o[k + 3]), d3);
+          for (int ch = 0; ch < 4; ++ch) {     // chunk ch + 1 streams out of TMEM while chunk ch is consumed
+            uint32_t (&o)[32] = (ch & 1) ? ob : oa;
+            uint32_t (&nx)[32] = (ch & 1) ? oa : ob;
+            if (ch < 3) tmem_ld32(tO + (ch + 1) * 32, nx);
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              d0 = fmaf(__shfl_sync(0xffffffffu, greg[ch], k + 0), __uint_as_float(o[k + 0]), d0);
+              d1 = fmaf(__shfl_sync(0xffffffffu, greg[ch], k + 1), __uint_as_float(o[k + 1]), d1);
+              d2 = fmaf(__shfl_sync(0xffffffffu, greg[ch], k + 2), __uint_as_float(o[k + 2]), d2);
+              d3 = fmaf(__shfl_sync(0xffffffffu, greg[ch], k + 3), __uint_as_float(o[k + 3]), d3);
+            }
+            if (ch < 3) tmem_ld_wait();
           }
         }
         float dot = (d0 + d1) + (d2 + d3);
+        if (warp == 0) TRG(13);
         const float other = pair_exchange(dot, xbuf, seq++, wg, rloc, quad);
+        if (warp == 0) TRG(14);
         dot = (wg == 0) ? (dot + other) : (other + dot);   // same summation order in both halves
         const float logit = dot * inv + (p.gate_b ? __ldg(p.gate_b) : 0.f);
         const float gate = 1.0f / (1.0f + __expf(-logit));
         const float sc = inv * gate;
         float* ccol = (pass ? p.cat_b : p.cat_a) + ((size_t)n * p.out_channels + c0) * p.L + row;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t o[32];
-          tmem_ld32(tO + ch * 32, o);
+        {
+          uint32_t oa[32], ob[32];
+          tmem_ld32(tO, oa);
           tmem_ld_wait();
-          if (valid) {
+          if (warp == 0) TRG(7);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) ccol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * sc;
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t (&o)[32] = (ch & 1) ? ob : oa;
+            uint32_t (&nx)[32] = (ch & 1) ? oa : ob;
+            if (ch < 3) tmem_ld32(tO + (ch + 1) * 32, nx);
+            if (valid) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) __stcs(ccol + (size_t)(ch * 32 + k) * p.L, __uint_as_float(o[k]) * sc);
+            }
+            if (ch < 3) tmem_ld_wait();
           }
         }
         if (valid && wg == 0 && p.mask != nullptr) p.mask[(size_t)(pass * p.N + n) * p.L + row] = gate;
       }
       if (valid && wg == 0) p.lse[(size_t)(pass * p.N + n) * p.L + row] = m + __logf(l);
+      if (warp == 0) TRG(12);
 #ifdef COATTN_TRACE
       if (blockIdx.x == 0 && threadIdx.x == 0 && it < 6) printf("softmax item %u: drain (from last P arrive to end) %lld cycles\n", it, clock64() - td0);
 #endif

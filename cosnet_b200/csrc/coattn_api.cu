@@ -337,6 +337,39 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     int clusters = sms / 2;
     if (q.num_items < clusters) clusters = q.num_items;
     kern2<<<2 * clusters, k2Threads, k2SmemBytes, st>>>(tm_q, tm_k2, tm_v2, q);
+#ifdef COATTN_TRACE2
+    {
+      static int calls = 0;
+      if (++calls == 3) {
+        long long hb[16 * 16];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(hb, g_attend2_trace, sizeof(hb));
+        long long tb[32 * 8];
+        cudaMemcpyFromSymbol(tb, g_attend2_tiles, sizeof(tb));
+        for (int j = 1; j < 29; ++j) {
+          const long long* r = tb + j * 8;
+          printf("tile %2d: MMA saw P at +%6lld (%5lld after warp 0's arrive) | PV issue %4lld | v_full wait %4lld | S(j+2) issue %5lld"
+                 " || softmax saw S at +%6lld | busy %5lld | period %5lld\n", j, r[0] - tb[8], r[0] - r[5], r[1] - r[0], r[2] - r[1],
+                 r[3] - r[2], r[4] - tb[8], r[5] - r[4], r[4] - tb[(j - 1) * 8 + 4]);
+        }
+        long long wb[2 * 32 * 8];
+        cudaMemcpyFromSymbol(wb, g_attend2_warps, sizeof(wb));
+        for (int j = 1; j < 29; ++j) {
+          printf("tile %2d warps saw S / arrived P (relative to warp 0 seeing S):", j);
+          for (int w = 0; w < 8; ++w) printf("  %5lld/%5lld", wb[j * 8 + w] - wb[j * 8], wb[256 + j * 8 + w] - wb[j * 8]);
+          printf("\n");
+        }
+        const long long t0 = hb[0];
+        for (int it = 0; it < 14; ++it) {
+          const long long* r = hb + it * 16;
+          printf("item %2d  MMA: start +%7lld | q_full +%5lld | S0,S1 issued +%5lld | P(0) ready +%5lld | last PV issued +%6lld"
+                 "  || softmax: start +%7lld | S(0) ready +%5lld | last P +%6lld | O complete +%5lld | probe ld %5lld | l xchg +%5lld | first ld +%5lld | dot pass +%5lld | xchg +%5lld | sigmoid+first ld +%5lld | stores +%5lld\n", it,
+                 r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[8] - t0, r[9] - r[8], r[10] - r[9],
+                 r[11] - r[10], r[15] ? r[15] - r[11] : 0, r[5] - (r[15] ? r[15] : r[11]), r[6] - r[5], r[13] - r[6], r[14] - r[13], r[7] - r[14], r[12] - r[7]);
+        }
+      }
+    }
+#endif
     return (int)cudaGetLastError();
   }
   if (flags & (COATTN_FLAG_A_ONLY | COATTN_FLAG_GATED_ONLY)) return COATTN_E_UNSUPPORTED;   // cross-check kernel: full concat only
