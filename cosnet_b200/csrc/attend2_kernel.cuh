@@ -580,8 +580,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       const float inv = 1.0f / l;
       const bool valid = row < p.L;
       const int c0 = wg * 128;
-      if (p.z != nullptr) {
-        float* zcol = p.z + ((size_t)(pass * p.N + n) * kC + c0) * p.L + row;
+      // raw Z (kept for the backward pass): written in the same sweep over O as the gated output below; a sweep of its
+      // own only when there is no fused gate (coattn_stage_attend)
+      float* zcol = p.z ? p.z + ((size_t)(pass * p.N + n) * kC + c0) * p.L + row : nullptr;
+      if (zcol != nullptr && p.cat_a == nullptr) {
 #pragma unroll 1
         for (int ch = 0; ch < 4; ++ch) {
           uint32_t o[32];
@@ -640,6 +642,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             if (valid) {
 #pragma unroll
               for (int k = 0; k < 32; ++k) __stcs(ccol + (size_t)(ch * 32 + k) * p.L, __uint_as_float(o[k]) * sc);
+              if (zcol != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) zcol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * inv;
+              }
             }
             if (ch < 3) tmem_ld_wait();
           }
