@@ -3,8 +3,9 @@
 // The softmax matrices are NOT kept from the forward pass (the reference keeps S_row and S_column, 104 MB per
 // sample and modality at L = 3600): S is recomputed from the 16-bit operands and the saved log-sum-exp vectors.
 //
-//   bwd_prep      d_cat_a/b, Z, mask, g  ->  dZ_a, dZ_b (16-bit, both layouts), delta_a, delta_b, d_gate, dA init
-//   bwd_tile      per 128x128 tile: S = Qt Bt^T, dP_a = dZa_t Bt^T, dP_b = At dZb_t^T in TMEM, combined on the fly into
+//   bwd_prep      d_cat_a/b, Z, mask, g  ->  dZ_a, dZ_b (bf16 planes [C][Lp]), delta_a, delta_b, d_gate, dA init
+//   bwd_tile      per 128x128 tile: S = Q^T B, dP_a = dZ_a^T B, dP_b = A^T dZ_b in TMEM (operands read MN-major from
+//                 the channel-major planes), combined on the fly into
 //                 dS = P_a (dP_a - delta_a) + P_b (dP_b - delta_b) and P_b            (bf16, [L, L], transient)
 //   gemm_nt  x4   dQ = dS B^T;  dA += P_b dZ_b^T;  dA += dQ W;  dW += dQ^T A^T
 //
@@ -31,8 +32,7 @@ enum GemmMode : int {
   kGemmStoreF32 = 0,        // out0[(b*rows0 + m)*ld0 + n] = d                               (m < m_valid)
   kGemmStore16Both = 1,     // out0 (bf16 [m][n]) and out1 (bf16 transposed [n][m])
   kGemmAddF32T = 2,         // out0[(b*rows0 + n)*ld0 + m] += d   transposed, m < m_valid       (dA contributions)
-  kGemmAtomicF32 = 3,       // atomicAdd(out0[m*ld0 + n], d)      no batch offset               (dW, reduced over b)
-  kGemmStore16 = 4          // out0 (bf16 [m][n]) only
+  kGemmAtomicF32 = 3        // red.add(out0[m*ld0 + n], d)        no batch offset, K may be split    (dW, reduced over b)
 };
 
 struct GemmParams {
@@ -134,15 +134,6 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K]
             dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
                                  __uint_as_float(v[4 * q + 3]));
         }
-      } else if constexpr (MODE == kGemmStore16) {
-        unsigned short* o0 = static_cast<unsigned short*>(p.out0) + ((int64_t)b * p.rows0 + m) * p.ld0 + n;
-        uint4* d4 = reinterpret_cast<uint4*>(o0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          d4[q] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1])),
-                             pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
-                             pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
-                             pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
       } else if constexpr (MODE == kGemmStore16Both) {
         unsigned short* o0 = static_cast<unsigned short*>(p.out0) + ((int64_t)b * p.rows0 + m) * p.ld0 + n;
         unsigned short* o1 = static_cast<unsigned short*>(p.out1) + ((int64_t)b * p.rows1 + n) * p.ld1 + m;

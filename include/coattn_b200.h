@@ -162,8 +162,8 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
  *                                          (depth modality: the B branch is gradient dead, :240-247)
  *   outputs  d_v_a [N,256,H,W], d_w [256,256], d_gate_w [256], d_gate_b [1] (may be NULL); all overwritten
  *            d_v_b [N,256,H,W] or NULL: gradient for the counterpart frame, only needed with
- *            no_grad_for_counterpart=False (:147-148); costs two more [L,L] transposes and three GEMMs and the
- *            larger workspace (`counterpart` = 1 in the size query).
+ *            no_grad_for_counterpart=False (:147-148); costs two more [L,L] transposes, two GEMMs, a second
+ *            projection and the larger workspace (`counterpart` = 1 in the size query).
  */
 int64_t coattn_backward_workspace_bytes(int n, int c, int h, int w, int counterpart);
 int coattn_backward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* z,
