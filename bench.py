@@ -225,6 +225,8 @@ def run_ours(args):
     lib = _lib.load()
     peaks = read_peaks()
     FLAGS = _lib.FLAG_BF16 if args.operands == "bf16" else 0
+    if args.softmax16:
+        FLAGS |= _lib.FLAG_SOFTMAX16
 
     # pair-sharded weak scaling: the global batch is world * 32 pairs, this rank owns a contiguous slice
     total_pairs = PAIRS_PER_GPU * world
@@ -300,7 +302,7 @@ def run_ours(args):
 
     # ---------------- end to end: host buffers in, host buffers out, through the public host API
     e2e_steps = max(2, min(args.steps, 5))
-    pipe = HostPipeline(n, C, H, W, chunk=4, slots=3, device=dev, bf16_operands=bool(FLAGS))
+    pipe = HostPipeline(n, C, H, W, chunk=4, slots=3, device=dev, bf16_operands=bool(FLAGS & _lib.FLAG_BF16))
     hin = [t.cpu().pin_memory() for t in (v_a, v_b, d_a, d_b)]
     hout = [torch.empty((n, 2 * C, H, W), dtype=torch.float32).pin_memory() for _ in range(4)]
 
@@ -367,7 +369,7 @@ def run_ours(args):
         "unit": "TFLOP/s", "frac": achieved_tflops / sustained,
         # dram__bytes_read.sum + dram__bytes_write.sum of one attend2 launch at this shape, from the committed
         # `ncu --set full` capture (profiles/r1_ncu_kernels.txt): 439.7 MB read + 429.7 MB written
-        "traffic": 869.4e6 if (n == PAIRS_PER_GPU and FLAGS == 0) else None,
+        "traffic": 869.4e6 if (n == PAIRS_PER_GPU and (FLAGS & _lib.FLAG_BF16) == 0) else None,
         "peak_kind": (f"{peaks['source']} sustained dense bf16 (kernel timed inside the {args.steps}-step loop, SM clock "
                       f"{clk.get('sm_mhz')} MHz under the power cap); burst peak {peaks['bf16_tflops']}") if capped else
                      f"{peaks['source']} burst dense bf16 (clocks stayed at boost)",
@@ -414,6 +416,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--operands", default="f16", choices=["f16", "bf16"], help="16-bit tensor-core operand format")
+    ap.add_argument("--softmax16", action="store_true", help="attend kernel with 16 instead of 8 softmax warps (cross-check)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -24,6 +24,7 @@ FLAG_A_ONLY = 8  # COATTN_FLAG_A_ONLY
 FLAG_UNFUSED_PREP = 16  # COATTN_FLAG_UNFUSED_PREP
 FLAG_GATED_ONLY = 32  # COATTN_FLAG_GATED_ONLY
 FLAG_KMAJOR = 64  # COATTN_FLAG_KMAJOR
+FLAG_SOFTMAX16 = 128  # COATTN_FLAG_SOFTMAX16
 
 # name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
 SIGNATURES = {

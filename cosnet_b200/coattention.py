@@ -57,7 +57,8 @@ def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
 
 
 def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False,
-                            unfused_gate=False, want_mask=False, want_z=True, single_cta=False, a_only=False, unfused_prep=False, gated_only=False, kmajor=False):
+                            unfused_gate=False, want_mask=False, want_z=True, single_cta=False, a_only=False, unfused_prep=False, gated_only=False, kmajor=False,
+                            softmax16=False):
     """Runs the CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L]
     (plus mask [2,N,L] when want_mask=True; fused path only).
 
@@ -84,7 +85,7 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         mask = torch.empty((2, n, h * w), dtype=torch.float32, device=dev) if want_mask else None
         flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)
                  | (_lib.FLAG_SINGLE_CTA if single_cta else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
-                 | (_lib.FLAG_UNFUSED_PREP if unfused_prep else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0) | (_lib.FLAG_KMAJOR if kmajor else 0))
+                 | (_lib.FLAG_UNFUSED_PREP if unfused_prep else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0) | (_lib.FLAG_KMAJOR if kmajor else 0) | (_lib.FLAG_SOFTMAX16 if softmax16 else 0))
         code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
                                   None if gb is None else gb.data_ptr(), cat_a.data_ptr(),
                                   None if cat_b is None else cat_b.data_ptr(),

@@ -25,23 +25,34 @@ namespace coattn {
 
 constexpr int k2BM = 128;           // query rows per CTA (256 per pair)
 constexpr int k2BN = 128;           // key/value positions per tile (pair wide)
-constexpr int k2KStages = 3;
 constexpr int k2VStages = 2;
 constexpr int k2QBytes = k2BM * kC * 2;          // 64 KB : 4 k-blocks x [128 rows x 128 B]
 constexpr int k2KBytes = (k2BN / 2) * kC * 2;    // 32 KB : 4 k-blocks x [ 64 rows x 128 B]   (this CTA's key rows)
 constexpr int k2VBytes = (kC / 2) * k2BN * 2;    // 32 KB : 2 k-blocks x [128 rows x 128 B]   (this CTA's channels)
-constexpr int k2Threads = 384;
-constexpr int k2SoftmaxWarps = 8;
-constexpr int k2KProducerWarp = 8;
-constexpr int k2MmaWarp = 9;
-constexpr int k2VProducerWarp = 10;
-constexpr int k2CopyWarp = 11;         // passthrough half of the concat: cat[:, C + c, rows] = v[:, c, rows]
-constexpr int k2ScratchBytes = 2 * 2 * 128 * 4;  // exchange buffer [parity][warpgroup][row]
-constexpr int k2SmemBytes = k2QBytes + k2KStages * k2KBytes + k2VStages * k2VBytes + k2ScratchBytes + 256;
 constexpr uint32_t k2TmemO = 0;
 constexpr uint32_t k2TmemS = 256;
 
-static_assert(k2SmemBytes <= 232448, "attend2 shared memory exceeds the 227 KB per-CTA limit");
+// G = softmax warps per TMEM lane quadrant ("column groups"): the G warps of a quadrant own the same 32 query rows and
+// split the 128 key columns of a tile (and the 256 channels of the drain) G ways.
+//   G = 2:  8 softmax warps, 64 columns / 128 channels per thread, 384 threads, 3 key stages
+//   G = 4: 16 softmax warps, 32 columns /  64 channels per thread, 640 threads (<= 102 registers), 2 key stages
+template <int G>
+struct Attend2Cfg {
+  static constexpr int kSoftmaxWarps = 4 * G;
+  static constexpr int kKProducerWarp = 4 * G;
+  static constexpr int kMmaWarp = 4 * G + 1;
+  static constexpr int kVProducerWarp = 4 * G + 2;
+  static constexpr int kCopyWarp = 4 * G + 3;   // passthrough half of the concat: cat[:, C + c, rows] = v[:, c, rows]
+  static constexpr int kThreads = 32 * (4 * G + 4);
+  static constexpr int kKStages = (G == 2) ? 3 : 2;
+  static constexpr int kCols = k2BN / G;            // key columns per softmax thread
+  static constexpr int kLoads = kCols / 32;         // 32-column TMEM loads per thread and tile
+  static constexpr int kChans = kC / G;             // channels per thread in the drain / rescale
+  static constexpr int kChunks = kChans / 32;
+  static constexpr int kScratchBytes = 2 * G * 128 * 4;   // exchange buffer [parity][group][row]
+  static constexpr int kSmemBytes = k2QBytes + kKStages * k2KBytes + k2VStages * k2VBytes + kScratchBytes + 256;
+  static_assert(kSmemBytes <= 232448, "attend2 shared memory exceeds the 227 KB per-CTA limit");
+};
 
 // Debug builds (-DCOATTN_TRACE2): per-item clock64 stamps of CTA 0 (MMA issuer: slots 0-4, softmax warp 0: slots 8-12),
 // dumped by the host after the third launch.  No device printf -- it perturbs the pipeline it is meant to observe.
@@ -50,7 +61,7 @@ __device__ long long g_attend2_trace[16 * 16];
 #define TRG(slot) do { if (blockIdx.x == 0 && lane == 0 && it < 16) g_attend2_trace[it * 16 + (slot)] = clock64(); } while (0)
 // per-tile stamps of item 3 (warm): MMA issuer slots 0-3, softmax warp 0 slots 4-7
 __device__ long long g_attend2_tiles[32 * 8];
-__device__ long long g_attend2_warps[2 * 32 * 8];   // [saw S | arrived P][tile][softmax warp] of item 3, CTA 0
+__device__ long long g_attend2_warps[2 * 32 * 16];   // [saw S | arrived P][tile][softmax warp] of item 3, CTA 0
 #define TRT(j, slot) do { if (blockIdx.x == 0 && lane == 0 && it == 3 && (j) < 32) g_attend2_tiles[(j) * 8 + (slot)] = clock64(); } while (0)
 #else
 #define TRG(slot) do {} while (0)
@@ -75,22 +86,44 @@ struct Attend2Params {
   int passes;    // 2, or 1 = frame-A outputs only (pass 0; test.py averages x1 only, test.py:301)
 };
 
-// exchange one float between the two threads that own the same query row (warp w and warp w + 4)
-__device__ __forceinline__ float pair_exchange(float v, float* xbuf, uint32_t seq, int wg, int row, int quad) {
-  xbuf[((seq & 1u) * 2 + wg) * 128 + row] = v;
-  named_bar_sync(1 + quad, 64);
-  return xbuf[((seq & 1u) * 2 + (wg ^ 1)) * 128 + row];
+// exchange one float between the G threads that own the same query row (warps quad, quad + 4, ...): every thread gets
+// the maximum / the sum over all G contributions, combined in group order so that all of them hold the same bits
+template <int G>
+__device__ __forceinline__ float group_exchange_max(float v, float* xbuf, uint32_t seq, int g, int row, int quad) {
+  float* base = xbuf + (seq & 1u) * (G * 128);
+  base[g * 128 + row] = v;
+  named_bar_sync(1 + quad, 32 * G);
+  float r = base[row];
+#pragma unroll
+  for (int i = 1; i < G; ++i) r = fmaxf(r, base[i * 128 + row]);
+  return r;
+}
+template <int G>
+__device__ __forceinline__ float group_exchange_sum(float v, float* xbuf, uint32_t seq, int g, int row, int quad) {
+  float* base = xbuf + (seq & 1u) * (G * 128);
+  base[g * 128 + row] = v;
+  named_bar_sync(1 + quad, 32 * G);
+  float r = base[row];
+#pragma unroll
+  for (int i = 1; i < G; ++i) r += base[i * 128 + row];
+  return r;
 }
 
 // MN = false: queries / keys come from the position-major arrays T = [Bt, Qt] ([Lp][C], K-major operands).
 // MN = true : queries / keys come from the channel-major arrays X = [B16, A16, Q16] ([C][Lp], the NCHW orientation)
 //             as MN-major UMMA operands -- no transposed copies of the features exist at all.
-template <bool BF16, bool MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+template <bool BF16, bool MN, int G>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Attend2Cfg<G>::kThreads, 1)
 attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C], box {64, 128};  MN: X [3*N*C][Lp], box {64, 256}
                const __grid_constant__ CUtensorMap tmap_k,  // !MN: T [2*N*Lp][C], box {64, 64};   MN: same map as tmap_q
                const __grid_constant__ CUtensorMap tmap_v,  // VV [2*N*C][Lp],  box {64, 128}
                Attend2Params p) {
+  using Cfg = Attend2Cfg<G>;
+  constexpr int k2KStages = Cfg::kKStages;
+  constexpr int k2SoftmaxWarps = Cfg::kSoftmaxWarps;
+  constexpr int k2KProducerWarp = Cfg::kKProducerWarp, k2MmaWarp = Cfg::kMmaWarp, k2VProducerWarp = Cfg::kVProducerWarp,
+                k2CopyWarp = Cfg::kCopyWarp;
+  constexpr int k2ScratchBytes = Cfg::kScratchBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + k2QBytes;
@@ -104,7 +137,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
   uint64_t* v_full = k_empty + k2KStages;       // (L) [k2VStages]
   uint64_t* v_empty = v_full + k2VStages;       // [k2VStages]
   uint64_t* s_full = v_empty + k2VStages;       // [2]
-  uint64_t* p_full = s_full + 2;                // (L) [2] 16 arrivals: 8 softmax warps of each CTA
+  uint64_t* p_full = s_full + 2;                // (L) [2] one arrival per softmax warp of each CTA
   uint64_t* o_full = p_full + 2;                // one completion per PV step
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
@@ -269,17 +302,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       const uint64_t qd0 = MN ? make_sdesc_mn_sw128(smem_u32(sQ), 32768, 1024) : make_sdesc_k_sw128(smem_u32(sQ));
       const uint32_t sK_addr = smem_u32(sK);
       const uint32_t sV_addr = smem_u32(sV);
-#ifdef COATTN_TRACE
-      long long tr[24][6]; int tc = 0;
-#define TR2(i) do { if (tc < 24) tr[tc][i] = clock64(); } while (0)
-#else
-#define TR2(i) do {} while (0)
-#endif
       for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
         auto issue_s = [&](int j) {
           const uint32_t s = kcnt % k2KStages, ph = (kcnt / k2KStages) & 1;
           warp_mbar_wait(k_full + s, ph, lane, 10);
-          TR2(1);
           tc_fence_after();
           const uint32_t tS = tmem + k2TmemS + (uint32_t)(j & 1) * k2BN;
           const uint64_t kd0 = MN ? make_sdesc_mn_sw128(sK_addr + s * k2KBytes, 32768, 1024) : make_sdesc_k_sw128(sK_addr + s * k2KBytes);
@@ -298,19 +324,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           __syncwarp();
           ++kcnt;
         };
-#ifdef COATTN_TRACE
-        long long ti0 = clock64();
-#endif
         TRG(0);
-#ifdef COATTN_EXP_DELAY_S
-        if (it > 0) { const long long tw = clock64(); while (clock64() - tw < COATTN_EXP_DELAY_S) {} }
-#endif
         warp_mbar_wait(q_full, it & 1, lane, 11);
         tc_fence_after();
         TRG(1);
-#ifdef COATTN_TRACE
-        long long ti1 = clock64(), ti2 = 0;
-#endif
         // Tensor-pipe order per item: S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ... | PV(T-1).  S(j+2) reuses the buffer
         // of P(j) and is issued right behind PV(j) (in-order execution).  The waits for TMA tiles are hoisted to
         // just after the long PV MMAs were queued, so only the wait for P(j) sits between two issue bursts.
@@ -323,18 +340,13 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           warp_mbar_wait(v_full + s, ph, lane, 14);
         }
         for (int j = 0; j < T; ++j) {
-          TR2(0);
           const int b = j & 1;
           // P(0) of an item is only produced after the previous item's O was drained, so no separate O barrier
           if (b == 0) { warp_mbar_wait(p_full + 0, pphase0, lane, 13); pphase0 ^= 1; }
           else        { warp_mbar_wait(p_full + 1, pphase1, lane, 13); pphase1 ^= 1; }
           tc_fence_after();
-          TR2(3);
           if (j == 0) TRG(3);
           TRT(j, 0);
-#ifdef COATTN_TRACE
-          if (j == 0) ti2 = clock64();
-#endif
           const uint32_t s = vcnt % k2VStages;
           const uint32_t tP = tmem + k2TmemS + (uint32_t)b * k2BN;
           const uint64_t vd0 = make_sdesc_k_sw128(sV_addr + s * k2VBytes);
@@ -352,7 +364,6 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           }
           __syncwarp();
           ++vcnt;
-          TR2(4);
           if (j == T - 1) TRG(4);
           TRT(j, 1);
           if (j + 1 < T) {   // value tile of the next step: waited while PV(j) executes
@@ -364,47 +375,27 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             issue_s(j + 2);
             if (j + 3 == T) { if (elect_one()) umma2_commit_mc(q_empty, 3); __syncwarp(); }   // last S of the item issued
           }
-          TR2(5);
           TRT(j, 3);
-#ifdef COATTN_TRACE
-          ++tc;
-#endif
         }
-#ifdef COATTN_TRACE
-        if (blockIdx.x == 0 && lane == 0 && it < 6)
-          printf("MMA item %u: q_full wait %lld | first P wait (incl. S0,S1 issue) %lld | rest of item %lld | total %lld\n", it,
-                 ti1 - ti0, ti2 - ti1, clock64() - ti2, clock64() - ti0);
-#endif
       }
-#ifdef COATTN_TRACE
-      if (blockIdx.x == 0 && lane == 0)
-        for (int i = 2; i < 22; ++i)
-          printf("tile %2d: +%6lld | k_full %5lld | S_issue %5lld | p_full %5lld | v_full %5lld | PV_issue %5lld\n", i,
-                 tr[i][0] - tr[2][0], tr[i][1] - tr[i][0], tr[i][2] - tr[i][1], tr[i][3] - tr[i][2], tr[i][4] - tr[i][3],
-                 tr[i][5] - tr[i][4]);
-#endif
     }
   } else {
     // ------------------------------------------------------------------ softmax + drain
-    const int wg = warp >> 2;            // 0: key columns [0,64) / channels [0,128);  1: the other halves
+    constexpr int kCols = Cfg::kCols, kLoads = Cfg::kLoads, kChans = Cfg::kChans, kChunks = Cfg::kChunks;
+    const int g = warp >> 2;             // column group: key columns [g kCols, (g+1) kCols) / channels [g kChans, (g+1) kChans)
     const int quad = warp & 3;           // TMEM lane quadrant
     const int rloc = quad * 32 + lane;   // query row inside this CTA's 128-row tile
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const uint32_t tO = tmem + lane_base + k2TmemO + (uint32_t)wg * 128;   // this warpgroup's 128 channels
+    const uint32_t tO = tmem + lane_base + k2TmemO + (uint32_t)(g * kChans);   // this group's channels
     const uint32_t p_full_l0 = mapa_u32(smem_u32(p_full + 0), 0);
     const uint32_t p_full_l1 = mapa_u32(smem_u32(p_full + 1), 0);
     uint32_t sphase0 = 0, sphase1 = 0, it = 0, seq = 0;
-    float greg[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.cat_a != nullptr) {
+    // gate weights of this group's channels live in registers, one value per lane and 32-channel chunk, and are
+    // broadcast by shuffles in the drain: 128 global loads per item used to queue behind the copy warp's traffic in the
+    // LSU and made the gate dot the longest part of the drain
+    float greg[kChunks];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) greg[ch] = __ldg(p.gate_w + wg * 128 + ch * 32 + lane);
-    }
-#ifdef COATTN_TRACE
-    long long ts[24][6]; int sc = 0;
-#define TS2(i) do { if (sc < 24) ts[sc][i] = clock64(); } while (0)
-#else
-#define TS2(i) do {} while (0)
-#endif
+    for (int ch = 0; ch < kChunks; ++ch) greg[ch] = (p.cat_a != nullptr) ? __ldg(p.gate_w + g * kChans + ch * 32 + lane) : 0.f;
     for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
       const int qp = item % p.q_pairs;
       const int np = item / p.q_pairs;
@@ -420,64 +411,55 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       for (int j = 0; j < T; ++j) {
         const int b = j & 1;
         const uint32_t tSb = tmem + lane_base + k2TmemS + (uint32_t)b * k2BN;
+        if (b == 0) { warp_mbar_wait(s_full + 0, sphase0, lane, 20); sphase0 ^= 1; }
+        else        { warp_mbar_wait(s_full + 1, sphase1, lane, 20); sphase1 ^= 1; }
+        tc_fence_after();
         if (warp_is_padding) {
-          if (b == 0) { warp_mbar_wait(s_full + 0, sphase0, lane, 20); sphase0 ^= 1; }
-          else        { warp_mbar_wait(s_full + 1, sphase1, lane, 20); sphase1 ^= 1; }
-          tc_fence_after();
-          // the partner warp (same rows) takes the same branch; the exchange barrier still orders its S reads
-          (void)pair_exchange(0.f, xbuf, seq++, wg, rloc, quad);
-          uint32_t zero[32];
+          // the other warps of the row group take the same branch; the exchange barrier still orders their S reads
+          (void)group_exchange_max<G>(0.f, xbuf, seq++, g, rloc, quad);
+          uint32_t zero[kCols / 2];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) zero[k] = 0u;
-          tmem_st32(tSb + wg * 32, zero);
+          for (int k = 0; k < kCols / 2; ++k) zero[k] = 0u;
+          if constexpr (kCols == 64) tmem_st32(tSb + g * 32, zero); else tmem_st16(tSb + g * 16, zero);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(b == 0 ? p_full_l0 : p_full_l1);
           continue;
         }
-        TS2(0);
-        if (b == 0) { warp_mbar_wait(s_full + 0, sphase0, lane, 20); sphase0 ^= 1; }
-        else        { warp_mbar_wait(s_full + 1, sphase1, lane, 20); sphase1 ^= 1; }
-        tc_fence_after();
-        TS2(1);
         if (warp == 0 && j == 0) TRG(9);
         if (warp == 0) TRT(j, 4);
 #ifdef COATTN_TRACE2
-        if (blockIdx.x == 0 && lane == 0 && it == 3 && j < 32) g_attend2_warps[j * 8 + warp] = clock64();
+        if (blockIdx.x == 0 && lane == 0 && it == 3 && j < 32) g_attend2_warps[j * 16 + warp] = clock64();
 #endif
-        uint32_t s0[32], s1[32];
-        tmem_ld32(tSb + wg * 64, s0);
-        tmem_ld32(tSb + wg * 64 + 32, s1);
-        tmem_ld_wait();
-        TS2(2);
-        if (j == T - 1) {
-          const int nvalid = p.L - j * k2BN - wg * 64;   // may be <= 0 for warpgroup 1: everything masked
-          if (nvalid < 64) {
+        uint32_t sv[kLoads][32];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              if (k >= nvalid) s0[k] = 0xff800000u;        // -inf
-              if (32 + k >= nvalid) s1[k] = 0xff800000u;
-            }
+        for (int c = 0; c < kLoads; ++c) tmem_ld32(tSb + g * kCols + c * 32, sv[c]);
+        tmem_ld_wait();
+        if (j == T - 1) {
+          const int nvalid = p.L - j * k2BN - g * kCols;   // may be <= 0 for the upper groups: everything masked
+          if (nvalid < kCols) {
+#pragma unroll
+            for (int c = 0; c < kLoads; ++c)
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (c * 32 + k >= nvalid) sv[c][k] = 0xff800000u;        // -inf
           }
         }
-        // four independent chains (a single 64-deep chain of dependent max operations costs ~250 cycles of latency)
-        float h0 = __uint_as_float(s0[0]), h1 = __uint_as_float(s0[1]), h2 = __uint_as_float(s0[2]), h3 = __uint_as_float(s0[3]);
+        // four independent chains (a single deep chain of dependent max operations costs ~4 cycles per element)
+        float h0 = __uint_as_float(sv[0][0]), h1 = __uint_as_float(sv[0][1]), h2 = __uint_as_float(sv[0][2]),
+              h3 = __uint_as_float(sv[0][3]);
 #pragma unroll
-        for (int k = 4; k < 32; k += 4) {
-          h0 = fmaxf(h0, __uint_as_float(s0[k]));     h1 = fmaxf(h1, __uint_as_float(s0[k + 1]));
-          h2 = fmaxf(h2, __uint_as_float(s0[k + 2])); h3 = fmaxf(h3, __uint_as_float(s0[k + 3]));
-        }
+        for (int c = 0; c < kLoads; ++c)
 #pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-          h0 = fmaxf(h0, __uint_as_float(s1[k]));     h1 = fmaxf(h1, __uint_as_float(s1[k + 1]));
-          h2 = fmaxf(h2, __uint_as_float(s1[k + 2])); h3 = fmaxf(h3, __uint_as_float(s1[k + 3]));
-        }
+          for (int k = (c == 0 ? 4 : 0); k < 32; k += 4) {
+            h0 = fmaxf(h0, __uint_as_float(sv[c][k]));     h1 = fmaxf(h1, __uint_as_float(sv[c][k + 1]));
+            h2 = fmaxf(h2, __uint_as_float(sv[c][k + 2])); h3 = fmaxf(h3, __uint_as_float(sv[c][k + 3]));
+          }
         const float hmax = fmaxf(fmaxf(h0, h1), fmaxf(h2, h3));
-        // both halves of the row agree on the tile max; the exchange barrier also orders "both warpgroups have
-        // read their S columns" before either overwrites them with P (P of warpgroup 1 lands on S of warpgroup 0)
-        const float tmax = fmaxf(hmax, pair_exchange(hmax, xbuf, seq++, wg, rloc, quad));
-        TS2(3);
+        // all groups of the row agree on the tile max; the exchange barrier also orders "every group has read its S
+        // columns" before any of them overwrites S with P (the packed P of the upper groups lands on S of the lower ones)
+        const float tmax = group_exchange_max<G>(hmax, xbuf, seq++, g, rloc, quad);
         if (j == 0) {
           m = tmax;
         } else {
@@ -494,7 +476,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             warp_mbar_wait(o_full, (pv_base + (uint32_t)j - 1u) & 1u, lane, 21);
             tc_fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int ch = 0; ch < kChunks; ++ch) {
               uint32_t o[32];
               tmem_ld32(tO + ch * 32, o);
               tmem_ld_wait();
@@ -508,84 +490,57 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           }
         }
         const float neg_m = -m * kLog2e;
-        uint32_t pk[32];
+        uint32_t pk[kCols / 2];
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float x0 = fmaf(__uint_as_float(s0[2 * k]), kLog2e, neg_m);
-          const float x1 = fmaf(__uint_as_float(s0[2 * k + 1]), kLog2e, neg_m);
-          const float p0 = fast_exp2(x0);
-          const float p1 = fast_exp2(x1);
-          pk[k] = pack16x2<BF16>(p0, p1);
-          if constexpr (BF16) { l0 += bf16lo_to_f32(pk[k]); l1 += bf16hi_to_f32(pk[k]); }
-          else { l0 += p0; l1 += p1; }
-        }
+        for (int c = 0; c < kLoads; ++c)
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float x0 = fmaf(__uint_as_float(s1[2 * k]), kLog2e, neg_m);
-          const float x1 = fmaf(__uint_as_float(s1[2 * k + 1]), kLog2e, neg_m);
-          const float p0 = fast_exp2(x0);
-          const float p1 = fast_exp2(x1);
-          pk[16 + k] = pack16x2<BF16>(p0, p1);
-          if constexpr (BF16) { l2 += bf16lo_to_f32(pk[16 + k]); l3 += bf16hi_to_f32(pk[16 + k]); }
-          else { l2 += p0; l3 += p1; }
-        }
+          for (int k = 0; k < 16; ++k) {
+            const float x0 = fmaf(__uint_as_float(sv[c][2 * k]), kLog2e, neg_m);
+            const float x1 = fmaf(__uint_as_float(sv[c][2 * k + 1]), kLog2e, neg_m);
+            const float p0 = fast_exp2(x0);
+            const float p1 = fast_exp2(x1);
+            const uint32_t w = pack16x2<BF16>(p0, p1);
+            pk[c * 16 + k] = w;
+            if constexpr (BF16) {
+              if (k & 1) { l2 += bf16lo_to_f32(w); l3 += bf16hi_to_f32(w); } else { l0 += bf16lo_to_f32(w); l1 += bf16hi_to_f32(w); }
+            } else {
+              if (k & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
+            }
+          }
         l += (l0 + l1) + (l2 + l3);
-        TS2(4);
-        tmem_st32(tSb + wg * 32, pk);   // packed P: 64 keys of this warpgroup -> 32 columns
+        // packed P: the kCols keys of this group -> kCols / 2 columns
+        if constexpr (kCols == 64) tmem_st32(tSb + g * 32, pk); else tmem_st16(tSb + g * 16, pk);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(b == 0 ? p_full_l0 : p_full_l1);
-        TS2(5);
         if (warp == 0) TRT(j, 5);
 #ifdef COATTN_TRACE2
-        if (blockIdx.x == 0 && lane == 0 && it == 3 && j < 32) g_attend2_warps[256 + j * 8 + warp] = clock64();
-#endif
-#ifdef COATTN_TRACE
-        ++sc;
+        if (blockIdx.x == 0 && lane == 0 && it == 3 && j < 32) g_attend2_warps[512 + j * 16 + warp] = clock64();
 #endif
       }
-#ifdef COATTN_TRACE
-      if (blockIdx.x == 0 && threadIdx.x == 0 && it == 0)
-        for (int i = 2; i < 20; ++i)
-          printf("softmax tile %2d: +%6lld | wait S %5lld | ld %5lld | max+xchg %5lld | exp %5lld | st+arrive %5lld\n", i,
-                 ts[i][0] - ts[2][0], ts[i][1] - ts[i][0], ts[i][2] - ts[i][1], ts[i][3] - ts[i][2], ts[i][4] - ts[i][3],
-                 ts[i][5] - ts[i][4]);
-#endif
-#ifdef COATTN_TRACE
-      long long td0 = clock64();
-#endif
       if (warp == 0) TRG(10);
       // ---- drain.  Wait the last two PV phases one by one (see attend_kernel for the aliasing argument).
       if (T >= 2) warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 2u) & 1u, lane, 23);
       warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, lane, 22);
       tc_fence_after();
       if (warp == 0) TRG(11);
-#ifdef COATTN_EXP_EARLY_LD
-      {
-        uint32_t tmp[32];
-        tmem_ld32(tmem + lane_base + k2TmemS + COATTN_EXP_EARLY_LD, tmp);   // probe: a load right behind the last PV
-        tmem_ld_wait();
-        if (tmp[0] == 0x7fc12345u) l += 1.0f;
-        if (warp == 0) TRG(15);
-      }
-#endif
-      l += pair_exchange(l, xbuf, seq++, wg, rloc, quad);
+      l = group_exchange_sum<G>(l, xbuf, seq++, g, rloc, quad);
       if (warp == 0) TRG(5);
       if (warp_is_padding) {     // nothing to store; keep the exchange sequence of the gate dot in step
-        if (p.cat_a != nullptr) (void)pair_exchange(0.f, xbuf, seq++, wg, rloc, quad);
+        if (p.cat_a != nullptr) (void)group_exchange_sum<G>(0.f, xbuf, seq++, g, rloc, quad);
         continue;
       }
       const float inv = 1.0f / l;
       const bool valid = row < p.L;
-      const int c0 = wg * 128;
+      const int c0 = g * kChans;
       // raw Z (kept for the backward pass): written in the same sweep over O as the gated output below; a sweep of its
       // own only when there is no fused gate (coattn_stage_attend)
       float* zcol = p.z ? p.z + ((size_t)(pass * p.N + n) * kC + c0) * p.L + row : nullptr;
       if (zcol != nullptr && p.cat_a == nullptr) {
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < kChunks; ++ch) {
           uint32_t o[32];
           tmem_ld32(tO + ch * 32, o);
           tmem_ld_wait();
@@ -596,9 +551,6 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         }
       }
       if (p.cat_a != nullptr) {
-        // gate weights of this warpgroup's 128 channels live in registers, one value per lane and 32-channel chunk
-        // (greg, loaded once per kernel) and are broadcast by shuffles: 128 global loads per item used to queue behind
-        // the copy warp's traffic in the LSU and made this pass the longest part of the drain
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
         {
           uint32_t oa[32], ob[32];
@@ -606,10 +558,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           tmem_ld_wait();
           if (warp == 0) TRG(6);
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {     // chunk ch + 1 streams out of TMEM while chunk ch is consumed
+          for (int ch = 0; ch < kChunks; ++ch) {     // chunk ch + 1 streams out of TMEM while chunk ch is consumed
             uint32_t (&o)[32] = (ch & 1) ? ob : oa;
             uint32_t (&nx)[32] = (ch & 1) ? oa : ob;
-            if (ch < 3) tmem_ld32(tO + (ch + 1) * 32, nx);
+            if (ch + 1 < kChunks) tmem_ld32(tO + (ch + 1) * 32, nx);
 #pragma unroll
             for (int k = 0; k < 32; k += 4) {
               d0 = fmaf(__shfl_sync(0xffffffffu, greg[ch], k + 0), __uint_as_float(o[k + 0]), d0);
@@ -617,14 +569,13 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
               d2 = fmaf(__shfl_sync(0xffffffffu, greg[ch], k + 2), __uint_as_float(o[k + 2]), d2);
               d3 = fmaf(__shfl_sync(0xffffffffu, greg[ch], k + 3), __uint_as_float(o[k + 3]), d3);
             }
-            if (ch < 3) tmem_ld_wait();
+            if (ch + 1 < kChunks) tmem_ld_wait();
           }
         }
         float dot = (d0 + d1) + (d2 + d3);
         if (warp == 0) TRG(13);
-        const float other = pair_exchange(dot, xbuf, seq++, wg, rloc, quad);
+        dot = group_exchange_sum<G>(dot, xbuf, seq++, g, rloc, quad);   // same summation order in every group
         if (warp == 0) TRG(14);
-        dot = (wg == 0) ? (dot + other) : (other + dot);   // same summation order in both halves
         const float logit = dot * inv + (p.gate_b ? __ldg(p.gate_b) : 0.f);
         const float gate = 1.0f / (1.0f + __expf(-logit));
         const float sc = inv * gate;
@@ -635,10 +586,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           tmem_ld_wait();
           if (warp == 0) TRG(7);
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = 0; ch < kChunks; ++ch) {
             uint32_t (&o)[32] = (ch & 1) ? ob : oa;
             uint32_t (&nx)[32] = (ch & 1) ? oa : ob;
-            if (ch < 3) tmem_ld32(tO + (ch + 1) * 32, nx);
+            if (ch + 1 < kChunks) tmem_ld32(tO + (ch + 1) * 32, nx);
             if (valid) {
 #pragma unroll
               for (int k = 0; k < 32; ++k) __stcs(ccol + (size_t)(ch * 32 + k) * p.L, __uint_as_float(o[k]) * sc);
@@ -647,16 +598,13 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
                 for (int k = 0; k < 32; ++k) zcol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * inv;
               }
             }
-            if (ch < 3) tmem_ld_wait();
+            if (ch + 1 < kChunks) tmem_ld_wait();
           }
         }
-        if (valid && wg == 0 && p.mask != nullptr) p.mask[(size_t)(pass * p.N + n) * p.L + row] = gate;
+        if (valid && g == 0 && p.mask != nullptr) p.mask[(size_t)(pass * p.N + n) * p.L + row] = gate;
       }
-      if (valid && wg == 0) p.lse[(size_t)(pass * p.N + n) * p.L + row] = m + __logf(l);
+      if (valid && g == 0) p.lse[(size_t)(pass * p.N + n) * p.L + row] = m + __logf(l);
       if (warp == 0) TRG(12);
-#ifdef COATTN_TRACE
-      if (blockIdx.x == 0 && threadIdx.x == 0 && it < 6) printf("softmax item %u: drain (from last P arrive to end) %lld cycles\n", it, clock64() - td0);
-#endif
     }
   }
   tc_fence_before();

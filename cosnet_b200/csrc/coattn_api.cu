@@ -330,13 +330,21 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     q.kv_tiles = (ly.L + k2BN - 1) / k2BN;
     q.passes = (flags & COATTN_FLAG_A_ONLY) ? 1 : 2;
     q.num_items = q.passes * n * q.q_pairs;
-    auto kern2 = mn ? (bf16 ? attend2_kernel<true, true> : attend2_kernel<false, true>)
-                    : (bf16 ? attend2_kernel<true, false> : attend2_kernel<false, false>);
-    cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+    // 8 softmax warps (two column groups per TMEM lane quadrant) by default; COATTN_FLAG_SOFTMAX16 selects the 16-warp
+    // layout (four groups)
+    const bool g4 = (flags & COATTN_FLAG_SOFTMAX16) != 0;
+    void (*kern2)(CUtensorMap, CUtensorMap, CUtensorMap, Attend2Params);
+    if (g4) kern2 = mn ? (bf16 ? attend2_kernel<true, true, 4> : attend2_kernel<false, true, 4>)
+                       : (bf16 ? attend2_kernel<true, false, 4> : attend2_kernel<false, false, 4>);
+    else    kern2 = mn ? (bf16 ? attend2_kernel<true, true, 2> : attend2_kernel<false, true, 2>)
+                       : (bf16 ? attend2_kernel<true, false, 2> : attend2_kernel<false, false, 2>);
+    const int smem2 = g4 ? Attend2Cfg<4>::kSmemBytes : Attend2Cfg<2>::kSmemBytes;
+    const int threads2 = g4 ? Attend2Cfg<4>::kThreads : Attend2Cfg<2>::kThreads;
+    cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
     if (e2 != cudaSuccess) return (int)e2;
     int clusters = sms / 2;
     if (q.num_items < clusters) clusters = q.num_items;
-    kern2<<<2 * clusters, k2Threads, k2SmemBytes, st>>>(tm_q, tm_k2, tm_v2, q);
+    kern2<<<2 * clusters, threads2, smem2, st>>>(tm_q, tm_k2, tm_v2, q);
 #ifdef COATTN_TRACE2
     {
       static int calls = 0;

@@ -94,6 +94,13 @@ enum {
  *                          operands, so the prep stage is a pure cast.  Same arithmetic, bit-identical results.
  */
 #define COATTN_FLAG_KMAJOR 64u
+/*
+ *   COATTN_FLAG_SOFTMAX16  attend kernel with 16 softmax warps (four column groups per TMEM lane quadrant, 32 key columns
+ *                          per thread, two key stages) instead of the default 8 (two groups, 64 columns per thread).
+ *                          Measured ~3 % slower at 60x60 (the softmax chain is bound by the MUFU pipe, not by warp
+ *                          count); kept as a cross-check of the column-group logic.
+ */
+#define COATTN_FLAG_SOFTMAX16 128u
 
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);

@@ -420,3 +420,22 @@ def test_forward_is_cuda_graph_capturable(op):
         torch.cuda.synchronize()
         want = op(fa, fb, W, g, b)
         assert torch.equal(cat_a, want[0]) and torch.equal(cat_b, want[1])
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 1, 1), (2, 12, 11), (1, 31, 41), (1, 60, 60), (2, 61, 81)])
+def test_softmax16_cross_check_kernel(op, n, h, w):
+    """COATTN_FLAG_SOFTMAX16: the attend kernel with 16 softmax warps (four column groups, 32 key columns per thread)
+    against the default 8-warp layout (two groups): same MMAs, same exponentials, only the order of a few fp32
+    additions differs; both against the oracle.  Shapes cover single-tile, ragged and multi-item cases."""
+    v_a, v_b = orc.synthetic_features(89, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(90, bias=True)
+    dev = torch.device("cuda:0")
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    narrow = op(t(v_a), t(v_b), t(W), t(g), t(b))
+    wide = op(t(v_a), t(v_b), t(W), t(g), t(b), softmax16=True)
+    torch.cuda.synchronize()
+    ref = orc.coattention(v_a, v_b, W, g, b)
+    for out in (wide, narrow):
+        assert rel_l2(out[0].cpu().numpy(), ref["cat_a"]) < TOL and rel_l2(out[1].cpu().numpy(), ref["cat_b"]) < TOL
+    for x, y in zip(wide, narrow):    # cat_a, cat_b, z, lse
+        assert (x - y).abs().max() <= 1e-5 * max(1.0, float(y.abs().max()))
