@@ -16,7 +16,9 @@
 //   warp 11     copies this CTA's 128 positions of the original fp32 features into channels [256,512) of the
 //               concat (the passthrough half, :186-187) while the tensor pipe is busy -- ~3.5 B/clk per SM
 //
-//   TMEM columns (per CTA): [0,256) O accumulator | [256,384) S/P buffer 0 | [384,512) S/P buffer 1
+//   TMEM columns (per CTA): [0,256) O accumulator | [256,384) S (one buffer) | [384,448) P buffer 0 | [448,512) P buffer 1
+//   The softmax warps pull S(j) into registers and release the S buffer at once (s_free), so S(j+1) is computed while
+//   they exponentiate; P(j) goes to its own buffer, so S never waits for a PV.
 //   Barriers with a "(L)" are only used in the leader CTA and are signalled from both CTAs.
 #pragma once
 #include "coattn_kernels.cuh"
@@ -30,7 +32,8 @@ constexpr int k2QBytes = k2BM * kC * 2;          // 64 KB : 4 k-blocks x [128 ro
 constexpr int k2KBytes = (k2BN / 2) * kC * 2;    // 32 KB : 4 k-blocks x [ 64 rows x 128 B]   (this CTA's key rows)
 constexpr int k2VBytes = (kC / 2) * k2BN * 2;    // 32 KB : 2 k-blocks x [128 rows x 128 B]   (this CTA's channels)
 constexpr uint32_t k2TmemO = 0;
-constexpr uint32_t k2TmemS = 256;
+constexpr uint32_t k2TmemS = 256;   // 128 columns: fp32 affinity tile
+constexpr uint32_t k2TmemP = 384;   // 2 x 64 columns: 16-bit softmax numerators of two consecutive tiles
 
 // G = softmax warps per TMEM lane quadrant ("column groups"): the G warps of a quadrant own the same 32 query rows and
 // split the 128 key columns of a tile (and the 256 channels of the drain) G ways.
@@ -136,10 +139,12 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
   uint64_t* k_empty = k_full + k2KStages;       // [k2KStages]
   uint64_t* v_full = k_empty + k2KStages;       // (L) [k2VStages]
   uint64_t* v_empty = v_full + k2VStages;       // [k2VStages]
-  uint64_t* s_full = v_empty + k2VStages;       // [2]
+  uint64_t* s_full = v_empty + k2VStages;       // S(j) complete (both CTAs)
+  uint64_t* s_free = s_full + 1;                // (L) S(j) sits in the registers of every softmax warp of the pair
   uint64_t* p_full = s_full + 2;                // (L) [2] one arrival per softmax warp of each CTA
-  uint64_t* o_full = p_full + 2;                // one completion per PV step
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* o_full = p_full + 2;                // [2] PV(j) complete, on barrier j & 1: a waiter can then never be two
+                                                //     phases behind (the next completion on the same barrier needs P(j+2))
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,8 +164,11 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     mbar_init(q_empty, 1);
     for (int s = 0; s < k2KStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
     for (int s = 0; s < k2VStages; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(s_full + b, 1); mbar_init(p_full + b, 2 * k2SoftmaxWarps); }
-    mbar_init(o_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 2 * k2SoftmaxWarps);
+    for (int b = 0; b < 2; ++b) mbar_init(p_full + b, 2 * k2SoftmaxWarps);
+    mbar_init(o_full + 0, 1);
+    mbar_init(o_full + 1, 1);
     fence_mbar_init();
   }
   if (warp == k2MmaWarp) {
@@ -299,15 +307,18 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       uint32_t it = 0, kcnt = 0, vcnt = 0;
       uint32_t pphase0 = 0, pphase1 = 0;
       const uint32_t tO = tmem + k2TmemO;
+      const uint32_t tS = tmem + k2TmemS;
       const uint64_t qd0 = MN ? make_sdesc_mn_sw128(smem_u32(sQ), 32768, 1024) : make_sdesc_k_sw128(smem_u32(sQ));
       const uint32_t sK_addr = smem_u32(sK);
       const uint32_t sV_addr = smem_u32(sV);
       for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
+        // S(j) of this item; kcnt counts every S tile of the kernel (key stage ring and s_free phases)
         auto issue_s = [&](int j) {
           const uint32_t s = kcnt % k2KStages, ph = (kcnt / k2KStages) & 1;
           warp_mbar_wait(k_full + s, ph, lane, 10);
+          // the single S buffer: every softmax warp of the pair has pulled the previous tile into registers
+          if (kcnt > 0) warp_mbar_wait(s_free, (kcnt - 1) & 1, lane, 12);
           tc_fence_after();
-          const uint32_t tS = tmem + k2TmemS + (uint32_t)(j & 1) * k2BN;
           const uint64_t kd0 = MN ? make_sdesc_mn_sw128(sK_addr + s * k2KBytes, 32768, 1024) : make_sdesc_k_sw128(sK_addr + s * k2KBytes);
           const uint32_t idesc = (j == T - 1) ? idesc_s_last : idesc_s;
           if (elect_one()) {
@@ -319,7 +330,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
               umma2_ss(tS, ad, bd, idesc, kk > 0);
             }
             umma2_commit_mc(k_empty + s, 3);
-            umma2_commit_mc(s_full + (j & 1), 3);
+            umma2_commit_mc(s_full, 3);
+            if (j == T - 1) umma2_commit_mc(q_empty, 3);     // last affinity tile of the item: the query tile is free
           }
           __syncwarp();
           ++kcnt;
@@ -328,19 +340,22 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         warp_mbar_wait(q_full, it & 1, lane, 11);
         tc_fence_after();
         TRG(1);
-        // Tensor-pipe order per item: S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ... | PV(T-1).  S(j+2) reuses the buffer
-        // of P(j) and is issued right behind PV(j) (in-order execution).  The waits for TMA tiles are hoisted to
-        // just after the long PV MMAs were queued, so only the wait for P(j) sits between two issue bursts.
+        // Tensor-pipe order per item: S(0) S(1) | S(2) PV(0) | S(3) PV(1) | ... | PV(T-1).  S(j+2) only needs the S buffer
+        // back (s_free(j+1): the softmax warps hold S(j+1) in registers) and is computed while they work on tile j+1;
+        // PV(j) follows when P(j) is complete.  Both conditions arrive when softmax(j) ends, and the affinity tile goes
+        // first, so the next S is ready when the softmax warps come back for it.
         issue_s(0);
         if (T > 1) issue_s(1);
-        if (T <= 2) { if (elect_one()) umma2_commit_mc(q_empty, 3); __syncwarp(); }
         TRG(2);
-        {
-          const uint32_t s = vcnt % k2VStages, ph = (vcnt / k2VStages) & 1;
-          warp_mbar_wait(v_full + s, ph, lane, 14);
-        }
         for (int j = 0; j < T; ++j) {
           const int b = j & 1;
+          TRT(j, 2);
+          if (j + 2 < T) issue_s(j + 2);
+          TRT(j, 3);
+          {
+            const uint32_t s = vcnt % k2VStages, ph = (vcnt / k2VStages) & 1;
+            warp_mbar_wait(v_full + s, ph, lane, 14);
+          }
           // P(0) of an item is only produced after the previous item's O was drained, so no separate O barrier
           if (b == 0) { warp_mbar_wait(p_full + 0, pphase0, lane, 13); pphase0 ^= 1; }
           else        { warp_mbar_wait(p_full + 1, pphase1, lane, 13); pphase1 ^= 1; }
@@ -348,7 +363,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           if (j == 0) TRG(3);
           TRT(j, 0);
           const uint32_t s = vcnt % k2VStages;
-          const uint32_t tP = tmem + k2TmemS + (uint32_t)b * k2BN;
+          const uint32_t tP = tmem + k2TmemP + (uint32_t)b * (k2BN / 2);
           const uint64_t vd0 = make_sdesc_k_sw128(sV_addr + s * k2VBytes);
           const int ksteps = (j == T - 1) ? ksteps_last : k2BN / 16;
           if (elect_one()) {
@@ -360,22 +375,12 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
               }
             }
             umma2_commit_mc(v_empty + s, 3);
-            umma2_commit_mc(o_full, 3);
+            umma2_commit_mc(o_full + b, 3);
           }
           __syncwarp();
           ++vcnt;
           if (j == T - 1) TRG(4);
           TRT(j, 1);
-          if (j + 1 < T) {   // value tile of the next step: waited while PV(j) executes
-            const uint32_t s1 = vcnt % k2VStages, ph1 = (vcnt / k2VStages) & 1;
-            warp_mbar_wait(v_full + s1, ph1, lane, 14);
-          }
-          TRT(j, 2);
-          if (j + 2 < T) {
-            issue_s(j + 2);
-            if (j + 3 == T) { if (elect_one()) umma2_commit_mc(q_empty, 3); __syncwarp(); }   // last S of the item issued
-          }
-          TRT(j, 3);
         }
       }
     }
@@ -389,7 +394,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     const uint32_t tO = tmem + lane_base + k2TmemO + (uint32_t)(g * kChans);   // this group's channels
     const uint32_t p_full_l0 = mapa_u32(smem_u32(p_full + 0), 0);
     const uint32_t p_full_l1 = mapa_u32(smem_u32(p_full + 1), 0);
-    uint32_t sphase0 = 0, sphase1 = 0, it = 0, seq = 0;
+    const uint32_t s_free_l = mapa_u32(smem_u32(s_free), 0);
+    uint32_t scnt = 0, it = 0, seq = 0;     // scnt: S tiles consumed so far (phase of s_full)
     // gate weights of this group's channels live in registers, one value per lane and 32-channel chunk, and are
     // broadcast by shuffles in the drain: 128 global loads per item used to queue behind the copy warp's traffic in the
     // LSU and made the gate dot the longest part of the drain
@@ -402,7 +408,12 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       const int pass = (p.passes == 2) ? (np & 1) : 0;
       const int n = (p.passes == 2) ? (np >> 1) : np;
       const int row = qp * (2 * k2BM) + (int)rank * k2BM + rloc;
-      const uint32_t pv_base = it * (uint32_t)T;
+      // phase index of PV(j) on o_full[j & 1]: tiles of that parity in the earlier items + (j >> 1)
+      const uint32_t pv_base0 = it * (uint32_t)((T + 1) / 2), pv_base1 = it * (uint32_t)(T / 2);
+      auto wait_pv = [&](int jj, int tag) {      // PV(jj) complete; requires PV(jj - 2) to be known complete
+        const uint32_t ph = ((jj & 1) ? pv_base1 : pv_base0) + (uint32_t)(jj >> 1);
+        warp_mbar_wait(o_full + (jj & 1), ph & 1u, lane, tag);
+      };
       // rows of this warp that lie entirely in the padding of the last query tile: no softmax math, P = 0
       // (zero MMA operands also draw less power, and this kernel runs against the power cap)
       const bool warp_is_padding = (qp * (2 * k2BM) + (int)rank * k2BM + quad * 32) >= p.L;
@@ -410,17 +421,22 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       if (warp == 0) TRG(8);
       for (int j = 0; j < T; ++j) {
         const int b = j & 1;
-        const uint32_t tSb = tmem + lane_base + k2TmemS + (uint32_t)b * k2BN;
-        if (b == 0) { warp_mbar_wait(s_full + 0, sphase0, lane, 20); sphase0 ^= 1; }
-        else        { warp_mbar_wait(s_full + 1, sphase1, lane, 20); sphase1 ^= 1; }
+        const uint32_t tSg = tmem + lane_base + k2TmemS + (uint32_t)(g * kCols);                       // this group's S columns
+        const uint32_t tPg = tmem + lane_base + k2TmemP + (uint32_t)(b * (k2BN / 2) + g * (kCols / 2));  // ... and its P slot
+        warp_mbar_wait(s_full, scnt & 1, lane, 20);
+        ++scnt;
         tc_fence_after();
         if (warp_is_padding) {
-          // the other warps of the row group take the same branch; the exchange barrier still orders their S reads
+          // nothing to read: hand the S buffer back, keep the exchange sequence in step, P = 0
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(s_free_l);
           (void)group_exchange_max<G>(0.f, xbuf, seq++, g, rloc, quad);
           uint32_t zero[kCols / 2];
 #pragma unroll
           for (int k = 0; k < kCols / 2; ++k) zero[k] = 0u;
-          if constexpr (kCols == 64) tmem_st32(tSb + g * 32, zero); else tmem_st16(tSb + g * 16, zero);
+          if (j >= 2) { wait_pv(j - 2, 24); tc_fence_after(); }
+          if constexpr (kCols == 64) tmem_st32(tPg, zero); else tmem_st16(tPg, zero);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
@@ -434,8 +450,12 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
 #endif
         uint32_t sv[kLoads][32];
 #pragma unroll
-        for (int c = 0; c < kLoads; ++c) tmem_ld32(tSb + g * kCols + c * 32, sv[c]);
+        for (int c = 0; c < kLoads; ++c) tmem_ld32(tSg + c * 32, sv[c]);
         tmem_ld_wait();
+        // S(j) is in registers: release the buffer so that S(j+1) is computed while this tile is exponentiated
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(s_free_l);
         if (j == T - 1) {
           const int nvalid = p.L - j * k2BN - g * kCols;   // may be <= 0 for the upper groups: everything masked
           if (nvalid < kCols) {
@@ -457,8 +477,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             h2 = fmaxf(h2, __uint_as_float(sv[c][k + 2])); h3 = fmaxf(h3, __uint_as_float(sv[c][k + 3]));
           }
         const float hmax = fmaxf(fmaxf(h0, h1), fmaxf(h2, h3));
-        // all groups of the row agree on the tile max; the exchange barrier also orders "every group has read its S
-        // columns" before any of them overwrites S with P (the packed P of the upper groups lands on S of the lower ones)
+        // all groups of the row agree on the tile max
         const float tmax = group_exchange_max<G>(hmax, xbuf, seq++, g, rloc, quad);
         if (j == 0) {
           m = tmax;
@@ -472,8 +491,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           if (__any_sync(0xffffffffu, need)) {
             const float m_new = fmaxf(m, tmax);
             const float scale = fast_exp2((m - m_new) * kLog2e);
-            // PV(j-2) is complete (s_full(j) was observed), so the barrier is in phase j-1 or later
-            warp_mbar_wait(o_full, (pv_base + (uint32_t)j - 1u) & 1u, lane, 21);
+            // S(j) follows PV(j-3) in the tensor pipe, so s_full(j) implies PV(j-3) is complete
+            wait_pv(j - 1, 21);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < kChunks; ++ch) {
@@ -509,8 +528,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             }
           }
         l += (l0 + l1) + (l2 + l3);
-        // packed P: the kCols keys of this group -> kCols / 2 columns
-        if constexpr (kCols == 64) tmem_st32(tSb + g * 32, pk); else tmem_st16(tSb + g * 16, pk);
+        // packed P: the kCols keys of this group -> kCols / 2 columns of P buffer b, once PV(j-2) has read its previous
+        // content (S(j) is issued ahead of PV(j-2), so s_full(j) does not imply it; the wait is almost always over)
+        if (j >= 2) { wait_pv(j - 2, 24); tc_fence_after(); }
+        if constexpr (kCols == 64) tmem_st32(tPg, pk); else tmem_st16(tPg, pk);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -521,9 +542,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
 #endif
       }
       if (warp == 0) TRG(10);
-      // ---- drain.  Wait the last two PV phases one by one (see attend_kernel for the aliasing argument).
-      if (T >= 2) warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 2u) & 1u, lane, 23);
-      warp_mbar_wait(o_full, (pv_base + (uint32_t)T - 1u) & 1u, lane, 22);
+      // ---- drain.  s_full(T-1) only implies PV(T-4): wait PV(T-2) first (completions are in order), then PV(T-1).
+      if (T >= 2) wait_pv(T - 2, 23);
+      wait_pv(T - 1, 22);
       tc_fence_after();
       if (warp == 0) TRG(11);
       l = group_exchange_sum<G>(l, xbuf, seq++, g, rloc, quad);

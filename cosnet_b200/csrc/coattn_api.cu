@@ -356,9 +356,9 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
         cudaMemcpyFromSymbol(tb, g_attend2_tiles, sizeof(tb));
         for (int j = 1; j < 29; ++j) {
           const long long* r = tb + j * 8;
-          printf("tile %2d: MMA saw P at +%6lld (%5lld after warp 0's arrive) | PV issue %4lld | v_full wait %4lld | S(j+2) issue %5lld"
-                 " || softmax saw S at +%6lld | busy %5lld | period %5lld\n", j, r[0] - tb[8], r[0] - r[5], r[1] - r[0], r[2] - r[1],
-                 r[3] - r[2], r[4] - tb[8], r[5] - r[4], r[4] - tb[(j - 1) * 8 + 4]);
+          printf("tile %2d: MMA loop top +%6lld | S(j+2): waits+issue %5lld | then P(j) seen after %5lld | PV issue %4lld"
+                 " || softmax saw S at +%6lld | busy %5lld | period %5lld | P(j) arrive (warp 0) +%6lld\n", j, r[2] - tb[8 + 2],
+                 r[3] - r[2], r[0] - r[3], r[1] - r[0], r[4] - tb[8 + 2], r[5] - r[4], r[4] - tb[(j - 1) * 8 + 4], r[5] - tb[8 + 2]);
         }
         long long wb[2 * 32 * 8];
         cudaMemcpyFromSymbol(wb, g_attend2_warps, sizeof(wb));
