@@ -227,6 +227,8 @@ def run_ours(args):
     FLAGS = _lib.FLAG_BF16 if args.operands == "bf16" else 0
     if args.softmax16:
         FLAGS |= _lib.FLAG_SOFTMAX16
+    if args.kmajor:
+        FLAGS |= _lib.FLAG_KMAJOR
 
     # pair-sharded weak scaling: the global batch is world * 32 pairs, this rank owns a contiguous slice
     total_pairs = PAIRS_PER_GPU * world
@@ -416,6 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--operands", default="f16", choices=["f16", "bf16"], help="16-bit tensor-core operand format")
+    ap.add_argument("--kmajor", action="store_true", help="position-major (transposed) operand copies instead of the default "
+                    "channel-major planes (cross-check path)")
     ap.add_argument("--softmax16", action="store_true", help="attend kernel with 16 instead of 8 softmax warps (cross-check)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
