@@ -370,8 +370,8 @@ def run_ours(args):
         "kernel": "attend2_kernel", "bound": "tensor", "achieved": achieved_tflops, "peak": sustained,
         "unit": "TFLOP/s", "frac": achieved_tflops / sustained,
         # dram__bytes_read.sum + dram__bytes_write.sum of one attend2 launch at this shape, from the committed
-        # `ncu --set full` capture (profiles/r1_ncu_kernels.txt): 439.7 MB read + 429.7 MB written
-        "traffic": 869.4e6 if (n == PAIRS_PER_GPU and (FLAGS & _lib.FLAG_BF16) == 0) else None,
+        # `ncu --set full` capture (profiles/r1_ncu_kernels.txt): 440.3 MB read + 427.9 MB written
+        "traffic": 868.3e6 if (n == PAIRS_PER_GPU and (FLAGS & _lib.FLAG_BF16) == 0) else None,
         "peak_kind": (f"{peaks['source']} sustained dense bf16 (kernel timed inside the {args.steps}-step loop, SM clock "
                       f"{clk.get('sm_mhz')} MHz under the power cap); burst peak {peaks['bf16_tflops']}") if capped else
                      f"{peaks['source']} burst dense bf16 (clocks stayed at boost)",
