@@ -6,12 +6,16 @@ Tolerances (floating point path, fp32 accumulation; rel-L2 on the module output,
   TOL_BF = 5e-3  COATTN_FLAG_BF16 operands: bf16 quantisation alone costs ~1e-3 at tiny L and ~2e-3 at
                  train-like logit scales (sigma = 1.0, S std ~ 5) -- reported, not hidden.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import coattn_oracle as orc
 from tests.helpers import golden_inputs, load_golden, rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -439,3 +443,12 @@ def test_softmax16_cross_check_kernel(op, n, h, w):
         assert rel_l2(out[0].cpu().numpy(), ref["cat_a"]) < TOL and rel_l2(out[1].cpu().numpy(), ref["cat_b"]) < TOL
     for x, y in zip(wide, narrow):    # cat_a, cat_b, z, lse
         assert (x - y).abs().max() <= 1e-5 * max(1.0, float(y.abs().max()))
+
+
+def test_concurrent_host_threads():
+    """SURVEY.md 8b threading contract (nn.DataParallel's parallel_apply, train.py:493): concurrent calls from several
+    host threads -- one per visible device, or two streams of one device -- give the single-threaded results bit for bit."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_threads.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
