@@ -7,6 +7,7 @@
   hd         cfg 3: 480x854 input -> 61x107x256 features (what the reference really produces), batch 16 per GPU
   inference  cfg 4: test.py-style, each query co-attended with 5 reference frames (frame-A outputs only),
              480x640 input -> 61x81x256 features, 8 queries (40 pairs) per GPU
+  train_abi  the same through the C ABI only (no autograd, allocator or stand-in loss inside the timed region)
   train      cfg 5: forward + hand-written backward of both modalities, 8 pairs per GPU, NCCL all-reduce of the
              hot-path gradients (W, gate: 131 585 floats per step)
 Prints one JSON line (rank 0).  Times are CUDA events, max over ranks.
@@ -25,7 +26,7 @@ import torch.nn.functional as F
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["hd", "inference", "train"])
+    ap.add_argument("--workload", required=True, choices=["hd", "inference", "train", "train_abi"])
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
@@ -67,6 +68,44 @@ def main():
             coattention_forward_raw(d, db, W[1], G[1], Bd, want_z=False, a_only=True)
         pairs = qn * r
         desc = "test.py-style inference: 8 queries x 5 references per GPU, 61x81x256 features, frame-A outputs only"
+    elif args.workload == "train_abi":
+        # the same forward + backward as `train`, but through the C ABI with preallocated buffers: only the library's own
+        # kernels are inside the timed region (no autograd, no allocator, no stand-in loss)
+        from cosnet_b200 import _lib
+        from cosnet_b200.coattention import backward_workspace_bytes, workspace_bytes
+        lib = _lib.load()
+        n, h, w = 8, 60, 60
+        L = h * w
+        va, da, vb, db = feats(n, h, w), feats(n, h, w), feats(n, h, w), feats(n, h, w)
+        gws = [G[0].reshape(-1).contiguous(), G[1].reshape(-1).contiguous()]
+        ra = torch.randn((n, 2 * C, h, w), generator=g, device=dev) * 1e-3
+        rb = torch.randn((n, 2 * C, h, w), generator=g, device=dev) * 1e-3
+        nb_f, nb_b = workspace_bytes(n, C, h, w), backward_workspace_bytes(n, C, h, w, False)
+        ws = torch.empty(max(nb_f, nb_b) + 1024, dtype=torch.uint8, device=dev)
+        wsp = (ws.data_ptr() + 1023) // 1024 * 1024
+        st = torch.cuda.current_stream(dev).cuda_stream
+        mods = []
+        for (a, b, wt, gw, gb, has_b) in ((va, vb, W[0], gws[0], None, True), (da, db, W[1], gws[1], Bd, False)):
+            mods.append(dict(a=a, b=b, w=wt, gw=gw, gb=gb, has_b=has_b,
+                             ca=torch.empty((n, 2 * C, h, w), device=dev), cb=torch.empty((n, 2 * C, h, w), device=dev),
+                             z=torch.empty((2, n, C, L), device=dev), lse=torch.empty((2, n, L), device=dev),
+                             mask=torch.empty((2, n, L), device=dev), dva=torch.empty((n, C, h, w), device=dev),
+                             dw=torch.empty((C, C), device=dev), dgw=torch.empty((C,), device=dev), dgb=torch.empty((1,), device=dev)))
+        P = lambda t: None if t is None else t.data_ptr()
+        def step():
+            for m in mods:
+                _lib.check(lib.coattn_forward(P(m["a"]), P(m["b"]), P(m["w"]), P(m["gw"]), P(m["gb"]), P(m["ca"]), P(m["cb"]),
+                                              P(m["z"]), P(m["lse"]), P(m["mask"]), wsp, nb_f, n, C, h, w, 0, st), "coattn_forward")
+            for m in mods:
+                _lib.check(lib.coattn_backward(P(m["a"]), P(m["b"]), P(m["w"]), P(m["gw"]), P(m["z"]), P(m["lse"]), P(m["mask"]),
+                                               P(ra), P(rb) if m["has_b"] else None, P(m["dva"]), None, P(m["dw"]), P(m["dgw"]),
+                                               P(m["dgb"]) if m["gb"] is not None else None, wsp, nb_b, n, C, h, w, 0, st),
+                           "coattn_backward")
+            if world > 1:
+                dist.all_reduce(torch.cat([mods[0]["dw"].reshape(-1), mods[0]["dgw"], mods[1]["dw"].reshape(-1), mods[1]["dgw"], mods[1]["dgb"]]))
+        pairs = n
+        desc = ("train step on the hot path through the C ABI: coattn_forward + coattn_backward of both modalities (RGB full, "
+                "depth A-branch), 8 pairs per GPU, preallocated buffers, NCCL all-reduce of hot-path grads")
     else:
         n, h, w = 8, 60, 60
         va, da = feats(n, h, w, True), feats(n, h, w, True)
@@ -104,7 +143,8 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "co-attn frame-pairs/sec", "workload": args.workload, "config": desc, "value": pairs * world * args.steps / (ms * 1e-3),
                           "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "scaling": "weak",
-                          "includes": "tensor allocations of the Python operator (caching allocator), all kernels of both modalities"}), flush=True)
+                          "includes": ("only the library's kernels (C ABI, preallocated buffers)" if args.workload == "train_abi" else
+                                       "tensor allocations of the Python operator (caching allocator), all kernels of both modalities")}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
