@@ -1,5 +1,12 @@
+"""Runs forward + backward (8 pairs, 60x60x256, RGB-style: both concat gradients) through a trace build of the library:
+
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --shared -Xcompiler -fPIC -DCOATTN_TRACE_BWD \
+         -o build_trace/libcoattn_trace.so cosnet_b200/csrc/coattn_api.cu
+    COATTN_B200_LIB=build_trace/libcoattn_trace.so python tools/bwd_trace.py
+
+CTA 0 of `bwd_tile_kernel` prints where its producer, MMA issuer and epilogue warp 0 spent their cycles."""
 import os, sys, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cosnet_b200 import coattention
 dev = torch.device("cuda:0")
 n, h, w = 8, 60, 60

@@ -1,4 +1,11 @@
-"""Runs one batch-32 forward through a -DCOATTN_TRACE build (clock64 stamps printed by CTA 0 of the attend kernel)."""
+"""Runs batch-32 forwards (bench.py's shape and feature distribution) through a trace build of the library:
+
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --shared -Xcompiler -fPIC -DCOATTN_TRACE2 \
+         -o build_trace/libcoattn_trace2.so cosnet_b200/csrc/coattn_api.cu
+    COATTN_B200_LIB=build_trace/libcoattn_trace2.so python tools/fwd_trace.py
+
+After the third launch the host dumps the clock64 stamps CTA 0 of `attend2_kernel` left in global memory: per item
+(MMA issuer and softmax warp 0) and per key tile of one warm item."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cosnet_b200.coattention import coattention_forward_raw
