@@ -360,20 +360,21 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
                  " || softmax saw S at +%6lld | busy %5lld | period %5lld | P(j) arrive (warp 0) +%6lld\n", j, r[2] - tb[8 + 2],
                  r[3] - r[2], r[0] - r[3], r[1] - r[0], r[4] - tb[8 + 2], r[5] - r[4], r[4] - tb[(j - 1) * 8 + 4], r[5] - tb[8 + 2]);
         }
-        long long wb[2 * 32 * 8];
+        long long wb[2 * 32 * 16];
         cudaMemcpyFromSymbol(wb, g_attend2_warps, sizeof(wb));
         for (int j = 1; j < 29; ++j) {
-          printf("tile %2d warps saw S / arrived P (relative to warp 0 seeing S):", j);
-          for (int w = 0; w < 8; ++w) printf("  %5lld/%5lld", wb[j * 8 + w] - wb[j * 8], wb[256 + j * 8 + w] - wb[j * 8]);
+          printf("tile %2d warps 0-7 saw S / arrived P (relative to warp 0 seeing S):", j);
+          for (int w = 0; w < 8; ++w) printf("  %5lld/%5lld", wb[j * 16 + w] - wb[j * 16], wb[512 + j * 16 + w] - wb[j * 16]);
           printf("\n");
         }
         const long long t0 = hb[0];
         for (int it = 0; it < 14; ++it) {
           const long long* r = hb + it * 16;
-          printf("item %2d  MMA: start +%7lld | q_full +%5lld | S0,S1 issued +%5lld | P(0) ready +%5lld | last PV issued +%6lld"
-                 "  || softmax: start +%7lld | S(0) ready +%5lld | last P +%6lld | O complete +%5lld | probe ld %5lld | l xchg +%5lld | first ld +%5lld | dot pass +%5lld | xchg +%5lld | sigmoid+first ld +%5lld | stores +%5lld\n", it,
+          printf("item %2d  MMA: start +%7lld | q_full +%5lld | S(0), S(1) issued +%5lld | P(0) ready +%5lld | last PV issued +%6lld"
+                 "  || softmax: start +%7lld | S(0) ready +%5lld | last P +%6lld | O complete +%5lld | l xchg +%5lld | first ld +%5lld"
+                 " | dot pass +%5lld | xchg +%5lld | sigmoid+first ld +%5lld | stores +%5lld\n", it,
                  r[0] - t0, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[8] - t0, r[9] - r[8], r[10] - r[9],
-                 r[11] - r[10], r[15] ? r[15] - r[11] : 0, r[5] - (r[15] ? r[15] : r[11]), r[6] - r[5], r[13] - r[6], r[14] - r[13], r[7] - r[14], r[12] - r[7]);
+                 r[11] - r[10], r[5] - r[11], r[6] - r[5], r[13] - r[6], r[14] - r[13], r[7] - r[14], r[12] - r[7]);
         }
       }
     }
