@@ -7,6 +7,7 @@
   hd         cfg 3: 480x854 input -> 61x107x256 features (what the reference really produces), batch 16 per GPU
   inference  cfg 4: test.py-style, each query co-attended with 5 reference frames (frame-A outputs only),
              480x640 input -> 61x81x256 features, 8 queries (40 pairs) per GPU
+  eager / eager_bf16 / sdpa   secondary comparators: the reference's op sequence and PyTorch's fused attention on the same GPU
   train_abi  the same through the C ABI only (no autograd, allocator or stand-in loss inside the timed region)
   train      cfg 5: forward + hand-written backward of both modalities, 8 pairs per GPU, NCCL all-reduce of the
              hot-path gradients (W, gate: 131 585 floats per step)
@@ -26,7 +27,7 @@ import torch.nn.functional as F
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["hd", "inference", "train", "train_abi"])
+    ap.add_argument("--workload", required=True, choices=["hd", "inference", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
@@ -68,6 +69,45 @@ def main():
             coattention_forward_raw(d, db, W[1], G[1], Bd, want_z=False, a_only=True)
         pairs = qn * r
         desc = "test.py-style inference: 8 queries x 5 references per GPU, 61x81x256 features, frame-A outputs only"
+    elif args.workload in ("eager", "eager_bf16", "sdpa"):
+        # secondary GPU comparators at the headline shape: the reference's own op sequence run eagerly on the
+        # B200 (fp32 as written, or bf16), and two scaled_dot_product_attention calls (scale 1) + the gate epilogue
+        n, h, w = 32, 60, 60
+        dt = torch.float32 if args.workload == "eager" else torch.bfloat16
+        va, vb, da, db = (feats(n, h, w).to(dt) for _ in range(4))
+        Wd = [x.to(dt) for x in W]; Gd = [x.to(dt).view(1, C, 1, 1) for x in G]; Bdd = Bd.to(dt)
+
+        def epilogue(z_a, z_b, v_a, v_b, gw, gb):
+            m_a = torch.sigmoid(F.conv2d(z_a, gw, gb)); m_b = torch.sigmoid(F.conv2d(z_b, gw, gb))
+            return torch.cat([z_a * m_a, v_a], 1), torch.cat([z_b * m_b, v_b], 1)
+
+        def eager(v_a, v_b, wt, gw, gb):
+            a, b = v_a.view(n, C, h * w), v_b.view(n, C, h * w)
+            q = F.linear(a.transpose(1, 2).contiguous(), wt)
+            s_ = torch.bmm(q, b)
+            s_row = F.softmax(s_.clone(), dim=1)
+            s_col = F.softmax(s_.transpose(1, 2), dim=1)
+            z_b = torch.bmm(a, s_row).view(n, C, h, w)
+            z_a = torch.bmm(b, s_col).view(n, C, h, w)
+            return epilogue(z_a, z_b, v_a, v_b, gw, gb)
+
+        def sdpa(v_a, v_b, wt, gw, gb):
+            a, b = v_a.view(n, C, h * w).transpose(1, 2), v_b.view(n, C, h * w).transpose(1, 2)      # [n, L, C]
+            q = F.linear(a, wt)
+            z_a = F.scaled_dot_product_attention(q.unsqueeze(1), b.unsqueeze(1), b.unsqueeze(1), scale=1.0).squeeze(1)
+            z_b = F.scaled_dot_product_attention(b.unsqueeze(1), q.unsqueeze(1), a.unsqueeze(1), scale=1.0).squeeze(1)
+            z_a = z_a.transpose(1, 2).reshape(n, C, h, w); z_b = z_b.transpose(1, 2).reshape(n, C, h, w)
+            return epilogue(z_a, z_b, v_a, v_b, gw, gb)
+
+        fn = sdpa if args.workload == "sdpa" else eager
+        def step():
+            with torch.no_grad():
+                fn(va, vb, Wd[0], Gd[0], None)
+                fn(da, db, Wd[1], Gd[1], Bdd)
+        pairs = n
+        desc = {"eager": "reference op sequence (rgbd_segmentation_RAA.py:154-187) eagerly on the GPU, fp32, batch 32, 60x60x256",
+                "eager_bf16": "reference op sequence eagerly on the GPU in bf16, batch 32, 60x60x256",
+                "sdpa": "2 x F.scaled_dot_product_attention(scale=1) in bf16 + eager projection / gate / concat, batch 32, 60x60x256"}[args.workload]
     elif args.workload == "train_abi":
         # the same forward + backward as `train`, but through the C ABI with preallocated buffers: only the library's own
         # kernels are inside the timed region (no autograd, no allocator, no stand-in loss)
@@ -144,6 +184,7 @@ def main():
         print(json.dumps({"metric": "co-attn frame-pairs/sec", "workload": args.workload, "config": desc, "value": pairs * world * args.steps / (ms * 1e-3),
                           "unit": "frame-pairs/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms / args.steps, "scaling": "weak",
                           "includes": ("only the library's kernels (C ABI, preallocated buffers)" if args.workload == "train_abi" else
+                                       "PyTorch kernels only (none of this repository's)" if args.workload in ("eager", "eager_bf16", "sdpa") else
                                        "tensor allocations of the Python operator (caching allocator), all kernels of both modalities")}), flush=True)
     if world > 1:
         dist.destroy_process_group()
