@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
 constexpr int kTileThreads = 320;            // warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
 constexpr int kTileProducerWarp = 8;
 constexpr int kTileMmaWarp = 9;
-constexpr int kTileRingBytes = 12 * 16384;   // HAS_B: 2 stages x 6 operand blocks;  otherwise 3 stages x 4 blocks
+constexpr int kTileRingBytes = 12 * 16384;   // 6 stages x (A block + B block) of one product and one 64-channel k-block
 constexpr int kTileSmemBytes = kTileRingBytes + 8 * 2048 /*store staging*/ + 1024 /*align*/ + 2048 /*column vectors x2*/ + 128;
 
 struct BwdTileParams {
@@ -419,8 +419,12 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   // operand blocks per stage: Q, B | dZ_a, B(bf16) | A(bf16), dZ_b   (64 channels x 128 positions = 16 KB each, stored as
   // two 64-position chunks of 64 channel rows x 128 B, 128-byte swizzle)
-  constexpr int kTileStages = HAS_B ? 2 : 3;
-  constexpr int kTileStageBytes = (HAS_B ? 6 : 4) * 16384;
+  // Stage = the operand pair (two 16 KB blocks) of ONE product for one k-block.  The loads and MMAs of a tile run product
+  // by product (S: 16 MMAs, then dP_a, then dP_b): switching the accumulator every four MMAs stalls the tensor pipe
+  // (measured on the attend kernel), three switches per tile do not.
+  constexpr int kTileStages = 6;
+  constexpr int kTileStageBytes = 2 * 16384;
+  constexpr int kProducts = HAS_B ? 3 : 2;
   uint8_t* smem = align_1024(smem_raw);
   uint8_t* stage_out = smem + kTileRingBytes;                                      // 8 warps x 2 KB
   float* colv = reinterpret_cast<float*>(stage_out + 8 * 2048);                    // 2 x ([0,128) lse_b, [128,256) delta_b)
@@ -466,23 +470,22 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int n = t / per_sample, r = t - n * per_sample;
         const int ipos = (r % p.tiles_1d) * 128, jpos = (r / p.tiles_1d) * 128;
-        for (int kb = 0; kb < kNumKb; ++kb, ++cnt) {
-          const uint32_t s = cnt % kTileStages, ph = (cnt / kTileStages) & 1;
-          BT_T0();
-          mbar_wait(empty + s, ph ^ 1, 40);
-          BT_ACC(0);
-          mbar_arrive_expect_tx(full + s, kTileStageBytes);
-          uint8_t* st = smem + s * kTileStageBytes;
-          const int crow = n * kC + kb * 64;     // channel row of this k-block in a [N*C][Lp] plane
+        for (int pr = 0; pr < kProducts; ++pr) {
+          // product 0: S = Q^T B (forward format) | 1: dP_a = dZ_a^T B (bf16) | 2: dP_b = A^T dZ_b (bf16)
+          const CUtensorMap* ta = (pr == 0) ? &tm_qt : (pr == 1) ? &tm_dza : &tm_atg;    // i-side operand
+          const CUtensorMap* tb = (pr == 0) ? &tm_bt : (pr == 1) ? &tm_btg : &tm_dzb;    // j-side operand
+          for (int kb = 0; kb < kNumKb; ++kb, ++cnt) {
+            const uint32_t s = cnt % kTileStages, ph = (cnt / kTileStages) & 1;
+            BT_T0();
+            mbar_wait(empty + s, ph ^ 1, 40);
+            BT_ACC(0);
+            mbar_arrive_expect_tx(full + s, kTileStageBytes);
+            uint8_t* st = smem + s * kTileStageBytes;
+            const int crow = n * kC + kb * 64;     // channel row of this k-block in a [N*C][Lp] plane
 #pragma unroll
-          for (int mc = 0; mc < 2; ++mc) {
-            tma_load_2d(st + 0 * 16384 + mc * 8192, &tm_qt, full + s, ipos + mc * 64, crow);
-            tma_load_2d(st + 1 * 16384 + mc * 8192, &tm_bt, full + s, jpos + mc * 64, crow);
-            tma_load_2d(st + 2 * 16384 + mc * 8192, &tm_dza, full + s, ipos + mc * 64, crow);
-            tma_load_2d(st + 3 * 16384 + mc * 8192, &tm_btg, full + s, jpos + mc * 64, crow);
-            if (HAS_B) {
-              tma_load_2d(st + 4 * 16384 + mc * 8192, &tm_atg, full + s, ipos + mc * 64, crow);
-              tma_load_2d(st + 5 * 16384 + mc * 8192, &tm_dzb, full + s, jpos + mc * 64, crow);
+            for (int mc = 0; mc < 2; ++mc) {
+              tma_load_2d(st + mc * 8192, ta, full + s, ipos + mc * 64, crow);
+              tma_load_2d(st + 16384 + mc * 8192, tb, full + s, jpos + mc * 64, crow);
             }
           }
         }
@@ -498,30 +501,26 @@ bwd_tile_kernel(const __grid_constant__ CUtensorMap tm_qt, const __grid_constant
       warp_mbar_wait(d_empty + acc, aph ^ 1, lane, 43);   // the epilogue has read this set's previous accumulators
       BT_ACC(1);
       tc_fence_after();
-      for (int kb = 0; kb < kNumKb; ++kb, ++cnt) {
-        const uint32_t s = cnt % kTileStages, ph = (cnt / kTileStages) & 1;
-        BT_T0();
-        warp_mbar_wait(full + s, ph, lane, 41);
-        BT_ACC(2);
-        tc_fence_after();
-        const uint32_t sb = base + s * kTileStageBytes;
-        // MN-major tiles: 64-position chunks 8192 B apart (LBO), 8-channel groups 1024 B apart (SBO); 16 channels = 2048 B
-        const uint64_t d0 = make_sdesc_mn_sw128(sb, 8192, 1024), d1 = make_sdesc_mn_sw128(sb + 16384, 8192, 1024),
-                       d2 = make_sdesc_mn_sw128(sb + 2 * 16384, 8192, 1024), d3 = make_sdesc_mn_sw128(sb + 3 * 16384, 8192, 1024),
-                       d4 = make_sdesc_mn_sw128(sb + 4 * 16384, 8192, 1024), d5 = make_sdesc_mn_sw128(sb + 5 * 16384, 8192, 1024);
-        if (elect_one()) {
+      for (int pr = 0; pr < kProducts; ++pr) {
+        const uint32_t idesc = (pr == 0) ? p.idesc_fwd : p.idesc_bf16;
+        const uint32_t td = tacc + (uint32_t)pr * 128;
+        for (int kb = 0; kb < kNumKb; ++kb, ++cnt) {
+          const uint32_t s = cnt % kTileStages, ph = (cnt / kTileStages) & 1;
+          BT_T0();
+          warp_mbar_wait(full + s, ph, lane, 41);
+          BT_ACC(2);
+          tc_fence_after();
+          const uint32_t sb = base + s * kTileStageBytes;
+          // MN-major tiles: 64-position chunks 8192 B apart (LBO), 8-channel groups 1024 B apart (SBO); 16 channels = 2048 B
+          const uint64_t da = make_sdesc_mn_sw128(sb, 8192, 1024), db = make_sdesc_mn_sw128(sb + 16384, 8192, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tacc, d0 + 128 * k, d1 + 128 * k, p.idesc_fwd, (kb > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tacc + 128, d2 + 128 * k, d3 + 128 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
-          if (HAS_B) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(tacc + 256, d4 + 128 * k, d5 + 128 * k, p.idesc_bf16, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_ss(td, da + 128 * k, db + 128 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(empty + s);
+            if (pr == kProducts - 1 && kb == kNumKb - 1) umma_commit(d_full + acc);
           }
-          umma_commit(empty + s);
-          if (kb == kNumKb - 1) umma_commit(d_full + acc);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
