@@ -354,20 +354,4 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// exp2 on the FMA pipe (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error ~1e-4 -- below the
-// 2^-9..2^-11 rounding of the 16-bit P it feeds).  Used for a fraction of the softmax elements so that the MUFU
-// pipe (16 ex2 / clk / SM) stops being the longest part of the per-tile softmax.  x <= 0 expected; clamped at -126.
-__device__ __forceinline__ float exp2_fma(float x) {
-  x = fmaxf(x, -126.0f);
-  float r;                                     // x + 1.5*2^23, rounded towards -inf: low mantissa bits = floor(x)
-  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(12582912.0f));
-  const float fl = r - 12582912.0f;            // floor(x) as a float (exact)
-  const float f = x - fl;                      // fractional part in [0, 1)
-  float pol = fmaf(0.077119089663028717f, f, 0.227564394474029541f);
-  pol = fmaf(pol, f, 0.695146143436431885f);
-  pol = fmaf(pol, f, 1.0f);
-  // multiply by 2^floor(x): add floor(x) to the exponent field
-  return __int_as_float(__float_as_int(pol) + (__float_as_int(r) << 23));
-}
-
 }  // namespace coattn
