@@ -1,0 +1,36 @@
+"""bench.py on a B200: one JSON line with every key of the contract, sensible values, and the host-buffer (e2e) legs
+reproducing the resident results bit for bit."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_line_has_the_contract_keys():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--cpu-budget", "0.5"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["value"] > 1000 and abs(d["value"] - 32 * 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
+    assert d["gpu_launches"] == 8 * d["steps"]
+    rf = d["roofline"]
+    assert rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s" and 0.2 < rf["frac"] < 1.0
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 4 * 32 * 256 * 3600 * 4 and e["d2h_bytes_per_step"] == 2 * e["h2d_bytes_per_step"]
+    assert e["matches_resident_path"] is True and e["gated_only_contract"]["matches_resident_path"] is True
+    assert 0 < e["value"] < d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
