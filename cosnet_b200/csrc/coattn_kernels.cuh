@@ -997,7 +997,7 @@ __global__ void __launch_bounds__(256) passthrough_kernel(PassParams p) {
 // HBM-bound: 16 L C bytes per (sample, side).  One block = kGatePos positions x all 256 channels;
 // warp w owns channels [32w, 32w+32), lanes run along positions (coalesced, VEC floats each).
 // ==============================================================================================
-constexpr int kGateThreads = 256;
+constexpr int kGateThreads = 512;   // 16 warps x 16 channels: 64 registers of Z per thread, two CTAs' worth of loads in flight
 
 struct GateParams {
   const float* z;      // [2][N][C][L] raw attended features (side 0: Z_a, side 1: Z_b)
@@ -1012,27 +1012,28 @@ struct GateParams {
 
 template <int VEC>
 __global__ void __launch_bounds__(kGateThreads) gate_kernel(GateParams p) {
-  __shared__ float part[8][32 * VEC];
+  constexpr int kWarps = kGateThreads / 32, kCh = kC / kWarps;     // 16 warps, 16 channels each
+  __shared__ float part[kWarps][32 * VEC];
   __shared__ float gw[kC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int side = blockIdx.y / p.N;
   const int n = blockIdx.y - side * p.N;
   const int pos = (blockIdx.x * 32 + lane) * VEC;
-  gw[threadIdx.x] = p.gate_w[threadIdx.x];
+  if (threadIdx.x < kC) gw[threadIdx.x] = p.gate_w[threadIdx.x];
   __syncthreads();
   const bool valid = pos < p.L;   // L % VEC == 0 is guaranteed by the launcher
   const float* z = p.z + (size_t)blockIdx.y * kC * p.L + pos;
   const float* v = (side ? p.v_b : p.v_a) + (size_t)n * kC * p.L + pos;
   float* cat = (side ? p.cat_b : p.cat_a) + (size_t)n * 2 * kC * p.L + pos;
 
-  float zr[32][VEC];
+  float zr[kCh][VEC];
   float dot[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) dot[e] = 0.f;
   if (valid) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int c = warp * 32 + k;
+    for (int k = 0; k < kCh; ++k) {
+      const int c = warp * kCh + k;
       if constexpr (VEC == 4) {
         const float4 t = __ldcs(reinterpret_cast<const float4*>(z + (size_t)c * p.L));
         zr[k][0] = t.x; zr[k][1] = t.y; zr[k][2] = t.z; zr[k][3] = t.w;
@@ -1041,25 +1042,28 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(GateParams p) {
       }
     }
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float g = gw[warp * 32 + k];
+    for (int k = 0; k < kCh; ++k) {
+      const float g = gw[warp * kCh + k];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) dot[e] = fmaf(g, zr[k][e], dot[e]);
     }
   }
 #pragma unroll
   for (int e = 0; e < VEC; ++e) part[warp][lane * VEC + e] = dot[e];
-  // passthrough copy of the original features while the partial sums settle
+  // passthrough copy of the original features while the partial sums settle (all loads first, then the stores)
   if (valid) {
+    if constexpr (VEC == 4) {
+      float4 t[kCh];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int c = warp * 32 + k;
-      if constexpr (VEC == 4) {
-        const float4 t = __ldcs(reinterpret_cast<const float4*>(v + (size_t)c * p.L));
-        __stcs(reinterpret_cast<float4*>(cat + (size_t)(kC + c) * p.L), t);
-      } else {
-        __stcs(cat + (size_t)(kC + c) * p.L, __ldcs(v + (size_t)c * p.L));
-      }
+      for (int k = 0; k < kCh; ++k) t[k] = __ldcs(reinterpret_cast<const float4*>(v + (size_t)(warp * kCh + k) * p.L));
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) __stcs(reinterpret_cast<float4*>(cat + (size_t)(kC + warp * kCh + k) * p.L), t[k]);
+    } else {
+      float t[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) t[k] = __ldcs(v + (size_t)(warp * kCh + k) * p.L);
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) __stcs(cat + (size_t)(kC + warp * kCh + k) * p.L, t[k]);
     }
   }
   __syncthreads();
@@ -1070,12 +1074,12 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(GateParams p) {
     for (int e = 0; e < VEC; ++e) {
       float t = bias;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += part[w][lane * VEC + e];
+      for (int w = 0; w < kWarps; ++w) t += part[w][lane * VEC + e];
       mask[e] = 1.0f / (1.0f + __expf(-t));
     }
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int c = warp * 32 + k;
+    for (int k = 0; k < kCh; ++k) {
+      const int c = warp * kCh + k;
       if constexpr (VEC == 4) {
         float4 t;
         t.x = zr[k][0] * mask[0]; t.y = zr[k][1] * mask[1]; t.z = zr[k][2] * mask[2]; t.w = zr[k][3] * mask[3];
