@@ -302,6 +302,29 @@ def run_ours(args):
         elapsed_ms = float(t.item())
     value = total_pairs * args.steps / (elapsed_ms * 1e-3)
 
+    # ---------------- the stand-alone gate / sigmoid / concat epilogue (cross-check path; the product fuses it into the
+    # attend kernel's drain): HBM-bound, 16 L C bytes per sample and side (read Z and V, write the concat)
+    zbuf = torch.empty((2, n, C, L), device=dev)
+    _lib.check(lib.coattn_stage_prep_project(v_a.data_ptr(), v_b.data_ptr(), w_rgb.data_ptr(), wsp, nbytes, n, C, H, W, FLAGS, st),
+               "prep_project")
+    _lib.check(lib.coattn_stage_attend(zbuf.data_ptr(), lse.data_ptr(), wsp, nbytes, n, C, H, W, FLAGS, st), "attend")
+    gate_events = []
+    for i in range(13):
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        _lib.check(lib.coattn_stage_gate(zbuf.data_ptr(), v_a.data_ptr(), v_b.data_ptr(), g_rgb.data_ptr(), None,
+                                         cat[0].data_ptr(), cat[1].data_ptr(), n, C, H, W, st), "gate")
+        g1.record(stream)
+        if i >= 3:
+            gate_events.append((g0, g1))
+    torch.cuda.synchronize()
+    gate_ms = sum(a.elapsed_time(b) for a, b in gate_events) / len(gate_events)
+    gate_bytes = 2 * n * 16.0 * L * C
+    del zbuf
+    # restore cat[0] / cat[1] (the e2e legs compare against them)
+    step()
+    torch.cuda.synchronize()
+
     # ---------------- end to end: host buffers in, host buffers out, through the public host API
     e2e_steps = max(2, min(args.steps, 5))
     pipe = HostPipeline(n, C, H, W, chunk=4, slots=3, device=dev, bf16_operands=bool(FLAGS & _lib.FLAG_BF16))
@@ -402,6 +425,12 @@ def run_ours(args):
                                                 "is not sent back; for the split-reduce-conv consumer"}},
         "gpu_launches": 8 * args.steps,   # per modality call: cast(V_a, V_b), cast_w, project_mn, attend2(+gate+concat)
         "roofline": roofline,
+        "epilogue_roofline": {
+            "kernel": "gate_kernel (stand-alone gate/sigmoid/scale/concat; the default path fuses it into attend2's drain)",
+            "bound": "hbm", "achieved": gate_bytes / (gate_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": gate_bytes / (gate_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms_per_launch": gate_ms,
+            "algorithmic_bytes_per_launch": gate_bytes, "launches_outside_timed_region": 13,
+        },
     }
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_budget)
