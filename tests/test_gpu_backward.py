@@ -23,7 +23,7 @@ def coattention():
     return op
 
 
-def run_backward(op, v_a, v_b, W, g, b, r_a, r_b):
+def run_backward(op, v_a, v_b, W, g, b, r_a, r_b, bf16=False):
     dev = torch.device("cuda:0")
     t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
     va = t(v_a).requires_grad_(True)
@@ -31,7 +31,7 @@ def run_backward(op, v_a, v_b, W, g, b, r_a, r_b):
     w = t(W).requires_grad_(True)
     gw = t(g).view(1, -1, 1, 1).requires_grad_(True)
     gb = None if b is None else t(b).requires_grad_(True)
-    cat_a, cat_b = op(va, vb, w, gw, gb)
+    cat_a, cat_b = op(va, vb, w, gw, gb, bf16)
     loss = (cat_a * t(r_a)).sum()
     if r_b is not None:
         loss = loss + (cat_b * t(r_b)).sum()
@@ -72,6 +72,22 @@ def test_gradients_against_oracle(coattention, n, h, w, bias, with_b):
     assert rel_l2(got["d_gate_w"], ref["d_gate_w"]) < GRAD_TOL
     if bias:
         assert abs(float(got["d_gate_b"][0]) - float(ref["d_gate_b"])) < GRAD_TOL * max(1.0, abs(float(ref["d_gate_b"])))
+    assert np.isfinite(got["d_v_a"]).all()
+
+
+@pytest.mark.parametrize("n,h,w,bias,with_b", [(2, 12, 11, True, True), (1, 31, 41, False, True), (2, 20, 20, True, False)])
+def test_gradients_with_bf16_forward(coattention, n, h, w, bias, with_b):
+    """COATTN_FLAG_BF16 forward: the backward then recomputes S from the bf16 operands and needs no second operand set
+    (one format for every product).  Tolerance 2e-2: the forward's own softmax is bf16-quantised here."""
+    v_a, v_b = orc.synthetic_features(400 + h * w, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(401 + h * w, bias=bias)
+    rng = np.random.default_rng(6)
+    r_a = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    r_b = rng.standard_normal((n, 512, h, w), dtype=np.float32) if with_b else None
+    got = run_backward(coattention, v_a, v_b, W, g, b, r_a, r_b, bf16=True)
+    ref = orc.coattention_grads(v_a, v_b, W, g, b, r_a, np.zeros_like(r_a) if r_b is None else r_b)
+    for k in ("d_v_a", "d_w", "d_gate_w"):
+        assert rel_l2(got[k], ref[k]) < 2e-2, (k, rel_l2(got[k], ref[k]))
     assert np.isfinite(got["d_v_a"]).all()
 
 
