@@ -588,6 +588,8 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
     return COATTN_E_NULL;
   const bool counterpart = d_v_b != nullptr;
   if (int e = check_dims(n, c, h, w_)) return e;
+  // d_w is accumulated with 16-byte vector reductions; every other tensor falls back to scalar accesses when unaligned
+  if ((reinterpret_cast<uintptr_t>(d_w) & 15) != 0) return COATTN_E_ALIGN;
   const BwdLayout bl = make_bwd_layout(n, h, w_);
   const Layout& ly = bl.fwd;
   if (!workspace) return COATTN_E_NULL;

@@ -167,7 +167,8 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
  *            z [2,N,256,L], lse [2,N,L], mask [2,N,L]      saved outputs of coattn_forward
  *            d_cat_a, d_cat_b [N,512,H,W]  gradients w.r.t. the two concat tensors; d_cat_b may be NULL
  *                                          (depth modality: the B branch is gradient dead, :240-247)
- *   outputs  d_v_a [N,256,H,W], d_w [256,256], d_gate_w [256], d_gate_b [1] (may be NULL); all overwritten
+ *   outputs  d_v_a [N,256,H,W], d_w [256,256] (16-byte aligned, else COATTN_E_ALIGN), d_gate_w [256], d_gate_b [1]
+ *            (may be NULL); all overwritten
  *            d_v_b [N,256,H,W] or NULL: gradient for the counterpart frame, only needed with
  *            no_grad_for_counterpart=False (:147-148); costs two more [L,L] transposes, two GEMMs, a second
  *            projection and the larger workspace (`counterpart` = 1 in the size query).

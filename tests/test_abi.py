@@ -64,6 +64,12 @@ def test_argument_errors_before_any_cuda_work(lib):
     assert lib.coattn_forward(None, None, None, None, None, None, None, None, None, None, None, 0, 1, 256, 4, 4, 0, None) == -1
     assert lib.coattn_stage_gate(None, None, None, None, None, None, None, 1, 256, 4, 4, None) == -1
     assert lib.coattn_stage_project(None, 0, 1, 64, 4, 4, 0, None) == -2
+    # coattn_backward: the weight gradient is reduced with 16-byte vector operations -> a misaligned d_w is refused
+    # (fake, never dereferenced pointers: the check comes before any device work)
+    P = 0x10000
+    args = [P] * 8 + [None, P, None, P + 4, P, None, P, 1 << 40, 1, 256, 4, 4, 0, None]
+    assert lib.coattn_backward(*args) == -6
+    assert b"aligned" in lib.coattn_b200_strerror(-6)
 
 
 def test_host_operator_refuses_cpu_tensors():

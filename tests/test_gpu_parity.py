@@ -452,3 +452,29 @@ def test_concurrent_host_threads():
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_threads.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_unaligned_tensors_take_the_scalar_paths(op):
+    """Feature tensors that are only 4-byte aligned (views into a larger buffer at an odd element offset): the cast,
+    passthrough and gate stages fall back to scalar accesses; the result is the aligned one bit for bit."""
+    n, c, h, w = 2, 256, 12, 12
+    dev = torch.device("cuda:0")
+    v_a, v_b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_features(97, n, h, w, 0.66))
+    W, g, b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_weights(98, bias=True))
+
+    def shifted(x):
+        buf = torch.empty(x.numel() + 1, device=dev)
+        view = buf[1:].view_as(x)
+        view.copy_(x)
+        assert view.data_ptr() % 16 == 4 and view.is_contiguous()
+        return view
+    want = op(v_a, v_b, W, g, b)
+    got = op(shifted(v_a), shifted(v_b), W, g, b)
+    torch.cuda.synchronize()
+    for x, y in zip(got, want):
+        assert torch.equal(x, y)
+    got = op(shifted(v_a), shifted(v_b), W, g, b, unfused_gate=True)
+    ref = op(v_a, v_b, W, g, b, unfused_gate=True)
+    torch.cuda.synchronize()
+    for x, y in zip(got, ref):
+        assert torch.equal(x, y)
