@@ -105,6 +105,32 @@ def backward_workspace_bytes(n: int, c: int, h: int, w: int, counterpart: bool =
     return int(r)
 
 
+def coattention_queries_raw(v_a, v_b, weight, gate_weight, gate_bias=None, refs: int = 1, bf16_operands=False,
+                            gated_only=False):
+    """test.py-style inference (test.py:287-305): v_a [Q, C, H, W] query features, v_b [Q * refs, C, H, W] reference
+    features (pair p = query p // refs); returns cat_a [Q * refs, 2C (C with gated_only), H, W].  The query side (16-bit
+    cast and Q = W V_a) is prepared once per query frame; the result equals the A_ONLY forward on repeated queries."""
+    n, c, h, w = _check_inputs(v_a, v_a, weight, gate_weight, gate_bias)      # n = number of query frames
+    if v_b.shape[0] != n * refs or tuple(v_b.shape[1:]) != (c, h, w) or not v_b.is_cuda or v_b.dtype != torch.float32:
+        raise _lib.CoattnError(f"v_b must be a CUDA fp32 tensor [{n * refs}, {c}, {h}, {w}], got {tuple(v_b.shape)}")
+    lib = _lib.load()
+    dev = v_a.device
+    with torch.cuda.device(dev):
+        v_a = v_a.contiguous(); v_b = v_b.contiguous()
+        weight = weight.contiguous(); gw = gate_weight.reshape(-1).contiguous()
+        pairs = n * refs
+        cat_a = torch.empty((pairs, (c if gated_only else 2 * c), h, w), dtype=torch.float32, device=dev)
+        nbytes = workspace_bytes(pairs, c, h, w)
+        ws = _workspace(dev, nbytes)
+        flags = (_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0)
+        code = lib.coattn_forward_queries(v_a.data_ptr(), v_b.data_ptr(), weight.data_ptr(), gw.data_ptr(),
+                                          None if gate_bias is None else gate_bias.data_ptr(), cat_a.data_ptr(),
+                                          _aligned_ptr(ws), nbytes, n, refs, c, h, w, flags,
+                                          torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(code, "coattn_forward_queries")
+    return cat_a
+
+
 class _CoAttentionFn(torch.autograd.Function):
     """Autograd bridge: forward = coattn_forward (keeps z, lse, mask), backward = coattn_backward.
 

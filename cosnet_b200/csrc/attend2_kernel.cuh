@@ -87,6 +87,7 @@ struct Attend2Params {
   int kv_tiles;  // ceil(L / 128)
   int num_items; // passes * N * q_pairs
   int passes;    // 2, or 1 = frame-A outputs only (pass 0; test.py averages x1 only, test.py:301)
+  int q_group;   // 1, or (passes == 1 only) pairs per query frame: pair n uses sample n / q_group of V_a and Q = W V_a
 };
 
 // exchange one float between the G threads that own the same query row (warps quad, quad + 4, ...): every thread gets
@@ -199,7 +200,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         if constexpr (MN) {
           // X planes: 0 = B16, 1 = A16, 2 = Q16.  pass 0: queries Q16, keys B16;  pass 1: queries B16, keys Q16
           const int qplane = pass ? 0 : 2, kplane = pass ? 2 : 0;
-          const int qch0 = (qplane * p.N + n) * kC, kch0 = (kplane * p.N + n) * kC;
+          const int nq = pass ? n : n / p.q_group;      // q_group > 1 only with passes == 1 (pass 0: queries from V_a)
+          const int qch0 = (qplane * p.N + nq) * kC, kch0 = (kplane * p.N + n) * kC;
           const int qpos0 = qp * (2 * k2BM) + (int)rank * k2BM;
 #pragma unroll
           for (int mc = 0; mc < 2; ++mc)     // two 64-position chunks x 256 channel rows
@@ -265,7 +267,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         const int pass = (p.passes == 2) ? (np & 1) : 0;
         const int n = (p.passes == 2) ? (np >> 1) : np;
         const int row0 = qp * (2 * k2BM) + (int)rank * k2BM;
-        const float* src = (pass ? p.v_b : p.v_a) + (size_t)n * kC * p.L;
+        const float* src = (pass ? p.v_b : p.v_a) + (size_t)(pass ? n : n / p.q_group) * kC * p.L;
         float* dst = (pass ? p.cat_b : p.cat_a) + ((size_t)n * 2 * kC + kC) * p.L;
         if (vec) {
           const int r = row0 + 4 * lane;

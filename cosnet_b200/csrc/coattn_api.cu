@@ -231,9 +231,10 @@ static int prep_and_project_fused(const float* v_a, const float* v_b, const floa
 //   x   [3][N][C][Lp] 16-bit planes: 0 = V_b, 1 = V_a (written by the cast), 2 = Q = W V_a (written by the projection)
 //   w16 [C][C] 16-bit copy of W
 static int cast_project_core(const float* v_a, const float* v_b, const float* w, unsigned short* x, unsigned short* w16,
-                             int n, const Layout& ly, bool bf16, bool project, cudaStream_t st) {
+                             int n, const Layout& ly, bool bf16, bool project, cudaStream_t st, int n_a = -1) {
+  if (n_a < 0) n_a = n;       // samples of V_a (query frames); the planes are laid out for n samples either way
   CastParams cp;
-  cp.va = v_a; cp.vb = v_b; cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp;
+  cp.va = v_a; cp.vb = v_b; cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp; cp.Na = n_a;
   const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   const dim3 cgrid(n * kC, 2);
   if (bf16) {
@@ -255,7 +256,7 @@ static int cast_project_core(const float* v_a, const float* v_b, const float* w,
   pp.q16 = x + 2 * ly.t_pass_elems();
   pp.Lp = ly.Lp;
   pp.tiles_per_sample = ly.Lp / kProjMnTile;
-  pp.num_tiles = n * pp.tiles_per_sample;
+  pp.num_tiles = n_a * pp.tiles_per_sample;
   pp.a_row0_base = n * kC;
   auto kern = bf16 ? project_mn_kernel<true> : project_mn_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjMnSmemBytes);
@@ -291,7 +292,7 @@ extern "C" int coattn_stage_prep_project(const float* v_a, const float* v_b, con
 
 static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float* cat_b, float* z, float* lse,
                          float* mask, const float* gate_w, const float* gate_b, void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
-                         unsigned flags, void* stream) {
+                         unsigned flags, void* stream, int q_group = 1) {
   const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
@@ -329,6 +330,8 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     q.q_pairs = (ly.L + 2 * k2BM - 1) / (2 * k2BM);
     q.kv_tiles = (ly.L + k2BN - 1) / k2BN;
     q.passes = (flags & COATTN_FLAG_A_ONLY) ? 1 : 2;
+    q.q_group = q_group;
+    if (q_group != 1 && (q.passes != 1 || !mn)) return COATTN_E_UNSUPPORTED;
     q.num_items = q.passes * n * q.q_pairs;
     // 8 softmax warps (two column groups per TMEM lane quadrant) by default; COATTN_FLAG_SOFTMAX16 selects the 16-warp
     // layout (four groups)
@@ -488,6 +491,27 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
     gate_kernel<1><<<dim3((p.L + 31) / 32, 2 * n), kGateThreads, 0, st>>>(p);
   }
   return (int)cudaGetLastError();
+}
+
+int coattn_forward_queries(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* gate_b,
+                           float* cat_a, void* workspace, int64_t workspace_bytes, int nq, int refs, int c, int h, int w_,
+                           unsigned flags, void* stream) {
+  if (!v_a || !v_b || !w || !gate_w || !cat_a) return COATTN_E_NULL;
+  if (nq < 1 || refs < 1) return COATTN_E_SHAPE;
+  if (flags & (COATTN_FLAG_UNFUSED_GATE | COATTN_FLAG_SINGLE_CTA | COATTN_FLAG_KMAJOR | COATTN_FLAG_UNFUSED_PREP))
+    return COATTN_E_UNSUPPORTED;
+  const int n = nq * refs;
+  if (int e = check_dims(n, c, h, w_)) return e;
+  const Layout ly = make_layout(n, h, w_);
+  if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
+  if (int e = check_arch(nullptr)) return e;
+  // the query side (16-bit cast of V_a and Q = W V_a) is prepared once per query frame, not once per pair
+  if (int e = cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
+                                reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
+                                (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq))
+    return e;
+  return launch_attend(v_a, v_b, cat_a, nullptr, nullptr, nullptr, nullptr, gate_w, gate_b, workspace, workspace_bytes, n, c,
+                       h, w_, flags | COATTN_FLAG_A_ONLY, stream, refs);
 }
 
 int coattn_forward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* gate_b,

@@ -412,12 +412,14 @@ struct CastParams {
   const float* vb;
   unsigned short* x;   // [3][N][C][Lp]; planes 0 (V_b) and 1 (V_a) are written here
   int N, L, Lp;
+  int Na;              // samples of V_a (= N, or the number of query frames when each is paired with several references)
 };
 
 template <bool BF16, int VEC>
 __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
   const int row = blockIdx.x;                 // n * C + c
   const int plane = blockIdx.y;               // 0: V_b, 1: V_a
+  if (plane == 1 && row >= p.Na * kC) return;
   const float* src = (plane ? p.va : p.vb) + (size_t)row * p.L;
   unsigned short* dst = p.x + ((size_t)plane * p.N * kC + row) * p.Lp;
   if constexpr (VEC == 4) {

@@ -4,8 +4,9 @@
 The reference runs the full model once per (query, reference) pair, so the query frame is re-encoded
 `sample_range` times and the B-side head is computed although only `output[0]` is kept (test.py:293, :301).
 Here the query is encoded ONCE, the references of all queries go through the encoders as one batch, the
-co-attention runs as one batched launch computing the frame-A outputs only (COATTN_FLAG_A_ONLY: half the
-attend work) and only the A-side head is evaluated.  Queries are the unit that is sharded across GPUs
+co-attention runs as one batched launch computing the frame-A outputs only (half the attend work), with the query
+side of the operator (16-bit cast, Q = W V_a) prepared once per query (`coattn_forward_queries`), and only the A-side
+head is evaluated.  Queries are the unit that is sharded across GPUs
 (`pair_batcher.shard_range`), so the mean over references never crosses a device.
 """
 from __future__ import annotations
@@ -13,7 +14,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from .coattention import coattention_forward_raw
+from .coattention import coattention_forward_raw, coattention_queries_raw
 
 
 @torch.no_grad()
@@ -21,6 +22,13 @@ def coattention_frame_a(v_a, v_b, weight, gate_weight, gate_bias=None):
     """cat_a only ([N, 2C, H, W]) for N (query, reference) feature pairs."""
     cat_a, _, _, _ = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias, want_z=False, a_only=True)
     return cat_a
+
+
+@torch.no_grad()
+def coattention_queries_frame_a(v_a, v_b, weight, gate_weight, gate_bias=None, refs: int = 1):
+    """cat_a only for Q query feature maps v_a [Q, C, H, W], each paired with `refs` consecutive reference maps of
+    v_b [Q * refs, C, H, W]; the query side of the operator is prepared once per query (coattn_forward_queries)."""
+    return coattention_queries_raw(v_a, v_b, weight, gate_weight, gate_bias, refs=refs)
 
 
 @torch.no_grad()
@@ -36,12 +44,10 @@ def segment_with_references(model, target_rgb, target_depth, ref_rgbs, ref_depth
     d_a = model.depth_encoder(target_depth)
     v_b, _ = model.encoder(ref_rgbs.flatten(0, 1))            # all references of all queries in one batch
     d_b = model.depth_encoder(ref_depths.flatten(0, 1))
-    v_a = v_a.repeat_interleave(r, dim=0)
-    d_a = d_a.repeat_interleave(r, dim=0)
-    cat = coattention_frame_a(v_a, v_b, model.rgb_similarity_weights.weight, model.gate.weight, None)
+    cat = coattention_queries_frame_a(v_a, v_b, model.rgb_similarity_weights.weight, model.gate.weight, None, refs=r)
     z = model.bn_A(model.reduce_channels_A(cat))                                             # :188, :190
-    dcat = coattention_frame_a(d_a, d_b, model.depth_similarity_weights.weight, model.depth_gate.weight,
-                               model.depth_gate.bias)
+    dcat = coattention_queries_frame_a(d_a, d_b, model.depth_similarity_weights.weight, model.depth_gate.weight,
+                                       model.depth_gate.bias, refs=r)
     z = model.prelu(z + model.depth_weights(model.depth_bn(model.depth_reduce_channels(dcat))))  # :239-256
     x1 = torch.sigmoid(F.interpolate(model.segmentation_classifier_A(z), size, mode="bilinear"))  # :260-265
     return x1.view(q, r, *x1.shape[1:]).mean(dim=1)

@@ -123,6 +123,18 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
                    void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
                    unsigned flags, void* stream);
 
+/*
+ * test.py-style inference (test.py:287-305): `nq` query (target) frames, each co-attended with `refs` reference frames;
+ * pair p = (query p / refs, reference p), n = nq * refs pairs, frame-A outputs only (what test.py:301 keeps).
+ *   v_a [nq, 256, H, W] query features, v_b [nq * refs, 256, H, W] reference features,
+ *   cat_a [nq * refs, 512 (256 with COATTN_FLAG_GATED_ONLY), H, W]; workspace as for n = nq * refs pairs.
+ * The reference re-encodes and re-projects the query for every pair; here its 16-bit cast and Q = W V_a are computed
+ * once per query.  Same results as coattn_forward(COATTN_FLAG_A_ONLY) on the query features repeated `refs` times.
+ */
+int coattn_forward_queries(const float* v_a, const float* v_b, const float* w, const float* gate_w,
+                           const float* gate_b, float* cat_a, void* workspace, int64_t workspace_bytes, int nq,
+                           int refs, int c, int h, int w_, unsigned flags, void* stream);
+
 /* ---- the four stages, exported individually for unit parity tests and per-kernel timing ---- */
 
 /* stage 1 (:154-158): 16-bit operands.  Fills the workspace segments At, Bt, A16, B16 and W16. */

@@ -478,3 +478,18 @@ def test_unaligned_tensors_take_the_scalar_paths(op):
     torch.cuda.synchronize()
     for x, y in zip(got, ref):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("q,refs,h,w,gated", [(3, 5, 12, 11, False), (2, 2, 31, 41, False), (1, 1, 8, 8, False), (2, 3, 20, 20, True)])
+def test_grouped_queries_equal_repeated_queries(op, q, refs, h, w, gated):
+    """coattn_forward_queries (query side prepared once per query frame, test.py:287-305) == the frame-A forward on the
+    query features repeated `refs` times, bit for bit."""
+    from cosnet_b200.coattention import coattention_queries_raw
+    dev = torch.device("cuda:0")
+    v_a = torch.from_numpy(orc.synthetic_features(91, q, h, w, 0.66)[0]).to(dev)
+    v_b = torch.from_numpy(orc.synthetic_features(92, q * refs, h, w, 0.66)[1]).to(dev)
+    W, g, b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_weights(93, bias=True))
+    want = op(v_a.repeat_interleave(refs, 0), v_b, W, g, b, want_z=False, a_only=True, gated_only=gated)[0]
+    got = coattention_queries_raw(v_a, v_b, W, g, b, refs=refs, gated_only=gated)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and torch.equal(got, want)

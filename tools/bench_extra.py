@@ -63,10 +63,10 @@ def main():
         qn, r, h, w = 8, 5, 61, 81
         va, da = feats(qn, h, w), feats(qn, h, w)
         vb, db = feats(qn * r, h, w), feats(qn * r, h, w)
-        def step():
-            a = va.repeat_interleave(r, 0); d = da.repeat_interleave(r, 0)
-            coattention_forward_raw(a, vb, W[0], G[0], None, want_z=False, a_only=True)
-            coattention_forward_raw(d, db, W[1], G[1], Bd, want_z=False, a_only=True)
+        from cosnet_b200.coattention import coattention_queries_raw
+        def step():     # the query side (cast, Q = W V_a) is prepared once per query: coattn_forward_queries
+            coattention_queries_raw(va, vb, W[0], G[0], None, refs=r)
+            coattention_queries_raw(da, db, W[1], G[1], Bd, refs=r)
         pairs = qn * r
         desc = "test.py-style inference: 8 queries x 5 references per GPU, 61x81x256 features, frame-A outputs only"
     elif args.workload in ("eager", "eager_bf16", "sdpa"):
