@@ -39,6 +39,7 @@ SIGNATURES = {
     "coattn_stage_project": (_i, [_vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_prep_project": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_forward_queries": (_i, [_vp] * 7 + [_i64, _i, _i, _i, _i, _i, _u, _vp]),
+    "coattn_forward16": (_i, [_vp] * 10 + [_i64, _i, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_attend": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_gate": (_i, [_vp] * 7 + [_i, _i, _i, _i, _vp]),
     "coattn_backward_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),

@@ -131,6 +131,56 @@ def coattention_queries_raw(v_a, v_b, weight, gate_weight, gate_bias=None, refs:
     return cat_a
 
 
+def coattention_forward16_raw(v_a, v_b, weight, gate_weight, gate_bias=None, refs: int = 1, a_only=False,
+                              gated_only=False, want_lse=False):
+    """16-bit feature interface (`coattn_forward16`): v_a [Q, C, H, W] and v_b [Q * refs, C, H, W] are both float16
+    (IEEE half operands) or both bfloat16 (bf16 operands); returns (cat_a, cat_b) in the same dtype (cat_b None with
+    a_only / refs > 1), plus lse [passes, n, L] and mask [passes, n, L] in fp32 with want_lse.  With H*W % 8 == 0 the
+    tensor cores read the features in place (no cast pass); the module's parameters stay fp32.  Forward only."""
+    if not (v_a.is_cuda and v_b.is_cuda):
+        raise _lib.CoattnError("co-attention runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+    if v_a.dtype not in (torch.float16, torch.bfloat16) or v_b.dtype != v_a.dtype:
+        raise TypeError(f"features must both be float16 or both bfloat16, got {v_a.dtype} / {v_b.dtype}")
+    if v_a.dim() != 4 or v_b.dim() != 4 or refs < 1 or v_b.shape[0] != v_a.shape[0] * refs or v_b.shape[1:] != v_a.shape[1:]:
+        raise ValueError(f"expected v_a [Q, C, H, W] and v_b [Q * {refs}, C, H, W], got {tuple(v_a.shape)} / {tuple(v_b.shape)}")
+    nq, c, h, w = v_a.shape
+    if weight.shape != (c, c):
+        raise ValueError(f"weight must be [{c}, {c}], got {tuple(weight.shape)}")
+    if gate_weight.numel() != c:
+        raise ValueError(f"gate weight must have {c} elements, got {tuple(gate_weight.shape)}")
+    if gate_bias is not None and gate_bias.numel() != 1:
+        raise ValueError("gate bias must have one element")
+    a_only = a_only or refs > 1
+    lib = _lib.load()
+    dev = v_a.device
+    with torch.cuda.device(dev):
+        v_a = v_a.contiguous(); v_b = v_b.contiguous()
+        wt = weight.detach().to(device=dev, dtype=torch.float32).contiguous()
+        gw = gate_weight.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
+        gb = None if gate_bias is None else gate_bias.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
+        n = nq * refs
+        oc = c if gated_only else 2 * c
+        cat_a = torch.empty((n, oc, h, w), dtype=v_a.dtype, device=dev)
+        cat_b = None if a_only else torch.empty((n, oc, h, w), dtype=v_a.dtype, device=dev)
+        passes = 1 if a_only else 2
+        lse = torch.empty((passes, n, h * w), dtype=torch.float32, device=dev) if want_lse else None
+        mask = torch.empty((passes, n, h * w), dtype=torch.float32, device=dev) if want_lse else None
+        nbytes = workspace_bytes(n, c, h, w)
+        ws = _workspace(dev, nbytes)
+        flags = ((_lib.FLAG_BF16 if v_a.dtype == torch.bfloat16 else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
+                 | (_lib.FLAG_GATED_ONLY if gated_only else 0))
+        code = lib.coattn_forward16(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
+                                    None if gb is None else gb.data_ptr(), cat_a.data_ptr(),
+                                    None if cat_b is None else cat_b.data_ptr(),
+                                    None if lse is None else lse.data_ptr(), None if mask is None else mask.data_ptr(),
+                                    _aligned_ptr(ws), nbytes, nq, refs, c, h, w, flags,
+                                    torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(code, "coattn_forward16")
+    if want_lse:
+        return cat_a, cat_b, lse, mask
+    return cat_a, cat_b
+
+
 class _CoAttentionFn(torch.autograd.Function):
     """Autograd bridge: forward = coattn_forward (keeps z, lse, mask), backward = coattn_backward.
 

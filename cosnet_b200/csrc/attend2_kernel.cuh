@@ -21,6 +21,8 @@
 //   they exponentiate; P(j) goes to its own buffer, so S never waits for a PV.
 //   Barriers with a "(L)" are only used in the leader CTA and are signalled from both CTAs.
 #pragma once
+#include <type_traits>
+
 #include "coattn_kernels.cuh"
 
 namespace coattn {
@@ -88,6 +90,12 @@ struct Attend2Params {
   int num_items; // passes * N * q_pairs
   int passes;    // 2, or 1 = frame-A outputs only (pass 0; test.py averages x1 only, test.py:301)
   int q_group;   // 1, or (passes == 1 only) pairs per query frame: pair n uses sample n / q_group of V_a and Q = W V_a
+  // row of sample 0 in each tensor map (MN path).  Workspace planes X = [B16, A16, Q16]: xq_row0 = 2 N C, xb_row0 = 0,
+  // v0_row0 = 0, v1_row0 = N C;  16-bit features consumed in place (IO16, one map per tensor): all 0
+  int xq_row0;   // Q16 in tmap_q
+  int xb_row0;   // V_b in tmap_k
+  int v0_row0;   // values of pass 0 (V_b) in tmap_v
+  int v1_row0;   // values of pass 1 (V_a) in tmap_v1
 };
 
 // exchange one float between the G threads that own the same query row (warps quad, quad + 4, ...): every thread gets
@@ -116,11 +124,14 @@ __device__ __forceinline__ float group_exchange_sum(float v, float* xbuf, uint32
 // MN = false: queries / keys come from the position-major arrays T = [Bt, Qt] ([Lp][C], K-major operands).
 // MN = true : queries / keys come from the channel-major arrays X = [B16, A16, Q16] ([C][Lp], the NCHW orientation)
 //             as MN-major UMMA operands -- no transposed copies of the features exist at all.
-template <bool BF16, bool MN, int G>
+// IO16 = true: the features (passthrough source) and the cat_* outputs are 16-bit (fp16, or bf16 with BF16); the
+//             operands may then be read straight from the caller's tensors (one tensor map per tensor, see *_row0).
+template <bool BF16, bool MN, int G, bool IO16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Attend2Cfg<G>::kThreads, 1)
-attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C], box {64, 128};  MN: X [3*N*C][Lp], box {64, 256}
-               const __grid_constant__ CUtensorMap tmap_k,  // !MN: T [2*N*Lp][C], box {64, 64};   MN: same map as tmap_q
-               const __grid_constant__ CUtensorMap tmap_v,  // VV [2*N*C][Lp],  box {64, 128}
+attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C], box {64, 128};  MN: holds Q16, rows [..][C] x Lp, box {64, 256}
+               const __grid_constant__ CUtensorMap tmap_k,  // !MN: T [2*N*Lp][C], box {64, 64};   MN: holds V_b, box {64, 256}
+               const __grid_constant__ CUtensorMap tmap_v,  // holds V_b (values of pass 0), box {64, 128}
+               const __grid_constant__ CUtensorMap tmap_v1, // holds V_a (values of pass 1), box {64, 128}
                Attend2Params p) {
   using Cfg = Attend2Cfg<G>;
   constexpr int k2KStages = Cfg::kKStages;
@@ -161,6 +172,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_v1);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     for (int s = 0; s < k2KStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
@@ -198,14 +210,16 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         mbar_wait(q_empty, (it & 1) ^ 1, 1);
         if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * k2QBytes);
         if constexpr (MN) {
-          // X planes: 0 = B16, 1 = A16, 2 = Q16.  pass 0: queries Q16, keys B16;  pass 1: queries B16, keys Q16
-          const int qplane = pass ? 0 : 2, kplane = pass ? 2 : 0;
+          // pass 0: queries Q16 (tmap_q), keys V_b (tmap_k);  pass 1: queries V_b, keys Q16
+          const CUtensorMap* mq = pass ? &tmap_k : &tmap_q;
+          const CUtensorMap* mk = pass ? &tmap_q : &tmap_k;
           const int nq = pass ? n : n / p.q_group;      // q_group > 1 only with passes == 1 (pass 0: queries from V_a)
-          const int qch0 = (qplane * p.N + nq) * kC, kch0 = (kplane * p.N + n) * kC;
+          const int qch0 = pass ? p.xb_row0 + n * kC : p.xq_row0 + nq * kC;
+          const int kch0 = pass ? p.xq_row0 + n * kC : p.xb_row0 + n * kC;
           const int qpos0 = qp * (2 * k2BM) + (int)rank * k2BM;
 #pragma unroll
           for (int mc = 0; mc < 2; ++mc)     // two 64-position chunks x 256 channel rows
-            tma_load_2d_pair(sQ + mc * 32768, &tmap_q, q_full_l, qpos0 + mc * 64, qch0);
+            tma_load_2d_pair(sQ + mc * 32768, mq, q_full_l, qpos0 + mc * 64, qch0);
           for (int j = 0; j < T; ++j, ++cnt) {
             const uint32_t s = cnt % k2KStages, ph = (cnt / k2KStages) & 1;
             mbar_wait(k_empty + s, ph ^ 1, 2);
@@ -213,7 +227,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             const uint32_t full_l = mapa_u32(smem_u32(k_full + s), 0);
             // this CTA's half of the keys: 64 positions (n_last / 2 in the ragged last tile) x 256 channel rows
             const int kpos = j * k2BN + (int)rank * ((j == T - 1) ? (n_last / 2) : (k2BN / 2));
-            tma_load_2d_pair(sK + s * k2KBytes, &tmap_k, full_l, kpos, kch0);
+            tma_load_2d_pair(sK + s * k2KBytes, mk, full_l, kpos, kch0);
           }
         } else {
           const int qrow0 = ((1 - pass) * p.N + n) * p.Lp + qp * (2 * k2BM) + (int)rank * k2BM;
@@ -243,7 +257,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         const int np = item / p.q_pairs;
         const int vpass = (p.passes == 2) ? (np & 1) : 0;
         const int vn = (p.passes == 2) ? (np >> 1) : np;
-        const int vrow0 = (vpass * p.N + vn) * kC + (int)rank * (kC / 2);
+        const CUtensorMap* mv = vpass ? &tmap_v1 : &tmap_v;
+        const int vrow0 = (vpass ? p.v1_row0 : p.v0_row0) + vn * kC + (int)rank * (kC / 2);
         for (int j = 0; j < T; ++j, ++cnt) {
           const uint32_t s = cnt % k2VStages, ph = (cnt / k2VStages) & 1;
           mbar_wait(v_empty + s, ph ^ 1, 3);
@@ -251,44 +266,46 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           const uint32_t full_l = mapa_u32(smem_u32(v_full + s), 0);
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb)
-            tma_load_2d_pair(sV + s * k2VBytes + kb * ((kC / 2) * 128), &tmap_v, full_l, j * k2BN + kb * 64, vrow0);
+            tma_load_2d_pair(sV + s * k2VBytes + kb * ((kC / 2) * 128), mv, full_l, j * k2BN + kb * 64, vrow0);
         }
       }
     }
   } else if (warp == k2CopyWarp) {
-    // ------------------------------------------------------------------ passthrough copy (fp32, bit exact)
+    // ------------------------------------------------------------------ passthrough copy (bit exact; fp32, or 16-bit with IO16)
     if (p.v_a != nullptr && p.cat_a != nullptr) {
+      using T = typename std::conditional<IO16, unsigned short, float>::type;   // element
+      using V = typename std::conditional<IO16, uint2, float4>::type;           // four elements
       const bool vec = (p.L % 4 == 0) &&
                        (((reinterpret_cast<uintptr_t>(p.v_a) | reinterpret_cast<uintptr_t>(p.v_b) |
-                          reinterpret_cast<uintptr_t>(p.cat_a) | reinterpret_cast<uintptr_t>(p.cat_b)) & 15) == 0);
+                          reinterpret_cast<uintptr_t>(p.cat_a) | reinterpret_cast<uintptr_t>(p.cat_b)) & (sizeof(V) - 1)) == 0);
       for (int item = cluster_id; item < p.num_items; item += num_clusters) {
         const int qp = item % p.q_pairs;
         const int np = item / p.q_pairs;
         const int pass = (p.passes == 2) ? (np & 1) : 0;
         const int n = (p.passes == 2) ? (np >> 1) : np;
         const int row0 = qp * (2 * k2BM) + (int)rank * k2BM;
-        const float* src = (pass ? p.v_b : p.v_a) + (size_t)(pass ? n : n / p.q_group) * kC * p.L;
-        float* dst = (pass ? p.cat_b : p.cat_a) + ((size_t)n * 2 * kC + kC) * p.L;
+        const T* src = reinterpret_cast<const T*>(pass ? p.v_b : p.v_a) + (size_t)(pass ? n : n / p.q_group) * kC * p.L;
+        T* dst = reinterpret_cast<T*>(pass ? p.cat_b : p.cat_a) + ((size_t)n * 2 * kC + kC) * p.L;
         if (vec) {
           const int r = row0 + 4 * lane;
           if (r < p.L) {
 #pragma unroll 1
             for (int c = 0; c < kC; c += 8) {
-              float4 t[8];
+              V t[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) t[u] = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(c + u) * p.L + r));
+              for (int u = 0; u < 8; ++u) t[u] = __ldcs(reinterpret_cast<const V*>(src + (size_t)(c + u) * p.L + r));
 #pragma unroll
-              for (int u = 0; u < 8; ++u) __stcs(reinterpret_cast<float4*>(dst + (size_t)(c + u) * p.L + r), t[u]);
+              for (int u = 0; u < 8; ++u) __stcs(reinterpret_cast<V*>(dst + (size_t)(c + u) * p.L + r), t[u]);
             }
           }
         } else {
 #pragma unroll 1
           for (int c = 0; c < kC; c += 2) {
-            float t[8];
+            T t[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int r = row0 + (u & 3) * 32 + lane;
-              t[u] = (r < p.L) ? __ldcs(src + (size_t)(c + (u >> 2)) * p.L + r) : 0.f;
+              t[u] = (r < p.L) ? __ldcs(src + (size_t)(c + (u >> 2)) * p.L + r) : T(0);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -602,7 +619,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         const float logit = dot * inv + (p.gate_b ? __ldg(p.gate_b) : 0.f);
         const float gate = 1.0f / (1.0f + __expf(-logit));
         const float sc = inv * gate;
-        float* ccol = (pass ? p.cat_b : p.cat_a) + ((size_t)n * p.out_channels + c0) * p.L + row;
+        using OutT = typename std::conditional<IO16, unsigned short, float>::type;
+        OutT* ccol = reinterpret_cast<OutT*>(pass ? p.cat_b : p.cat_a) + ((size_t)n * p.out_channels + c0) * p.L + row;
         {
           uint32_t oa[32], ob[32];
           tmem_ld32(tO, oa);
@@ -615,7 +633,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             if (ch + 1 < kChunks) tmem_ld32(tO + (ch + 1) * 32, nx);
             if (valid) {
 #pragma unroll
-              for (int k = 0; k < 32; ++k) __stcs(ccol + (size_t)(ch * 32 + k) * p.L, __uint_as_float(o[k]) * sc);
+              for (int k = 0; k < 32; ++k) {
+                if constexpr (IO16) __stcs(ccol + (size_t)(ch * 32 + k) * p.L, cvt16<BF16>(__uint_as_float(o[k]) * sc));
+                else __stcs(ccol + (size_t)(ch * 32 + k) * p.L, __uint_as_float(o[k]) * sc);
+              }
               if (zcol != nullptr) {
 #pragma unroll
                 for (int k = 0; k < 32; ++k) zcol[(size_t)(ch * 32 + k) * p.L] = __uint_as_float(o[k]) * inv;

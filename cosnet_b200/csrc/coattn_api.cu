@@ -230,14 +230,21 @@ static int prep_and_project_fused(const float* v_a, const float* v_b, const floa
 // MN-major path: cast both frames (no transposes) + channel-major projection.
 //   x   [3][N][C][Lp] 16-bit planes: 0 = V_b, 1 = V_a (written by the cast), 2 = Q = W V_a (written by the projection)
 //   w16 [C][C] 16-bit copy of W
+//   in16: 0 = fp32 features (cast), 1 = 16-bit features copied into the padded planes (pad16_kernel),
+//         2 = 16-bit features consumed in place: nothing is copied and the projection reads V_a through its own map
 static int cast_project_core(const float* v_a, const float* v_b, const float* w, unsigned short* x, unsigned short* w16,
-                             int n, const Layout& ly, bool bf16, bool project, cudaStream_t st, int n_a = -1) {
+                             int n, const Layout& ly, bool bf16, bool project, cudaStream_t st, int n_a = -1,
+                             int in16 = 0) {
   if (n_a < 0) n_a = n;       // samples of V_a (query frames); the planes are laid out for n samples either way
   CastParams cp;
   cp.va = v_a; cp.vb = v_b; cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp; cp.Na = n_a;
   const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   const dim3 cgrid(n * kC, 2);
-  if (bf16) {
+  if (in16 == 1) {
+    pad16_kernel<<<cgrid, 256, 0, st>>>(cp);
+  } else if (in16 == 2) {
+    // in place
+  } else if (bf16) {
     if (vec) cast_kernel<true, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<true, 1><<<cgrid, 256, 0, st>>>(cp);
   } else {
     if (vec) cast_kernel<false, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<false, 1><<<cgrid, 256, 0, st>>>(cp);
@@ -249,7 +256,11 @@ static int cast_project_core(const float* v_a, const float* v_b, const float* w,
   if (!enc) return COATTN_E_DRIVER;
   CUtensorMap tm_w, tm_x;
   if (int e = make_tmap(enc, &tm_w, w16, kC, kC, 128, bf16)) return e;
-  if (int e = make_tmap(enc, &tm_x, x, (uint64_t)3 * n * kC, ly.Lp, 256, bf16)) return e;
+  if (in16 == 2) {     // positions past L are out of bounds of the map: TMA fills them with zeros, as the padded planes do
+    if (int e = make_tmap(enc, &tm_x, v_a, (uint64_t)n_a * kC, ly.L, 256, bf16)) return e;
+  } else {
+    if (int e = make_tmap(enc, &tm_x, x, (uint64_t)3 * n * kC, ly.Lp, 256, bf16)) return e;
+  }
   int sms = 148;
   if (int e = check_arch(&sms)) return e;
   ProjectMnParams pp;
@@ -257,7 +268,7 @@ static int cast_project_core(const float* v_a, const float* v_b, const float* w,
   pp.Lp = ly.Lp;
   pp.tiles_per_sample = ly.Lp / kProjMnTile;
   pp.num_tiles = n_a * pp.tiles_per_sample;
-  pp.a_row0_base = n * kC;
+  pp.a_row0_base = (in16 == 2) ? 0 : n * kC;
   auto kern = bf16 ? project_mn_kernel<true> : project_mn_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjMnSmemBytes);
   if (e != cudaSuccess) return (int)e;
@@ -292,7 +303,8 @@ extern "C" int coattn_stage_prep_project(const float* v_a, const float* v_b, con
 
 static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float* cat_b, float* z, float* lse,
                          float* mask, const float* gate_w, const float* gate_b, void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
-                         unsigned flags, void* stream, int q_group = 1) {
+                         unsigned flags, void* stream, int q_group = 1, int in16 = 0) {
+  // in16 (coattn_forward16): v_a, v_b, cat_a, cat_b hold 16-bit elements; 2 = the operands are read from v_a / v_b in place
   const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
@@ -309,17 +321,32 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
   if (!(flags & COATTN_FLAG_SINGLE_CTA)) {
     // default: CTA-pair kernel (cluster of 2, tcgen05 cta_group::2)
     const bool mn = !(flags & (COATTN_FLAG_KMAJOR | COATTN_FLAG_UNFUSED_PREP));
-    CUtensorMap tm_q, tm_k2, tm_v2;
-    if (mn) {
-      // queries and keys straight from the channel-major planes X = [B16, A16, Q16]
-      if (int e = make_tmap(enc, &tm_q, seg(workspace, ly.off_vv), (uint64_t)3 * n * kC, ly.Lp, kC, bf16)) return e;
-      tm_k2 = tm_q;
-    } else {
-      if (int e = make_tmap(enc, &tm_q, seg(workspace, ly.off_t), t_rows, kC, k2BM, bf16)) return e;
-      if (int e = make_tmap(enc, &tm_k2, seg(workspace, ly.off_t), t_rows, kC, k2BN / 2, bf16)) return e;
-    }
-    if (int e = make_tmap(enc, &tm_v2, seg(workspace, ly.off_vv), (uint64_t)3 * n * kC, ly.Lp, kC / 2, bf16)) return e;
+    CUtensorMap tm_q, tm_k2, tm_v2, tm_v3;
     Attend2Params q;
+    if (in16 && !mn) return COATTN_E_UNSUPPORTED;
+    if (in16 == 2) {
+      // 16-bit features consumed in place: one map per tensor (positions past L are zero-filled by TMA); Q16 is the
+      // only operand that lives in the workspace
+      const int n_a = n / q_group;
+      const uint8_t* q16 = seg(workspace, ly.off_vv) + 2 * ly.t_pass_elems() * 2;
+      if (int e = make_tmap(enc, &tm_q, q16, (uint64_t)n * kC, ly.Lp, kC, bf16)) return e;
+      if (int e = make_tmap(enc, &tm_k2, v_b, (uint64_t)n * kC, ly.L, kC, bf16)) return e;
+      if (int e = make_tmap(enc, &tm_v2, v_b, (uint64_t)n * kC, ly.L, kC / 2, bf16)) return e;
+      if (int e = make_tmap(enc, &tm_v3, v_a, (uint64_t)n_a * kC, ly.L, kC / 2, bf16)) return e;
+      q.xq_row0 = 0; q.xb_row0 = 0; q.v0_row0 = 0; q.v1_row0 = 0;
+    } else {
+      if (mn) {
+        // queries and keys straight from the channel-major planes X = [B16, A16, Q16]
+        if (int e = make_tmap(enc, &tm_q, seg(workspace, ly.off_vv), (uint64_t)3 * n * kC, ly.Lp, kC, bf16)) return e;
+        tm_k2 = tm_q;
+      } else {
+        if (int e = make_tmap(enc, &tm_q, seg(workspace, ly.off_t), t_rows, kC, k2BM, bf16)) return e;
+        if (int e = make_tmap(enc, &tm_k2, seg(workspace, ly.off_t), t_rows, kC, k2BN / 2, bf16)) return e;
+      }
+      if (int e = make_tmap(enc, &tm_v2, seg(workspace, ly.off_vv), (uint64_t)3 * n * kC, ly.Lp, kC / 2, bf16)) return e;
+      tm_v3 = tm_v2;
+      q.xq_row0 = 2 * n * kC; q.xb_row0 = 0; q.v0_row0 = 0; q.v1_row0 = n * kC;
+    }
     q.z = z;
     q.lse = lse ? lse : reinterpret_cast<float*>(seg(workspace, ly.off_lse));
     q.cat_a = cat_a; q.cat_b = cat_b; q.mask = mask; q.gate_w = gate_w; q.gate_b = gate_b;
@@ -336,8 +363,11 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     // 8 softmax warps (two column groups per TMEM lane quadrant) by default; COATTN_FLAG_SOFTMAX16 selects the 16-warp
     // layout (four groups)
     const bool g4 = (flags & COATTN_FLAG_SOFTMAX16) != 0;
-    void (*kern2)(CUtensorMap, CUtensorMap, CUtensorMap, Attend2Params);
-    if (g4) kern2 = mn ? (bf16 ? attend2_kernel<true, true, 4> : attend2_kernel<false, true, 4>)
+    void (*kern2)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Attend2Params);
+    if (in16) {
+      if (g4) return COATTN_E_UNSUPPORTED;
+      kern2 = bf16 ? attend2_kernel<true, true, 2, true> : attend2_kernel<false, true, 2, true>;
+    } else if (g4) kern2 = mn ? (bf16 ? attend2_kernel<true, true, 4> : attend2_kernel<false, true, 4>)
                        : (bf16 ? attend2_kernel<true, false, 4> : attend2_kernel<false, false, 4>);
     else    kern2 = mn ? (bf16 ? attend2_kernel<true, true, 2> : attend2_kernel<false, true, 2>)
                        : (bf16 ? attend2_kernel<true, false, 2> : attend2_kernel<false, false, 2>);
@@ -347,7 +377,7 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     if (e2 != cudaSuccess) return (int)e2;
     int clusters = sms / 2;
     if (q.num_items < clusters) clusters = q.num_items;
-    kern2<<<2 * clusters, threads2, smem2, st>>>(tm_q, tm_k2, tm_v2, q);
+    kern2<<<2 * clusters, threads2, smem2, st>>>(tm_q, tm_k2, tm_v2, tm_v3, q);
 #ifdef COATTN_TRACE2
     {
       static int calls = 0;
@@ -512,6 +542,36 @@ int coattn_forward_queries(const float* v_a, const float* v_b, const float* w, c
     return e;
   return launch_attend(v_a, v_b, cat_a, nullptr, nullptr, nullptr, nullptr, gate_w, gate_b, workspace, workspace_bytes, n, c,
                        h, w_, flags | COATTN_FLAG_A_ONLY, stream, refs);
+}
+
+int coattn_forward16(const void* v_a, const void* v_b, const float* w, const float* gate_w, const float* gate_b,
+                     void* cat_a, void* cat_b, float* lse, float* mask, void* workspace, int64_t workspace_bytes,
+                     int nq, int refs, int c, int h, int w_, unsigned flags, void* stream) {
+  if (!v_a || !v_b || !w || !gate_w || !cat_a) return COATTN_E_NULL;
+  if (nq < 1 || refs < 1) return COATTN_E_SHAPE;
+  if (flags & ~(COATTN_FLAG_BF16 | COATTN_FLAG_A_ONLY | COATTN_FLAG_GATED_ONLY)) return COATTN_E_UNSUPPORTED;
+  if (refs > 1) flags |= COATTN_FLAG_A_ONLY;        // several references per query frame: frame-A outputs (test.py:301)
+  if (!cat_b && !(flags & COATTN_FLAG_A_ONLY)) return COATTN_E_NULL;
+  const int n = nq * refs;
+  if (int e = check_dims(n, c, h, w_)) return e;
+  const Layout ly = make_layout(n, h, w_);
+  if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
+  if (int e = check_arch(nullptr)) return e;
+  const uintptr_t ptrs = reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b) |
+                         reinterpret_cast<uintptr_t>(cat_a) | reinterpret_cast<uintptr_t>(cat_b);
+  if (ptrs & 1) return COATTN_E_ALIGN;
+  // TMA reads a tensor in place when its base is 16-byte aligned and its rows (L elements) are a multiple of 16 bytes
+  const bool in_place = (ly.L % 8 == 0) &&
+                        (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
+  const int in16 = in_place ? 2 : 1;
+  const float* fa = static_cast<const float*>(v_a);   // element type is carried by in16, not by the pointer type
+  const float* fb = static_cast<const float*>(v_b);
+  if (int e = cast_project_core(fa, fb, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
+                                reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
+                                (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq, in16))
+    return e;
+  return launch_attend(fa, fb, static_cast<float*>(cat_a), static_cast<float*>(cat_b), nullptr, lse, mask, gate_w, gate_b,
+                       workspace, workspace_bytes, n, c, h, w_, flags, stream, refs, in16);
 }
 
 int coattn_forward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* gate_b,

@@ -437,6 +437,18 @@ __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
   }
 }
 
+// 16-bit features (coattn_forward16) whose rows cannot be read by TMA directly (L % 8 != 0 or a base pointer that is
+// not 16-byte aligned): copied into the same zero-padded planes the cast writes.  CastParams::va / vb then point to
+// 16-bit data.  Only the fallback of that entry point; aligned 16-bit features are consumed in place.
+__global__ void __launch_bounds__(256) pad16_kernel(CastParams p) {
+  const int row = blockIdx.x;                 // n * C + c
+  const int plane = blockIdx.y;               // 0: V_b, 1: V_a
+  if (plane == 1 && row >= p.Na * kC) return;
+  const unsigned short* src = reinterpret_cast<const unsigned short*>(plane ? p.va : p.vb) + (size_t)row * p.L;
+  unsigned short* dst = p.x + ((size_t)plane * p.N * kC + row) * p.Lp;
+  for (int i = threadIdx.x; i < p.Lp; i += 256) dst[i] = (i < p.L) ? __ldcs(src + i) : (unsigned short)0;
+}
+
 constexpr int kProjMnTile = 64;            // positions per tile
 constexpr int kProjMnXStages = 2;
 constexpr int kProjMnThreads = 320;          // warps 0-7 epilogue (TMEM lane quadrant x m-tile), 8 TMA producer, 9 MMA issuer

@@ -135,6 +135,25 @@ int coattn_forward_queries(const float* v_a, const float* v_b, const float* w, c
                            const float* gate_b, float* cat_a, void* workspace, int64_t workspace_bytes, int nq,
                            int refs, int c, int h, int w_, unsigned flags, void* stream);
 
+/*
+ * 16-bit feature interface ("V_a, V_b fp32 (or bf16) ... out cat_a, cat_b (same dtype as input)";
+ * 8(f) N4: the producer -- deeplab/deeplabv3_encoder.py:80-82 under autocast -- hands over 16-bit features).
+ *   v_a   [nq, 256, H, W]         16-bit: IEEE half, or bfloat16 with COATTN_FLAG_BF16 (= the operand format)
+ *   v_b   [nq * refs, 256, H, W]  16-bit; pair p = (query frame p / refs, v_b[p]); refs == 1: ordinary pair batch
+ *   cat_a, cat_b [nq * refs, 512 (256 with COATTN_FLAG_GATED_ONLY), H, W] 16-bit, same format; cat_b may be NULL with
+ *         COATTN_FLAG_A_ONLY, which refs > 1 implies (test.py:301 keeps the frame-A output only)
+ *   lse [passes, n, L], mask [passes, n, L] fp32, optional (NULL: not kept)
+ *   w, gate_w, gate_b stay fp32 (the module's parameters).  Flags: COATTN_FLAG_BF16 | _A_ONLY | _GATED_ONLY, others
+ *   -> COATTN_E_UNSUPPORTED.  Workspace as for coattn_forward with n = nq * refs.
+ * With H*W % 8 == 0 and 16-byte aligned v_a / v_b the tensor cores' operands are read by TMA straight from the caller's
+ * tensors (no cast, no copy; only Q = W V_a is written to the workspace); otherwise the features are first copied into
+ * zero-padded planes.  The arithmetic is that of coattn_forward on the same 16-bit values; outputs are rounded to
+ * 16 bits once, at the store, and the passthrough half of the concat is a bit copy of the inputs.
+ */
+int coattn_forward16(const void* v_a, const void* v_b, const float* w, const float* gate_w, const float* gate_b,
+                     void* cat_a, void* cat_b, float* lse, float* mask, void* workspace, int64_t workspace_bytes,
+                     int nq, int refs, int c, int h, int w_, unsigned flags, void* stream);
+
 /* ---- the four stages, exported individually for unit parity tests and per-kernel timing ---- */
 
 /* stage 1 (:154-158): 16-bit operands.  Fills the workspace segments At, Bt, A16, B16 and W16. */

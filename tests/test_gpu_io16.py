@@ -1,0 +1,130 @@
+"""16-bit feature interface (`coattn_forward16`, SURVEY.md 8(b) "fp32 (or bf16)" / 8(f) N4) against the fp32 interface
+and the CPU oracle.  Needs a B200: run with `pytest -m gpu`.
+
+The 16-bit path performs the arithmetic of `coattn_forward` on the same 16-bit values (the fp32 entry point casts its
+features to exactly these values), so its outputs must be the fp32 entry point's outputs rounded once to 16 bits --
+BIT FOR BIT -- whether TMA reads the features in place (L % 8 == 0) or from padded copies.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import coattn_oracle as orc
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+C = 256
+TOL = 1e-3      # fp16 features and outputs, module output vs the fp64 oracle on the ORIGINAL fp32 features
+TOL_BF = 1e-2   # bf16 features and outputs: 2^-9 rounding of inputs, operands and outputs
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import __graft_entry__ as ge
+    ge.build()
+    from cosnet_b200.coattention import coattention_forward16_raw, coattention_forward_raw
+    assert torch.cuda.is_available()
+    return coattention_forward_raw, coattention_forward16_raw
+
+
+def _inputs(seed, n, h, w, dtype, bias=True, sigma=0.66):
+    dev = torch.device("cuda:0")
+    v_a, v_b = orc.synthetic_features(seed, n, h, w, sigma)
+    W, g, b = orc.synthetic_weights(seed + 1, bias=bias)
+    t = lambda x: None if x is None else torch.from_numpy(x).to(dev)
+    return (v_a, v_b, W, g, b), (t(v_a).to(dtype), t(v_b).to(dtype), t(W), t(g), t(b))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n,h,w", [
+    (2, 12, 12),    # L = 144: read in place, ragged key and query tiles
+    (1, 16, 16),    # L = 256: read in place, exactly one query tile pair
+    (3, 20, 20),    # L = 400: read in place, odd batch
+    (2, 12, 11),    # L = 132: L % 8 != 0 -> padded copies
+    (1, 7, 9),      # L = 63 : odd L
+    (1, 40, 47),    # L = 1880: in place, several query tiles
+])
+def test_io16_is_the_fp32_interface_rounded_once(ops, dtype, n, h, w):
+    fwd32, fwd16 = ops
+    _, (a16, b16, W, g, b) = _inputs(31, n, h, w, dtype)
+    bf = dtype == torch.bfloat16
+    want_a, want_b, _, lse32, mask32 = fwd32(a16.float(), b16.float(), W, g, b, bf16_operands=bf, want_mask=True)
+    got_a, got_b, lse, mask = fwd16(a16, b16, W, g, b, want_lse=True)
+    torch.cuda.synchronize()
+    assert got_a.dtype == dtype and got_a.shape == want_a.shape
+    assert torch.equal(got_a, want_a.to(dtype)) and torch.equal(got_b, want_b.to(dtype))
+    assert torch.equal(got_a[:, C:], a16) and torch.equal(got_b[:, C:], b16)       # passthrough half: bit copy
+    assert torch.equal(lse, lse32) and torch.equal(mask, mask32)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, TOL), (torch.bfloat16, TOL_BF)])
+@pytest.mark.parametrize("n,h,w,bias", [(2, 12, 12, False), (1, 31, 41, True), (1, 60, 60, True)])
+def test_io16_against_oracle(ops, dtype, tol, n, h, w, bias):
+    _, fwd16 = ops
+    (v_a, v_b, W, g, b), (a16, b16, tW, tg, tb) = _inputs(47, n, h, w, dtype, bias=bias)
+    ref = orc.coattention(v_a, v_b, W, g, b)
+    got_a, got_b = fwd16(a16, b16, tW, tg, tb)
+    torch.cuda.synchronize()
+    ea, eb = rel_l2(got_a.float().cpu().numpy(), ref["cat_a"]), rel_l2(got_b.float().cpu().numpy(), ref["cat_b"])
+    assert ea < tol and eb < tol, (ea, eb)
+
+
+@pytest.mark.parametrize("q,refs,h,w,gated", [(3, 5, 12, 12, False), (2, 2, 31, 41, False), (2, 3, 20, 20, True)])
+def test_io16_grouped_queries_and_gated_only(ops, q, refs, h, w, gated):
+    """refs > 1 (test.py:287-305): pair p = (query p // refs, reference p), frame-A outputs only."""
+    _, fwd16 = ops
+    dev = torch.device("cuda:0")
+    v_a = torch.from_numpy(orc.synthetic_features(91, q, h, w, 0.66)[0]).to(dev).half()
+    v_b = torch.from_numpy(orc.synthetic_features(92, q * refs, h, w, 0.66)[1]).to(dev).half()
+    W, g, b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_weights(93, bias=True))
+    want, none_b = fwd16(v_a.repeat_interleave(refs, 0), v_b, W, g, b, a_only=True, gated_only=gated)
+    got, got_b = fwd16(v_a, v_b, W, g, b, refs=refs, gated_only=gated)
+    torch.cuda.synchronize()
+    assert none_b is None and got_b is None
+    assert got.shape == (q * refs, C if gated else 2 * C, h, w) and torch.equal(got, want)
+    full_a, _ = fwd16(v_a.repeat_interleave(refs, 0), v_b, W, g, b)
+    assert torch.equal(got[:, :C], full_a[:, :C])
+
+
+def test_io16_unaligned_views_take_the_copy_path(ops):
+    """A feature tensor whose base is not 16-byte aligned cannot be a TMA source: same bits through the padded copies."""
+    _, fwd16 = ops
+    _, (a16, b16, W, g, b) = _inputs(5, 2, 16, 16, torch.float16)
+    want_a, want_b = fwd16(a16, b16, W, g, b)
+
+    def shifted(x):      # same values, base pointer moved by 2 bytes
+        buf = torch.empty(x.numel() + 1, dtype=x.dtype, device=x.device)
+        v = buf[1:].view(x.shape)
+        v.copy_(x)
+        assert v.data_ptr() % 16 != 0 and v.is_contiguous()
+        return v
+    got_a, got_b = fwd16(shifted(a16), shifted(b16), W, g, b)
+    torch.cuda.synchronize()
+    assert torch.equal(got_a, want_a) and torch.equal(got_b, want_b)
+
+
+def test_io16_argument_checks(ops):
+    from cosnet_b200 import _lib
+    _, fwd16 = ops
+    _, (a16, b16, W, g, b) = _inputs(5, 1, 8, 8, torch.float16)
+    with pytest.raises(TypeError):
+        fwd16(a16.float(), b16.float(), W, g, b)
+    with pytest.raises(TypeError):
+        fwd16(a16, b16.bfloat16(), W, g, b)
+    with pytest.raises(ValueError):
+        fwd16(a16, torch.cat([b16, b16, b16]), W, g, b, refs=2)
+    with pytest.raises(_lib.CoattnError):
+        fwd16(a16.cpu(), b16.cpu(), W, g, b)
+    lib = _lib.load()
+    ws = torch.empty(lib.coattn_workspace_bytes(1, C, 8, 8) + 1024, dtype=torch.uint8, device="cuda:0")
+    wp = (ws.data_ptr() + 1023) // 1024 * 1024
+    out = torch.empty((1, 2 * C, 8, 8), dtype=torch.float16, device="cuda:0")
+    args = lambda flags, cat_b=out.data_ptr(): (a16.data_ptr(), b16.data_ptr(), W.data_ptr(), g.data_ptr(), None,
+                                               out.data_ptr(), cat_b, None, None, wp, ws.numel() - 1024, 1, 1, C, 8, 8,
+                                               flags, None)
+    assert lib.coattn_forward16(*args(_lib.FLAG_UNFUSED_GATE)) == -7
+    assert lib.coattn_forward16(*args(_lib.FLAG_SINGLE_CTA)) == -7
+    assert lib.coattn_forward16(*args(0, None)) == -1          # cat_b required unless A_ONLY
+    assert lib.coattn_forward16(*args(_lib.FLAG_A_ONLY, None)) == 0
+    torch.cuda.synchronize()

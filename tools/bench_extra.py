@@ -7,6 +7,7 @@
   hd         cfg 3: 480x854 input -> 61x107x256 features (what the reference really produces), batch 16 per GPU
   inference  cfg 4: test.py-style, each query co-attended with 5 reference frames (frame-A outputs only),
              480x640 input -> 61x81x256 features, 8 queries (40 pairs) per GPU
+  io16 / io16_bf16   cfg 2 through the 16-bit feature interface (coattn_forward16); inference16: cfg 4 likewise
   eager / eager_bf16 / sdpa   secondary comparators: the reference's op sequence and PyTorch's fused attention on the same GPU
   train_abi  the same through the C ABI only (no autograd, allocator or stand-in loss inside the timed region)
   train      cfg 5: forward + hand-written backward of both modalities, 8 pairs per GPU, NCCL all-reduce of the
@@ -27,7 +28,7 @@ import torch.nn.functional as F
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["hd", "inference", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
+    ap.add_argument("--workload", required=True, choices=["hd", "inference", "io16", "io16_bf16", "inference16", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
@@ -69,6 +70,28 @@ def main():
             coattention_queries_raw(da, db, W[1], G[1], Bd, refs=r)
         pairs = qn * r
         desc = "test.py-style inference: 8 queries x 5 references per GPU, 61x81x256 features, frame-A outputs only"
+    elif args.workload in ("io16", "io16_bf16"):
+        # the headline shape through the 16-bit feature interface (coattn_forward16): fp16 (or bf16) features in and out,
+        # read in place by TMA -- no cast pass, half the concat bytes
+        from cosnet_b200.coattention import coattention_forward16_raw
+        n, h, w = 32, 60, 60
+        dt = torch.float16 if args.workload == "io16" else torch.bfloat16
+        va, vb, da, db = (feats(n, h, w).to(dt) for _ in range(4))
+        def step():
+            coattention_forward16_raw(va, vb, W[0], G[0], None)
+            coattention_forward16_raw(da, db, W[1], G[1], Bd)
+        pairs = n
+        desc = f"co-attention module alone, 60x60x256 feature pairs, batch 32 per GPU, {dt} features in and out (coattn_forward16)"
+    elif args.workload == "inference16":
+        from cosnet_b200.coattention import coattention_forward16_raw
+        qn, r, h, w = 8, 5, 61, 81
+        va, da = feats(qn, h, w).half(), feats(qn, h, w).half()
+        vb, db = feats(qn * r, h, w).half(), feats(qn * r, h, w).half()
+        def step():
+            coattention_forward16_raw(va, vb, W[0], G[0], None, refs=r)
+            coattention_forward16_raw(da, db, W[1], G[1], Bd, refs=r)
+        pairs = qn * r
+        desc = "test.py-style inference, fp16 features in and out: 8 queries x 5 references per GPU, 61x81x256 (L = 4941, copy path), frame-A outputs only"
     elif args.workload in ("eager", "eager_bf16", "sdpa"):
         # secondary GPU comparators at the headline shape: the reference's own op sequence run eagerly on the
         # B200 (fp32 as written, or bf16), and two scaled_dot_product_attention calls (scale 1) + the gate epilogue
