@@ -265,8 +265,19 @@ class HostPipeline:
     """
 
     def __init__(self, n: int, c: int, h: int, w: int, chunk: int = 4, slots: int = 3, device="cuda:0",
-                 bf16_operands: bool = False, host_passthrough: bool = False, gated_only: bool = False):
+                 bf16_operands: bool = False, host_passthrough: bool = False, gated_only: bool = False,
+                 feature_dtype: torch.dtype = torch.float32):
         self.n, self.c, self.h, self.w = n, c, h, w
+        # feature_dtype float16 / bfloat16: host and device buffers hold 16-bit features and results (coattn_forward16;
+        # the operand format follows the dtype) -- half the bytes on the wire in both directions
+        if feature_dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            raise TypeError(f"feature_dtype must be float32, float16 or bfloat16, got {feature_dtype}")
+        self.dtype = feature_dtype
+        self.io16 = feature_dtype != torch.float32
+        if self.io16:
+            bf16_operands = feature_dtype == torch.bfloat16
+            host_passthrough = False
+        esize = 2 if self.io16 else 4
         self.flags = _lib.FLAG_BF16 if bf16_operands else 0
         # gated_only: outputs are [n, C, h, w] (Z * sigmoid(gate) only) for a consumer that applies the reduce conv to the
         # two halves separately (split_reduce_conv) -- the passthrough half never exists, on the device or on the wire
@@ -284,17 +295,19 @@ class HostPipeline:
             for _ in range(slots):
                 s = {
                     "stream": torch.cuda.Stream(self.device),
-                    "va": torch.empty((self.chunk, c, h, w), dtype=torch.float32, device=self.device),
-                    "vb": torch.empty((self.chunk, c, h, w), dtype=torch.float32, device=self.device),
-                    "ca": torch.empty((self.chunk, (c if gated_only else 2 * c), h, w), dtype=torch.float32, device=self.device),
-                    "cb": torch.empty((self.chunk, (c if gated_only else 2 * c), h, w), dtype=torch.float32, device=self.device),
+                    "va": torch.empty((self.chunk, c, h, w), dtype=self.dtype, device=self.device),
+                    "vb": torch.empty((self.chunk, c, h, w), dtype=self.dtype, device=self.device),
+                    "ca": torch.empty((self.chunk, (c if gated_only else 2 * c), h, w), dtype=self.dtype, device=self.device),
+                    "cb": torch.empty((self.chunk, (c if gated_only else 2 * c), h, w), dtype=self.dtype, device=self.device),
                     "ws": torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device),
                     "nbytes": nbytes,
                 }
                 self.slots.append(s)
-        self.h2d_bytes = 2 * n * c * h * w * 4
-        self.d2h_bytes = 2 * n * (c if (host_passthrough or gated_only) else 2 * c) * h * w * 4
-        self.launches_per_call = 4 * ((n + self.chunk - 1) // self.chunk)
+        self.h2d_bytes = 2 * n * c * h * w * esize
+        self.d2h_bytes = 2 * n * (c if (host_passthrough or gated_only) else 2 * c) * h * w * esize
+        # fp32: cast, cast_w, project_mn, attend2;  16-bit features read in place: cast_w, project_mn, attend2
+        in_place = self.io16 and (h * w) % 8 == 0
+        self.launches_per_call = (3 if in_place else 4) * ((n + self.chunk - 1) // self.chunk)
         self._worker = None
 
     def _host_copy(self, v_a, v_b, out_a, out_b, lo, hi):
@@ -332,6 +345,14 @@ class HostPipeline:
                 pass_b = None if no_pass else s["vb"].data_ptr()
                 nb = s["nbytes"]
                 wsp = _aligned_ptr(s["ws"])
+                if self.io16:
+                    _lib.check(self.lib.coattn_forward16(
+                        s["va"].data_ptr(), s["vb"].data_ptr(), weight.data_ptr(), gw.data_ptr(),
+                        None if gate_bias is None else gate_bias.data_ptr(), s["ca"].data_ptr(), s["cb"].data_ptr(), None,
+                        None, wsp, nb, m, 1, c, h, w, self.flags, st.cuda_stream), "coattn_forward16")
+                    out_a[lo:hi].copy_(s["ca"][:m], non_blocking=True)
+                    out_b[lo:hi].copy_(s["cb"][:m], non_blocking=True)
+                    continue
                 _lib.check(self.lib.coattn_stage_prep_project(s["va"].data_ptr(), s["vb"].data_ptr(), weight.data_ptr(), wsp,
                                                               nb, m, c, h, w, self.flags, st.cuda_stream),
                            "coattn_stage_prep_project")

@@ -31,6 +31,9 @@ def test_bench_line_has_the_contract_keys():
     assert e["h2d_bytes_per_step"] == 4 * 32 * 256 * 3600 * 4 and e["d2h_bytes_per_step"] == 2 * e["h2d_bytes_per_step"]
     assert e["matches_resident_path"] is True and e["gated_only_contract"]["matches_resident_path"] is True
     assert 0 < e["value"] < d["value"]
+    io = d["io16"]      # 16-bit feature interface beside the headline: half the bytes per step, host legs bit-exact
+    assert io["value"] > 1000 and io["rel_l2_vs_fp32_interface"] < 1e-3
+    assert io["e2e"]["h2d_bytes_per_step"] * 2 == e["h2d_bytes_per_step"] and io["e2e"]["matches_resident_path"] is True
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -128,3 +128,22 @@ def test_io16_argument_checks(ops):
     assert lib.coattn_forward16(*args(0, None)) == -1          # cat_b required unless A_ONLY
     assert lib.coattn_forward16(*args(_lib.FLAG_A_ONLY, None)) == 0
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("gated", [False, True])
+def test_io16_host_pipeline_matches_resident_path(ops, dtype, gated):
+    """HostPipeline(feature_dtype=16-bit): pinned 16-bit host buffers in and out, chunks over three streams."""
+    from cosnet_b200.coattention import HostPipeline
+    _, fwd16 = ops
+    n, h, w = 7, 16, 12      # 7 pairs in chunks of 2: a ragged last chunk
+    _, (a16, b16, W, g, b) = _inputs(77, n, h, w, dtype)
+    want_a, want_b = fwd16(a16, b16, W, g, b, gated_only=gated)
+    pipe = HostPipeline(n, C, h, w, chunk=2, slots=3, device="cuda:0", feature_dtype=dtype, gated_only=gated)
+    oc = C if gated else 2 * C
+    out_a = torch.empty((n, oc, h, w), dtype=dtype).pin_memory()
+    out_b = torch.empty((n, oc, h, w), dtype=dtype).pin_memory()
+    pipe(a16.cpu().pin_memory(), b16.cpu().pin_memory(), W, g, b, out_a, out_b)
+    torch.cuda.synchronize()
+    assert pipe.h2d_bytes == 2 * n * C * h * w * 2 and pipe.d2h_bytes == 2 * n * oc * h * w * 2
+    assert torch.equal(out_a, want_a.cpu()) and torch.equal(out_b, want_b.cpu())
