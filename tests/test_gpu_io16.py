@@ -147,3 +147,67 @@ def test_io16_host_pipeline_matches_resident_path(ops, dtype, gated):
     torch.cuda.synchronize()
     assert pipe.h2d_bytes == 2 * n * C * h * w * 2 and pipe.d2h_bytes == 2 * n * oc * h * w * 2
     assert torch.equal(out_a, want_a.cpu()) and torch.equal(out_b, want_b.cpu())
+
+
+class _Stub(torch.nn.Module):
+    """Encoder stand-in that replays queued synthetic features (as in tests/test_gpu_parity.py)."""
+
+    def __init__(self, as_tuple):
+        super().__init__()
+        self.queue, self.as_tuple = [], as_tuple
+
+    def forward(self, x):
+        f = self.queue.pop(0)
+        return (f, x.new_zeros(1)) if self.as_tuple else f
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_module_with_16bit_operator_and_half_precision_module(ops, split):
+    """(1) The fp32 drop-in module with the co-attention block swapped for the 16-bit interface (features rounded to
+    fp16 on the way in, fp16 concat widened on the way out): binarised masks agree with the fp32 operator on >= 99.9 %
+    of pixels (BASELINE.json's bar).  (2) `model.half()` -- what an fp16 deployment of test.py runs: the encoders hand
+    over fp16 features, the module routes them through coattn_forward16 and the fp16 concat feeds fp16 reduce convs; the
+    remaining distance to the fp32 model is that of the half-precision convolutions around the block."""
+    from cosnet_b200.backbone import Bottleneck
+    from cosnet_b200.coattention import coattention
+    from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1234)
+    model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).eval()
+    model.encoder, model.depth_encoder = _Stub(True), _Stub(False)
+    model = model.to(dev)
+    model.split_reduce_conv = split
+    n, h, w = 2, 40, 40
+    feats = [torch.from_numpy(f).to(dev) for f in orc.synthetic_features(91, n, h, w, 0.66, count=4)]
+    img = torch.zeros(n, 3, h * 8, w * 8, device=dev)
+    dimg = torch.zeros(n, 1, h * 8, w * 8, device=dev)
+
+    def run_model(m, dtype):
+        m.encoder.queue = [feats[0].to(dtype), feats[1].to(dtype)]
+        m.depth_encoder.queue = [feats[2].to(dtype), feats[3].to(dtype)]
+        with torch.no_grad():
+            return m(img.to(dtype), img.to(dtype), dimg.to(dtype), dimg.to(dtype))
+
+    r1, r2, _ = run_model(model, torch.float32)
+
+    def impl16(v_a, v_b, weight, gate_weight, gate_bias, gated_only=False):
+        a, b = coattention(v_a.half(), v_b.half(), weight, gate_weight, gate_bias, gated_only=gated_only)
+        assert a.dtype == torch.float16
+        return a.float(), b.float()
+    model.coattention_impl = impl16
+    x1, x2, _ = run_model(model, torch.float32)
+    for got, ref in ((x1, r1), (x2, r2)):
+        assert float(ref.min()) < 0.5 < float(ref.max())      # only meaningful if the maps straddle the threshold
+        agree = ((got > 0.5) == (ref > 0.5)).float().mean().item()
+        assert agree >= 0.999, agree
+        assert (got - ref).abs().max().item() < 2e-3
+
+    model.coattention_impl = coattention
+    h1, h2, _ = run_model(model.half(), torch.float16)
+    for got, ref in ((h1, r1), (h2, r2)):
+        assert got.dtype == torch.float16 and got.shape == ref.shape and bool(torch.isfinite(got).all())
+        assert (got.float() - ref).abs().max().item() < 1e-2
+    with pytest.raises(RuntimeError):      # 16-bit features are forward only
+        model.encoder.queue = [feats[0].half().requires_grad_(True), feats[1].half()]
+        model.depth_encoder.queue = [feats[2].half(), feats[3].half()]
+        model(img.half(), img.half(), dimg.half(), dimg.half())
