@@ -237,18 +237,22 @@ class _CoAttentionFn(torch.autograd.Function):
 
 def coattention(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False, gated_only=False):
     """Drop-in for rgbd_segmentation_RAA.py:150-187: returns (cat_a, cat_b), each [N, 2C, H, W].  Differentiable
-    w.r.t. v_a, v_b, weight, gate_weight and gate_bias (hand-written CUDA backward).  float16 / bfloat16 features are
-    accepted without gradients and give outputs of the same dtype (`coattention_forward16_raw`).
+    w.r.t. v_a, v_b, weight, gate_weight and gate_bias (hand-written CUDA backward).  float16 / bfloat16 features give
+    outputs of the same dtype: `coattention_forward16_raw` without gradients, the fp32 path on the widened features with.
 
     gated_only=True returns only the gated attended features Z * sigmoid(gate(Z)), [N, C, H, W] each (the first half of
     the concat), for consumers that apply the reduce conv in two halves and never need the concat itself."""
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (v_a, v_b, weight, gate_weight, gate_bias))
     if v_a.dtype in (torch.float16, torch.bfloat16):
-        # 16-bit features (a half-precision or autocast encoder): coattn_forward16, outputs in the same dtype; the operand
-        # format follows the feature dtype.  Inference only -- the hand-written backward takes fp32 features.
+        # 16-bit features (a half-precision or autocast encoder): outputs in the same dtype, the operand format follows
+        # the feature dtype.  Without gradients: coattn_forward16 (features read in place).  With gradients (mixed-precision
+        # training): the hand-written backward takes fp32 features, so they are widened first -- the same 16-bit values
+        # reach the tensor cores, the concat is rounded once at the end and autograd narrows d_v_a / d_v_b.
         if needs_grad:
-            raise _lib.CoattnError("16-bit features are a forward-only path: run under torch.no_grad() or feed fp32 features")
+            cat_a, cat_b = _CoAttentionFn.apply(v_a.float(), v_b.float(), weight, gate_weight, gate_bias,
+                                                v_a.dtype == torch.bfloat16, gated_only)
+            return cat_a.to(v_a.dtype), cat_b.to(v_a.dtype)
         return coattention_forward16_raw(v_a, v_b, weight, gate_weight, gate_bias, gated_only=gated_only)
     if needs_grad:
         return _CoAttentionFn.apply(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands, gated_only)

@@ -207,7 +207,28 @@ def test_module_with_16bit_operator_and_half_precision_module(ops, split):
     for got, ref in ((h1, r1), (h2, r2)):
         assert got.dtype == torch.float16 and got.shape == ref.shape and bool(torch.isfinite(got).all())
         assert (got.float() - ref).abs().max().item() < 1e-2
-    with pytest.raises(RuntimeError):      # 16-bit features are forward only
-        model.encoder.queue = [feats[0].half().requires_grad_(True), feats[1].half()]
-        model.depth_encoder.queue = [feats[2].half(), feats[3].half()]
-        model(img.half(), img.half(), dimg.half(), dimg.half())
+
+
+def test_16bit_features_with_gradients(ops):
+    """Mixed-precision training: fp16 features that require grad go through the fp32 interface on the widened values --
+    same forward bits as coattn_forward16, gradients those of the fp32 path rounded to fp16."""
+    from cosnet_b200.coattention import coattention
+    _, fwd16 = ops
+    _, (a16, b16, W, g, b) = _inputs(63, 2, 12, 12, torch.float16)
+    want_a, want_b = fwd16(a16, b16, W, g, b)
+    W1, g1, b1 = (t.clone().requires_grad_(True) for t in (W, g, b))
+    a1 = a16.clone().requires_grad_(True)
+    cat_a, cat_b = coattention(a1, b16, W1, g1, b1)
+    assert cat_a.dtype == torch.float16 and torch.equal(cat_a, want_a) and torch.equal(cat_b, want_b)
+    ra, rb = torch.randn_like(cat_a), torch.randn_like(cat_b)
+    ((cat_a * ra).sum() + (cat_b * rb).sum()).backward()
+    W2, g2, b2 = (t.clone().requires_grad_(True) for t in (W, g, b))
+    a2 = a16.float().requires_grad_(True)
+    ca2, cb2 = coattention(a2, b16.float(), W2, g2, b2)
+    ((ca2 * ra.float()).sum() + (cb2 * rb.float()).sum()).backward()
+    torch.cuda.synchronize()
+    # (the backward accumulates d_w / d_gate_w with floating-point atomics: equal to rounding, not bit for bit)
+    rel = lambda x, y: float((x.float() - y.float()).norm() / y.float().norm())
+    assert a1.grad.dtype == torch.float16 and rel(a1.grad, a2.grad) < 1e-3
+    for x, y in ((W1, W2), (g1, g2), (b1, b2)):
+        assert rel(x.grad, y.grad) < 1e-4
