@@ -14,7 +14,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from .coattention import coattention_forward_raw, coattention_queries_raw
+from .coattention import coattention_forward16_raw, coattention_forward_raw, coattention_queries_raw
 
 
 @torch.no_grad()
@@ -28,6 +28,8 @@ def coattention_frame_a(v_a, v_b, weight, gate_weight, gate_bias=None):
 def coattention_queries_frame_a(v_a, v_b, weight, gate_weight, gate_bias=None, refs: int = 1):
     """cat_a only for Q query feature maps v_a [Q, C, H, W], each paired with `refs` consecutive reference maps of
     v_b [Q * refs, C, H, W]; the query side of the operator is prepared once per query (coattn_forward_queries)."""
+    if v_a.dtype in (torch.float16, torch.bfloat16):      # half-precision model: 16-bit features in and out
+        return coattention_forward16_raw(v_a, v_b, weight, gate_weight, gate_bias, refs=refs, a_only=True)[0]
     return coattention_queries_raw(v_a, v_b, weight, gate_weight, gate_bias, refs=refs)
 
 

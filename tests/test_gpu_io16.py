@@ -232,3 +232,26 @@ def test_16bit_features_with_gradients(ops):
     assert a1.grad.dtype == torch.float16 and rel(a1.grad, a2.grad) < 1e-3
     for x, y in ((W1, W2), (g1, g2), (b1, b2)):
         assert rel(x.grad, y.grad) < 1e-4
+
+
+def test_half_precision_multi_reference_inference():
+    """test.py:278-305 with `model.half()`: the query-hoisted batched path (coattn_forward16 with refs > 1) equals running
+    the half-precision drop-in module once per (query, reference) pair."""
+    from cosnet_b200.backbone import Bottleneck
+    from cosnet_b200.inference import segment_with_references
+    from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).to(dev).eval().half()
+    q, r, hw = 2, 3, 97
+    tgt, tgt_d = torch.randn(q, 3, hw, hw, device=dev).half(), torch.randn(q, 1, hw, hw, device=dev).half()
+    refs, refs_d = torch.randn(q, r, 3, hw, hw, device=dev).half(), torch.randn(q, r, 1, hw, hw, device=dev).half()
+    got = segment_with_references(model, tgt, tgt_d, refs, refs_d)
+    want = torch.zeros_like(got, dtype=torch.float32)
+    with torch.no_grad():
+        for i in range(r):                                       # the reference's loop (test.py:287-301)
+            want += model(tgt, refs[:, i], tgt_d, refs_d[:, i])[0].float()
+    want /= r
+    assert got.dtype == torch.float16 and got.shape == (q, 1, hw, hw)
+    # the encoders see other batch compositions (cuDNN picks other fp16 algorithms): equal to half-precision rounding
+    assert (got.float() - want).abs().max().item() < 5e-3
