@@ -477,6 +477,9 @@ def run_ours(args):
                                                 "is not sent back; for the split-reduce-conv consumer"}},
         "io16": {"value": total_pairs * io16_steps / (io16_ms * 1e-3), "unit": UNIT, "ms_per_step": io16_ms / io16_steps,
                  "steps": io16_steps, "feature_dtype": str(dt16), "gpu_launches_per_step": 6,
+                 # whole modality call (cast_w + project_mn + attend2), algorithmic flops 6 L^2 C + 2 L C^2 per pair
+                 "whole_call_tflops": 2 * n * FLOPS_PER_PAIR_MODALITY / (io16_ms / io16_steps * 1e-3) / 1e12,
+                 "whole_call_frac_of_burst_peak": 2 * n * FLOPS_PER_PAIR_MODALITY / (io16_ms / io16_steps * 1e-3) / 1e12 / peaks["bf16_tflops"],
                  "rel_l2_vs_fp32_interface": rel16,
                  "e2e": {"value": total_pairs * e2e_steps / e2e16_s, "unit": UNIT,
                          "h2d_bytes_per_step": 2 * pipe16.h2d_bytes * world, "d2h_bytes_per_step": 2 * pipe16.d2h_bytes * world,

@@ -25,6 +25,7 @@ FLAG_UNFUSED_PREP = 16  # COATTN_FLAG_UNFUSED_PREP
 FLAG_GATED_ONLY = 32  # COATTN_FLAG_GATED_ONLY
 FLAG_KMAJOR = 64  # COATTN_FLAG_KMAJOR
 FLAG_SOFTMAX16 = 128  # COATTN_FLAG_SOFTMAX16
+FLAG_SPLIT_KEYS = 256  # COATTN_FLAG_SPLIT_KEYS
 
 # name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
 SIGNATURES = {

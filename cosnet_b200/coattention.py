@@ -58,12 +58,14 @@ def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
 
 def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False,
                             unfused_gate=False, want_mask=False, want_z=True, single_cta=False, a_only=False, unfused_prep=False, gated_only=False, kmajor=False,
-                            softmax16=False):
+                            softmax16=False, split_keys=False):
     """Runs the CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L]
     (plus mask [2,N,L] when want_mask=True; fused path only).
 
     bf16_operands=False (default): fp16 tensor-core operands with fp32 accumulation (COATTN_FLAG_BF16 unset);
     True: bf16 operands (see include/coattn_b200.h for the trade-off).
+    split_keys=True: COATTN_FLAG_SPLIT_KEYS, the latency mode for one or two pairs (key range of every item swept in parts
+    by different CTA pairs + a merge kernel; equal to the default path to fp32 rounding, not bit for bit).
     """
     n, c, h, w = _check_inputs(v_a, v_b, weight, gate_weight, gate_bias)
     lib = _lib.load()
@@ -85,7 +87,8 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         mask = torch.empty((2, n, h * w), dtype=torch.float32, device=dev) if want_mask else None
         flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)
                  | (_lib.FLAG_SINGLE_CTA if single_cta else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
-                 | (_lib.FLAG_UNFUSED_PREP if unfused_prep else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0) | (_lib.FLAG_KMAJOR if kmajor else 0) | (_lib.FLAG_SOFTMAX16 if softmax16 else 0))
+                 | (_lib.FLAG_UNFUSED_PREP if unfused_prep else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0) | (_lib.FLAG_KMAJOR if kmajor else 0) | (_lib.FLAG_SOFTMAX16 if softmax16 else 0)
+                 | (_lib.FLAG_SPLIT_KEYS if split_keys else 0))
         code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
                                   None if gb is None else gb.data_ptr(), cat_a.data_ptr(),
                                   None if cat_b is None else cat_b.data_ptr(),
@@ -106,7 +109,7 @@ def backward_workspace_bytes(n: int, c: int, h: int, w: int, counterpart: bool =
 
 
 def coattention_queries_raw(v_a, v_b, weight, gate_weight, gate_bias=None, refs: int = 1, bf16_operands=False,
-                            gated_only=False):
+                            gated_only=False, split_keys=False):
     """test.py-style inference (test.py:287-305): v_a [Q, C, H, W] query features, v_b [Q * refs, C, H, W] reference
     features (pair p = query p // refs); returns cat_a [Q * refs, 2C (C with gated_only), H, W].  The query side (16-bit
     cast and Q = W V_a) is prepared once per query frame; the result equals the A_ONLY forward on repeated queries."""
@@ -122,7 +125,8 @@ def coattention_queries_raw(v_a, v_b, weight, gate_weight, gate_bias=None, refs:
         cat_a = torch.empty((pairs, (c if gated_only else 2 * c), h, w), dtype=torch.float32, device=dev)
         nbytes = workspace_bytes(pairs, c, h, w)
         ws = _workspace(dev, nbytes)
-        flags = (_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0)
+        flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0)
+                 | (_lib.FLAG_SPLIT_KEYS if split_keys else 0))
         code = lib.coattn_forward_queries(v_a.data_ptr(), v_b.data_ptr(), weight.data_ptr(), gw.data_ptr(),
                                           None if gate_bias is None else gate_bias.data_ptr(), cat_a.data_ptr(),
                                           _aligned_ptr(ws), nbytes, n, refs, c, h, w, flags,

@@ -88,6 +88,9 @@ struct Attend2Params {
   int q_pairs;   // ceil(L / 256)
   int kv_tiles;  // ceil(L / 128)
   int num_items; // passes * N * q_pairs
+  int splits;    // 1, or key-range splits per item (COATTN_FLAG_SPLIT_KEYS, few items): unit = (item, part) sweeps key tiles
+                 // [T part / splits, T (part + 1) / splits) and writes z / lse of ITS range to z[part], lse[part]
+                 // ([splits][passes][N]...); merge_gate_kernel combines the parts.  No fused gate / passthrough then.
   int passes;    // 2, or 1 = frame-A outputs only (pass 0; test.py averages x1 only, test.py:301)
   int q_group;   // 1, or (passes == 1 only) pairs per query frame: pair n uses sample n / q_group of V_a and Q = W V_a
   // row of sample 0 in each tensor map (MN path).  Workspace planes X = [B16, A16, Q16]: xq_row0 = 2 N C, xb_row0 = 0,
@@ -202,7 +205,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     if (lane == 0) {
       const uint32_t q_full_l = mapa_u32(smem_u32(q_full), 0);
       uint32_t it = 0, cnt = 0;
-      for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
+      for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters, ++it) {
+        const int item = unit / p.splits, part = unit - item * p.splits;
+        const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
+        (void)part;
         const int qp = item % p.q_pairs;
         const int np = item / p.q_pairs;
         const int pass = (p.passes == 2) ? (np & 1) : 0;
@@ -220,7 +226,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
 #pragma unroll
           for (int mc = 0; mc < 2; ++mc)     // two 64-position chunks x 256 channel rows
             tma_load_2d_pair(sQ + mc * 32768, mq, q_full_l, qpos0 + mc * 64, qch0);
-          for (int j = 0; j < T; ++j, ++cnt) {
+          for (int j = j0; j < j1; ++j, ++cnt) {
             const uint32_t s = cnt % k2KStages, ph = (cnt / k2KStages) & 1;
             mbar_wait(k_empty + s, ph ^ 1, 2);
             if (rank == 0) mbar_arrive_expect_tx(k_full + s, 2 * k2KBytes);
@@ -235,7 +241,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           const int krow0 = krow_base + (int)rank * (k2BN / 2);
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) tma_load_2d_pair(sQ + kb * (k2BM * 128), &tmap_q, q_full_l, kb * 64, qrow0);
-          for (int j = 0; j < T; ++j, ++cnt) {
+          for (int j = j0; j < j1; ++j, ++cnt) {
             const uint32_t s = cnt % k2KStages, ph = (cnt / k2KStages) & 1;
             mbar_wait(k_empty + s, ph ^ 1, 2);
             if (rank == 0) mbar_arrive_expect_tx(k_full + s, 2 * k2KBytes);
@@ -253,13 +259,16 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     // ------------------------------------------------------------------ TMA producer: value tiles
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (int item = cluster_id; item < p.num_items; item += num_clusters) {
+      for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters) {
+        const int item = unit / p.splits, part = unit - item * p.splits;
+        const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
+        (void)part;
         const int np = item / p.q_pairs;
         const int vpass = (p.passes == 2) ? (np & 1) : 0;
         const int vn = (p.passes == 2) ? (np >> 1) : np;
         const CUtensorMap* mv = vpass ? &tmap_v1 : &tmap_v;
         const int vrow0 = (vpass ? p.v1_row0 : p.v0_row0) + vn * kC + (int)rank * (kC / 2);
-        for (int j = 0; j < T; ++j, ++cnt) {
+        for (int j = j0; j < j1; ++j, ++cnt) {
           const uint32_t s = cnt % k2VStages, ph = (cnt / k2VStages) & 1;
           mbar_wait(v_empty + s, ph ^ 1, 3);
           if (rank == 0) mbar_arrive_expect_tx(v_full + s, 2 * k2VBytes);
@@ -330,7 +339,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       const uint64_t qd0 = MN ? make_sdesc_mn_sw128(smem_u32(sQ), 32768, 1024) : make_sdesc_k_sw128(smem_u32(sQ));
       const uint32_t sK_addr = smem_u32(sK);
       const uint32_t sV_addr = smem_u32(sV);
-      for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
+      for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters, ++it) {
+        const int part = unit % p.splits;
+        const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
         // S(j) of this item; kcnt counts every S tile of the kernel (key stage ring and s_free phases)
         auto issue_s = [&](int j) {
           const uint32_t s = kcnt % k2KStages, ph = (kcnt / k2KStages) & 1;
@@ -350,7 +361,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             }
             umma2_commit_mc(k_empty + s, 3);
             umma2_commit_mc(s_full, 3);
-            if (j == T - 1) umma2_commit_mc(q_empty, 3);     // last affinity tile of the item: the query tile is free
+            if (j == j1 - 1) umma2_commit_mc(q_empty, 3);    // last affinity tile of the unit: the query tile is free
           }
           __syncwarp();
           ++kcnt;
@@ -363,13 +374,13 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         // back (s_free(j+1): the softmax warps hold S(j+1) in registers) and is computed while they work on tile j+1;
         // PV(j) follows when P(j) is complete.  Both conditions arrive when softmax(j) ends, and the affinity tile goes
         // first, so the next S is ready when the softmax warps come back for it.
-        issue_s(0);
-        if (T > 1) issue_s(1);
+        issue_s(j0);
+        if (j1 - j0 > 1) issue_s(j0 + 1);
         TRG(2);
-        for (int j = 0; j < T; ++j) {
-          const int b = j & 1;
+        for (int j = j0; j < j1; ++j) {
+          const int b = (j - j0) & 1;
           TRT(j, 2);
-          if (j + 2 < T) issue_s(j + 2);
+          if (j + 2 < j1) issue_s(j + 2);
           TRT(j, 3);
           {
             const uint32_t s = vcnt % k2VStages, ph = (vcnt / k2VStages) & 1;
@@ -390,7 +401,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             for (int kk = 0; kk < k2BN / 16; ++kk) {
               if (kk < ksteps) {
                 const uint64_t bd = vd0 + (uint64_t)(((kk >> 2) * ((kC / 2) * 128) + (kk & 3) * 32) >> 4);
-                umma2_ts(tO, tP + kk * 8, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+                umma2_ts(tO, tP + kk * 8, bd, idesc_o, (j > j0 || kk > 0) ? 1u : 0u);
               }
             }
             umma2_commit_mc(v_empty + s, 3);
@@ -421,14 +432,21 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     float greg[kChunks];
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) greg[ch] = (p.cat_a != nullptr) ? __ldg(p.gate_w + g * kChans + ch * 32 + lane) : 0.f;
-    for (int item = cluster_id; item < p.num_items; item += num_clusters, ++it) {
+    uint32_t pv_acc0 = 0, pv_acc1 = 0;      // PV tiles of even / odd local index completed by the earlier units
+    for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters, ++it) {
+      const int item = unit / p.splits, part = unit - item * p.splits;
+      const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
+      const int Tu = j1 - j0;
       const int qp = item % p.q_pairs;
       const int np = item / p.q_pairs;
       const int pass = (p.passes == 2) ? (np & 1) : 0;
       const int n = (p.passes == 2) ? (np >> 1) : np;
       const int row = qp * (2 * k2BM) + (int)rank * k2BM + rloc;
-      // phase index of PV(j) on o_full[j & 1]: tiles of that parity in the earlier items + (j >> 1)
-      const uint32_t pv_base0 = it * (uint32_t)((T + 1) / 2), pv_base1 = it * (uint32_t)(T / 2);
+      // phase index of PV(jj) (jj = tile index inside the unit) on o_full[jj & 1]: tiles of that parity in the earlier
+      // units + (jj >> 1)
+      const uint32_t pv_base0 = pv_acc0, pv_base1 = pv_acc1;
+      pv_acc0 += (uint32_t)((Tu + 1) / 2);
+      pv_acc1 += (uint32_t)(Tu / 2);
       auto wait_pv = [&](int jj, int tag) {      // PV(jj) complete; requires PV(jj - 2) to be known complete
         const uint32_t ph = ((jj & 1) ? pv_base1 : pv_base0) + (uint32_t)(jj >> 1);
         warp_mbar_wait(o_full + (jj & 1), ph & 1u, lane, tag);
@@ -438,8 +456,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       const bool warp_is_padding = (qp * (2 * k2BM) + (int)rank * k2BM + quad * 32) >= p.L;
       float m = -INFINITY, l = 0.0f;
       if (warp == 0) TRG(8);
-      for (int j = 0; j < T; ++j) {
-        const int b = j & 1;
+      for (int j = j0; j < j1; ++j) {
+        const int jr = j - j0;      // tile index inside the unit: buffer parities and PV phases count from the unit's start
+        const int b = jr & 1;
         const uint32_t tSg = tmem + lane_base + k2TmemS + (uint32_t)(g * kCols);                       // this group's S columns
         const uint32_t tPg = tmem + lane_base + k2TmemP + (uint32_t)(b * (k2BN / 2) + g * (kCols / 2));  // ... and its P slot
         warp_mbar_wait(s_full, scnt & 1, lane, 20);
@@ -454,7 +473,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           uint32_t zero[kCols / 2];
 #pragma unroll
           for (int k = 0; k < kCols / 2; ++k) zero[k] = 0u;
-          if (j >= 2) { wait_pv(j - 2, 24); tc_fence_after(); }
+          if (jr >= 2) { wait_pv(jr - 2, 24); tc_fence_after(); }
           if constexpr (kCols == 64) tmem_st32(tPg, zero); else tmem_st16(tPg, zero);
           tmem_st_wait();
           tc_fence_before();
@@ -498,7 +517,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         const float hmax = fmaxf(fmaxf(h0, h1), fmaxf(h2, h3));
         // all groups of the row agree on the tile max
         const float tmax = group_exchange_max<G>(hmax, xbuf, seq++, g, rloc, quad);
-        if (j == 0) {
+        if (jr == 0) {
           m = tmax;
         } else {
           // lazy rescale: the reference max only moves when the row max jumps by more than 2^13 (fp16 P stays below
@@ -511,7 +530,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             const float m_new = fmaxf(m, tmax);
             const float scale = fast_exp2((m - m_new) * kLog2e);
             // S(j) follows PV(j-3) in the tensor pipe, so s_full(j) implies PV(j-3) is complete
-            wait_pv(j - 1, 21);
+            wait_pv(jr - 1, 21);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < kChunks; ++ch) {
@@ -549,7 +568,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         l += (l0 + l1) + (l2 + l3);
         // packed P: the kCols keys of this group -> kCols / 2 columns of P buffer b, once PV(j-2) has read its previous
         // content (S(j) is issued ahead of PV(j-2), so s_full(j) does not imply it; the wait is almost always over)
-        if (j >= 2) { wait_pv(j - 2, 24); tc_fence_after(); }
+        if (jr >= 2) { wait_pv(jr - 2, 24); tc_fence_after(); }
         if constexpr (kCols == 64) tmem_st32(tPg, pk); else tmem_st16(tPg, pk);
         tmem_st_wait();
         tc_fence_before();
@@ -562,8 +581,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       }
       if (warp == 0) TRG(10);
       // ---- drain.  s_full(T-1) only implies PV(T-4): wait PV(T-2) first (completions are in order), then PV(T-1).
-      if (T >= 2) wait_pv(T - 2, 23);
-      wait_pv(T - 1, 22);
+      if (Tu >= 2) wait_pv(Tu - 2, 23);
+      wait_pv(Tu - 1, 22);
       tc_fence_after();
       if (warp == 0) TRG(11);
       l = group_exchange_sum<G>(l, xbuf, seq++, g, rloc, quad);
@@ -577,7 +596,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       const int c0 = g * kChans;
       // raw Z (kept for the backward pass): written in the same sweep over O as the gated output below; a sweep of its
       // own only when there is no fused gate (coattn_stage_attend)
-      float* zcol = p.z ? p.z + ((size_t)(pass * p.N + n) * kC + c0) * p.L + row : nullptr;
+      const size_t out_idx = (size_t)(part * p.passes + pass) * p.N + n;     // part = 0 unless the keys are split
+      float* zcol = p.z ? p.z + (out_idx * kC + c0) * p.L + row : nullptr;
       if (zcol != nullptr && p.cat_a == nullptr) {
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ++ch) {
@@ -647,7 +667,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         }
         if (valid && g == 0 && p.mask != nullptr) p.mask[(size_t)(pass * p.N + n) * p.L + row] = gate;
       }
-      if (valid && g == 0) p.lse[(size_t)(pass * p.N + n) * p.L + row] = m + __logf(l);
+      if (valid && g == 0) p.lse[out_idx * p.L + row] = m + __logf(l);
       if (warp == 0) TRG(12);
     }
   }

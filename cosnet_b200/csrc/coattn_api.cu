@@ -22,11 +22,22 @@ inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
   int N, L, Lp;
+  int parts;   // key-range parts the z / lse segments have room for (COATTN_FLAG_SPLIT_KEYS)
   int64_t off_t, off_at, off_vv, off_w16, off_z, off_lse, total;
   int64_t bytes_t, bytes_at, bytes_vv, bytes_w16, bytes_z, bytes_lse;
   // element strides
   int64_t t_pass_elems() const { return (int64_t)N * Lp * kC; }   // T[pass] and VV[pass]
 };
+
+// COATTN_FLAG_SPLIT_KEYS: parts per item.  `items` work items of T key tiles each on `clusters` CTA pairs: split only
+// when at least two parts per item fit beside each other, never below four key tiles per part.
+int choose_splits(int items, int T, int clusters) {
+  if (items < 1 || 2 * items > clusters) return 1;
+  int s = clusters / items;
+  if (s > kMaxKeySplits) s = kMaxKeySplits;
+  if (s > T / 4) s = T / 4;
+  return s < 1 ? 1 : s;
+}
 
 Layout make_layout(int n, int h, int w) {
   Layout ly{};
@@ -39,8 +50,12 @@ Layout make_layout(int n, int h, int w) {
   ly.off_at = off;  ly.bytes_at = plane;      off = round_up(off + ly.bytes_at, kAlign);
   ly.off_vv = off;  ly.bytes_vv = 3 * plane;  off = round_up(off + ly.bytes_vv, kAlign);   // B16, A16, Q16 ([C][Lp] each)
   ly.off_w16 = off; ly.bytes_w16 = (int64_t)kC * kC * 2; off = round_up(off + ly.bytes_w16, kAlign);
-  ly.off_z = off;   ly.bytes_z = (int64_t)2 * n * kC * ly.L * 4; off = round_up(off + ly.bytes_z, kAlign);
-  ly.off_lse = off; ly.bytes_lse = (int64_t)2 * n * ly.L * 4;    off = round_up(off + ly.bytes_lse, kAlign);
+  // room for the parts of COATTN_FLAG_SPLIT_KEYS (more than one only for the few-pair shapes that can use them:
+  // frame-A-only items on the 74 CTA pairs of a B200 is the case with the most parts)
+  const int parts = choose_splits(n * ((ly.L + 2 * k2BM - 1) / (2 * k2BM)), (ly.L + k2BN - 1) / k2BN, 74);
+  ly.off_z = off;   ly.bytes_z = (int64_t)parts * 2 * n * kC * ly.L * 4; off = round_up(off + ly.bytes_z, kAlign);
+  ly.off_lse = off; ly.bytes_lse = (int64_t)parts * 2 * n * ly.L * 4;    off = round_up(off + ly.bytes_lse, kAlign);
+  ly.parts = parts;
   ly.total = off;
   return ly;
 }
@@ -303,7 +318,7 @@ extern "C" int coattn_stage_prep_project(const float* v_a, const float* v_b, con
 
 static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float* cat_b, float* z, float* lse,
                          float* mask, const float* gate_w, const float* gate_b, void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
-                         unsigned flags, void* stream, int q_group = 1, int in16 = 0) {
+                         unsigned flags, void* stream, int q_group = 1, int in16 = 0, int splits = 1) {
   // in16 (coattn_forward16): v_a, v_b, cat_a, cat_b hold 16-bit elements; 2 = the operands are read from v_a / v_b in place
   const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
   if (int e = check_dims(n, c, h, w_)) return e;
@@ -358,7 +373,9 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     q.kv_tiles = (ly.L + k2BN - 1) / k2BN;
     q.passes = (flags & COATTN_FLAG_A_ONLY) ? 1 : 2;
     q.q_group = q_group;
+    q.splits = splits;
     if (q_group != 1 && (q.passes != 1 || !mn)) return COATTN_E_UNSUPPORTED;
+    if (splits != 1 && (cat_a || v_a || mask || !z || !lse || !mn)) return COATTN_E_UNSUPPORTED;   // parts: z / lse only
     q.num_items = q.passes * n * q.q_pairs;
     // 8 softmax warps (two column groups per TMEM lane quadrant) by default; COATTN_FLAG_SOFTMAX16 selects the 16-warp
     // layout (four groups)
@@ -376,7 +393,7 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
     cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
     if (e2 != cudaSuccess) return (int)e2;
     int clusters = sms / 2;
-    if (q.num_items < clusters) clusters = q.num_items;
+    if (q.num_items * splits < clusters) clusters = q.num_items * splits;
     kern2<<<2 * clusters, threads2, smem2, st>>>(tm_q, tm_k2, tm_v2, tm_v3, q);
 #ifdef COATTN_TRACE2
     {
@@ -523,6 +540,52 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
   return (int)cudaGetLastError();
 }
 
+// COATTN_FLAG_SPLIT_KEYS: parts to use for this call (1 = the default single-sweep path)
+static int split_parts(unsigned flags, int n, const Layout& ly, int* parts) {
+  *parts = 1;
+  if (!(flags & COATTN_FLAG_SPLIT_KEYS)) return COATTN_OK;
+  if (flags & (COATTN_FLAG_UNFUSED_GATE | COATTN_FLAG_SINGLE_CTA | COATTN_FLAG_KMAJOR | COATTN_FLAG_UNFUSED_PREP |
+               COATTN_FLAG_SOFTMAX16))
+    return COATTN_E_UNSUPPORTED;
+  int sms = 0;
+  if (int e = check_arch(&sms)) return e;
+  const int passes = (flags & COATTN_FLAG_A_ONLY) ? 1 : 2;
+  int s = choose_splits(passes * n * ((ly.L + 2 * k2BM - 1) / (2 * k2BM)), (ly.L + k2BN - 1) / k2BN, sms / 2);
+  if (s > ly.parts) s = ly.parts;
+  *parts = s;
+  return COATTN_OK;
+}
+
+// attend2 over `parts` key ranges per item (z / lse of every part in the workspace), then merge + gate + concat
+static int attend_split_merge(const float* v_a, const float* v_b, const float* gate_w, const float* gate_b, float* cat_a,
+                              float* cat_b, float* z, float* lse, float* mask, void* workspace, int64_t workspace_bytes,
+                              int n, int c, int h, int w_, unsigned flags, void* stream, int q_group, int parts) {
+  const Layout ly = make_layout(n, h, w_);
+  float* zp = reinterpret_cast<float*>(seg(workspace, ly.off_z));
+  float* lsep = reinterpret_cast<float*>(seg(workspace, ly.off_lse));
+  if (int e = launch_attend(nullptr, nullptr, nullptr, nullptr, zp, lsep, nullptr, gate_w, gate_b, workspace, workspace_bytes,
+                            n, c, h, w_, flags, stream, q_group, 0, parts))
+    return e;
+  MergeParams m;
+  m.zp = zp; m.lsep = lsep;
+  m.v_a = (flags & COATTN_FLAG_GATED_ONLY) ? nullptr : v_a;
+  m.v_b = (flags & COATTN_FLAG_GATED_ONLY) ? nullptr : v_b;
+  m.gate_w = gate_w; m.gate_b = gate_b; m.cat_a = cat_a; m.cat_b = cat_b; m.z = z; m.lse = lse; m.mask = mask;
+  m.N = n; m.L = ly.L; m.splits = parts; m.passes = (flags & COATTN_FLAG_A_ONLY) ? 1 : 2;
+  m.out_channels = (flags & COATTN_FLAG_GATED_ONLY) ? kC : 2 * kC;
+  m.q_group = q_group;
+  const uintptr_t ptrs = reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b) |
+                         reinterpret_cast<uintptr_t>(cat_a) | reinterpret_cast<uintptr_t>(cat_b) |
+                         reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(lse) | reinterpret_cast<uintptr_t>(mask);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // few pairs by construction: 32-position blocks (4-byte accesses, 128-byte rows per warp) unless the 128-position
+  // blocks of the float4 variant already give every SM two CTAs
+  const bool vec4 = (ly.L % 4) == 0 && (ptrs & 15) == 0 && ((ly.L + 127) / 128) * m.passes * n >= 296;
+  if (vec4) merge_gate_kernel<4><<<dim3((ly.L + 127) / 128, m.passes * n), kGateThreads, 0, st>>>(m);
+  else merge_gate_kernel<1><<<dim3((ly.L + 31) / 32, m.passes * n), kGateThreads, 0, st>>>(m);
+  return (int)cudaGetLastError();
+}
+
 int coattn_forward_queries(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* gate_b,
                            float* cat_a, void* workspace, int64_t workspace_bytes, int nq, int refs, int c, int h, int w_,
                            unsigned flags, void* stream) {
@@ -540,8 +603,13 @@ int coattn_forward_queries(const float* v_a, const float* v_b, const float* w, c
                                 reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
                                 (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq))
     return e;
+  int parts = 1;
+  if (int e = split_parts(flags | COATTN_FLAG_A_ONLY, n, ly, &parts)) return e;
+  if (parts > 1)
+    return attend_split_merge(v_a, v_b, gate_w, gate_b, cat_a, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes,
+                              n, c, h, w_, (flags | COATTN_FLAG_A_ONLY) & ~COATTN_FLAG_SPLIT_KEYS, stream, refs, parts);
   return launch_attend(v_a, v_b, cat_a, nullptr, nullptr, nullptr, nullptr, gate_w, gate_b, workspace, workspace_bytes, n, c,
-                       h, w_, flags | COATTN_FLAG_A_ONLY, stream, refs);
+                       h, w_, (flags | COATTN_FLAG_A_ONLY) & ~COATTN_FLAG_SPLIT_KEYS, stream, refs);
 }
 
 int coattn_forward16(const void* v_a, const void* v_b, const float* w, const float* gate_w, const float* gate_b,
@@ -584,6 +652,14 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);
   if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
+  int parts = 1;
+  if (int e = split_parts(flags, n, ly, &parts)) return e;
+  flags &= ~COATTN_FLAG_SPLIT_KEYS;
+  if (parts > 1) {
+    if (int e = coattn_stage_prep_project(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+    return attend_split_merge(v_a, v_b, gate_w, gate_b, cat_a, cat_b, z, lse, mask, workspace, workspace_bytes, n, c, h, w_,
+                              flags, stream, 1, parts);
+  }
   if (flags & COATTN_FLAG_SINGLE_CTA) flags |= COATTN_FLAG_KMAJOR;   // the cross-check kernel only knows K-major operands
   if (flags & COATTN_FLAG_UNFUSED_PREP) {
     if (int e = coattn_stage_prep(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;

@@ -1105,4 +1105,149 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(GateParams p) {
   }
 }
 
+// ==============================================================================================
+// merge_gate_kernel: COATTN_FLAG_SPLIT_KEYS (few pairs: fewer work items than CTA pairs).  attend2 swept the key range
+// of every item in `splits` parts; part s left Z_s (normalised over ITS keys) and lse_s.  Per position
+//   lse = log sum_s exp(lse_s),   Z = sum_s exp(lse_s - lse) Z_s                      (the softmax over all keys)
+// followed by the epilogue of gate_kernel (:175-187): gate logit, sigmoid, scale, concat; lse / mask / raw Z are kept
+// when asked for.  HBM-bound: reads splits * C L * 4 bytes of parts per sample and side.
+// ==============================================================================================
+constexpr int kMaxKeySplits = 4;
+
+struct MergeParams {
+  const float* zp;     // [splits][passes][N][C][L]
+  const float* lsep;   // [splits][passes][N][L]
+  const float* v_a;    // [N / q_group][C][L] or null (no passthrough half: gated-only output)
+  const float* v_b;    // [N][C][L] or null
+  const float* gate_w; // [C]
+  const float* gate_b; // [1] or null
+  float* cat_a;        // [N][out_channels][L]
+  float* cat_b;        // [N][out_channels][L] (unused with passes == 1)
+  float* z;            // [passes][N][C][L] or null
+  float* lse;          // [passes][N][L] or null
+  float* mask;         // [passes][N][L] or null
+  int N, L, splits, passes, out_channels, q_group;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kGateThreads) merge_gate_kernel(MergeParams p) {
+  constexpr int kWarps = kGateThreads / 32, kCh = kC / kWarps;     // 16 warps, 16 channels each
+  __shared__ float part[kWarps][32 * VEC];
+  __shared__ float gw[kC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int side = blockIdx.y / p.N;
+  const int n = blockIdx.y - side * p.N;
+  const int pos = (blockIdx.x * 32 + lane) * VEC;
+  if (threadIdx.x < kC) gw[threadIdx.x] = p.gate_w[threadIdx.x];
+  __syncthreads();
+  const bool valid = pos < p.L;   // L % VEC == 0 is guaranteed by the launcher
+  const size_t part_stride = (size_t)p.passes * p.N;               // samples-and-sides per part
+  const size_t sn = (size_t)side * p.N + n;
+  float* cat = (side ? p.cat_b : p.cat_a) + (size_t)n * p.out_channels * p.L + pos;
+
+  float wgt[kMaxKeySplits][VEC];
+  float lse_out[VEC];
+  float zr[kCh][VEC];
+  float dot[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { dot[e] = 0.f; lse_out[e] = 0.f; }
+  if (valid) {
+    float ls[kMaxKeySplits][VEC];
+#pragma unroll
+    for (int s = 0; s < kMaxKeySplits; ++s)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e)
+        ls[s][e] = (s < p.splits) ? __ldg(p.lsep + ((size_t)s * part_stride + sn) * p.L + pos + e) : -INFINITY;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float m = ls[0][e];
+#pragma unroll
+      for (int s = 1; s < kMaxKeySplits; ++s) m = fmaxf(m, ls[s][e]);
+      float sum = 0.f;
+#pragma unroll
+      for (int s = 0; s < kMaxKeySplits; ++s) { wgt[s][e] = __expf(ls[s][e] - m); sum += wgt[s][e]; }
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int s = 0; s < kMaxKeySplits; ++s) wgt[s][e] *= inv;
+      lse_out[e] = m + __logf(sum);
+    }
+#pragma unroll
+    for (int k = 0; k < kCh; ++k)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) zr[k][e] = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+      const float* z = p.zp + (((size_t)s * part_stride + sn) * kC + warp * kCh) * p.L + pos;
+      float w[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {      // wgt[s] with a run-time s: select without indexing the register array
+        w[e] = wgt[0][e];
+#pragma unroll
+        for (int t = 1; t < kMaxKeySplits; ++t) w[e] = (s == t) ? wgt[t][e] : w[e];
+      }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        if constexpr (VEC == 4) {
+          const float4 t = __ldcs(reinterpret_cast<const float4*>(z + (size_t)k * p.L));
+          zr[k][0] = fmaf(w[0], t.x, zr[k][0]); zr[k][1] = fmaf(w[1], t.y, zr[k][1]);
+          zr[k][2] = fmaf(w[2], t.z, zr[k][2]); zr[k][3] = fmaf(w[3], t.w, zr[k][3]);
+        } else {
+          zr[k][0] = fmaf(w[0], __ldcs(z + (size_t)k * p.L), zr[k][0]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) {
+      const float g = gw[warp * kCh + k];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) dot[e] = fmaf(g, zr[k][e], dot[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) part[warp][lane * VEC + e] = dot[e];
+  // passthrough half of the concat while the partial sums settle
+  const float* vsrc = side ? p.v_b : p.v_a;
+  if (valid && vsrc != nullptr) {
+    const float* v = vsrc + (size_t)(side ? n : n / p.q_group) * kC * p.L + pos;
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) {
+      const int c = warp * kCh + k;
+      if constexpr (VEC == 4) __stcs(reinterpret_cast<float4*>(cat + (size_t)(kC + c) * p.L), __ldcs(reinterpret_cast<const float4*>(v + (size_t)c * p.L)));
+      else __stcs(cat + (size_t)(kC + c) * p.L, __ldcs(v + (size_t)c * p.L));
+    }
+  }
+  __syncthreads();
+  if (valid) {
+    const float bias = p.gate_b ? __ldg(p.gate_b) : 0.f;
+    float mask[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float t = bias;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += part[w][lane * VEC + e];
+      mask[e] = 1.0f / (1.0f + __expf(-t));
+    }
+    float* zout = p.z ? p.z + (sn * kC) * p.L + pos : nullptr;
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) {
+      const int c = warp * kCh + k;
+      if constexpr (VEC == 4) {
+        float4 t;
+        t.x = zr[k][0] * mask[0]; t.y = zr[k][1] * mask[1]; t.z = zr[k][2] * mask[2]; t.w = zr[k][3] * mask[3];
+        __stcs(reinterpret_cast<float4*>(cat + (size_t)c * p.L), t);
+        if (zout) *reinterpret_cast<float4*>(zout + (size_t)c * p.L) = make_float4(zr[k][0], zr[k][1], zr[k][2], zr[k][3]);
+      } else {
+        __stcs(cat + (size_t)c * p.L, zr[k][0] * mask[0]);
+        if (zout) zout[(size_t)c * p.L] = zr[k][0];
+      }
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        if (p.lse) p.lse[sn * p.L + pos + e] = lse_out[e];
+        if (p.mask) p.mask[sn * p.L + pos + e] = mask[e];
+      }
+    }
+  }
+}
+
 }  // namespace coattn

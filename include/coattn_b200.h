@@ -101,6 +101,16 @@ enum {
  *                          count); kept as a cross-check of the column-group logic.
  */
 #define COATTN_FLAG_SOFTMAX16 128u
+/*
+ *   COATTN_FLAG_SPLIT_KEYS  latency mode for a few pairs (one or two at 60x60: fewer work items than the 74 CTA pairs of
+ *                          a B200): the key range of every (sample, pass, query tile) item is swept in up to 4 parts by
+ *                          different CTA pairs, and a small HBM-bound kernel merges the parts (log-sum-exp weights) and
+ *                          applies the gate / concat epilogue.  Same softmax, other summation order: results equal the
+ *                          default path to fp32 rounding (~1e-6), not bit for bit -- which is why it is opt-in (the default
+ *                          path is batch invariant).  No effect (default path) when the batch already fills the GPU.
+ *                          coattn_forward and coattn_forward_queries; not with the cross-check flags.
+ */
+#define COATTN_FLAG_SPLIT_KEYS 256u
 
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);

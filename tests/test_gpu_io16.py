@@ -255,3 +255,43 @@ def test_half_precision_multi_reference_inference():
     assert got.dtype == torch.float16 and got.shape == (q, 1, hw, hw)
     # the encoders see other batch compositions (cuDNN picks other fp16 algorithms): equal to half-precision rounding
     assert (got.float() - want).abs().max().item() < 5e-3
+
+
+def test_forward16_is_cuda_graph_capturable(ops):
+    """3 launches (cast_w, project_mn, attend2), no host synchronisation, no allocation: capturable, and the tensor maps
+    over the caller's feature tensors stay valid for replays on new contents of the same buffers."""
+    from cosnet_b200 import _lib
+    from cosnet_b200.coattention import workspace_bytes
+    _, fwd16 = ops
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    n, c, h, w = 2, 256, 12, 12
+    v_a = torch.empty(n, c, h, w, device=dev, dtype=torch.float16)
+    v_b = torch.empty_like(v_a)
+    W, g, b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_weights(71, bias=True))
+    cat_a = torch.empty(n, 2 * c, h, w, device=dev, dtype=torch.float16)
+    cat_b = torch.empty_like(cat_a)
+    nbytes = workspace_bytes(n, c, h, w)
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    wsp = (ws.data_ptr() + 1023) // 1024 * 1024
+
+    def call(stream):
+        _lib.check(lib.coattn_forward16(v_a.data_ptr(), v_b.data_ptr(), W.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                        cat_a.data_ptr(), cat_b.data_ptr(), None, None, wsp, nbytes, n, 1, c, h, w, 0,
+                                        stream.cuda_stream), "coattn_forward16")
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        call(side)                                  # warm-up outside the capture (function attributes)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        call(torch.cuda.current_stream(dev))
+    for seed in (72, 73):
+        fa, fb = (torch.from_numpy(x).to(dev).half() for x in orc.synthetic_features(seed, n, h, w, 0.66))
+        v_a.copy_(fa); v_b.copy_(fb)
+        graph.replay()
+        torch.cuda.synchronize()
+        want = fwd16(fa, fb, W, g, b)
+        assert torch.equal(cat_a, want[0]) and torch.equal(cat_b, want[1])

@@ -1,0 +1,93 @@
+"""COATTN_FLAG_SPLIT_KEYS (latency mode for one or two pairs: key range of every work item swept in parts by different
+CTA pairs, parts merged with log-sum-exp weights) against the default path and the CPU oracle.  `pytest -m gpu`.
+
+The parts start their running maxima independently, so the 16-bit softmax numerators P are rounded against other
+reference maxima than in the single sweep: the two paths agree to that rounding (1e-5 ... 7e-5 rel-L2 measured, bound 3e-4 here),
+not bit for bit; both sit at the same distance from the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import coattn_oracle as orc
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+C = 256
+
+
+@pytest.fixture(scope="module")
+def op():
+    import __graft_entry__ as ge
+    ge.build()
+    from cosnet_b200 import coattention_forward_raw
+    assert torch.cuda.is_available()
+    return coattention_forward_raw
+
+
+def _inputs(seed, n, h, w, bias=True, sigma=0.66):
+    dev = torch.device("cuda:0")
+    v_a, v_b = orc.synthetic_features(seed, n, h, w, sigma)
+    W, g, b = orc.synthetic_weights(seed + 1, bias=bias)
+    t = lambda x: None if x is None else torch.from_numpy(x).to(dev)
+    return (v_a, v_b, W, g, b), (t(v_a), t(v_b), t(W), t(g), t(b))
+
+
+@pytest.mark.parametrize("n,h,w", [
+    (1, 60, 60),    # 30 items of 29 key tiles -> 2 parts
+    (1, 40, 40),    # 14 items of 13 tiles -> 3 parts (tile-count bound)
+    (1, 31, 41),    # L = 1271 (odd): scalar merge path, ragged last key tile in the last part
+    (2, 24, 24),    # 12 items of 5 tiles -> 1 part per 4 tiles: no split (default path)
+    (1, 61, 81),    # L = 4941
+    (1, 30, 30),    # 8 items of 8 tiles -> 2 parts
+])
+def test_split_keys_matches_default_path_and_oracle(op, n, h, w):
+    (v_a, v_b, W, g, b), t = _inputs(11, n, h, w)
+    want = op(*t, want_mask=True)
+    got = op(*t, want_mask=True, split_keys=True)
+    torch.cuda.synchronize()
+    for name, x, y in zip(("cat_a", "cat_b", "z", "lse", "mask"), got, want):
+        assert x.shape == y.shape
+        assert rel_l2(x.cpu().numpy(), y.cpu().numpy()) < 3e-4, name
+    assert torch.equal(got[0][:, C:], t[0]) and torch.equal(got[1][:, C:], t[1])      # passthrough half: bit copy
+    ref = orc.coattention(v_a, v_b, W, g, b)
+    assert rel_l2(got[0].cpu().numpy(), ref["cat_a"]) < 1e-3 and rel_l2(got[1].cpu().numpy(), ref["cat_b"]) < 1e-3
+
+
+def test_split_keys_variants(op):
+    """frame-A only, gated-only, no bias, bf16 operands, grouped queries."""
+    from cosnet_b200.coattention import coattention_queries_raw
+    _, t = _inputs(21, 1, 48, 48, bias=False)
+    for kw in ({"a_only": True}, {"gated_only": True}, {"bf16_operands": True}, {"a_only": True, "gated_only": True}):
+        want = op(*t, want_z=False, **kw)
+        got = op(*t, want_z=False, split_keys=True, **kw)
+        torch.cuda.synchronize()
+        for x, y in zip(got, want):
+            if x is None or y is None:
+                assert x is None and y is None
+                continue
+            if kw.get("a_only") and x.dim() == 3:      # lse [2, n, L]: only side 0 is written for frame-A-only calls
+                x, y = x[:1], y[:1]
+            assert x.shape == y.shape and rel_l2(x.cpu().numpy(), y.cpu().numpy()) < 3e-4, kw
+    dev = torch.device("cuda:0")
+    v_a = torch.from_numpy(orc.synthetic_features(91, 1, 40, 40, 0.66)[0]).to(dev)
+    v_b = torch.from_numpy(orc.synthetic_features(92, 3, 40, 40, 0.66)[1]).to(dev)
+    W, g, b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_weights(93, bias=True))
+    want = coattention_queries_raw(v_a, v_b, W, g, b, refs=3)
+    got = coattention_queries_raw(v_a, v_b, W, g, b, refs=3, split_keys=True)
+    torch.cuda.synchronize()
+    assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) < 3e-4 and torch.equal(got[:, C:], v_a.expand(3, -1, -1, -1))
+
+
+def test_split_keys_is_a_no_op_for_full_batches_and_rejects_cross_check_flags(op):
+    from cosnet_b200 import _lib
+    _, t = _inputs(31, 8, 24, 24)
+    want = op(*t)
+    got = op(*t, split_keys=True)        # 8 * 2 * 3 = 48 items > 37: default path, bit for bit
+    torch.cuda.synchronize()
+    for x, y in zip(got, want):
+        assert torch.equal(x, y)
+    with pytest.raises(_lib.CoattnError):
+        op(*t, split_keys=True, unfused_gate=True)
+    with pytest.raises(_lib.CoattnError):
+        op(*t, split_keys=True, softmax16=True)

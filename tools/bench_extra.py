@@ -7,6 +7,7 @@
   hd         cfg 3: 480x854 input -> 61x107x256 features (what the reference really produces), batch 16 per GPU
   inference  cfg 4: test.py-style, each query co-attended with 5 reference frames (frame-A outputs only),
              480x640 input -> 61x81x256 features, 8 queries (40 pairs) per GPU
+  latency / latency_split   one pair per step: default path vs COATTN_FLAG_SPLIT_KEYS
   io16 / io16_bf16   cfg 2 through the 16-bit feature interface (coattn_forward16); inference16: cfg 4 likewise
   eager / eager_bf16 / sdpa   secondary comparators: the reference's op sequence and PyTorch's fused attention on the same GPU
   train_abi  the same through the C ABI only (no autograd, allocator or stand-in loss inside the timed region)
@@ -28,7 +29,7 @@ import torch.nn.functional as F
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["hd", "inference", "io16", "io16_bf16", "inference16", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
+    ap.add_argument("--workload", required=True, choices=["hd", "inference", "latency", "latency_split", "io16", "io16_bf16", "inference16", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     args = ap.parse_args()
@@ -70,6 +71,16 @@ def main():
             coattention_queries_raw(da, db, W[1], G[1], Bd, refs=r)
         pairs = qn * r
         desc = "test.py-style inference: 8 queries x 5 references per GPU, 61x81x256 features, frame-A outputs only"
+    elif args.workload in ("latency", "latency_split"):
+        # cfg 1 regime: ONE frame pair (60x60x256), RGB + depth call, default path vs COATTN_FLAG_SPLIT_KEYS
+        n, h, w = 1, 60, 60
+        va, vb, da, db = (feats(n, h, w) for _ in range(4))
+        sk = args.workload == "latency_split"
+        def step():
+            coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False, split_keys=sk)
+            coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, split_keys=sk)
+        pairs = n
+        desc = ("one frame pair per step (60x60x256, RGB + depth call)" + (", COATTN_FLAG_SPLIT_KEYS" if sk else ", default path"))
     elif args.workload in ("io16", "io16_bf16"):
         # the headline shape through the 16-bit feature interface (coattn_forward16): fp16 (or bf16) features in and out,
         # read in place by TMA -- no cast pass, half the concat bytes
