@@ -118,7 +118,10 @@ int coattn_b200_abi_version(void);
 /* Static, human readable description of a return code of this library. */
 const char* coattn_b200_strerror(int code);
 
-/* Bytes of scratch `coattn_forward` needs for a batch of n pairs of [c, h, w] features. */
+/* Bytes of scratch `coattn_forward` (and coattn_forward_queries / coattn_forward16 with n = nq * refs) needs for a batch of
+ * n pairs of [c, h, w] features: six 16-bit operand planes of n * round_up(h w, 256) * c elements, W in 16 bits, and the
+ * z / lse segments -- one copy per key-range part COATTN_FLAG_SPLIT_KEYS can use at this size (1 once the batch fills the
+ * GPU).  Independent of the flags. */
 int64_t coattn_workspace_bytes(int n, int c, int h, int w);
 
 /*

@@ -44,13 +44,18 @@ def test_version_and_errors(lib):
 
 
 def test_workspace_size_and_shape_errors(lib):
-    # 60x60 -> Lp = 3840: six 16-bit planes of N*Lp*C (Bt, Qt, At, B16, A16, Q16) plus W16, z, lse
-    n, c, h, w = 2, 256, 60, 60
+    # 60x60 -> Lp = 3840: six 16-bit planes of N*Lp*C (Bt, Qt, At, B16, A16, Q16) plus W16, z, lse; the z / lse segments
+    # hold one part per key-range split COATTN_FLAG_SPLIT_KEYS may use at this size (2 pairs: 30 frame-A items -> 2 parts;
+    # 8 pairs fill the 74 CTA pairs -> 1)
+    c, h, w = 256, 60, 60
     lp = 3840
+    for n, parts in ((2, 2), (8, 1), (32, 1)):
+        plane = n * lp * c * 2
+        expect_min = 6 * plane + c * c * 2 + parts * (2 * n * c * h * w * 4 + 2 * n * h * w * 4)
+        got = lib.coattn_workspace_bytes(n, c, h, w)
+        assert expect_min <= got <= expect_min + 8 * 1024, (n, parts)
+    n = 2
     plane = n * lp * c * 2
-    expect_min = 6 * plane + c * c * 2 + 2 * n * c * h * w * 4 + 2 * n * h * w * 4
-    got = lib.coattn_workspace_bytes(n, c, h, w)
-    assert expect_min <= got <= expect_min + 8 * 1024
     assert lib.coattn_workspace_bytes(n, 128, h, w) == -2      # C must be 256
     assert lib.coattn_workspace_bytes(0, c, h, w) == -2
     off, nb = ctypes.c_int64(), ctypes.c_int64()
