@@ -206,9 +206,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       const uint32_t q_full_l = mapa_u32(smem_u32(q_full), 0);
       uint32_t it = 0, cnt = 0;
       for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters, ++it) {
-        const int item = unit / p.splits, part = unit - item * p.splits;
+        const int item = unit / p.splits, part = unit % p.splits;
         const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
-        (void)part;
         const int qp = item % p.q_pairs;
         const int np = item / p.q_pairs;
         const int pass = (p.passes == 2) ? (np & 1) : 0;
@@ -260,9 +259,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     if (lane == 0) {
       uint32_t cnt = 0;
       for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters) {
-        const int item = unit / p.splits, part = unit - item * p.splits;
+        const int item = unit / p.splits, part = unit % p.splits;
         const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
-        (void)part;
         const int np = item / p.q_pairs;
         const int vpass = (p.passes == 2) ? (np & 1) : 0;
         const int vn = (p.passes == 2) ? (np >> 1) : np;
@@ -282,39 +280,39 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
   } else if (warp == k2CopyWarp) {
     // ------------------------------------------------------------------ passthrough copy (bit exact; fp32, or 16-bit with IO16)
     if (p.v_a != nullptr && p.cat_a != nullptr) {
-      using T = typename std::conditional<IO16, unsigned short, float>::type;   // element
-      using V = typename std::conditional<IO16, uint2, float4>::type;           // four elements
+      using Elem = typename std::conditional<IO16, unsigned short, float>::type;
+      using Vec4 = typename std::conditional<IO16, uint2, float4>::type;     // four elements
       const bool vec = (p.L % 4 == 0) &&
                        (((reinterpret_cast<uintptr_t>(p.v_a) | reinterpret_cast<uintptr_t>(p.v_b) |
-                          reinterpret_cast<uintptr_t>(p.cat_a) | reinterpret_cast<uintptr_t>(p.cat_b)) & (sizeof(V) - 1)) == 0);
+                          reinterpret_cast<uintptr_t>(p.cat_a) | reinterpret_cast<uintptr_t>(p.cat_b)) & (sizeof(Vec4) - 1)) == 0);
       for (int item = cluster_id; item < p.num_items; item += num_clusters) {
         const int qp = item % p.q_pairs;
         const int np = item / p.q_pairs;
         const int pass = (p.passes == 2) ? (np & 1) : 0;
         const int n = (p.passes == 2) ? (np >> 1) : np;
         const int row0 = qp * (2 * k2BM) + (int)rank * k2BM;
-        const T* src = reinterpret_cast<const T*>(pass ? p.v_b : p.v_a) + (size_t)(pass ? n : n / p.q_group) * kC * p.L;
-        T* dst = reinterpret_cast<T*>(pass ? p.cat_b : p.cat_a) + ((size_t)n * 2 * kC + kC) * p.L;
+        const Elem* src = reinterpret_cast<const Elem*>(pass ? p.v_b : p.v_a) + (size_t)(pass ? n : n / p.q_group) * kC * p.L;
+        Elem* dst = reinterpret_cast<Elem*>(pass ? p.cat_b : p.cat_a) + ((size_t)n * 2 * kC + kC) * p.L;
         if (vec) {
           const int r = row0 + 4 * lane;
           if (r < p.L) {
 #pragma unroll 1
             for (int c = 0; c < kC; c += 8) {
-              V t[8];
+              Vec4 t[8];
 #pragma unroll
-              for (int u = 0; u < 8; ++u) t[u] = __ldcs(reinterpret_cast<const V*>(src + (size_t)(c + u) * p.L + r));
+              for (int u = 0; u < 8; ++u) t[u] = __ldcs(reinterpret_cast<const Vec4*>(src + (size_t)(c + u) * p.L + r));
 #pragma unroll
-              for (int u = 0; u < 8; ++u) __stcs(reinterpret_cast<V*>(dst + (size_t)(c + u) * p.L + r), t[u]);
+              for (int u = 0; u < 8; ++u) __stcs(reinterpret_cast<Vec4*>(dst + (size_t)(c + u) * p.L + r), t[u]);
             }
           }
         } else {
 #pragma unroll 1
           for (int c = 0; c < kC; c += 2) {
-            T t[8];
+            Elem t[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int r = row0 + (u & 3) * 32 + lane;
-              t[u] = (r < p.L) ? __ldcs(src + (size_t)(c + (u >> 2)) * p.L + r) : T(0);
+              t[u] = (r < p.L) ? __ldcs(src + (size_t)(c + (u >> 2)) * p.L + r) : Elem(0);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
