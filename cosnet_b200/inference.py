@@ -14,7 +14,8 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from .coattention import coattention_forward16_raw, coattention_forward_raw, coattention_queries_raw
+from .coattention import (coattention_forward16_raw, coattention_forward_raw, coattention_queries_raw,
+                          modality_overlap_pays, run_modalities)
 
 
 @torch.no_grad()
@@ -46,10 +47,14 @@ def segment_with_references(model, target_rgb, target_depth, ref_rgbs, ref_depth
     d_a = model.depth_encoder(target_depth)
     v_b, _ = model.encoder(ref_rgbs.flatten(0, 1))            # all references of all queries in one batch
     d_b = model.depth_encoder(ref_depths.flatten(0, 1))
-    cat = coattention_queries_frame_a(v_a, v_b, model.rgb_similarity_weights.weight, model.gate.weight, None, refs=r)
+    # the two modality calls are independent: when the batch leaves the last wave of the attend kernel partly empty they
+    # run on two streams and fill each other's holes (same results, bit for bit)
+    cat, dcat = run_modalities(
+        lambda: coattention_queries_frame_a(v_a, v_b, model.rgb_similarity_weights.weight, model.gate.weight, None, refs=r),
+        lambda: coattention_queries_frame_a(d_a, d_b, model.depth_similarity_weights.weight, model.depth_gate.weight,
+                                            model.depth_gate.bias, refs=r),
+        (d_a, d_b), overlap=modality_overlap_pays(q * r, v_a.shape[2], v_a.shape[3], passes=1, device=v_a.device))
     z = model.bn_A(model.reduce_channels_A(cat))                                             # :188, :190
-    dcat = coattention_queries_frame_a(d_a, d_b, model.depth_similarity_weights.weight, model.depth_gate.weight,
-                                       model.depth_gate.bias, refs=r)
     z = model.prelu(z + model.depth_weights(model.depth_bn(model.depth_reduce_channels(dcat))))  # :239-256
     x1 = torch.sigmoid(F.interpolate(model.segmentation_classifier_A(z), size, mode="bilinear"))  # :260-265
     return x1.view(q, r, *x1.shape[1:]).mean(dim=1)

@@ -13,7 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .backbone import DepthEncoder_ResNetASPP, Encoder, init_reference_style
-from .coattention import coattention
+from .coattention import coattention, modality_overlap_pays, run_modalities
 
 # legacy checkpoint prefixes -> current names (rgbd_segmentation_RAA.py:114-133); first match wins,
 # "encoder.main_classifier" must be tested before the generic "encoder." rule
@@ -78,6 +78,9 @@ class RGBDSegmentation_RAA(nn.Module):
         # True: never materialise the concat -- conv(cat([Zg, V]), W) is evaluated as conv(Zg, W[:, :C]) + conv(V, W[:, C:])
         # (same parameters and state_dict; fp32 summation order differs by ~1e-6).  SURVEY.md 8f, row N3.
         self.split_reduce_conv = False
+        # eval-mode forward under no_grad: run the RGB and the depth co-attention on two CUDA streams when that needs fewer
+        # waves of the attend kernel (None = decide from the batch shape, True / False = force).  Bit-identical outputs.
+        self.overlap_modalities = None
 
     # ------------------------------------------------------------------ optimiser groups (:65-100)
     def get_params(self, subset="none"):
@@ -131,7 +134,41 @@ class RGBDSegmentation_RAA(nn.Module):
         return (F.conv2d(gated, w[:, :c], None, conv.stride, conv.padding, conv.dilation) +
                 F.conv2d(passthrough, w[:, c:], conv.bias, conv.stride, conv.padding, conv.dilation))
 
+    def _forward_eval(self, rgbs_a, rgbs_b, depths_a, depths_b):
+        """Inference (eval mode, no autograd): the same operators as `forward`, with both encoders evaluated first so that
+        the two co-attention calls -- independent of each other -- can share the GPU (`run_modalities`)."""
+        input_size = rgbs_a.shape[2:]
+        v_a, v_b, labels = self._encode_pair(self.encoder, rgbs_a, rgbs_b, True)
+        d_a, d_b, _ = self._encode_pair(self.depth_encoder, depths_a, depths_b, False)
+        split = self.split_reduce_conv
+        overlap = self.overlap_modalities
+        if overlap is None:
+            overlap = modality_overlap_pays(v_a.shape[0], v_a.shape[2], v_a.shape[3], 2, v_a.device)
+        (r_a, r_b), (q_a, q_b) = run_modalities(
+            lambda: coattention(v_a, v_b, self.rgb_similarity_weights.weight, self.gate.weight, None, gated_only=split),
+            lambda: coattention(d_a, d_b, self.depth_similarity_weights.weight, self.depth_gate.weight, self.depth_gate.bias,
+                                gated_only=split),
+            (d_a, d_b), overlap)
+        if split:
+            z_a = self.bn_A(self._split_conv(self.reduce_channels_A, r_a, v_a))
+            z_b = self.bn_B(self._split_conv(self.reduce_channels_B, r_b, v_b))
+            dz_a = self.depth_weights(self.depth_bn(self._split_conv(self.depth_reduce_channels, q_a, d_a)))
+            dz_b = self.depth_weights(self.depth_bn(self._split_conv(self.depth_reduce_channels, q_b, d_b)))
+        else:
+            z_a = self.bn_A(self.reduce_channels_A(r_a))            # :188, :190
+            z_b = self.bn_B(self.reduce_channels_B(r_b))            # :189, :191
+            dz_a = self.depth_weights(self.depth_bn(self.depth_reduce_channels(q_a)))       # :239, :242, :245
+            dz_b = self.depth_weights(self.depth_bn(self.depth_reduce_channels(q_b)))       # :240-247
+        z_a = self.prelu(z_a + dz_a)                            # :251, :256
+        z_b = self.prelu(z_b + dz_b)                            # :252, :257
+        x1 = self.softmax(F.interpolate(self.segmentation_classifier_A(z_a), input_size, mode="bilinear"))  # :260-265
+        x2 = self.softmax(F.interpolate(self.segmentation_classifier_B(z_b), input_size, mode="bilinear"))
+        return x1, x2, labels
+
     def forward(self, rgbs_a, rgbs_b, depths_a, depths_b):
+        if (not self.training and not torch.is_grad_enabled() and rgbs_a.is_cuda and self.coattention_impl is coattention
+                and self.overlap_modalities is not False):
+            return self._forward_eval(rgbs_a, rgbs_b, depths_a, depths_b)
         input_size = rgbs_a.shape[2:]
 
         v_a, v_b, labels = self._encode_pair(self.encoder, rgbs_a, rgbs_b, True)

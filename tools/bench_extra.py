@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--workload", required=True, choices=["hd", "inference", "latency", "latency_split", "io16", "io16_bf16", "inference16", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--pairs", type=int, default=0, help="hd: pairs per GPU instead of 16 (cfg 3 strong-scaled over 8 GPUs = 2)")
+    ap.add_argument("--two-streams", action="store_true", help="hd / inference: the depth modality call runs on a second "
+                    "stream, so its CTA pairs back-fill the tail wave of the RGB attend kernel")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
@@ -54,13 +57,22 @@ def main():
     Bd = (torch.rand((1,), generator=g, device=dev) * 2 - 1) * k
 
     if args.workload == "hd":
-        n, h, w = 16, 61, 107
+        n, h, w = (args.pairs or 16), 61, 107
         va, vb, da, db = (feats(n, h, w) for _ in range(4))
+        side = torch.cuda.Stream(dev)
         def step():
+            if args.two_streams:
+                cur = torch.cuda.current_stream(dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False)
+                coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False)
+                cur.wait_stream(side)
+                return
             coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False)
             coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False)
         pairs = n
-        desc = "co-attention at 480x854 input (61x107x256 features), batch 16 per GPU"
+        desc = f"co-attention at 480x854 input (61x107x256 features), batch {n} per GPU" + (", modalities on two streams" if args.two_streams else "")
     elif args.workload == "inference":
         qn, r, h, w = 8, 5, 61, 81
         va, da = feats(qn, h, w), feats(qn, h, w)

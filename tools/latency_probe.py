@@ -52,6 +52,22 @@ def main():
                                           st), "fwd")
         return call
 
+    side = torch.cuda.Stream(dev)
+    ws2 = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)      # the modalities run concurrently: own workspaces
+    wsp2 = (ws2.data_ptr() + 1023) // 1024 * 1024
+
+    def fwd32_two_streams(flags):
+        def call(st):
+            cur = torch.cuda.current_stream(dev)
+            side.wait_stream(cur)
+            _lib.check(lib.coattn_forward(va.data_ptr(), vb.data_ptr(), W[0].data_ptr(), G[0].data_ptr(), None, out32[0].data_ptr(),
+                                          out32[1].data_ptr(), None, None, None, wsp, nbytes, n, C, h, w, flags, st), "fwd")
+            _lib.check(lib.coattn_forward(da.data_ptr(), db.data_ptr(), W[1].data_ptr(), G[1].data_ptr(), Bd.data_ptr(),
+                                          out32[2].data_ptr(), out32[3].data_ptr(), None, None, None, wsp2, nbytes, n, C, h, w, flags,
+                                          side.cuda_stream), "fwd")
+            cur.wait_stream(side)
+        return call
+
     def fwd16(st):
         _lib.check(lib.coattn_forward16(f16[0].data_ptr(), f16[1].data_ptr(), W[0].data_ptr(), G[0].data_ptr(), None,
                                         out16[0].data_ptr(), out16[1].data_ptr(), None, None, wsp, nbytes, n, 1, C, h, w, 0, st), "fwd16")
@@ -60,12 +76,14 @@ def main():
 
     for name, call in (("default path (coattn_forward)", fwd32(0)),
                        ("COATTN_FLAG_SPLIT_KEYS", fwd32(_lib.FLAG_SPLIT_KEYS)),
-                       ("16-bit interface (coattn_forward16)", fwd16)):
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            call(side.cuda_stream)
-        torch.cuda.current_stream(dev).wait_stream(side)
+                       ("16-bit interface (coattn_forward16)", fwd16),
+                       ("default path, RGB and depth calls on two streams", fwd32_two_streams(0)),
+                       ("COATTN_FLAG_SPLIT_KEYS, RGB and depth calls on two streams", fwd32_two_streams(_lib.FLAG_SPLIT_KEYS))):
+        warm = torch.cuda.Stream(dev)
+        warm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(warm):
+            call(warm.cuda_stream)
+        torch.cuda.current_stream(dev).wait_stream(warm)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
