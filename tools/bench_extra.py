@@ -178,7 +178,30 @@ def main():
                              mask=torch.empty((2, n, L), device=dev), dva=torch.empty((n, C, h, w), device=dev),
                              dw=torch.empty((C, C), device=dev), dgw=torch.empty((C,), device=dev), dgb=torch.empty((1,), device=dev)))
         P = lambda t: None if t is None else t.data_ptr()
+        ws2 = torch.empty(max(nb_f, nb_b) + 1024, dtype=torch.uint8, device=dev)
+        wsp2 = (ws2.data_ptr() + 1023) // 1024 * 1024
+        side2 = torch.cuda.Stream(dev)
+
+        def modality(m, wp, s_):      # forward + backward of one modality on one stream
+            _lib.check(lib.coattn_forward(P(m["a"]), P(m["b"]), P(m["w"]), P(m["gw"]), P(m["gb"]), P(m["ca"]), P(m["cb"]),
+                                          P(m["z"]), P(m["lse"]), P(m["mask"]), wp, nb_f, n, C, h, w, 0, s_), "coattn_forward")
+            _lib.check(lib.coattn_backward(P(m["a"]), P(m["b"]), P(m["w"]), P(m["gw"]), P(m["z"]), P(m["lse"]), P(m["mask"]),
+                                           P(ra), P(rb) if m["has_b"] else None, P(m["dva"]), None, P(m["dw"]), P(m["dgw"]),
+                                           P(m["dgb"]) if m["gb"] is not None else None, wp, nb_b, n, C, h, w, 0, s_),
+                       "coattn_backward")
+
+        def step_two_streams():       # the modalities are independent until the gradient all-reduce
+            cur = torch.cuda.current_stream(dev)
+            side2.wait_stream(cur)
+            modality(mods[1], wsp2, side2.cuda_stream)
+            modality(mods[0], wsp, st)
+            cur.wait_stream(side2)
+            if world > 1:
+                dist.all_reduce(torch.cat([mods[0]["dw"].reshape(-1), mods[0]["dgw"], mods[1]["dw"].reshape(-1), mods[1]["dgw"], mods[1]["dgb"]]))
+
         def step():
+            if args.two_streams:
+                return step_two_streams()
             for m in mods:
                 _lib.check(lib.coattn_forward(P(m["a"]), P(m["b"]), P(m["w"]), P(m["gw"]), P(m["gb"]), P(m["ca"]), P(m["cb"]),
                                               P(m["z"]), P(m["lse"]), P(m["mask"]), wsp, nb_f, n, C, h, w, 0, st), "coattn_forward")
@@ -191,18 +214,25 @@ def main():
                 dist.all_reduce(torch.cat([mods[0]["dw"].reshape(-1), mods[0]["dgw"], mods[1]["dw"].reshape(-1), mods[1]["dgw"], mods[1]["dgb"]]))
         pairs = n
         desc = ("train step on the hot path through the C ABI: coattn_forward + coattn_backward of both modalities (RGB full, "
-                "depth A-branch), 8 pairs per GPU, preallocated buffers, NCCL all-reduce of hot-path grads")
+                "depth A-branch), 8 pairs per GPU, preallocated buffers, NCCL all-reduce of hot-path grads"
+                + (", modalities on two streams" if args.two_streams else ""))
     else:
         n, h, w = 8, 60, 60
         va, da = feats(n, h, w, True), feats(n, h, w, True)
         vb, db = feats(n, h, w), feats(n, h, w)
         params = [W[0].requires_grad_(True), G[0].requires_grad_(True), W[1].requires_grad_(True), G[1].requires_grad_(True), Bd.requires_grad_(True)]
         ra = torch.randn((n, 2 * C, h, w), generator=g, device=dev); rb = torch.randn((n, 2 * C, h, w), generator=g, device=dev)
+        from cosnet_b200.coattention import run_modalities
         def step():
             for p in params + [va, da]:
                 p.grad = None
-            ca, cb = coattention(va, vb, params[0], params[1], None)
-            dca, dcb = coattention(da, db, params[2], params[3], params[4])
+            if args.two_streams:      # autograd replays each branch's backward on the stream its forward ran on
+                (ca, cb), (dca, dcb) = run_modalities(lambda: coattention(va, vb, params[0], params[1], None),
+                                                      lambda: coattention(da, db, params[2], params[3], params[4]),
+                                                      (da, db), True)
+            else:
+                ca, cb = coattention(va, vb, params[0], params[1], None)
+                dca, dcb = coattention(da, db, params[2], params[3], params[4])
             # depth: the B branch is gradient dead in the reference (:240-247) -> only cat_a carries gradient
             loss = (ca * ra).sum() + (cb * rb).sum() + (dca * ra).sum()
             loss.backward()
@@ -210,7 +240,8 @@ def main():
                 flat = torch.cat([p.grad.reshape(-1) for p in params])
                 dist.all_reduce(flat)
         pairs = n
-        desc = "train step on the hot path: forward + backward (RGB full, depth A-branch), 8 pairs per GPU, NCCL all-reduce of hot-path grads"
+        desc = ("train step on the hot path: forward + backward (RGB full, depth A-branch), 8 pairs per GPU, NCCL all-reduce of hot-path grads"
+                + (", modalities on two streams" if args.two_streams else ""))
 
     for _ in range(max(3, args.warmup)):
         step()
