@@ -31,7 +31,7 @@ class Guarded:
 
 
 @pytest.mark.parametrize("n,h,w,flags", [(1, 1, 1, 0), (2, 7, 9, 0), (1, 31, 41, 0), (1, 13, 20, 1), (2, 12, 11, 4), (1, 16, 16, 16),
-                                         (1, 12, 11, 2)])
+                                         (1, 12, 11, 2), (1, 31, 41, 256), (1, 60, 60, 256)])      # 256: split key ranges
 def test_forward_and_backward_stay_inside_their_buffers(n, h, w, flags):
     import __graft_entry__ as ge
     ge.build()
@@ -85,3 +85,66 @@ def test_forward_and_backward_stay_inside_their_buffers(n, h, w, flags):
     assert rel(d_va.view(n, c, h, w).cpu().numpy(), gr["d_v_a"]) < 1e-2
     assert rel(d_vb.view(n, c, h, w).cpu().numpy(), gr["d_v_b"]) < 1e-2
     assert rel(d_w.view(c, c).cpu().numpy(), gr["d_w"]) < 1.5e-2
+
+
+class Guarded16:
+    """The same for 16-bit buffers (sentinel bit pattern 0x7BFF: the largest finite half)."""
+    SENT16 = 0x7BFF
+
+    def __init__(self, numel, dev):
+        self.buf = torch.full((numel + 2 * GUARD,), self.SENT16, dtype=torch.int16, device=dev)
+        self.numel = numel
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + GUARD * 2
+
+    def view(self, dtype, *shape):
+        return self.buf[GUARD:GUARD + self.numel].view(dtype).view(*shape)
+
+    def intact(self):
+        return bool((self.buf[:GUARD] == self.SENT16).all() and (self.buf[GUARD + self.numel:] == self.SENT16).all())
+
+
+@pytest.mark.parametrize("nq,refs,h,w,flags", [
+    (2, 1, 12, 12, 0),     # features read in place by TMA (L % 8 == 0): boxes reach past L and past the last row block
+    (1, 1, 16, 16, 1),     # bf16
+    (2, 1, 7, 9, 0),       # odd L: padded copies
+    (1, 1, 31, 41, 32),    # gated half only: 256-channel outputs
+    (2, 3, 20, 20, 8),     # grouped queries, frame-A outputs only
+])
+def test_forward16_stays_inside_its_buffers(nq, refs, h, w, flags):
+    import __graft_entry__ as ge
+    ge.build()
+    from cosnet_b200 import _lib
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    c, L, n = 256, h * w, nq * refs
+    dt = torch.bfloat16 if flags & 1 else torch.float16
+    fa = torch.from_numpy(orc.synthetic_features(700 + L, nq, h, w, 0.66)[0]).to(dev).to(dt)
+    fb = torch.from_numpy(orc.synthetic_features(701 + L, n, h, w, 0.66)[1]).to(dev).to(dt)
+    # the inputs sit in guarded allocations too: a TMA box that reaches past the tensor must read zeros, not neighbours
+    ga, gb = Guarded16(fa.numel(), dev), Guarded16(fb.numel(), dev)
+    ga.view(dt, *fa.shape).copy_(fa); gb.view(dt, *fb.shape).copy_(fb)
+    W, g, b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_weights(901, bias=True))
+    oc = c if flags & 32 else 2 * c
+    a_only = bool(flags & 8) or refs > 1
+    cat_a, cat_b = Guarded16(n * oc * L, dev), Guarded16(n * oc * L, dev)
+    passes = 1 if a_only else 2
+    lse, mask = Guarded(passes * n * L, dev), Guarded(passes * n * L, dev)
+    nbytes = lib.coattn_workspace_bytes(n, c, h, w)
+    ws = Guarded(nbytes // 4 + 512, dev)
+    wsp = (ws.ptr + 1023) // 1024 * 1024
+    rc = lib.coattn_forward16(ga.ptr, gb.ptr, W.data_ptr(), g.data_ptr(), b.data_ptr(), cat_a.ptr,
+                              None if a_only else cat_b.ptr, lse.ptr, mask.ptr, wsp, nbytes, nq, refs, c, h, w, flags,
+                              torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.coattn_b200_strerror(rc)
+    torch.cuda.synchronize()
+    for name, gbuf in (("v_a", ga), ("v_b", gb), ("cat_a", cat_a), ("cat_b", cat_b), ("lse", lse), ("mask", mask), ("workspace", ws)):
+        assert gbuf.intact(), f"coattn_forward16 wrote outside {name}"
+    ref = orc.coattention(fa.float().repeat_interleave(refs, 0).cpu().numpy(), fb.float().cpu().numpy(), W.cpu().numpy(),
+                          g.cpu().numpy(), b.cpu().numpy())
+    got = cat_a.view(dt, n, oc, h, w).float().cpu().numpy()
+    want = ref["cat_a"][:, :oc]
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err < (1e-2 if flags & 1 else 1e-3), err
