@@ -424,6 +424,27 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         io16_ms, e2e16_s = float(t[0].item()), float(t[1].item())
     same16 = bool(torch.equal(hout16[0], c16[0].cpu()) and torch.equal(hout16[3], c16[3].cpu()))
+    # ... and with the gated-only contract on top (16-bit, no passthrough half on the wire): the least PCIe traffic per pair
+    gpipe16 = HostPipeline(n, C, H, W, chunk=4, slots=3, device=dev, feature_dtype=dt16, gated_only=True)
+    gout16 = [torch.empty((n, C, H, W), dtype=dt16).pin_memory() for _ in range(4)]
+
+    def e2e16_gated_step():
+        gpipe16(hin16[0], hin16[1], w_rgb, g_rgb, None, gout16[0], gout16[1])
+        gpipe16(hin16[2], hin16[3], w_dep, g_dep, b_dep, gout16[2], gout16[3])
+    e2e16_gated_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e16_gated_step()
+    torch.cuda.synchronize()
+    e2e16_gated_s = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([e2e16_gated_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e16_gated_s = float(t.item())
+    same16_gated = bool(torch.equal(gout16[0], c16[0][:, :C].cpu()) and torch.equal(gout16[3], c16[3][:, :C].cpu()))
     # the 16-bit results are the fp32-interface results rounded once (fp32 features that are not 16-bit values differ in the
     # passthrough half only by that rounding): report the distance instead of asserting bit equality here
     rel16 = float(((c16[0].float() - cat[0]).norm() / cat[0].norm()).item())
@@ -483,7 +504,10 @@ def run_ours(args):
                  "rel_l2_vs_fp32_interface": rel16,
                  "e2e": {"value": total_pairs * e2e_steps / e2e16_s, "unit": UNIT,
                          "h2d_bytes_per_step": 2 * pipe16.h2d_bytes * world, "d2h_bytes_per_step": 2 * pipe16.d2h_bytes * world,
-                         "matches_resident_path": same16},
+                         "matches_resident_path": same16,
+                         "gated_only_contract": {"value": total_pairs * e2e_steps / e2e16_gated_s, "unit": UNIT,
+                                                 "d2h_bytes_per_step": 2 * gpipe16.d2h_bytes * world,
+                                                 "matches_resident_path": same16_gated}},
                  "note": "coattn_forward16: 16-bit features in and out (host buffers 16-bit as well), operands read in place "
                          "by TMA, no cast pass; outside the headline's timed region"},
         "gpu_launches": 8 * args.steps,   # per modality call: cast(V_a, V_b), cast_w, project_mn, attend2(+gate+concat)
