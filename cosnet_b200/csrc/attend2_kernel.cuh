@@ -76,13 +76,13 @@ __device__ long long g_attend2_warps[2 * 32 * 16];   // [saw S | arrived P][tile
 struct Attend2Params {
   float* z;     // [2][N][C][L] raw attended features or null
   float* lse;   // [2][N][L]
-  float* cat_a; // [N][2C][L] or null: fused gate epilogue (see AttendParams)
-  float* cat_b;
+  void* cat_a;  // [N][2C][L] or null: fused gate epilogue (see AttendParams); fp32, or 16-bit elements with IO16
+  void* cat_b;
   float* mask;  // [2][N][L] or null
   const float* gate_w;
   const float* gate_b;
-  const float* v_a;   // [N][C][L] original fp32 features, or null: when set (together with cat_*), the copy warp also
-  const float* v_b;   //           writes the passthrough half of the concat (:186-187)
+  const void* v_a;    // [N][C][L] original features (fp32, or 16-bit with IO16), or null: when set (together with cat_*),
+  const void* v_b;    //           the copy warp also writes the passthrough half of the concat (:186-187)
   int out_channels;   // channels per sample of cat_*: 2C (concat layout) or C (gated half only, no passthrough)
   int N, L, Lp;
   int q_pairs;   // ceil(L / 256)

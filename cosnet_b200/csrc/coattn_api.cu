@@ -247,12 +247,14 @@ static int prep_and_project_fused(const float* v_a, const float* v_b, const floa
 //   w16 [C][C] 16-bit copy of W
 //   in16: 0 = fp32 features (cast), 1 = 16-bit features copied into the padded planes (pad16_kernel),
 //         2 = 16-bit features consumed in place: nothing is copied and the projection reads V_a through its own map
-static int cast_project_core(const float* v_a, const float* v_b, const float* w, unsigned short* x, unsigned short* w16,
+static int cast_project_core(const void* v_a, const void* v_b, const float* w, unsigned short* x, unsigned short* w16,
                              int n, const Layout& ly, bool bf16, bool project, cudaStream_t st, int n_a = -1,
                              int in16 = 0) {
   if (n_a < 0) n_a = n;       // samples of V_a (query frames); the planes are laid out for n samples either way
   CastParams cp;
-  cp.va = v_a; cp.vb = v_b; cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp; cp.Na = n_a;
+  cp.va = static_cast<const float*>(v_a);   // fp32 features; with in16 == 1 pad16_kernel reads the same pointers as 16-bit data
+  cp.vb = static_cast<const float*>(v_b);
+  cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp; cp.Na = n_a;
   const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   const dim3 cgrid(n * kC, 2);
   if (in16 == 1) {
@@ -316,7 +318,7 @@ extern "C" int coattn_stage_prep_project(const float* v_a, const float* v_b, con
   return prep_and_project_fused(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream);
 }
 
-static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float* cat_b, float* z, float* lse,
+static int launch_attend(const void* v_a, const void* v_b, void* cat_a, void* cat_b, float* z, float* lse,
                          float* mask, const float* gate_w, const float* gate_b, void* workspace, int64_t workspace_bytes, int n, int c, int h, int w_,
                          unsigned flags, void* stream, int q_group = 1, int in16 = 0, int splits = 1) {
   // in16 (coattn_forward16): v_a, v_b, cat_a, cat_b hold 16-bit elements; 2 = the operands are read from v_a / v_b in place
@@ -436,8 +438,8 @@ static int launch_attend(const float* v_a, const float* v_b, float* cat_a, float
   p.t = reinterpret_cast<const unsigned short*>(seg(workspace, ly.off_t));
   p.z = z;
   p.lse = lse ? lse : reinterpret_cast<float*>(seg(workspace, ly.off_lse));
-  p.cat_a = cat_a;
-  p.cat_b = cat_b;
+  p.cat_a = static_cast<float*>(cat_a);     // the cross-check kernel is fp32 only (coattn_forward16 rejects its flag)
+  p.cat_b = static_cast<float*>(cat_b);
   p.mask = mask;
   p.gate_w = gate_w;
   p.gate_b = gate_b;
@@ -632,13 +634,11 @@ int coattn_forward16(const void* v_a, const void* v_b, const float* w, const flo
   const bool in_place = (ly.L % 8 == 0) &&
                         (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   const int in16 = in_place ? 2 : 1;
-  const float* fa = static_cast<const float*>(v_a);   // element type is carried by in16, not by the pointer type
-  const float* fb = static_cast<const float*>(v_b);
-  if (int e = cast_project_core(fa, fb, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
+  if (int e = cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
                                 reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
                                 (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq, in16))
     return e;
-  return launch_attend(fa, fb, static_cast<float*>(cat_a), static_cast<float*>(cat_b), nullptr, lse, mask, gate_w, gate_b,
+  return launch_attend(v_a, v_b, cat_a, cat_b, nullptr, lse, mask, gate_w, gate_b,
                        workspace, workspace_bytes, n, c, h, w_, flags, stream, refs, in16);
 }
 
