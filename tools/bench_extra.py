@@ -29,7 +29,7 @@ import torch.nn.functional as F
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["hd", "inference", "latency", "latency_split", "io16", "io16_bf16", "inference16", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
+    ap.add_argument("--workload", required=True, choices=["hd", "inference", "latency", "latency_split", "latency_graph", "io16", "io16_bf16", "inference16", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pairs", type=int, default=0, help="hd: pairs per GPU instead of 16 (cfg 3 strong-scaled over 8 GPUs = 2)")
@@ -93,6 +93,16 @@ def main():
             coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, split_keys=sk)
         pairs = n
         desc = ("one frame pair per step (60x60x256, RGB + depth call)" + (", COATTN_FLAG_SPLIT_KEYS" if sk else ", default path"))
+    elif args.workload == "latency_graph":
+        # the same single pair through GraphedCoAttention: one graph launch per step (host time included, like `latency`)
+        from cosnet_b200.graphed import GraphedCoAttention
+        n, h, w = 1, 60, 60
+        gr = GraphedCoAttention(n, h, w, (W[0], G[0], None), (W[1], G[1], Bd), device=dev)
+        for buf in (gr.v_a, gr.v_b, gr.d_a, gr.d_b):
+            buf.copy_(feats(n, h, w))
+        step = gr.replay
+        pairs = n
+        desc = "one frame pair per step (60x60x256, RGB + depth call), GraphedCoAttention.replay() (CUDA graph, modalities on two streams)"
     elif args.workload in ("io16", "io16_bf16"):
         # the headline shape through the 16-bit feature interface (coattn_forward16): fp16 (or bf16) features in and out,
         # read in place by TMA -- no cast pass, half the concat bytes
