@@ -29,7 +29,7 @@ import torch.nn.functional as F
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["hd", "inference", "latency", "latency_split", "latency_graph", "io16", "io16_bf16", "inference16", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
+    ap.add_argument("--workload", required=True, choices=["hd", "inference", "gated", "gated16", "latency", "latency_split", "latency_graph", "io16", "io16_bf16", "inference16", "train", "train_abi", "eager", "eager_bf16", "sdpa"])
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pairs", type=int, default=0, help="hd: pairs per GPU instead of 16 (cfg 3 strong-scaled over 8 GPUs = 2)")
@@ -103,6 +103,23 @@ def main():
         step = gr.replay
         pairs = n
         desc = "one frame pair per step (60x60x256, RGB + depth call), GraphedCoAttention.replay() (CUDA graph, modalities on two streams)"
+    elif args.workload in ("gated", "gated16"):
+        # cfg 2 with the gated-only contract (the consumer splits the reduce conv, the concat and its passthrough
+        # copy never exist): fp32 features, or fp16 features through coattn_forward16
+        from cosnet_b200.coattention import coattention_forward16_raw
+        n, h, w = 32, 60, 60
+        half = args.workload == "gated16"
+        va, vb, da, db = ((feats(n, h, w).half() if half else feats(n, h, w)) for _ in range(4))
+        def step():
+            if half:
+                coattention_forward16_raw(va, vb, W[0], G[0], None, gated_only=True)
+                coattention_forward16_raw(da, db, W[1], G[1], Bd, gated_only=True)
+            else:
+                coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False, gated_only=True)
+                coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, gated_only=True)
+        pairs = n
+        desc = ("co-attention module alone, 60x60x256, batch 32 per GPU, gated half only (no concat / passthrough copy), "
+                + ("fp16 features in and out" if half else "fp32 features"))
     elif args.workload in ("io16", "io16_bf16"):
         # the headline shape through the 16-bit feature interface (coattn_forward16): fp16 (or bf16) features in and out,
         # read in place by TMA -- no cast pass, half the concat bytes
