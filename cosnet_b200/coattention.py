@@ -277,13 +277,14 @@ def _side_stream(device: torch.device) -> torch.cuda.Stream:
     return st
 
 
-def modality_overlap_pays(n: int, h: int, w: int, passes: int = 2, device=None) -> bool:
+def modality_overlap_pays(n: int, h: int, w: int, passes: int = 2, device=None, clusters: int = 0) -> bool:
     """True when running the RGB and the depth modality call concurrently needs fewer waves of the attend kernel than
     running them back to back.  A call is `passes * n * ceil(L / 256)` equal work items for SMs / 2 CTA pairs; the last
     wave of a call is partly empty, and a second call on another stream back-fills it.  Measured:
     one 60x60 pair 121 -> 65 us, two 61x107 pairs +27 %, 16 of them +3 %; no gain (or a few % loss) when the combined
     item count needs as many waves as the two calls separately, e.g. 32 pairs at 60x60."""
-    clusters = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count // 2
+    if clusters <= 0:      # CTA pairs of the device (74 on a B200); pass `clusters` to evaluate the rule without a GPU
+        clusters = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count // 2
     items = passes * n * ((h * w + 255) // 256)
     waves = lambda x: (x + clusters - 1) // clusters
     return 2 * waves(items) > waves(2 * items)
