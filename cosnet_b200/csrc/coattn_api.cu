@@ -258,7 +258,8 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   const dim3 cgrid(n * kC, 2);
   if (in16 == 1) {
-    pad16_kernel<<<cgrid, 256, 0, st>>>(cp);
+    if (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 3) == 0) pad16_kernel<true><<<cgrid, 256, 0, st>>>(cp);
+    else pad16_kernel<false><<<cgrid, 256, 0, st>>>(cp);
   } else if (in16 == 2) {
     // in place
   } else if (bf16) {

@@ -440,13 +440,34 @@ __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
 // 16-bit features (coattn_forward16) whose rows cannot be read by TMA directly (L % 8 != 0 or a base pointer that is
 // not 16-byte aligned): copied into the same zero-padded planes the cast writes.  CastParams::va / vb then point to
 // 16-bit data.  Only the fallback of that entry point; aligned 16-bit features are consumed in place.
+// WORDS = true: 4-byte accesses (needs 4-byte aligned base pointers); a row of odd L starts on an odd element in every
+// second row, where a destination word is assembled from the halves of two source words.
+template <bool WORDS>
 __global__ void __launch_bounds__(256) pad16_kernel(CastParams p) {
   const int row = blockIdx.x;                 // n * C + c
   const int plane = blockIdx.y;               // 0: V_b, 1: V_a
   if (plane == 1 && row >= p.Na * kC) return;
-  const unsigned short* src = reinterpret_cast<const unsigned short*>(plane ? p.va : p.vb) + (size_t)row * p.L;
+  const unsigned short* base = reinterpret_cast<const unsigned short*>(plane ? p.va : p.vb);
+  const size_t s0 = (size_t)row * p.L;        // first element of the row
   unsigned short* dst = p.x + ((size_t)plane * p.N * kC + row) * p.Lp;
-  for (int i = threadIdx.x; i < p.Lp; i += 256) dst[i] = (i < p.L) ? __ldcs(src + i) : (unsigned short)0;
+  if constexpr (WORDS) {
+    const uint32_t* src32 = reinterpret_cast<const uint32_t*>(base);
+    uint32_t* dst32 = reinterpret_cast<uint32_t*>(dst);      // Lp is a multiple of 256: rows of the planes are 512-byte aligned
+    const bool odd = (s0 & 1) != 0;
+    for (int i = threadIdx.x; i < p.Lp / 2; i += 256) {
+      const int e = 2 * i;
+      uint32_t w = 0;
+      if (e + 1 < p.L) {                      // both elements inside the row
+        const size_t wi = (s0 + e) >> 1;
+        w = odd ? (__ldcs(src32 + wi) >> 16) | (__ldcs(src32 + wi + 1) << 16) : __ldcs(src32 + wi);
+      } else if (e < p.L) {                   // last element of an odd-length row: never touch the word after it
+        w = __ldcs(base + s0 + e);
+      }
+      dst32[i] = w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < p.Lp; i += 256) dst[i] = (i < p.L) ? __ldcs(base + s0 + i) : (unsigned short)0;
+  }
 }
 
 constexpr int kProjMnTile = 64;            // positions per tile
