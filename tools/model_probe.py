@@ -85,6 +85,21 @@ def main():
             row[name] = {"ms_per_forward": ms, "ms_per_frame_pair": ms / n, "peak_gib": gib}
         print(json.dumps(row), flush=True)
 
+    # the same model in half precision (`model.half()`): fp16 encoders on cuDNN hand fp16 features to coattn_forward16
+    import copy
+    half = copy.deepcopy(model).half().eval()
+    half.coattention_impl = coattention
+    for n in args.batch:
+        x = tuple(t.half() for t in inputs(n))
+
+        def fwd16():
+            with torch.no_grad():
+                return half(*x)
+        ms, gib = timed(fwd16, 3, args.steps)
+        print(json.dumps({"workload": "model_probe", "mode": "eval forward, model.half()", "pairs": n, "input": [s, s],
+                          "b200": {"ms_per_forward": ms, "ms_per_frame_pair": ms / n, "peak_gib": gib}}), flush=True)
+    del half
+
     n = args.train_batch
     x = inputs(n)
     gt = (torch.rand(n, 1, s, s, device=dev) > 0.5).float()
