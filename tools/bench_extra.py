@@ -88,11 +88,17 @@ def main():
         n, h, w = 1, 60, 60
         va, vb, da, db = (feats(n, h, w) for _ in range(4))
         sk = args.workload == "latency_split"
+        from cosnet_b200.coattention import run_modalities
         def step():
+            if args.two_streams:      # what the drop-in module's eval forward does at this size
+                return run_modalities(lambda: coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False, split_keys=sk),
+                                      lambda: coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, split_keys=sk),
+                                      (da, db), True)
             coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False, split_keys=sk)
             coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, split_keys=sk)
         pairs = n
-        desc = ("one frame pair per step (60x60x256, RGB + depth call)" + (", COATTN_FLAG_SPLIT_KEYS" if sk else ", default path"))
+        desc = ("one frame pair per step (60x60x256, RGB + depth call)" + (", COATTN_FLAG_SPLIT_KEYS" if sk else ", default path")
+                + (", eager calls on two streams" if args.two_streams else ""))
     elif args.workload == "latency_graph":
         # the same single pair through GraphedCoAttention: one graph launch per step (host time included, like `latency`)
         from cosnet_b200.graphed import GraphedCoAttention

@@ -74,6 +74,21 @@ def main():
         _lib.check(lib.coattn_forward16(f16[2].data_ptr(), f16[3].data_ptr(), W[1].data_ptr(), G[1].data_ptr(), Bd.data_ptr(),
                                         out16[2].data_ptr(), out16[3].data_ptr(), None, None, wsp, nbytes, n, 1, C, h, w, 0, st), "fwd16")
 
+    # host cost of issuing one frame pair through the C ABI (no graph, no Python operator): the GPU is allowed to fall behind
+    import time
+    call = fwd32(0)
+    st0 = torch.cuda.current_stream(dev).cuda_stream
+    for _ in range(20):
+        call(st0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        call(st0)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    print(json.dumps({"workload": "latency_probe", "variant": "host time to issue the two coattn_forward calls (ctypes)",
+                      "pairs": n, "feat_hw": [h, w], "us_per_frame_pair_host": (t1 - t0) / 200 * 1e6}), flush=True)
+
     for name, call in (("default path (coattn_forward)", fwd32(0)),
                        ("COATTN_FLAG_SPLIT_KEYS", fwd32(_lib.FLAG_SPLIT_KEYS)),
                        ("16-bit interface (coattn_forward16)", fwd16),
