@@ -69,9 +69,21 @@ def test_argument_errors_before_any_cuda_work(lib):
     assert lib.coattn_forward(None, None, None, None, None, None, None, None, None, None, None, 0, 1, 256, 4, 4, 0, None) == -1
     assert lib.coattn_stage_gate(None, None, None, None, None, None, None, 1, 256, 4, 4, None) == -1
     assert lib.coattn_stage_project(None, 0, 1, 64, 4, 4, 0, None) == -2
+    P = 0x10000      # fake, never dereferenced pointer (1024-byte aligned): every check below fails before any device work
+    # the grouped-query and 16-bit entry points: NULL, shape, flag and alignment checks come first as well
+    assert lib.coattn_forward_queries(None, None, None, None, None, None, None, 0, 1, 1, 256, 4, 4, 0, None) == -1
+    assert lib.coattn_forward_queries(P, P, P, P, None, P, P, 1 << 40, 0, 1, 256, 4, 4, 0, None) == -2      # nq < 1
+    assert lib.coattn_forward_queries(P, P, P, P, None, P, P, 1 << 40, 1, 1, 256, 4, 4, 2, None) == -7      # UNFUSED_GATE
+    f16 = lambda *a: lib.coattn_forward16(*a)
+    assert f16(None, None, None, None, None, None, None, None, None, None, 0, 1, 1, 256, 4, 4, 0, None) == -1
+    assert f16(P, P, P, P, None, P, P, None, None, P, 1 << 40, 1, 0, 256, 4, 4, 0, None) == -2              # refs < 1
+    assert f16(P, P, P, P, None, P, P, None, None, P, 1 << 40, 1, 1, 256, 4, 4, 64, None) == -7             # KMAJOR
+    assert f16(P, P, P, P, None, P, P, None, None, P, 1 << 40, 1, 1, 256, 4, 4, 256, None) == -7            # SPLIT_KEYS
+    assert f16(P, P, P, P, None, P, None, None, None, P, 1 << 40, 1, 1, 256, 4, 4, 0, None) == -1           # cat_b needed
+    assert f16(P, P, P, P, None, P, P, None, None, P, 1 << 40, 1, 1, 128, 4, 4, 0, None) == -2              # C != 256
+    assert f16(P, P, P, P, None, P, P, None, None, P + 8, 1 << 40, 1, 1, 256, 4, 4, 0, None) == -3          # workspace alignment
     # coattn_backward: the weight gradient is reduced with 16-byte vector operations -> a misaligned d_w is refused
     # (fake, never dereferenced pointers: the check comes before any device work)
-    P = 0x10000
     args = [P] * 8 + [None, P, None, P + 4, P, None, P, 1 << 40, 1, 256, 4, 4, 0, None]
     assert lib.coattn_backward(*args) == -6
     assert b"aligned" in lib.coattn_b200_strerror(-6)
