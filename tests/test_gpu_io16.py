@@ -231,7 +231,7 @@ def test_16bit_features_with_gradients(ops):
     rel = lambda x, y: float((x.float() - y.float()).norm() / y.float().norm())
     assert a1.grad.dtype == torch.float16 and rel(a1.grad, a2.grad) < 1e-3
     for x, y in ((W1, W2), (g1, g2), (b1, b2)):
-        assert rel(x.grad, y.grad) < 1e-4
+        assert rel(x.grad, y.grad) < 1e-3
 
 
 def test_half_precision_multi_reference_inference():
