@@ -68,7 +68,8 @@ def test_split_keys_variants(op):
                 continue
             if kw.get("a_only") and x.dim() == 3:      # lse [2, n, L]: only side 0 is written for frame-A-only calls
                 x, y = x[:1], y[:1]
-            assert x.shape == y.shape and rel_l2(x.cpu().numpy(), y.cpu().numpy()) < 3e-4, kw
+            tol = 2e-3 if kw.get("bf16_operands") else 3e-4      # bf16 numerators carry 8 bits: coarser rounding noise
+            assert x.shape == y.shape and rel_l2(x.cpu().numpy(), y.cpu().numpy()) < tol, kw
     dev = torch.device("cuda:0")
     v_a = torch.from_numpy(orc.synthetic_features(91, 1, 40, 40, 0.66)[0]).to(dev)
     v_b = torch.from_numpy(orc.synthetic_features(92, 3, 40, 40, 0.66)[1]).to(dev)
