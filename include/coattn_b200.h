@@ -106,7 +106,7 @@ enum {
  *                          a B200): the key range of every (sample, pass, query tile) item is swept in up to 4 parts by
  *                          different CTA pairs, and a small HBM-bound kernel merges the parts (log-sum-exp weights) and
  *                          applies the gate / concat epilogue.  Same softmax, other summation order: results equal the
- *                          default path to fp32 rounding (~1e-6), not bit for bit -- which is why it is opt-in (the default
+ *                          default path to the rounding of the 16-bit softmax numerators (1e-5 ... 2e-4 rel-L2), not bit for bit -- which is why it is opt-in (the default
  *                          path is batch invariant).  No effect (default path) when the batch already fills the GPU.
  *                          coattn_forward and coattn_forward_queries; not with the cross-check flags.
  */
