@@ -129,7 +129,9 @@ __device__ __forceinline__ float group_exchange_sum(float v, float* xbuf, uint32
 //             as MN-major UMMA operands -- no transposed copies of the features exist at all.
 // IO16 = true: the features (passthrough source) and the cat_* outputs are 16-bit (fp16, or bf16 with BF16); the
 //             operands may then be read straight from the caller's tensors (one tensor map per tensor, see *_row0).
-template <bool BF16, bool MN, int G, bool IO16 = false>
+// SPLIT = true: the work units are (item, key-range part) pairs (Attend2Params::splits > 1); the default instantiation
+//             has splits == 1 folded away at compile time, so its loops are the plain per-item sweeps.
+template <bool BF16, bool MN, int G, bool IO16 = false, bool SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Attend2Cfg<G>::kThreads, 1)
 attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C], box {64, 128};  MN: holds Q16, rows [..][C] x Lp, box {64, 256}
                const __grid_constant__ CUtensorMap tmap_k,  // !MN: T [2*N*Lp][C], box {64, 64};   MN: holds V_b, box {64, 256}
@@ -137,6 +139,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
                const __grid_constant__ CUtensorMap tmap_v1, // holds V_a (values of pass 1), box {64, 128}
                Attend2Params p) {
   using Cfg = Attend2Cfg<G>;
+  const int kSplits = SPLIT ? p.splits : 1;
   constexpr int k2KStages = Cfg::kKStages;
   constexpr int k2SoftmaxWarps = Cfg::kSoftmaxWarps;
   constexpr int k2KProducerWarp = Cfg::kKProducerWarp, k2MmaWarp = Cfg::kMmaWarp, k2VProducerWarp = Cfg::kVProducerWarp,
@@ -205,9 +208,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     if (lane == 0) {
       const uint32_t q_full_l = mapa_u32(smem_u32(q_full), 0);
       uint32_t it = 0, cnt = 0;
-      for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters, ++it) {
-        const int item = unit / p.splits, part = unit % p.splits;
-        const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
+      for (int unit = cluster_id; unit < p.num_items * kSplits; unit += num_clusters, ++it) {
+        const int item = unit / kSplits, part = unit % kSplits;
+        const int j0 = (T * part) / kSplits, j1 = (T * (part + 1)) / kSplits;   // key tiles [j0, j1) of this unit
         const int qp = item % p.q_pairs;
         const int np = item / p.q_pairs;
         const int pass = (p.passes == 2) ? (np & 1) : 0;
@@ -258,9 +261,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     // ------------------------------------------------------------------ TMA producer: value tiles
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters) {
-        const int item = unit / p.splits, part = unit % p.splits;
-        const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
+      for (int unit = cluster_id; unit < p.num_items * kSplits; unit += num_clusters) {
+        const int item = unit / kSplits, part = unit % kSplits;
+        const int j0 = (T * part) / kSplits, j1 = (T * (part + 1)) / kSplits;   // key tiles [j0, j1) of this unit
         const int np = item / p.q_pairs;
         const int vpass = (p.passes == 2) ? (np & 1) : 0;
         const int vn = (p.passes == 2) ? (np >> 1) : np;
@@ -337,9 +340,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       const uint64_t qd0 = MN ? make_sdesc_mn_sw128(smem_u32(sQ), 32768, 1024) : make_sdesc_k_sw128(smem_u32(sQ));
       const uint32_t sK_addr = smem_u32(sK);
       const uint32_t sV_addr = smem_u32(sV);
-      for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters, ++it) {
-        const int part = unit % p.splits;
-        const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
+      for (int unit = cluster_id; unit < p.num_items * kSplits; unit += num_clusters, ++it) {
+        const int part = unit % kSplits;
+        const int j0 = (T * part) / kSplits, j1 = (T * (part + 1)) / kSplits;   // key tiles [j0, j1) of this unit
         // S(j) of this item; kcnt counts every S tile of the kernel (key stage ring and s_free phases)
         auto issue_s = [&](int j) {
           const uint32_t s = kcnt % k2KStages, ph = (kcnt / k2KStages) & 1;
@@ -431,9 +434,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) greg[ch] = (p.cat_a != nullptr) ? __ldg(p.gate_w + g * kChans + ch * 32 + lane) : 0.f;
     uint32_t pv_acc0 = 0, pv_acc1 = 0;      // PV tiles of even / odd local index completed by the earlier units
-    for (int unit = cluster_id; unit < p.num_items * p.splits; unit += num_clusters, ++it) {
-      const int item = unit / p.splits, part = unit - item * p.splits;
-      const int j0 = (T * part) / p.splits, j1 = (T * (part + 1)) / p.splits;   // key tiles [j0, j1) of this unit
+    for (int unit = cluster_id; unit < p.num_items * kSplits; unit += num_clusters, ++it) {
+      const int item = unit / kSplits, part = unit - item * kSplits;
+      const int j0 = (T * part) / kSplits, j1 = (T * (part + 1)) / kSplits;   // key tiles [j0, j1) of this unit
       const int Tu = j1 - j0;
       const int qp = item % p.q_pairs;
       const int np = item / p.q_pairs;

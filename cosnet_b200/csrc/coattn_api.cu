@@ -387,6 +387,9 @@ static int launch_attend(const void* v_a, const void* v_b, void* cat_a, void* ca
     if (in16) {
       if (g4) return COATTN_E_UNSUPPORTED;
       kern2 = bf16 ? attend2_kernel<true, true, 2, true> : attend2_kernel<false, true, 2, true>;
+    } else if (splits != 1) {
+      if (g4) return COATTN_E_UNSUPPORTED;
+      kern2 = bf16 ? attend2_kernel<true, true, 2, false, true> : attend2_kernel<false, true, 2, false, true>;
     } else if (g4) kern2 = mn ? (bf16 ? attend2_kernel<true, true, 4> : attend2_kernel<false, true, 4>)
                        : (bf16 ? attend2_kernel<true, false, 4> : attend2_kernel<false, false, 4>);
     else    kern2 = mn ? (bf16 ? attend2_kernel<true, true, 2> : attend2_kernel<false, true, 2>)
