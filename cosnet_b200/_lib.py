@@ -10,7 +10,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("COATTN_B200_LIB", os.path.join(_HERE, "lib", "libcoattn_b200.so"))
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lock = threading.Lock()
 _lib = None
@@ -26,12 +26,16 @@ FLAG_GATED_ONLY = 32  # COATTN_FLAG_GATED_ONLY
 FLAG_KMAJOR = 64  # COATTN_FLAG_KMAJOR
 FLAG_SOFTMAX16 = 128  # COATTN_FLAG_SOFTMAX16
 FLAG_SPLIT_KEYS = 256  # COATTN_FLAG_SPLIT_KEYS
+STATUS_WORDS = 8  # COATTN_STATUS_WORDS
+STATUS_OVERFLOW_B, STATUS_OVERFLOW_A, STATUS_OVERFLOW_Q = 1, 2, 4
 
 # name -> (restype, argtypes); mirrors include/coattn_b200.h one to one
 SIGNATURES = {
     "coattn_b200_abi_version": (_i, []),
     "coattn_b200_strerror": (ctypes.c_char_p, [_i]),
     "coattn_workspace_bytes": (_i64, [_i, _i, _i, _i]),
+    "coattn_status_clear": (_i, [_vp, _vp]),
+    "coattn_status_read": (_i, [_vp, _vp, _vp]),
     "coattn_workspace_segment": (_i, [ctypes.c_char_p, _i, _i, _i, _i, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
     "coattn_forward": (_i, [_vp] * 11 + [_i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_attend_gate": (_i, [_vp] * 10 + [_i64, _i, _i, _i, _i, _u, _vp]),

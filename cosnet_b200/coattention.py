@@ -6,6 +6,7 @@ tensors that feed `reduce_channels_A/B` (:188-189) / `depth_reduce_channels` (:2
 """
 from __future__ import annotations
 
+import os
 import threading
 
 import torch
@@ -13,7 +14,59 @@ import torch
 from . import _lib
 
 _ws_lock = threading.Lock()
-_ws_cache = {}  # (device index) -> uint8 tensor, grown on demand; one per device (DataParallel replicas)
+_ws_cache = {}  # (device index, stream handle, host thread) -> _Workspace, grown on demand
+
+# fp16 operand range guard (include/coattn_b200.h, "Status block").  "lazy" (default): after every forward call the status
+# words are copied to pinned host memory on the call's stream, and the NEXT call on the same workspace (or
+# `check_overflow()`) raises if the previous one clipped -- one call late, never silent, no host synchronisation.
+# "sync": every call waits for its own status (debugging).  "off": nothing is copied; `check_overflow()` still works.
+OVERFLOW_CHECK = os.environ.get("COSNET_OVERFLOW_CHECK", "lazy")
+
+
+class _Workspace:
+    """One scratch buffer + its status mirror.  Keyed per (device, stream, host thread): two host threads never share
+    one (ctypes releases the GIL, so calls of different threads interleave their launches)."""
+
+    def __init__(self, device, nbytes):
+        self.buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        self.ptr = (self.buf.data_ptr() + 1023) // 1024 * 1024
+        off = self.ptr - self.buf.data_ptr()
+        self.status = self.buf[off:off + 4 * _lib.STATUS_WORDS].view(torch.int32)
+        self.status.zero_()
+        self.host = torch.zeros(_lib.STATUS_WORDS, dtype=torch.int32).pin_memory()
+        self.event = None
+
+    def numel(self):
+        return self.buf.numel()
+
+    def post_call(self, stream):
+        """Queue the status read-back of the call just issued on `stream` (lazy / sync modes)."""
+        if OVERFLOW_CHECK == "off" or torch.cuda.is_current_stream_capturing():
+            return
+        self.host.copy_(self.status, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record(stream)
+        if OVERFLOW_CHECK == "sync":
+            self.raise_if_clipped(wait=True)
+
+    def raise_if_clipped(self, wait=False):
+        if self.event is None:
+            return
+        if wait:
+            self.event.synchronize()
+        elif not self.event.query():
+            return
+        self.event = None
+        flags = int(self.host[0])
+        if flags & 7:
+            self.status.zero_()
+            self.host.zero_()
+            what = [n for b, n in ((_lib.STATUS_OVERFLOW_B, "V_b"), (_lib.STATUS_OVERFLOW_A, "V_a"),
+                                   (_lib.STATUS_OVERFLOW_Q, "Q = W V_a")) if flags & b]
+            raise _lib.CoattnError(
+                f"co-attention: {', '.join(what)} exceeded the fp16 operand range (+-65504) or was not finite in an earlier "
+                "call on this stream; its result was clipped.  Use bf16_operands=True (fp32 exponent range) or rescale "
+                "the features.")
 
 
 def workspace_bytes(n: int, c: int, h: int, w: int) -> int:
@@ -23,15 +76,49 @@ def workspace_bytes(n: int, c: int, h: int, w: int) -> int:
     return int(r)
 
 
-def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+def _workspace_entry(device: torch.device, nbytes: int) -> _Workspace:
+    if torch.cuda.is_current_stream_capturing():
+        # a buffer allocated during capture lives in the graph's private pool: never cache it for eager use
+        return _Workspace(device, nbytes)
     key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream)
+           torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
     with _ws_lock:
-        buf = _ws_cache.get(key)
-        if buf is None or buf.numel() < nbytes + 1024:
-            buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
-            _ws_cache[key] = buf
-    return buf
+        ent = _ws_cache.get(key)
+    if ent is not None:
+        ent.raise_if_clipped()
+    if ent is None or ent.numel() < nbytes + 1024:
+        ent = _Workspace(device, nbytes)
+        with _ws_lock:
+            _ws_cache[key] = ent
+    return ent
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    return _workspace_entry(device, nbytes).buf
+
+
+def check_overflow(device=None) -> dict:
+    """Synchronous fp16-range check of every cached workspace of `device` (all devices if None): raises CoattnError if any
+    call since the last check clipped an operand, otherwise returns the largest |feature| the cast kernels have seen."""
+    with _ws_lock:
+        ents = [(k, e) for k, e in _ws_cache.items() if device is None or k[0] == torch.device(device).index]
+    amax = 0.0
+    for _, e in ents:
+        torch.cuda.synchronize(e.buf.device)
+        words = e.status.cpu()
+        e.host.copy_(words)
+        e.event = torch.cuda.Event()
+        e.event.record(torch.cuda.current_stream(e.buf.device))
+        amax = max(amax, float(words[1:3].view(torch.float32).max()))
+        e.raise_if_clipped(wait=True)
+    return {"absmax": amax}
+
+
+def release_workspaces(device=None):
+    """Drop the cached scratch buffers (they live outside the caching allocator's reuse until released)."""
+    with _ws_lock:
+        for k in [k for k in _ws_cache if device is None or k[0] == torch.device(device).index]:
+            del _ws_cache[k]
 
 
 def _aligned_ptr(buf: torch.Tensor) -> int:
@@ -82,8 +169,9 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         z = torch.empty((2, n, c, h * w), dtype=torch.float32, device=dev) if (want_z or unfused_gate) else None
         lse = torch.empty((2, n, h * w), dtype=torch.float32, device=dev)
         nbytes = workspace_bytes(n, c, h, w)
-        ws = _workspace(dev, nbytes)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _workspace_entry(dev, nbytes)
+        cur = torch.cuda.current_stream(dev)
+        stream = cur.cuda_stream
         mask = torch.empty((2, n, h * w), dtype=torch.float32, device=dev) if want_mask else None
         flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)
                  | (_lib.FLAG_SINGLE_CTA if single_cta else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
@@ -94,8 +182,10 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
                                   None if cat_b is None else cat_b.data_ptr(),
                                   None if z is None else z.data_ptr(), lse.data_ptr(),
                                   None if mask is None else mask.data_ptr(),
-                                  _aligned_ptr(ws), nbytes, n, c, h, w, flags, stream)
+                                  ws.ptr, nbytes, n, c, h, w, flags, stream)
         _lib.check(code, "coattn_forward")
+        if not bf16_operands:
+            ws.post_call(cur)
     if want_mask:
         return cat_a, cat_b, z, lse, mask
     return cat_a, cat_b, z, lse
@@ -124,14 +214,16 @@ def coattention_queries_raw(v_a, v_b, weight, gate_weight, gate_bias=None, refs:
         pairs = n * refs
         cat_a = torch.empty((pairs, (c if gated_only else 2 * c), h, w), dtype=torch.float32, device=dev)
         nbytes = workspace_bytes(pairs, c, h, w)
-        ws = _workspace(dev, nbytes)
+        ws = _workspace_entry(dev, nbytes)
         flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0)
                  | (_lib.FLAG_SPLIT_KEYS if split_keys else 0))
         code = lib.coattn_forward_queries(v_a.data_ptr(), v_b.data_ptr(), weight.data_ptr(), gw.data_ptr(),
                                           None if gate_bias is None else gate_bias.data_ptr(), cat_a.data_ptr(),
-                                          _aligned_ptr(ws), nbytes, n, refs, c, h, w, flags,
+                                          ws.ptr, nbytes, n, refs, c, h, w, flags,
                                           torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(code, "coattn_forward_queries")
+        if not bf16_operands:
+            ws.post_call(torch.cuda.current_stream(dev))
     return cat_a
 
 
@@ -170,16 +262,18 @@ def coattention_forward16_raw(v_a, v_b, weight, gate_weight, gate_bias=None, ref
         lse = torch.empty((passes, n, h * w), dtype=torch.float32, device=dev) if want_lse else None
         mask = torch.empty((passes, n, h * w), dtype=torch.float32, device=dev) if want_lse else None
         nbytes = workspace_bytes(n, c, h, w)
-        ws = _workspace(dev, nbytes)
+        ws = _workspace_entry(dev, nbytes)
         flags = ((_lib.FLAG_BF16 if v_a.dtype == torch.bfloat16 else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
                  | (_lib.FLAG_GATED_ONLY if gated_only else 0))
         code = lib.coattn_forward16(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
                                     None if gb is None else gb.data_ptr(), cat_a.data_ptr(),
                                     None if cat_b is None else cat_b.data_ptr(),
                                     None if lse is None else lse.data_ptr(), None if mask is None else mask.data_ptr(),
-                                    _aligned_ptr(ws), nbytes, nq, refs, c, h, w, flags,
+                                    ws.ptr, nbytes, nq, refs, c, h, w, flags,
                                     torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(code, "coattn_forward16")
+        if v_a.dtype == torch.float16:
+            ws.post_call(torch.cuda.current_stream(dev))
     if want_lse:
         return cat_a, cat_b, lse, mask
     return cat_a, cat_b
@@ -195,6 +289,10 @@ class _CoAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, v_a, v_b, weight, gate_weight, gate_bias, bf16_operands, gated_only=False):
+        # the backward hands raw pointers of the saved features to the library: save the contiguous NCHW tensors the
+        # forward kernels actually read (channels_last / strided encoder outputs are copied here, once)
+        v_a = v_a.contiguous()
+        v_b = v_b.contiguous()
         cat_a, cat_b, z, lse, mask = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands,
                                                              want_mask=True, want_z=True, gated_only=gated_only)
         ctx.gated_only = gated_only
@@ -222,11 +320,11 @@ class _CoAttentionFn(torch.autograd.Function):
             d_cat_b = None if d_cat_b is None else d_cat_b.contiguous().float()
             wt = weight.detach().float().contiguous()
             gw = gate_weight.detach().float().contiguous().view(-1)
-            d_v_a = torch.empty_like(v_a)
+            d_v_a = torch.empty(v_a.shape, dtype=torch.float32, device=dev)
             d_w = torch.empty((c, c), dtype=torch.float32, device=dev)
             d_gw = torch.empty((c,), dtype=torch.float32, device=dev)
             d_gb = torch.empty((1,), dtype=torch.float32, device=dev) if ctx.has_bias else None
-            d_v_b = torch.empty_like(v_b) if ctx.v_b_needs_grad else None
+            d_v_b = torch.empty(v_b.shape, dtype=torch.float32, device=dev) if ctx.v_b_needs_grad else None
             nbytes = backward_workspace_bytes(n, c, h, w, ctx.v_b_needs_grad)
             ws = _workspace(dev, nbytes)
             stream = torch.cuda.current_stream(dev).cuda_stream

@@ -23,7 +23,7 @@ inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 struct Layout {
   int N, L, Lp;
   int parts;   // key-range parts the z / lse segments have room for (COATTN_FLAG_SPLIT_KEYS)
-  int64_t off_t, off_at, off_vv, off_w16, off_z, off_lse, total;
+  int64_t off_status, off_t, off_at, off_vv, off_w16, off_z, off_lse, total;
   int64_t bytes_t, bytes_at, bytes_vv, bytes_w16, bytes_z, bytes_lse;
   // element strides
   int64_t t_pass_elems() const { return (int64_t)N * Lp * kC; }   // T[pass] and VV[pass]
@@ -46,6 +46,7 @@ Layout make_layout(int n, int h, int w) {
   ly.Lp = (int)round_up(ly.L, kLPad);
   const int64_t plane = (int64_t)n * ly.Lp * kC * 2;  // one bf16 [N][Lp][C] (or [N][C][Lp]) array
   int64_t off = 0;
+  ly.off_status = off; off = kAlign;   // status block (coattn_status_*): always the first bytes, whatever the problem size
   ly.off_t = off;   ly.bytes_t = 2 * plane;   off = round_up(off + ly.bytes_t, kAlign);
   ly.off_at = off;  ly.bytes_at = plane;      off = round_up(off + ly.bytes_at, kAlign);
   ly.off_vv = off;  ly.bytes_vv = 3 * plane;  off = round_up(off + ly.bytes_vv, kAlign);   // B16, A16, Q16 ([C][Lp] each)
@@ -155,8 +156,22 @@ int coattn_workspace_segment(const char* name, int n, int c, int h, int w, int64
   else if (!strcmp(name, "w16")) { *offset = ly.off_w16; *bytes = ly.bytes_w16; }
   else if (!strcmp(name, "z")) { *offset = ly.off_z; *bytes = ly.bytes_z; }
   else if (!strcmp(name, "lse")) { *offset = ly.off_lse; *bytes = ly.bytes_lse; }
+  else if (!strcmp(name, "status")) { *offset = ly.off_status; *bytes = COATTN_STATUS_WORDS * 4; }
   else return COATTN_E_NULL;
   return COATTN_OK;
+}
+
+int coattn_status_clear(void* workspace, void* stream) {
+  if (!workspace) return COATTN_E_NULL;
+  return (int)cudaMemsetAsync(workspace, 0, COATTN_STATUS_WORDS * 4, static_cast<cudaStream_t>(stream));
+}
+
+int coattn_status_read(const void* workspace, uint32_t* host_words, void* stream) {
+  if (!workspace || !host_words) return COATTN_E_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(host_words, workspace, COATTN_STATUS_WORDS * 4, cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamSynchronize(st);
 }
 
 int coattn_stage_prep(const float* v_a, const float* v_b, const float* w, void* workspace,
@@ -249,12 +264,13 @@ static int prep_and_project_fused(const float* v_a, const float* v_b, const floa
 //         2 = 16-bit features consumed in place: nothing is copied and the projection reads V_a through its own map
 static int cast_project_core(const void* v_a, const void* v_b, const float* w, unsigned short* x, unsigned short* w16,
                              int n, const Layout& ly, bool bf16, bool project, cudaStream_t st, int n_a = -1,
-                             int in16 = 0) {
+                             int in16 = 0, unsigned* status = nullptr) {
   if (n_a < 0) n_a = n;       // samples of V_a (query frames); the planes are laid out for n samples either way
   CastParams cp;
   cp.va = static_cast<const float*>(v_a);   // fp32 features; with in16 == 1 pad16_kernel reads the same pointers as 16-bit data
   cp.vb = static_cast<const float*>(v_b);
   cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp; cp.Na = n_a;
+  cp.status = status;
   const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   const dim3 cgrid(n * kC, 2);
   if (in16 == 1) {
@@ -287,6 +303,7 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   pp.tiles_per_sample = ly.Lp / kProjMnTile;
   pp.num_tiles = n_a * pp.tiles_per_sample;
   pp.a_row0_base = (in16 == 2) ? 0 : n * kC;
+  pp.status = status;
   auto kern = bf16 ? project_mn_kernel<true> : project_mn_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjMnSmemBytes);
   if (e != cudaSuccess) return (int)e;
@@ -302,7 +319,8 @@ static int cast_and_project_mn(const float* v_a, const float* v_b, const float* 
   if (int e = check_arch(nullptr)) return e;
   return cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
                            reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
-                           (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream));
+                           (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), -1, 0,
+                           reinterpret_cast<unsigned*>(seg(workspace, ly.off_status)));
 }
 
 extern "C" int coattn_stage_prep_project(const float* v_a, const float* v_b, const float* w, void* workspace,
@@ -607,7 +625,8 @@ int coattn_forward_queries(const float* v_a, const float* v_b, const float* w, c
   // the query side (16-bit cast of V_a and Q = W V_a) is prepared once per query frame, not once per pair
   if (int e = cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
                                 reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
-                                (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq))
+                                (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq, 0,
+                                reinterpret_cast<unsigned*>(seg(workspace, ly.off_status))))
     return e;
   int parts = 1;
   if (int e = split_parts(flags | COATTN_FLAG_A_ONLY, n, ly, &parts)) return e;
@@ -640,7 +659,8 @@ int coattn_forward16(const void* v_a, const void* v_b, const float* w, const flo
   const int in16 = in_place ? 2 : 1;
   if (int e = cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
                                 reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
-                                (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq, in16))
+                                (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq, in16,
+                                reinterpret_cast<unsigned*>(seg(workspace, ly.off_status))))
     return e;
   return launch_attend(v_a, v_b, cat_a, cat_b, nullptr, lse, mask, gate_w, gate_b,
                        workspace, workspace_bytes, n, c, h, w_, flags, stream, refs, in16);

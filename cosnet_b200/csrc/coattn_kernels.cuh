@@ -413,7 +413,27 @@ struct CastParams {
   unsigned short* x;   // [3][N][C][Lp]; planes 0 (V_b) and 1 (V_a) are written here
   int N, L, Lp;
   int Na;              // samples of V_a (= N, or the number of query frames when each is paired with several references)
+  unsigned* status;    // status block of the workspace (include/coattn_b200.h, COATTN_STATUS_*) or null
 };
+
+// fp16 operand range guard: the block's largest |v| goes into the status block (atomicMax on the bits of a non-negative
+// float orders like the float), and a value the fp16 conversion would clamp (> 65504, Inf, NaN) raises the overflow bit of
+// its frame.  One shuffle reduction + at most three atomics per 256-thread block; nothing is done for bf16 operands
+// (fp32 exponent range).
+__device__ __forceinline__ void report_absmax(float m, bool nan, unsigned* status, int plane) {
+  __shared__ float red_m[8];
+  __shared__ int red_n[8];
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  nan = __any_sync(0xffffffffu, nan);
+  if ((threadIdx.x & 31) == 0) { red_m[threadIdx.x >> 5] = m; red_n[threadIdx.x >> 5] = nan ? 1 : 0; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int bad = 0;
+    for (int i = 0; i < 8; ++i) { m = fmaxf(m, red_m[i]); bad |= red_n[i]; }
+    atomicMax(status + 1 + plane, __float_as_uint(m));
+    if (bad || m > 65504.0f) atomicOr(status, plane ? 2u /*COATTN_STATUS_OVERFLOW_A*/ : 1u /*COATTN_STATUS_OVERFLOW_B*/);
+  }
+}
 
 template <bool BF16, int VEC>
 __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
@@ -422,18 +442,28 @@ __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
   if (plane == 1 && row >= p.Na * kC) return;
   const float* src = (plane ? p.va : p.vb) + (size_t)row * p.L;
   unsigned short* dst = p.x + ((size_t)plane * p.N * kC + row) * p.Lp;
+  float amax = 0.f;
+  bool nan = false;
   if constexpr (VEC == 4) {
     for (int i = threadIdx.x * 4; i < p.Lp; i += 256 * 4) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < p.L) v = __ldcs(reinterpret_cast<const float4*>(src + i));     // L % 4 == 0
       *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack16x2<BF16>(v.x, v.y), pack16x2<BF16>(v.z, v.w));
+      if constexpr (!BF16) {
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));   // fmaxf drops NaN:
+        nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);                          // tracked apart
+      }
     }
   } else {
     for (int i = threadIdx.x * 2; i < p.Lp; i += 256 * 2) {
       const float a = (i < p.L) ? __ldcs(src + i) : 0.f;
       const float b = (i + 1 < p.L) ? __ldcs(src + i + 1) : 0.f;
       *reinterpret_cast<uint32_t*>(dst + i) = pack16x2<BF16>(a, b);
+      if constexpr (!BF16) { amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b))); nan |= (a != a) | (b != b); }
     }
+  }
+  if constexpr (!BF16) {
+    if (p.status != nullptr) report_absmax(amax, nan, p.status, plane);
   }
 }
 
@@ -483,6 +513,7 @@ struct ProjectMnParams {
   int tiles_per_sample;  // Lp / 64
   int num_tiles;         // N * Lp / 64
   int a_row0_base;       // first row of plane A16 in the X tensor map (= 1 * N * C)
+  unsigned* status;      // status block of the workspace or null: |Q| beyond the fp16 range raises COATTN_STATUS_OVERFLOW_Q
 };
 
 // Persistent: W16 (128 KB) is loaded once per CTA and stays in shared memory; 64-position tiles of A16 stream through
@@ -589,6 +620,13 @@ project_mn_kernel(const __grid_constant__ CUtensorMap tmap_w,   // W16 [C][C], b
       tmem_ld_wait();
       tc_fence_before();
       warp_mbar_arrive(d_empty + b, lane);      // accumulators are in registers: the next tile's MMAs may overwrite them
+      if constexpr (!BF16) {
+        // fp16 range guard for Q = W V_a (the pack below saturates at +-65504): !(x <= limit) also catches NaN
+        float qm = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) qm = fmaxf(qm, fmaxf(fabsf(__uint_as_float(v0[k])), fabsf(__uint_as_float(v1[k]))));
+        if (p.status != nullptr && __any_sync(0xffffffffu, !(qm <= 65504.0f)) && lane == 0) atomicOr(p.status, 4u);
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) =

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define COATTN_B200_ABI_VERSION 1
+#define COATTN_B200_ABI_VERSION 2
 
 enum {
   COATTN_OK = 0,
@@ -111,6 +111,25 @@ enum {
  *                          coattn_forward and coattn_forward_queries; not with the cross-check flags.
  */
 #define COATTN_FLAG_SPLIT_KEYS 256u
+
+/*
+ * Status block: the first COATTN_STATUS_WORDS 32-bit words of every workspace.  With fp16 operands (the default) the
+ * fp32 -> fp16 conversions of the features and of Q = W V_a clamp at +-65504; instead of clipping silently the kernels
+ * record it here (sticky bits; the library never clears them -- coattn_status_clear, or zero the words yourself):
+ *   word 0   COATTN_STATUS_OVERFLOW_B / _A : a feature of V_b / V_a was outside the fp16 range (or Inf / NaN)
+ *            COATTN_STATUS_OVERFLOW_Q      : an element of Q = W V_a was
+ *   word 1,2 bits of max |v| over V_b / V_a seen by the cast kernels (fp32; compare as floats).  Features whose
+ *            largest magnitude is below 2^-14 (fp16 subnormals) lose precision the same way: callers should scale them
+ *            or select COATTN_FLAG_BF16, whose operands have the fp32 exponent range and never set anything here.
+ */
+#define COATTN_STATUS_WORDS 8
+#define COATTN_STATUS_OVERFLOW_B 1u
+#define COATTN_STATUS_OVERFLOW_A 2u
+#define COATTN_STATUS_OVERFLOW_Q 4u
+/* zero the status block (asynchronous on `stream`) */
+int coattn_status_clear(void* workspace, void* stream);
+/* copy the status block to `host_words` (COATTN_STATUS_WORDS entries) and wait for `stream` */
+int coattn_status_read(const void* workspace, uint32_t* host_words, void* stream);
 
 /* ABI version of the loaded library (== COATTN_B200_ABI_VERSION it was built with). */
 int coattn_b200_abi_version(void);

@@ -31,3 +31,10 @@ def rel_l2(x, ref):
     x = np.asarray(x, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     return float(np.linalg.norm(x - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+def subsample(x, fx):
+    """The strided subsample the full-size fixtures keep: x [N, C, ...] -> [N, C / sub_c, L / sub_p]."""
+    x = np.asarray(x)
+    x = x.reshape(x.shape[0], x.shape[1], -1)
+    return x[:, ::int(fx["sub_c"]), ::int(fx["sub_p"])]

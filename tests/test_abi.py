@@ -60,7 +60,10 @@ def test_workspace_size_and_shape_errors(lib):
     assert lib.coattn_workspace_bytes(0, c, h, w) == -2
     off, nb = ctypes.c_int64(), ctypes.c_int64()
     assert lib.coattn_workspace_segment(b"qt", n, c, h, w, ctypes.byref(off), ctypes.byref(nb)) == 0
-    assert off.value == plane and nb.value == plane
+    assert off.value == 1024 + plane and nb.value == plane      # the status block takes the first 1024 bytes
+    assert lib.coattn_workspace_segment(b"status", n, c, h, w, ctypes.byref(off), ctypes.byref(nb)) == 0
+    assert off.value == 0 and nb.value == 4 * 8                  # COATTN_STATUS_WORDS
+    assert lib.coattn_status_clear(None, None) == -1 and lib.coattn_status_read(None, None, None) == -1
     assert lib.coattn_workspace_segment(b"nope", n, c, h, w, ctypes.byref(off), ctypes.byref(nb)) == -1
 
 

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import coattn_oracle as orc
-from tests.helpers import golden_inputs, load_golden, rel_l2
+from tests.helpers import golden_inputs, load_golden, rel_l2, subsample
 
 FWD = ["fwd_n2_4x5_s066", "fwd_n1_3x43_s100"]
 BWD = ["bwd_n1_4x5_s066_frozen", "bwd_n1_4x5_s066_both"]
@@ -28,6 +28,42 @@ def test_forward_matches_reference(name):
     # passthrough half is a bit-exact copy (rgbd_segmentation_RAA.py:186-187)
     assert np.array_equal(rgb["cat_a"][:, c:].astype(np.float32), inp["v_a"])
     assert np.array_equal(dep["cat_b"][:, c:].astype(np.float32), inp["d_b"])
+
+
+# reference-generated fixtures at the BASELINE.json sizes (strided subsample + full-tensor norms, oracle/make_golden.py)
+LARGE = ["fwd_n1_60x60_s066", "fwd_n1_60x60_s100", "fwd_n1_61x81_s066", "fwd_n1_61x107_s066"]
+
+
+@pytest.mark.parametrize("name", LARGE)
+def test_forward_matches_reference_at_baseline_sizes(name):
+    fx = load_golden(name)
+    inp = golden_inputs(fx)
+    c = 256
+    for mod, args in {"rgb": (inp["v_a"], inp["v_b"], inp["w_rgb"], inp["g_rgb"], None),
+                      "depth": (inp["d_a"], inp["d_b"], inp["w_dep"], inp["g_dep"], inp["b_dep"])}.items():
+        out = orc.coattention(*args)
+        for side in ("a", "b"):
+            gated = out[f"cat_{side}"][:, :c]
+            # fp32 reference (MKL sgemm over K = 3600..6527 + ATen softmax) against the fp64 restatement
+            assert rel_l2(subsample(gated, fx), fx[f"{mod}_gated_{side}_sub"]) < 2e-5, (mod, side)
+            assert abs(np.linalg.norm(gated) / float(fx[f"{mod}_gated_{side}_norm"]) - 1) < 1e-5
+        if mod == "rgb":
+            assert rel_l2(subsample(out["z_a"], fx), fx["rgb_z_a_sub"]) < 2e-5
+            assert rel_l2(subsample(out["z_b"], fx), fx["rgb_z_b_sub"]) < 2e-5
+
+
+def test_backward_matches_reference_autograd_at_headline_size():
+    fx = load_golden("bwd_n1_60x60_s066_frozen")
+    inp = golden_inputs(fx)
+    n, h, w, seed = int(fx["n"]), int(fx["h"]), int(fx["w"]), int(fx["seed"])
+    rng = np.random.default_rng(seed + 7)
+    r_a = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    r_b = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    g = orc.coattention_grads(inp["v_a"], inp["v_b"], inp["w_rgb"], inp["g_rgb"], None, r_a, r_b)
+    assert rel_l2(subsample(g["d_v_a"], fx), fx["d_v_a_sub"]) < 2e-5
+    assert abs(np.linalg.norm(g["d_v_a"]) / float(fx["d_v_a_norm"]) - 1) < 1e-5
+    assert rel_l2(g["d_w"], fx["d_w"]) < 2e-5
+    assert rel_l2(g["d_gate_w"], fx["d_gate_w"]) < 2e-5
 
 
 @pytest.mark.parametrize("name", BWD)
