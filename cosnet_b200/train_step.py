@@ -3,8 +3,11 @@
   loss       weighted BCE + 0.8 * L1 on both predictions               (train.py:176-216, :595-597)
   optimiser  SGD, two parameter groups (encoder | attention + depth + decoder)  (train.py:538-540, :220-346)
   schedule   poly LR; group 0 runs at 0.01 * lr, group 1 at 10 * lr     (train.py:161-174, :348-355)
-  parallel   one process per GPU, frame pairs sharded across ranks, gradients averaged with ONE flat NCCL all-reduce
-             per step (replaces nn.DataParallel's broadcast + reduce-to-GPU0, train.py:493)
+  parallel   one process per GPU, frame pairs sharded across ranks; gradients live in flat buckets (decoder + co-attention
+             first, then the encoders in ~25 MB buckets, i.e. the order the backward produces them) and each bucket's
+             NCCL all-reduce is launched from a post-accumulate hook the moment its last gradient is written, so the
+             collectives overlap the rest of the backward (replaces nn.DataParallel's per-step broadcast of all
+             parameters + reduce-to-GPU0, train.py:493)
 
 The reference's per-iteration `gc.collect()` / `torch.cuda.empty_cache()` (train.py:619-620) and the host sync on the
 positive-label count (`.item()`, train.py:184) are not reproduced: the weight is computed on the device.
@@ -91,6 +94,91 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], world_size: Option
         off += n
 
 
+class GradientBuckets:
+    """Gradients as views of flat buckets + one asynchronous all-reduce per bucket, issued DURING the backward.
+
+    Parameters are bucketed in reverse registration order (decoder -> co-attention -> depth encoder -> RGB encoder:
+    approximately the order in which autograd finishes them); `.grad` of every parameter is a view into its bucket, so
+    nothing is copied before or after the collective.  A post-accumulate-grad hook counts a bucket's parameters down and
+    launches `all_reduce(async_op=True)` when the last one is written: NCCL orders the collective after the work already
+    queued on the current stream and runs it on its own stream, concurrently with the remaining backward kernels.
+    `finish()` launches whatever is left (parameters that got no gradient this step keep zeros), waits and divides by the
+    world size."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 25 << 20, first_bucket_bytes: int = 1 << 20):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        plist = [p for p in params if p.requires_grad]
+        self.buckets = []          # dicts: flat, params, pending, work
+        self._bucket_of = {}
+        cur, cur_bytes = [], 0
+        limit = first_bucket_bytes     # a small first bucket gets the first collective going early (as DDP does)
+        for p in reversed(plist):
+            if cur and (cur_bytes + p.numel() * p.element_size() > limit or p.dtype != cur[0].dtype or p.device != cur[0].device):
+                self._close(cur)
+                cur, cur_bytes, limit = [], 0, bucket_bytes
+            cur.append(p)
+            cur_bytes += p.numel() * p.element_size()
+        if cur:
+            self._close(cur)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in plist]
+        self.launched_in_backward = 0
+
+    def _close(self, plist):
+        flat = torch.zeros(sum(p.numel() for p in plist), dtype=plist[0].dtype, device=plist[0].device)
+        off = 0
+        for p in plist:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            self._bucket_of[id(p)] = len(self.buckets)
+        self.buckets.append({"flat": flat, "params": plist, "pending": len(plist), "work": None})
+
+    def zero(self):
+        """Replaces optimizer.zero_grad(): the gradients must stay views of the buckets."""
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["pending"] = len(b["params"])
+            b["work"] = None
+            for p, off in zip(b["params"], self._offsets(b)):
+                if p.grad is None or p.grad.data_ptr() != b["flat"].data_ptr() + off * b["flat"].element_size():
+                    p.grad = b["flat"][off:off + p.numel()].view_as(p)
+        self.launched_in_backward = 0
+
+    @staticmethod
+    def _offsets(b):
+        off = 0
+        for p in b["params"]:
+            yield off
+            off += p.numel()
+
+    def _launch(self, b):
+        if self.dist is not None and self.world > 1 and b["work"] is None:
+            b["work"] = self.dist.all_reduce(b["flat"], async_op=True)
+
+    def _on_grad(self, p):
+        b = self.buckets[self._bucket_of[id(p)]]
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(b)
+            self.launched_in_backward += 1
+
+    def finish(self):
+        """After backward: launch the buckets that never completed, wait for all collectives, average."""
+        if self.dist is None or self.world == 1:
+            return
+        for b in self.buckets:
+            self._launch(b)
+        for b in self.buckets:
+            b["work"].wait()
+            b["flat"].div_(self.world)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 class TrainStep:
     """One optimiser step on a rank-local shard of frame pairs (train.py:582-602)."""
 
@@ -100,14 +188,24 @@ class TrainStep:
         self.base_lr, self.power, self.max_iter = learning_rate, power, max_iter
         self.optimizer = make_optimizer(model, learning_rate, momentum, weight_decay)
         self.iteration = 0
+        # bucketed, overlapped gradient all-reduce when a process group exists (one process per GPU); otherwise plain
+        # single-process gradients
+        import torch.distributed as dist
+        self.buckets = None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.buckets = GradientBuckets(p for g in self.optimizer.param_groups for p in g["params"])
 
     def __call__(self, rgb_a, rgb_b, depth_a, depth_b, gt_a, gt_b=None, epoch: int = 0) -> torch.Tensor:
-        self.optimizer.zero_grad(set_to_none=True)
+        if self.buckets is not None:
+            self.buckets.zero()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
         adjust_learning_rate(self.optimizer, self.base_lr, self.iteration, epoch, self.max_iter, self.power)
         pred1, pred2, _ = self.model(rgb_a, rgb_b, depth_a, depth_b)
         loss = segmentation_loss(pred1, gt_a, pred2 if gt_b is not None else None, gt_b)
         loss.backward()
-        allreduce_gradients(p for g in self.optimizer.param_groups for p in g["params"])
+        if self.buckets is not None:
+            self.buckets.finish()
         self.optimizer.step()
         self.iteration += 1
         return loss.detach()

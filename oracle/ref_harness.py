@@ -128,3 +128,30 @@ def run_reference(model, v_a, v_b, d_a, d_b, image_hw=None):
         "depth_cat_a": cap["depth_reduce"][0], "depth_cat_b": cap["depth_reduce"][1],
         "x1": x1, "x2": x2,
     }
+
+
+def seeded_state(model, seed: int):
+    """Fill EVERY tensor of model.state_dict() from a numpy stream (in key order) so that the reference and the drop-in
+    model -- identical keys and shapes, tests/test_module_dropin.py -- can be given bit-identical weights on any machine
+    without shipping a checkpoint.  Scales keep activations O(1): He-style fan-in scaling for conv / linear weights,
+    BN weight 1 +- 0.1, running_var in [0.5, 1.5], everything else small."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(seed)
+    with torch.no_grad():
+        for key, t in model.state_dict().items():
+            if not torch.is_floating_point(t):
+                t.zero_()
+                continue
+            x = rng.standard_normal(tuple(t.shape)).astype(np.float32) if t.dim() > 0 else np.float32(rng.standard_normal())
+            if key.endswith("running_var"):
+                x = 1.0 + 0.5 * np.tanh(x)
+            elif key.endswith("running_mean") or key.endswith(".bias"):
+                x = 0.05 * x
+            elif t.dim() == 1:                       # BN / PReLU weights
+                x = (0.25 if t.numel() == 1 else 1.0) + 0.1 * x
+            else:
+                fan_in = int(np.prod(t.shape[1:]))
+                x = x * np.float32(np.sqrt(2.0 / fan_in))
+            t.copy_(torch.from_numpy(np.asarray(x, dtype=np.float32)))
+    return model

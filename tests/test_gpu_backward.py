@@ -154,27 +154,76 @@ def test_module_backward_runs(coattention):
     assert model.rgb_similarity_weights.weight.grad.abs().sum() > 0
 
 
-def test_train_step_harness_updates_hot_path_parameters(coattention):
-    """Two optimiser steps of the reference's loop body (train.py:582-602) through the drop-in model."""
+def test_train_step_matches_reference_step(coattention):
+    """One optimiser step of the reference's loop body (train.py:582-602) on the drop-in model with the CUDA co-attention
+    against the SAME step on the unmodified reference (CPU fp32 autograd; fixture from oracle/make_golden.py: seeded
+    weights regenerated here bit for bit, oracle/ref_harness.seeded_state).  Compared: the loss and the UPDATE of every
+    hot-path parameter (lr * (momentum-free first step of SGD with weight decay))."""
     from cosnet_b200.backbone import Bottleneck
     from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
     from cosnet_b200.train_step import TrainStep
+    from oracle.make_golden import HOT_PARAMS, train_step_inputs
+    from oracle.ref_harness import seeded_state
+    fx = load_golden("train_step_n2_97x97")
     dev = torch.device("cuda:0")
-    torch.manual_seed(1)
-    model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).to(dev).train()
-    step = TrainStep(model, learning_rate=1e-2, max_iter=10)
-    before = {k: v.detach().clone() for k, v in model.named_parameters() if k in
-              ("rgb_similarity_weights.weight", "gate.weight", "depth_similarity_weights.weight", "depth_gate.bias")}
-    g = torch.Generator(device=dev).manual_seed(2)
-    rgb = torch.randn(2, 3, 97, 97, device=dev, generator=g)
-    dep = torch.randn(2, 1, 97, 97, device=dev, generator=g)
-    gt = (torch.rand(2, 1, 97, 97, device=dev, generator=g) > 0.6).float()
-    losses = [float(step(rgb, rgb.flip(0), dep, dep.flip(0), gt, gt.flip(0))) for _ in range(2)]
-    assert all(np.isfinite(l) for l in losses)
+    model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).train()
+    seeded_state(model, int(fx["seed"]))
+    model = model.to(dev)
+    before = {k: v.detach().clone() for k, v in model.named_parameters() if k in HOT_PARAMS}
+    rgb, dep, gt = (torch.from_numpy(x).to(dev) for x in train_step_inputs(int(fx["seed"]) + 1, int(fx["n"]), int(fx["hw"])))
+    step = TrainStep(model, learning_rate=float(fx["lr"]), max_iter=int(fx["max_iter"]))
+    loss = float(step(rgb[0], rgb[1], dep[0], dep[1], gt[0], gt[1]))
+    assert abs(loss / float(fx["loss"]) - 1) < 1e-3, (loss, float(fx["loss"]))
     after = dict(model.named_parameters())
-    for k, v in before.items():
-        assert not torch.equal(v, after[k].detach()), k
-        assert torch.isfinite(after[k]).all()
+    for k in HOT_PARAMS:
+        delta = (after[k].detach() - before[k]).cpu().numpy()
+        ref = fx["delta__" + k]
+        assert np.isfinite(delta).all()
+        assert rel_l2(delta, ref) < 2e-2, (k, rel_l2(delta, ref))
+    # a second step keeps everything finite (momentum buffers, BN statistics)
+    loss2 = float(step(rgb[0], rgb[1], dep[0], dep[1], gt[0], gt[1]))
+    assert np.isfinite(loss2)
+
+
+def test_channels_last_features_get_correct_gradients(coattention):
+    """Strided (channels_last) encoder outputs: the autograd bridge saves the contiguous copies the kernels read, so the
+    backward recomputes S from the right layout and returns NCHW-ordered gradients."""
+    n, h, w = 2, 12, 11
+    v_a, v_b = orc.synthetic_features(501, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(502, bias=True)
+    rng = np.random.default_rng(7)
+    r_a = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    r_b = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    dev = torch.device("cuda:0")
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    va = t(v_a).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    vb = t(v_b).contiguous(memory_format=torch.channels_last)
+    w_ = t(W).requires_grad_(True)
+    gw = t(g).view(1, -1, 1, 1).requires_grad_(True)
+    gb = t(b).requires_grad_(True)
+    assert not va.is_contiguous()
+    cat_a, cat_b = coattention(va, vb, w_, gw, gb)
+    ((cat_a * t(r_a)).sum() + (cat_b * t(r_b)).sum()).backward()
+    torch.cuda.synchronize()
+    ref = orc.coattention_grads(v_a, v_b, W, g, b, r_a, r_b)
+    assert rel_l2(va.grad.cpu().numpy(), ref["d_v_a"]) < GRAD_TOL
+    assert rel_l2(w_.grad.cpu().numpy(), ref["d_w"]) < GRAD_TOL
+
+
+def test_reference_gradients_at_headline_size(coattention):
+    """Reference autograd at 60x60 (L = 3600; fixture keeps a strided subsample of d_v_a, full d_w / d_gate_w)."""
+    from tests.helpers import subsample
+    fx = load_golden("bwd_n1_60x60_s066_frozen")
+    inp = golden_inputs(fx)
+    n, h, w, seed = int(fx["n"]), int(fx["h"]), int(fx["w"]), int(fx["seed"])
+    rng = np.random.default_rng(seed + 7)
+    r_a = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    r_b = rng.standard_normal((n, 512, h, w), dtype=np.float32)
+    got = run_backward(coattention, inp["v_a"], inp["v_b"], inp["w_rgb"], inp["g_rgb"], None, r_a, r_b)
+    assert rel_l2(subsample(got["d_v_a"], fx), fx["d_v_a_sub"]) < GRAD_TOL
+    assert abs(np.linalg.norm(got["d_v_a"].astype(np.float64)) / float(fx["d_v_a_norm"]) - 1) < GRAD_TOL
+    assert rel_l2(got["d_w"], fx["d_w"]) < GRAD_TOL, rel_l2(got["d_w"], fx["d_w"])
+    assert rel_l2(got["d_gate_w"], fx["d_gate_w"]) < GRAD_TOL
 
 
 def test_split_reduce_conv_module_forward_and_backward(coattention):

@@ -84,5 +84,40 @@ def _worker(rank, world, port):
         dist.destroy_process_group()
 
 
+def _bucket_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.Tanh(), torch.nn.Linear(32, 16), torch.nn.Tanh(),
+                                  torch.nn.Linear(16, 1))
+        unused = torch.nn.Parameter(torch.ones(7))          # never reaches the loss: its bucket is flushed by finish()
+        x, y = torch.randn(8, 6), torch.randn(8, 1)
+        ref = [g.clone() for g in torch.autograd.grad(F.mse_loss(net(x), y), list(net.parameters()))]
+        params = list(net.parameters()) + [unused]
+        gb = ts.GradientBuckets(params, bucket_bytes=600, first_bucket_bytes=100)     # several buckets
+        assert len(gb.buckets) >= 3
+        from cosnet_b200.pair_batcher import shard_range
+        s, c = shard_range(8, world, rank)
+        for _ in range(2):                                  # second step: zero() keeps the views, results identical
+            gb.zero()
+            F.mse_loss(net(x[s:s + c]), y[s:s + c]).backward()
+            assert gb.launched_in_backward >= len(gb.buckets) - 1     # all but the unused parameter's bucket overlapped
+            gb.finish()
+            for p, r in zip(net.parameters(), ref):
+                assert torch.allclose(p.grad, r, atol=1e-6), (p.grad - r).abs().max()
+            assert torch.equal(unused.grad, torch.zeros(7))
+            # gradients are views of the flat buckets (no copies around the collective)
+            b0 = gb.buckets[gb._bucket_of[id(net[0].weight)]]["flat"]
+            assert b0.data_ptr() <= net[0].weight.grad.data_ptr() < b0.data_ptr() + b0.numel() * 4
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bucketed_overlapped_allreduce_equals_single_process():
+    mp.spawn(_bucket_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
 def test_two_rank_gloo_gradient_allreduce_equals_single_process():
     mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
