@@ -92,3 +92,37 @@ def query_reference_groups(num_queries: int, sample_range: int, frames_per_seque
         k = min(sample_range, frames_per_sequence)
         groups.append((q % frames_per_sequence, rng.sample(range(frames_per_sequence), k)))
     return groups
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it allocates
+    afterwards are node-local (first touch) and its H2D / D2H traffic does not cross the inter-socket link.  With one
+    process per GPU (the launch model here) the unbound default puts every rank's buffers wherever the kernel scheduled
+    it -- usually node 0 -- and the ranks then share one socket's memory controllers.  Best effort: returns what it did."""
+    import os
+    import torch
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(os.path.join(base, "numa_node")) as f:
+            node = int(f.read().strip())
+        with open(os.path.join(base, "local_cpulist")) as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        info.update(pci=bdf, numa_node=node, cpus=len(cpus))
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+    except Exception as e:  # sysfs layout / permissions differ between hosts: never fatal
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
