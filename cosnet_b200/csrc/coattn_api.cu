@@ -11,6 +11,7 @@
 #include "coattn_kernels.cuh"
 #include "attend2_kernel.cuh"
 #include "backward_kernels.cuh"
+#include "bwd_flash_kernel.cuh"
 
 namespace {
 
@@ -707,35 +708,26 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
 namespace {
 struct BwdLayout {
   Layout fwd;
-  int64_t off_g;   // bf16 copies of the channel-major planes [B16, A16, (Q16)] (operands of the gradient GEMMs)
-  int64_t off_w16g, off_dza16, off_dzb16, off_delta, off_ds, off_pb, off_dqt, off_dq16, off_wt, total;
-  // counterpart gradients only (d_v_b requested): P_a, dS^T, P_a^T
-  int64_t off_pa, off_ds_t, off_pa_t, total_counterpart;
+  int64_t off_g;   // bf16 copies of the channel-major planes [B16, A16, (Q16)] (operands of the gradient products)
+  int64_t off_w16g, off_dza16, off_dzb16, off_delta, off_dqt, off_dq16, off_wt, total;
 };
+// Nothing of size L x L: 16-bit planes [N][C][Lp] and vectors only (the softmax matrices are recomputed tile by tile in
+// TMEM, bwd_flash_kernel.cuh).
 BwdLayout make_bwd_layout(int n, int h, int w) {
   BwdLayout b{};
   b.fwd = make_layout(n, h, w);
   const int64_t Lp = b.fwd.Lp, L = b.fwd.L;
   const int64_t plane = (int64_t)n * Lp * kC * 2;
-  const int64_t mat16 = (int64_t)n * Lp * Lp * 2;
   int64_t off = b.fwd.total;
   auto take = [&](int64_t bytes) { const int64_t o = off; off = round_up(off + bytes, kAlign); return o; };
   b.off_g = take(3 * plane);
   b.off_w16g = take((int64_t)kC * kC * 2);
   b.off_dza16 = take(plane); b.off_dzb16 = take(plane);
   b.off_delta = take((int64_t)2 * n * L * 4);
-  b.off_ds = take(mat16); b.off_pb = take(mat16);
   b.off_dqt = take(plane); b.off_dq16 = take(plane);
   b.off_wt = take((int64_t)kC * kC * 2);
   b.total = off;
-  b.off_pa = take(mat16); b.off_ds_t = take(mat16); b.off_pa_t = take(mat16);
-  b.total_counterpart = off;
   return b;
-}
-
-// 16-bit tensor map over channel-major planes [rows][Lp] with a {64 positions, 64 channels} box (MN-major operand chunks)
-int make_plane_tmap(EncodeTiledFn enc, CUtensorMap* out, const void* base, uint64_t rows, uint64_t lp, bool bf16) {
-  return make_tmap(enc, out, base, rows, lp, 64, bf16);
 }
 
 template <int MODE>
@@ -754,14 +746,52 @@ int launch_gemm(EncodeTiledFn enc, cudaStream_t st, const void* a, uint64_t a_ro
   kern<<<dim3(m_tiles, n_tiles, batch * k_split), kNumThreads, kGemmSmemBytes, st>>>(ta, tb, gp);
   return (int)cudaGetLastError();
 }
+
+int launch_flash(cudaStream_t st, const FlashMaps& maps, FlashParams& fp, int sms, const Layout& ly, bool fbf16) {
+  fp.L = ly.L; fp.Lp = ly.Lp;
+  fp.q_pairs = (ly.L + 2 * k2BM - 1) / (2 * k2BM);
+  fp.kv_tiles = (ly.L + k2BN - 1) / k2BN;
+  const uint32_t n_last = (uint32_t)(((ly.L - (fp.kv_tiles - 1) * k2BN) + 15) & ~15);
+  fp.idesc_s = make_idesc_16_major(2 * k2BM, k2BN, fbf16, true, true);
+  fp.idesc_s_last = make_idesc_16_major(2 * k2BM, n_last, fbf16, true, true);
+  fp.idesc_t = make_idesc_16_major(2 * k2BM, k2BN, true, true, true);
+  fp.idesc_t_last = make_idesc_16_major(2 * k2BM, n_last, true, true, true);
+  fp.idesc_o = make_idesc_16(2 * k2BM, kC, true);
+  cudaError_t e = cudaFuncSetAttribute(bwd_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  int clusters = sms / 2;
+  if (fp.items[0] + fp.items[1] < clusters) clusters = fp.items[0] + fp.items[1];
+  if (clusters < 1) return COATTN_OK;
+  bwd_flash_kernel<<<2 * clusters, kFThreads, kFSmemBytes, st>>>(maps, fp);
+#ifdef COATTN_TRACE_FLASH
+  {
+    static int calls = 0;
+    if (++calls == 3 || calls == 6) {
+      long long tb[64 * 16];
+      cudaStreamSynchronize(st);
+      cudaMemcpyFromSymbol(tb, g_flash_trace, sizeof(tb));
+      const long long t0 = tb[0];
+      printf("bwd_flash trace (call %d, kinds %d/%d items): cluster 0, second item, first phase\n", calls, fp.items[0], fp.items[1]);
+      for (int j = 0; j < 29 && j < fp.kv_tiles; ++j) {
+        const long long* r = tb + j * 16;
+        printf("tile %2d: top +%7lld | k_full(S j+1) +%5lld | st_free +%5lld | S issued +%5lld | v_full +%5lld | x_full +%5lld | T issued +%5lld"
+               " || warp0: S seen +%7lld | in regs +%5lld | P done +%5lld | T seen +%5lld | X stored +%5lld\n", j, r[0] - t0,
+               r[13] - r[0], r[14] - r[13], r[1] - r[14], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[8] - t0, r[9] - r[8], r[10] - r[9],
+               r[11] - r[10], r[12] - r[11]);
+      }
+    }
+  }
+#endif
+  return (int)cudaGetLastError();
+}
 }  // namespace
 
 extern "C" {
 
 int64_t coattn_backward_workspace_bytes(int n, int c, int h, int w, int counterpart) {
+  (void)counterpart;      // the counterpart-frame gradient needs no extra scratch any more
   if (check_dims(n, c, h, w) != COATTN_OK) return COATTN_E_SHAPE;
-  const BwdLayout bl = make_bwd_layout(n, h, w);
-  return counterpart ? bl.total_counterpart : bl.total;
+  return make_bwd_layout(n, h, w).total;
 }
 
 int coattn_backward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* z,
@@ -777,15 +807,13 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   const BwdLayout bl = make_bwd_layout(n, h, w_);
   const Layout& ly = bl.fwd;
   if (!workspace) return COATTN_E_NULL;
-  if ((reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) != 0 ||
-      workspace_bytes < (counterpart ? bl.total_counterpart : bl.total))
-    return COATTN_E_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) != 0 || workspace_bytes < bl.total) return COATTN_E_WORKSPACE;
   int sms = 148;
   if (int e = check_arch(&sms)) return e;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return COATTN_E_DRIVER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool fbf16 = (flags & COATTN_FLAG_BF16) != 0;   // format of the forward operands (Qt, Bt, At, A16, B16)
+  const bool fbf16 = (flags & COATTN_FLAG_BF16) != 0;   // format of the forward operands (Q16, B16)
   const bool has_b = d_cat_b != nullptr;
   const int L = ly.L, Lp = ly.Lp;
   const int64_t plane_elems = ly.t_pass_elems();
@@ -808,11 +836,10 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   unsigned short* q16f = xf + 2 * plane_elems;            // Q, forward format
   unsigned short* b16 = xg;                               // B, bf16
   unsigned short* a16 = xg + plane_elems;                 // A, bf16
+  unsigned short* q16g = xg + 2 * plane_elems;            // Q, bf16 (counterpart gradients only)
   unsigned short* dza16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dza16));
   unsigned short* dzb16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb16));
   float* delta = reinterpret_cast<float*>(seg(workspace, bl.off_delta));
-  unsigned short* ds = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_ds));
-  unsigned short* pb = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pb));
   unsigned short* dqt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dqt));
   unsigned short* dq16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dq16));
   unsigned short* wt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_wt));
@@ -824,9 +851,6 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
 
   BwdPrepParams bp;
   bp.d_cat_a = d_cat_a; bp.d_cat_b = d_cat_b; bp.z = z; bp.mask = mask; bp.gate_w = gate_w;
-  unsigned short* pa = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa));
-  unsigned short* ds_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_ds_t));
-  unsigned short* pa_t = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa_t));
   bp.d_vb = d_v_b;
   bp.dza16 = dza16; bp.dzb16 = dzb16; bp.delta = delta;
   bp.d_gate_w = d_gate_w; bp.d_gate_b = d_gate_b; bp.d_va = d_v_a; bp.N = n; bp.L = L; bp.Lp = Lp;
@@ -836,42 +860,53 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
 
   const uint64_t rowsL = (uint64_t)n * Lp, rowsC = (uint64_t)n * kC;
   const int lt = Lp / 128;
-  GemmParams gp{};
+  // ---- the L x L part: flash-style sweeps, nothing of that size is written (bwd_flash_kernel.cuh)
+  FlashMaps maps;
+  enum { mQf = 0, mBf = 1, mDza = 2, mBg = 3, mAg = 4, mDzb = 5, vBg = 6, vDzb = 7, vQg = 8, vDza = 9 };
   {
-    // S, dP_a, dP_b and their combination: one kernel, one 128 x 128 tile per CTA, outputs bf16 dS / P_b (/ P_a)
-    CUtensorMap t_qt, t_bt, t_dza, t_btg, t_atg, t_dzb;
-    if (int e = make_plane_tmap(enc, &t_qt, q16f, rowsC, Lp, fbf16)) return e;
-    if (int e = make_plane_tmap(enc, &t_bt, b16f, rowsC, Lp, fbf16)) return e;
-    if (int e = make_plane_tmap(enc, &t_dza, dza16, rowsC, Lp, true)) return e;
-    if (int e = make_plane_tmap(enc, &t_btg, b16, rowsC, Lp, true)) return e;
-    if (int e = make_plane_tmap(enc, &t_atg, a16, rowsC, Lp, true)) return e;
-    if (int e = make_plane_tmap(enc, &t_dzb, dzb16, rowsC, Lp, true)) return e;
-    BwdTileParams tp;
-    tp.lse = lse; tp.delta = delta; tp.ds = ds; tp.pb = pb;
-    tp.pa = counterpart ? reinterpret_cast<unsigned short*>(seg(workspace, bl.off_pa)) : nullptr;
-    tp.N = n; tp.L = L; tp.Lp = Lp;
-    tp.tiles_1d = lt; tp.num_tiles = n * lt * lt;
-    const uint32_t f = fbf16 ? 1u : 0u;
-    (void)f;
-    tp.idesc_fwd = make_idesc_16_major(128, 128, fbf16, true, true);    // both operands MN-major
-    tp.idesc_bf16 = make_idesc_16_major(128, 128, true, true, true);
-    auto kern = has_b ? bwd_tile_kernel<true> : bwd_tile_kernel<false>;
-    if ((ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes)) != cudaSuccess)
-      return (int)ce;
-    kern<<<tp.num_tiles < sms ? tp.num_tiles : sms, kTileThreads, kTileSmemBytes, st>>>(t_qt, t_bt, t_dza, t_btg, t_atg, t_dzb, tp);
-    if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
+    struct { int idx; const void* base; uint32_t box; bool bf; } defs[kFMaps] = {
+        {mQf, q16f, 256, fbf16}, {mBf, b16f, 256, fbf16}, {mDza, dza16, 256, true}, {mBg, b16, 256, true}, {mAg, a16, 256, true},
+        {mDzb, dzb16, 256, true}, {vBg, b16, 128, true}, {vDzb, dzb16, 128, true}, {vQg, q16g, 128, true}, {vDza, dza16, 128, true}};
+    for (const auto& d : defs)
+      if (int e = make_tmap(enc, &maps.m[d.idx], d.base, rowsC, Lp, d.box, d.bf)) return e;
   }
-  // dQ[i][c] = sum_j dS[i][j] B16[c][j]   -> dQt [N][Lp][C] and dQ16 [N][C][Lp] (bf16)
-  gp.out0 = dqt; gp.ld0 = kC; gp.rows0 = Lp; gp.out1 = dq16; gp.ld1 = Lp; gp.rows1 = kC;
-  gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = kC; gp.m_valid = Lp;
-  if (int e = launch_gemm<kGemmStore16Both>(enc, st, ds, rowsL, true, b16, rowsC, true, Lp, lt, kC / 128, n, gp)) return e;
-  // dA[c][i] += sum_j P_b[i][j] dZ_b[c][j]
-  gp.out0 = d_v_a; gp.ld0 = L; gp.rows0 = kC; gp.out1 = nullptr; gp.m_valid = L;
-  if (has_b) {
-    gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = kC;
-    if (int e = launch_gemm<kGemmAddF32T>(enc, st, pb, rowsL, true, dzb16, rowsC, true, Lp, lt, kC / 128, n, gp)) return e;
+  const float* lse_a = lse;
+  const float* lse_b = lse + (size_t)n * L;
+  const float* del_a = delta;
+  const float* del_b = delta + (size_t)n * L;
+  const int items = n * ((L + 2 * k2BM - 1) / (2 * k2BM));
+  {
+    // frame-A side: dQ (phase A [+ phase B]) and dA += P_b dZ_b^T
+    FlashParams fp{};
+    fp.N = n;
+    fp.ph[0] = FlashPhase{mQf, mBf, mDza, mBg, vBg, 0, lse_a, del_a};
+    fp.ph[1] = FlashPhase{mQf, mBf, mAg, mDzb, vBg, 1, lse_b, del_b};
+    fp.ph[2] = FlashPhase{mQf, mBf, -1, -1, vDzb, 1, lse_b, nullptr};
+    fp.kind[0] = FlashKind{0, has_b ? 2 : 1, 0, dqt, dq16, nullptr};
+    fp.kind[1] = FlashKind{2, 1, 1, nullptr, nullptr, d_v_a};
+    fp.items[0] = items;
+    fp.items[1] = has_b ? items : 0;
+    fp.ratio = 3;      // two phases of three products against one phase of two
+    if (int e = launch_flash(st, maps, fp, sms, ly, fbf16)) return e;
   }
+  if (counterpart) {
+    // frame-B side (no_grad_for_counterpart=False): the same sweeps with the roles of the frames swapped, all into d_v_b
+    //   dB[:, j] += sum_i dS[i, j] Q[:, i] + sum_i P_a[i, j] dZ_a[:, i]
+    FlashParams fp{};
+    fp.N = n;
+    fp.ph[0] = FlashPhase{mBf, mQf, mBg, mDza, vQg, 1, lse_a, del_a};        // P_a (dP_a - delta_a): vectors follow the columns (i)
+    fp.ph[1] = FlashPhase{mBf, mQf, -1, -1, vDza, 1, lse_a, nullptr};         // P_a dZ_a
+    fp.ph[2] = FlashPhase{mBf, mQf, mDzb, mAg, vQg, 0, lse_b, del_b};        // P_b (dP_b - delta_b): vectors follow the rows (j)
+    fp.kind[0] = FlashKind{0, has_b ? 3 : 2, 1, nullptr, nullptr, d_v_b};
+    fp.kind[1] = FlashKind{0, 0, 1, nullptr, nullptr, nullptr};
+    fp.items[0] = items;
+    fp.items[1] = 0;
+    fp.ratio = 1;
+    if (int e = launch_flash(st, maps, fp, sms, ly, fbf16)) return e;
+  }
+  GemmParams gp{};
   // dA[c][i] += sum_d dQt[i][d] W[d][c]
+  gp.out0 = d_v_a; gp.ld0 = L; gp.rows0 = kC; gp.out1 = nullptr; gp.m_valid = L;
   gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = 0;
   if (int e = launch_gemm<kGemmAddF32T>(enc, st, dqt, rowsL, true, wt, kC, true, kC, lt, kC / 128, n, gp)) return e;
   // dW[d][c] += sum_n sum_i dQ16[n][d][i] A16[n][c][i]
@@ -883,18 +918,6 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
     if ((Lp / 64) % cand == 0 && 4 * n * cand <= 2 * sms) dw_split = cand;
   if (int e = launch_gemm<kGemmAtomicF32>(enc, st, dq16, rowsC, true, a16, rowsC, true, Lp, kC / 128, kC / 128, n, gp, dw_split))
     return e;
-  if (counterpart) {
-    // dB[c][j] = sum_i Q[c][i] dS[i][j] + sum_i dZ_a[c][i] P_a[i][j]   (+ passthrough, written by bwd_prep)
-    transpose16_kernel<<<dim3(Lp / 32, Lp / 32, n), 256, 0, st>>>(ds, ds_t, Lp);
-    transpose16_kernel<<<dim3(Lp / 32, Lp / 32, n), 256, 0, st>>>(pa, pa_t, Lp);
-    if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
-    // Q in bf16, channel-major: plane 2 of the bf16 operand set (projected above when counterpart gradients are on)
-    unsigned short* q16 = xg + 2 * plane_elems;
-    gp.out0 = d_v_b; gp.ld0 = L; gp.rows0 = kC; gp.m_valid = L;
-    gp.a_rows_per_batch = Lp; gp.b_rows_per_batch = kC;
-    if (int e = launch_gemm<kGemmAddF32T>(enc, st, ds_t, rowsL, true, q16, rowsC, true, Lp, lt, kC / 128, n, gp)) return e;
-    if (int e = launch_gemm<kGemmAddF32T>(enc, st, pa_t, rowsL, true, dza16, rowsC, true, Lp, lt, kC / 128, n, gp)) return e;
-  }
   return COATTN_OK;
 }
 

@@ -153,5 +153,7 @@ def seeded_state(model, seed: int):
             else:
                 fan_in = int(np.prod(t.shape[1:]))
                 x = x * np.float32(np.sqrt(2.0 / fan_in))
+                if "similarity_weights" in key:      # keep the logits at the scale of a trained model (S std ~ 3, not
+                    x = x * np.float32(0.25)         # near-one-hot softmaxes whose gradients are ill-conditioned)
             t.copy_(torch.from_numpy(np.asarray(x, dtype=np.float32)))
     return model

@@ -166,6 +166,19 @@ def test_train_step_matches_reference_step(coattention):
     from oracle.ref_harness import seeded_state
     fx = load_golden("train_step_n2_97x97")
     dev = torch.device("cuda:0")
+    # the cuDNN convolutions around the operator run in fp32 like the CPU reference: with cuDNN's default TF32 convs the
+    # hot-path updates move by ~10 % whatever operator sits in the middle (tools/train_step_diag.py: an eager fp32
+    # co-attention gives 1e-1 with TF32 convs and 7e-5 without)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        _train_step_parity(fx, dev, Bottleneck, RGBDSegmentation_RAA, TrainStep, HOT_PARAMS, train_step_inputs, seeded_state)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def _train_step_parity(fx, dev, Bottleneck, RGBDSegmentation_RAA, TrainStep, HOT_PARAMS, train_step_inputs, seeded_state):
     model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).train()
     seeded_state(model, int(fx["seed"]))
     model = model.to(dev)
@@ -173,7 +186,7 @@ def test_train_step_matches_reference_step(coattention):
     rgb, dep, gt = (torch.from_numpy(x).to(dev) for x in train_step_inputs(int(fx["seed"]) + 1, int(fx["n"]), int(fx["hw"])))
     step = TrainStep(model, learning_rate=float(fx["lr"]), max_iter=int(fx["max_iter"]))
     loss = float(step(rgb[0], rgb[1], dep[0], dep[1], gt[0], gt[1]))
-    assert abs(loss / float(fx["loss"]) - 1) < 1e-3, (loss, float(fx["loss"]))
+    assert abs(loss / float(fx["loss"]) - 1) < 1e-4, (loss, float(fx["loss"]))
     after = dict(model.named_parameters())
     for k in HOT_PARAMS:
         delta = (after[k].detach() - before[k]).cpu().numpy()
