@@ -39,8 +39,15 @@ constexpr int kFRBytes = k2BM * kC * 2;          // 64 KB : row-side operand til
 constexpr int kFKBytes = (k2BN / 2) * kC * 2;    // 32 KB : this CTA's half of a column-side operand tile
 constexpr int kFVBytes = (kC / 2) * k2BN * 2;    // 32 KB : this CTA's channels of a V tile
 constexpr int kFKSlots = 2;
-constexpr int kFThreads = 384;                   // warps 0-7 X producers + drain, 8 TMA (R tiles, C1), 9 MMA issuer, 10 TMA (V), 11 TMA (C2)
-constexpr int kFProducerWarp = 8, kFMmaWarp = 9, kFVProducerWarp = 10, kFC2ProducerWarp = 11;
+// G = X-producer warps per TMEM lane quadrant (they split the 128 columns of a tile and the 256 channels of the drain):
+//   warps [0, 4G) X producers + drain | 4G TMA (R tiles, column slot 0) | 4G+1 MMA issuer | 4G+2 TMA (V) | 4G+3 TMA (column slot 1)
+template <int G> struct FlashCfg {
+  static constexpr int kXWarps = 4 * G;
+  static constexpr int kThreads = 32 * (4 * G + 4);
+  static constexpr int kCols = k2BN / G;      // tile columns per thread
+  static constexpr int kLd = kCols / 32;      // 32-column TMEM loads per thread and product
+  static constexpr int kCh = kC / G;          // channels per thread in the drain
+};
 constexpr int kFColvBytes = 2 * 256 * 4;         // [tile parity][normaliser x 128 | delta x 128]
 constexpr int kFSmemBytes = 2 * kFRBytes + kFKSlots * kFKBytes + kFVBytes + kFColvBytes + 256;
 static_assert(kFSmemBytes <= 232448, "bwd_flash shared memory exceeds the 227 KB per-CTA limit");
@@ -118,8 +125,12 @@ __device__ __forceinline__ FlashSched flash_schedule(int k, int K, int n0, int n
   return s;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
+template <int G>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FlashCfg<G>::kThreads, 1)
 bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__ FlashParams p) {
+  using Cfg = FlashCfg<G>;
+  constexpr int kXWarps = Cfg::kXWarps, kCols = Cfg::kCols, kLd = Cfg::kLd, kCh = Cfg::kCh;
+  constexpr int kFProducerWarp = kXWarps, kFMmaWarp = kXWarps + 1, kFVProducerWarp = kXWarps + 2, kFC2ProducerWarp = kXWarps + 3;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sR1 = smem;
   uint8_t* sR2 = sR1 + kFRBytes;
@@ -156,8 +167,8 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
     mbar_init(v_full, 1); mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(t_full, 1);
-    mbar_init(s_free, 16);
-    for (int b = 0; b < 2; ++b) { mbar_init(x_full + b, 16); mbar_init(o_full + b, 1); }
+    mbar_init(s_free, 2 * kXWarps);
+    for (int b = 0; b < 2; ++b) { mbar_init(x_full + b, 2 * kXWarps); mbar_init(o_full + b, 1); }
     fence_mbar_init();
   }
   if (warp == kFMmaWarp) {
@@ -363,16 +374,16 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
         __syncwarp();
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < kXWarps) {
     // ------------------------------------------------------------------ X producers + drain
-    const int g = warp >> 2;             // column group: columns [64 g, 64 g + 64) of a tile, channels [128 g, 128 g + 128) of O
+    const int g = warp >> 2;             // column group: columns [kCols g, kCols (g + 1)) of a tile, channels [kCh g, kCh (g + 1)) of O
     const int quad = warp & 3;
     const int rloc = quad * 32 + lane;
-    const int et = threadIdx.x;          // 0..255
+    const int et = threadIdx.x;          // 0 .. 128 G - 1
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const uint32_t tSg = tmem + lane_base + kFTmemS + (uint32_t)(g * 64);
-    const uint32_t tTg = tmem + lane_base + kFTmemT + (uint32_t)(g * 64);
-    const uint32_t tOg = tmem + lane_base + kFTmemO + (uint32_t)(g * 128);
+    const uint32_t tSg = tmem + lane_base + kFTmemS + (uint32_t)(g * kCols);
+    const uint32_t tTg = tmem + lane_base + kFTmemT + (uint32_t)(g * kCols);
+    const uint32_t tOg = tmem + lane_base + kFTmemO + (uint32_t)(g * kCh);
     const uint32_t s_free_l = mapa_u32(smem_u32(s_free), 0);
     const uint32_t x_full_l0 = mapa_u32(smem_u32(x_full + 0), 0);
     const uint32_t x_full_l1 = mapa_u32(smem_u32(x_full + 1), 0);
@@ -406,34 +417,34 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
         for (int j = 0; j < T; ++j) {
           float* cv = colv + (cvcnt & 1) * 256;
           if (vcol) {
-            cv[et] = cnext;
-            named_bar_sync(1, 256);       // also keeps a fast warp from overwriting the buffer of the tile before last
+            if (et < 256) cv[et] = cnext;
+            named_bar_sync(1, 128 * G);   // also keeps a fast warp from overwriting the buffer of the tile before last
             ++cvcnt;
-            if (j + 1 < T) cnext = fetch_col(j + 1);
+            if (j + 1 < T && et < 256) cnext = fetch_col(j + 1);
           }
-          const int jc0 = j * k2BN + g * 64;                 // first column position of this thread
-          const bool ragged = (j == T - 1) && (jc0 + 64 > p.L);
+          const int jc0 = j * k2BN + g * kCols;              // first column position of this thread
+          const bool ragged = (j == T - 1) && (jc0 + kCols > p.L);
           // ---- S
           warp_mbar_wait(s_full, scnt & 1, lane, 20);
           if (warp == 0 && pi == K.phase0) FTR(j, 8);
           ++scnt;
           tc_fence_after();
-          float pr[64];
+          float pr[kCols];
           {
-            uint32_t sv[2][32];
-            tmem_ld32(tSg, sv[0]);
-            tmem_ld32(tSg + 32, sv[1]);
+            uint32_t sv[kLd][32];
+#pragma unroll
+            for (int c = 0; c < kLd; ++c) tmem_ld32(tSg + c * 32, sv[c]);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(s_free_l);
             if (warp == 0 && pi == K.phase0) FTR(j, 9);
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < kLd; ++c)
 #pragma unroll
               for (int k = 0; k < 32; k += 4) {
                 float4 nc = make_float4(nrow, nrow, nrow, nrow);
-                if (vcol) nc = *reinterpret_cast<const float4*>(cv + g * 64 + c * 32 + k);
+                if (vcol) nc = *reinterpret_cast<const float4*>(cv + g * kCols + c * 32 + k);
                 pr[c * 32 + k + 0] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 0]), kLog2e, nc.x));
                 pr[c * 32 + k + 1] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 1]), kLog2e, nc.y));
                 pr[c * 32 + k + 2] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 2]), kLog2e, nc.z));
@@ -442,12 +453,12 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           }
           if (!vrow) {
 #pragma unroll
-            for (int k = 0; k < 64; ++k) pr[k] = 0.f;
+            for (int k = 0; k < kCols; ++k) pr[k] = 0.f;
           } else if (ragged) {
 #pragma unroll
-            for (int k = 0; k < 64; ++k) if (jc0 + k >= p.L) pr[k] = 0.f;
+            for (int k = 0; k < kCols; ++k) if (jc0 + k >= p.L) pr[k] = 0.f;
           }
-          uint32_t pk[32];
+          uint32_t pk[kCols / 2];
           if (warp == 0 && pi == K.phase0) FTR(j, 10);
           if (has_t) {
             // ---- T, in two 32-column chunks (P x 64 + T x 64 + the packed result would not fit the register file)
@@ -456,14 +467,14 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
             ++tcnt;
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < kLd; ++c) {
               uint32_t tv[32];
               tmem_ld32(tTg + c * 32, tv);
               tmem_ld_wait();
 #pragma unroll
               for (int k = 0; k < 32; k += 4) {
                 float4 dc = make_float4(drow, drow, drow, drow);
-                if (vcol) dc = *reinterpret_cast<const float4*>(cv + 128 + g * 64 + c * 32 + k);
+                if (vcol) dc = *reinterpret_cast<const float4*>(cv + 128 + g * kCols + c * 32 + k);
                 const float x0 = pr[c * 32 + k + 0] * (__uint_as_float(tv[k + 0]) - dc.x);
                 const float x1 = pr[c * 32 + k + 1] * (__uint_as_float(tv[k + 1]) - dc.y);
                 const float x2 = pr[c * 32 + k + 2] * (__uint_as_float(tv[k + 2]) - dc.z);
@@ -474,16 +485,17 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) pk[k] = pack_bf16x2(pr[2 * k], pr[2 * k + 1]);
+            for (int k = 0; k < kCols / 2; ++k) pk[k] = pack_bf16x2(pr[2 * k], pr[2 * k + 1]);
           }
           // X -> buffer xb once the PV that read its previous content has completed.  With T: always buffer 0, the first 64
           // columns of the T buffer -- every warp of this CTA must have T in registers before any of them overwrites it
           // (the named barrier), and t_full(j) already implies PV(j - 1), so the wait below returns at once.
           const uint32_t xb = has_t ? 0u : (nt_tile++ & 1u);
-          if (has_t) named_bar_sync(2 + quad, 64);      // the two warps of a lane quadrant: X overlaps the T columns of group 0
+          if (has_t) named_bar_sync(2 + quad, 32 * G);  // the warps of a lane quadrant: X overlaps the T columns of the lower groups
           const uint32_t xu = xb ? xuse1 : xuse0;
           if (xu > 0) { warp_mbar_wait(o_full + xb, (xu - 1) & 1, lane, 24); tc_fence_after(); }
-          tmem_st32(tmem + lane_base + kFTmemX + xb * (k2BN / 2) + (uint32_t)(g * 32), pk);
+          if constexpr (kCols == 64) tmem_st32(tmem + lane_base + kFTmemX + xb * (k2BN / 2) + (uint32_t)(g * 32), pk);
+          else tmem_st16(tmem + lane_base + kFTmemX + xb * (k2BN / 2) + (uint32_t)(g * 16), pk);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
@@ -496,14 +508,14 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
       // ---- drain: PV completions arrive in order; the last PV of the item read buffer last_xb
       warp_mbar_wait(o_full + last_xb, ((last_xb ? xuse1 : xuse0) - 1) & 1, lane, 22);
       tc_fence_after();
-      const int c0 = g * 128;
+      const int c0 = g * kCh;
       if (K.out_mode == 0) {
         // dQ: bf16, position-major [N][Lp][C] (contiguous 64-byte pieces per chunk) and channel-major [N][C][Lp]
         // (lanes = consecutive positions).  Padding rows are written as zeros: the GEMMs that follow contract over them.
         unsigned short* ot = K.out_t + ((size_t)n * p.Lp + row) * kC + c0;
         unsigned short* oc = K.out_c + ((size_t)n * kC + c0) * p.Lp + row;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < kCh / 32; ++ch) {
           uint32_t o[32];
           tmem_ld32(tOg + ch * 32, o);
           tmem_ld_wait();
@@ -520,7 +532,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
       } else {
         float* acc = K.acc + ((size_t)n * kC + c0) * p.L + row;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < kCh / 32; ++ch) {
           uint32_t o[32];
           tmem_ld32(tOg + ch * 32, o);
           tmem_ld_wait();

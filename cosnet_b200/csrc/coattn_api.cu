@@ -757,12 +757,18 @@ int launch_flash(cudaStream_t st, const FlashMaps& maps, FlashParams& fp, int sm
   fp.idesc_t = make_idesc_16_major(2 * k2BM, k2BN, true, true, true);
   fp.idesc_t_last = make_idesc_16_major(2 * k2BM, n_last, true, true, true);
   fp.idesc_o = make_idesc_16(2 * k2BM, kC, true);
-  cudaError_t e = cudaFuncSetAttribute(bwd_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes);
+  // X-producer warps per lane quadrant: 2 (8 warps, 64 tile columns per thread).  COATTN_FLASH_G=4 selects the 16-warp
+  // layout of the tuning runs (same arithmetic, identical results): measured SLOWER, 572 vs 540 us for the RGB backward of
+  // 8 pairs at 60x60 -- the chain is bound by the MUFU pipe and the hand-offs, not by the warp count (as in attend2).
+  static const int g_sel = []() { const char* e = getenv("COATTN_FLASH_G"); return (e && e[0] == '4') ? 4 : 2; }();
+  auto kern = g_sel == 2 ? bwd_flash_kernel<2> : bwd_flash_kernel<4>;
+  const int threads = g_sel == 2 ? FlashCfg<2>::kThreads : FlashCfg<4>::kThreads;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes);
   if (e != cudaSuccess) return (int)e;
   int clusters = sms / 2;
   if (fp.items[0] + fp.items[1] < clusters) clusters = fp.items[0] + fp.items[1];
   if (clusters < 1) return COATTN_OK;
-  bwd_flash_kernel<<<2 * clusters, kFThreads, kFSmemBytes, st>>>(maps, fp);
+  kern<<<2 * clusters, threads, kFSmemBytes, st>>>(maps, fp);
 #ifdef COATTN_TRACE_FLASH
   {
     static int calls = 0;
