@@ -233,8 +233,10 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
  *   outputs  d_v_a [N,256,H,W], d_w [256,256] (16-byte aligned, else COATTN_E_ALIGN), d_gate_w [256], d_gate_b [1]
  *            (may be NULL); all overwritten
  *            d_v_b [N,256,H,W] or NULL: gradient for the counterpart frame, only needed with
- *            no_grad_for_counterpart=False (:147-148); costs two more [L,L] transposes, two GEMMs, a second
- *            projection and the larger workspace (`counterpart` = 1 in the size query).
+ *            no_grad_for_counterpart=False (:147-148); costs a second flash sweep with the roles of the frames swapped
+ *            and a bf16 projection.  `counterpart` in the size query is kept for ABI stability and ignored.
+ * Nothing of size L x L exists in the workspace: S, dP_a and dP_b are recomputed per 256 x 128 tile in TMEM
+ * (csrc/bwd_flash_kernel.cuh); the scratch is 16-bit planes [N][256][round_up(L, 256)] and a few vectors, linear in L.
  */
 int64_t coattn_backward_workspace_bytes(int n, int c, int h, int w, int counterpart);
 int coattn_backward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* z,
