@@ -26,6 +26,7 @@ FLAG_GATED_ONLY = 32  # COATTN_FLAG_GATED_ONLY
 FLAG_KMAJOR = 64  # COATTN_FLAG_KMAJOR
 FLAG_SOFTMAX16 = 128  # COATTN_FLAG_SOFTMAX16
 FLAG_SPLIT_KEYS = 256  # COATTN_FLAG_SPLIT_KEYS
+FLAG_PLANES_READY = 512  # COATTN_FLAG_PLANES_READY
 STATUS_WORDS = 8  # COATTN_STATUS_WORDS
 STATUS_OVERFLOW_B, STATUS_OVERFLOW_A, STATUS_OVERFLOW_Q = 1, 2, 4
 
@@ -43,6 +44,7 @@ SIGNATURES = {
     "coattn_stage_prep": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_project": (_i, [_vp, _i64, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_prep_project": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),
+    "coattn_stage_tail": (_i, [_vp] * 6 + [_i64, _i, _i, _i, _i, _i, _u, _vp]),
     "coattn_forward_queries": (_i, [_vp] * 7 + [_i64, _i, _i, _i, _i, _i, _u, _vp]),
     "coattn_forward16": (_i, [_vp] * 10 + [_i64, _i, _i, _i, _i, _i, _u, _vp]),
     "coattn_stage_attend": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _u, _vp]),

@@ -151,13 +151,18 @@ class ASPP(nn.Module):
         self.prelu = nn.PReLU()
         init_reference_style(self)
 
-    def forward(self, x):
+    def pre_tail(self, x):
+        """Everything up to and including the 3x3 bottleneck conv; `forward` = prelu(bn(pre_tail(x))).  The drop-in model's
+        eval path hands this to the fused tail kernel (BN + PReLU + 16-bit operand cast, cosnet_b200.coattention.encoder_tail)."""
         size = x.shape[2:]
         pooled = self.relu(self.bn_x(self.conv(self.mean(x))))
         branches = [_bilinear(pooled, size, align_corners=True)]
         for i in range(4):
             branches.append(self.relu(getattr(self, f"bn_{i}")(getattr(self, f"conv2d_{i}")(x))))
-        return self.prelu(self.bn(self.bottleneck(torch.cat(branches, 1))))
+        return self.bottleneck(torch.cat(branches, 1))
+
+    def forward(self, x):
+        return self.prelu(self.bn(self.pre_tail(x)))
 
 
 class Encoder(nn.Module):

@@ -33,7 +33,9 @@ class _Workspace:
         off = self.ptr - self.buf.data_ptr()
         self.status = self.buf[off:off + 4 * _lib.STATUS_WORDS].view(torch.int32)
         self.status.zero_()
-        self.host = torch.zeros(_lib.STATUS_WORDS, dtype=torch.int32).pin_memory()
+        # no pinned host mirror for a buffer created inside a CUDA-graph capture (host allocations are not capturable; the
+        # status of graphed calls is read with check_overflow-style synchronous reads by whoever owns the graph)
+        self.host = None if torch.cuda.is_current_stream_capturing() else torch.zeros(_lib.STATUS_WORDS, dtype=torch.int32).pin_memory()
         self.event = None
 
     def numel(self):
@@ -41,7 +43,7 @@ class _Workspace:
 
     def post_call(self, stream):
         """Queue the status read-back of the call just issued on `stream` (lazy / sync modes)."""
-        if OVERFLOW_CHECK == "off" or torch.cuda.is_current_stream_capturing():
+        if OVERFLOW_CHECK == "off" or self.host is None or torch.cuda.is_current_stream_capturing():
             return
         self.host.copy_(self.status, non_blocking=True)
         self.event = torch.cuda.Event()
@@ -76,12 +78,36 @@ def workspace_bytes(n: int, c: int, h: int, w: int) -> int:
     return int(r)
 
 
-def _workspace_entry(device: torch.device, nbytes: int) -> _Workspace:
+_capture_local = threading.local()
+
+
+class capture_scope:
+    """Context for capturing calls of this module into a CUDA graph: workspaces that must be SHARED between calls (the
+    tagged ones: `encoder_tail` writes the operand planes, `coattention_planes_ready` reads them) are kept in a cache that
+    lives exactly as long as the scope's owner keeps it -- never in the eager cache, whose buffers must not come from a
+    graph's private pool."""
+
+    def __enter__(self):
+        self.cache = {}
+        _capture_local.cache = self.cache
+        return self.cache
+
+    def __exit__(self, *exc):
+        _capture_local.cache = None
+
+
+def _workspace_entry(device: torch.device, nbytes: int, tag=None) -> _Workspace:
     if torch.cuda.is_current_stream_capturing():
         # a buffer allocated during capture lives in the graph's private pool: never cache it for eager use
-        return _Workspace(device, nbytes)
+        scope = getattr(_capture_local, "cache", None)
+        if scope is None or tag is None:
+            return _Workspace(device, nbytes)
+        ent = scope.get(tag)
+        if ent is None or ent.numel() < nbytes + 1024:
+            ent = scope[tag] = _Workspace(device, nbytes)
+        return ent
     key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
+           torch.cuda.current_stream(device).cuda_stream, threading.get_ident(), tag)
     with _ws_lock:
         ent = _ws_cache.get(key)
     if ent is not None:
@@ -276,6 +302,62 @@ def coattention_forward16_raw(v_a, v_b, weight, gate_weight, gate_bias=None, ref
             ws.post_call(torch.cuda.current_stream(dev))
     if want_lse:
         return cat_a, cat_b, lse, mask
+    return cat_a, cat_b
+
+
+def bn_eval_affine(bn: torch.nn.BatchNorm2d):
+    """Eval-mode BatchNorm as y = x * scale + shift (running statistics)."""
+    scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+    shift = bn.bias.detach() - bn.running_mean * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+def encoder_tail(x, scale, shift, slope, frame: int, tag, bf16_operands=False, want_features=True):
+    """Producer side of the hot path (deeplab/deeplabv3_encoder.py:80-82), inference only:
+    features = PReLU(BN_eval(x)) for the bottleneck-conv output x [N, 256, H, W], fused with the co-attention's operand
+    cast: ONE kernel writes the fp32 features (returned; None with want_features=False) and the 16-bit operand plane of
+    frame A (frame=0) or B (frame=1) into the workspace tagged `tag`; `coattention_planes_ready(..., tag=tag)` then starts
+    at the projection.  Both frames of a pair batch must go through this before that call, on the same stream."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4:
+        raise _lib.CoattnError("encoder_tail needs a CUDA fp32 [N, 256, H, W] tensor; there is no CPU fallback")
+    n, c, h, w = x.shape
+    lib = _lib.load()
+    dev = x.device
+    with torch.cuda.device(dev):
+        x = x.contiguous()
+        y = torch.empty_like(x) if want_features else None
+        nbytes = workspace_bytes(n, c, h, w)
+        ws = _workspace_entry(dev, nbytes, tag=tag)
+        code = lib.coattn_stage_tail(x.data_ptr(), scale.data_ptr(), shift.data_ptr(), slope.detach().float().contiguous().data_ptr(),
+                                     None if y is None else y.data_ptr(), ws.ptr, nbytes, frame, n, c, h, w,
+                                     _lib.FLAG_BF16 if bf16_operands else 0, torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(code, "coattn_stage_tail")
+    return y
+
+
+def coattention_planes_ready(v_a, v_b, weight, gate_weight, gate_bias, tag, bf16_operands=False, gated_only=False):
+    """`coattention` for features whose 16-bit operand planes were already written by `encoder_tail(..., tag=tag)`:
+    no cast kernel.  v_a / v_b (fp32) are only read for the passthrough half of the concat (not at all with gated_only)."""
+    n, c, h, w = _check_inputs(v_a, v_b, weight, gate_weight, gate_bias)
+    lib = _lib.load()
+    dev = v_a.device
+    with torch.cuda.device(dev):
+        wt = weight.detach().float().contiguous()
+        gw = gate_weight.detach().float().contiguous().view(-1)
+        gb = None if gate_bias is None else gate_bias.detach().float().contiguous().view(-1)
+        oc = c if gated_only else 2 * c
+        cat_a = torch.empty((n, oc, h, w), dtype=torch.float32, device=dev)
+        cat_b = torch.empty((n, oc, h, w), dtype=torch.float32, device=dev)
+        nbytes = workspace_bytes(n, c, h, w)
+        ws = _workspace_entry(dev, nbytes, tag=tag)
+        cur = torch.cuda.current_stream(dev)
+        flags = _lib.FLAG_PLANES_READY | (_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0)
+        code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
+                                  None if gb is None else gb.data_ptr(), cat_a.data_ptr(), cat_b.data_ptr(), None, None, None,
+                                  ws.ptr, nbytes, n, c, h, w, flags, cur.cuda_stream)
+        _lib.check(code, "coattn_forward")
+        if not bf16_operands:
+            ws.post_call(cur)
     return cat_a, cat_b
 
 

@@ -277,8 +277,8 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   if (in16 == 1) {
     if (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 3) == 0) pad16_kernel<true><<<cgrid, 256, 0, st>>>(cp);
     else pad16_kernel<false><<<cgrid, 256, 0, st>>>(cp);
-  } else if (in16 == 2) {
-    // in place
+  } else if (in16 == 2 || in16 == 3) {
+    // 2: 16-bit features consumed in place; 3: the planes were already written by coattn_stage_tail
   } else if (bf16) {
     if (vec) cast_kernel<true, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<true, 1><<<cgrid, 256, 0, st>>>(cp);
   } else {
@@ -320,8 +320,34 @@ static int cast_and_project_mn(const float* v_a, const float* v_b, const float* 
   if (int e = check_arch(nullptr)) return e;
   return cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
                            reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
-                           (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), -1, 0,
+                           (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), -1,
+                           (flags & COATTN_FLAG_PLANES_READY) ? 3 : 0,
                            reinterpret_cast<unsigned*>(seg(workspace, ly.off_status)));
+}
+
+extern "C" int coattn_stage_tail(const float* x, const float* scale, const float* shift, const float* slope, float* y,
+                                 void* workspace, int64_t workspace_bytes, int frame, int n, int c, int h, int w_,
+                                 unsigned flags, void* stream) {
+  if (!x || !scale || !shift || !slope) return COATTN_E_NULL;
+  if (frame != 0 && frame != 1) return COATTN_E_SHAPE;
+  if (int e = check_dims(n, c, h, w_)) return e;
+  const Layout ly = make_layout(n, h, w_);
+  if (int e = check_workspace(workspace, workspace_bytes, ly)) return e;
+  if (int e = check_arch(nullptr)) return e;
+  TailParams p;
+  p.x = x; p.scale = scale; p.shift = shift; p.slope = slope; p.y = y;
+  // planes X = [B16, A16, Q16]: frame A (0) -> plane 1, frame B (1) -> plane 0
+  p.plane = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)) + (frame == 0 ? ly.t_pass_elems() : 0);
+  p.L = ly.L; p.Lp = ly.Lp;
+  p.status = reinterpret_cast<unsigned*>(seg(workspace, ly.off_status));
+  p.status_plane = frame == 0 ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0);
+  const bool bf16 = (flags & COATTN_FLAG_BF16) != 0;
+  const dim3 grid(n * kC);
+  if (bf16) { if (vec) aspp_tail_kernel<true, 4><<<grid, 256, 0, st>>>(p); else aspp_tail_kernel<true, 1><<<grid, 256, 0, st>>>(p); }
+  else      { if (vec) aspp_tail_kernel<false, 4><<<grid, 256, 0, st>>>(p); else aspp_tail_kernel<false, 1><<<grid, 256, 0, st>>>(p); }
+  return (int)cudaGetLastError();
 }
 
 extern "C" int coattn_stage_prep_project(const float* v_a, const float* v_b, const float* w, void* workspace,
@@ -673,6 +699,8 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
   if (!v_a || !v_b || !w || !gate_w || !cat_a) return COATTN_E_NULL;
   if (!cat_b && !(flags & COATTN_FLAG_A_ONLY)) return COATTN_E_NULL;
   if ((flags & (COATTN_FLAG_A_ONLY | COATTN_FLAG_GATED_ONLY)) && (flags & (COATTN_FLAG_UNFUSED_GATE | COATTN_FLAG_SINGLE_CTA)))
+    return COATTN_E_UNSUPPORTED;
+  if ((flags & COATTN_FLAG_PLANES_READY) && (flags & (COATTN_FLAG_KMAJOR | COATTN_FLAG_SINGLE_CTA | COATTN_FLAG_UNFUSED_PREP)))
     return COATTN_E_UNSUPPORTED;
   if (int e = check_dims(n, c, h, w_)) return e;
   const Layout ly = make_layout(n, h, w_);

@@ -467,6 +467,64 @@ __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
   }
 }
 
+// Producer side of the hot path (deeplab/deeplabv3_encoder.py:80-82): the ASPP tail
+//   features = PReLU(BatchNorm_eval(bottleneck_conv_output))
+// fused with the operand cast: ONE pass reads the conv output and writes the fp32 features (the concat's passthrough half,
+// the auxiliary classifier and the reduce conv still want them) AND the zero-padded 16-bit plane of the workspace that
+// project_mn / attend2 read -- the cast kernel and the two eager elementwise kernels (BN, PReLU) disappear.
+//   y = x * scale[c] + shift[c]   (scale = gamma / sqrt(var + eps), shift = beta - mean * scale: eval-mode BN)
+//   y = y >= 0 ? y : slope * y    (nn.PReLU() with its single parameter)
+struct TailParams {
+  const float* x;        // [N][C][L] bottleneck conv output (bias included)
+  const float* scale;    // [C]
+  const float* shift;    // [C]
+  const float* slope;    // [1]
+  float* y;              // [N][C][L] fp32 features, or null
+  unsigned short* plane; // [N][C][Lp] 16-bit operand plane of this frame
+  int L, Lp;
+  unsigned* status;      // status block or null (fp16 range guard, as in cast_kernel)
+  int status_plane;      // 0: V_b, 1: V_a
+};
+
+template <bool BF16, int VEC>
+__global__ void __launch_bounds__(256) aspp_tail_kernel(TailParams p) {
+  const int row = blockIdx.x;                 // n * C + c
+  const int c = row % kC;
+  const float sc = __ldg(p.scale + c), sh = __ldg(p.shift + c), a = __ldg(p.slope);
+  const float* src = p.x + (size_t)row * p.L;
+  float* dstf = p.y ? p.y + (size_t)row * p.L : nullptr;
+  unsigned short* dst = p.plane + (size_t)row * p.Lp;
+  float amax = 0.f;
+  bool nan = false;
+  auto act = [&](float v) { const float t = fmaf(v, sc, sh); return t >= 0.f ? t : a * t; };
+  if constexpr (VEC == 4) {
+    for (int i = threadIdx.x * 4; i < p.Lp; i += 256 * 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < p.L) {                          // L % 4 == 0
+        const float4 x = __ldcs(reinterpret_cast<const float4*>(src + i));
+        v = make_float4(act(x.x), act(x.y), act(x.z), act(x.w));
+        if (dstf) *reinterpret_cast<float4*>(dstf + i) = v;
+      }
+      *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack16x2<BF16>(v.x, v.y), pack16x2<BF16>(v.z, v.w));
+      if constexpr (!BF16) {
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x * 2; i < p.Lp; i += 256 * 2) {
+      const float v0 = (i < p.L) ? act(__ldcs(src + i)) : 0.f;
+      const float v1 = (i + 1 < p.L) ? act(__ldcs(src + i + 1)) : 0.f;
+      if (dstf) { if (i < p.L) dstf[i] = v0; if (i + 1 < p.L) dstf[i + 1] = v1; }
+      *reinterpret_cast<uint32_t*>(dst + i) = pack16x2<BF16>(v0, v1);
+      if constexpr (!BF16) { amax = fmaxf(amax, fmaxf(fabsf(v0), fabsf(v1))); nan |= (v0 != v0) | (v1 != v1); }
+    }
+  }
+  if constexpr (!BF16) {
+    if (p.status != nullptr) report_absmax(amax, nan, p.status, p.status_plane);
+  }
+}
+
 // 16-bit features (coattn_forward16) whose rows cannot be read by TMA directly (L % 8 != 0 or a base pointer that is
 // not 16-byte aligned): copied into the same zero-padded planes the cast writes.  CastParams::va / vb then point to
 // 16-bit data.  Only the fallback of that entry point; aligned 16-bit features are consumed in place.

@@ -13,7 +13,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .backbone import DepthEncoder_ResNetASPP, Encoder, init_reference_style
-from .coattention import coattention, modality_overlap_pays, run_modalities
+from .coattention import (bn_eval_affine, coattention, coattention_planes_ready, encoder_tail, modality_overlap_pays,
+                          run_modalities)
 
 # legacy checkpoint prefixes -> current names (rgbd_segmentation_RAA.py:114-133); first match wins,
 # "encoder.main_classifier" must be tested before the generic "encoder." rule
@@ -81,6 +82,13 @@ class RGBDSegmentation_RAA(nn.Module):
         # eval-mode forward under no_grad: run the RGB and the depth co-attention on two CUDA streams when that needs fewer
         # waves of the attend kernel (None = decide from the batch shape, True / False = force).  Bit-identical outputs.
         self.overlap_modalities = None
+        # eval-mode forward under no_grad: the encoder tails (BN + PReLU) are fused with the
+        # co-attention's 16-bit operand cast into one kernel each, the operators return the gated halves only, and the
+        # reduce convs run in two halves with their BatchNorm (and the depth branch's 1x1 weighting) folded into the conv
+        # weights -- no concat, no cast kernel, no stand-alone BN / PReLU launches around the hot path.  Same parameters
+        # and state_dict; outputs equal the plain path to fp32 rounding (~1e-6).
+        self.fuse_eval_path = True
+        self._folded = {}
 
     # ------------------------------------------------------------------ optimiser groups (:65-100)
     def get_params(self, subset="none"):
@@ -134,9 +142,72 @@ class RGBDSegmentation_RAA(nn.Module):
         return (F.conv2d(gated, w[:, :c], None, conv.stride, conv.padding, conv.dilation) +
                 F.conv2d(passthrough, w[:, c:], conv.bias, conv.stride, conv.padding, conv.dilation))
 
+    def _folded_reduce(self, name, conv, bn, pointwise=None):
+        """(weight [C, 2C, 3, 3], bias [C]) of conv -> BN_eval (-> 1x1 `pointwise` conv) as ONE convolution.  Cached until a
+        parameter or a running statistic changes."""
+        deps = [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var] + (
+            [pointwise.weight, pointwise.bias] if pointwise is not None else [])
+        key = tuple((t.data_ptr(), t._version) for t in deps)
+        hit = self._folded.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        with torch.no_grad():
+            scale, shift = bn_eval_affine(bn)
+            w = conv.weight * scale.view(-1, 1, 1, 1)
+            b = shift if conv.bias is None else shift + conv.bias * scale
+            if pointwise is not None:       # y = P (conv(x) * scale + shift) + p  is linear in conv's weights
+                pw = pointwise.weight.view(pointwise.out_channels, pointwise.in_channels)
+                w = torch.einsum("om,mikl->oikl", pw, w).contiguous()
+                b = pw @ b + pointwise.bias
+        self._folded[name] = (key, w, b)
+        return w, b
+
+    @staticmethod
+    def _split_conv_folded(w, b, conv, gated, passthrough):
+        c = gated.shape[1]
+        return (F.conv2d(gated, w[:, :c], None, conv.stride, conv.padding, conv.dilation) +
+                F.conv2d(passthrough, w[:, c:], b, conv.stride, conv.padding, conv.dilation))
+
+    def _encode_pair_fused(self, enc, x_a, x_b, returns_tuple, tag):
+        """Eval-mode encoders whose ASPP tail runs in the fused kernel: returns (V_a, V_b, labels) like `_encode_pair`, and
+        leaves the 16-bit operand planes of both frames in the workspace tagged `tag`."""
+        aspp = enc.aspp
+        scale, shift = bn_eval_affine(aspp.bn)
+        v_a = encoder_tail(aspp.pre_tail(enc.backbone(x_a)), scale, shift, aspp.prelu.weight, 0, tag)
+        v_b = encoder_tail(aspp.pre_tail(enc.backbone(x_b)), scale, shift, aspp.prelu.weight, 1, tag)
+        labels = None
+        if returns_tuple:       # the auxiliary map that survives is frame B's (:143, :146/148)
+            labels = enc.softmax(F.interpolate(enc.main_classifier(v_b), size=x_b.shape[2:], mode="bilinear"))
+        return v_a, v_b, labels
+
+    def _forward_eval_fused(self, rgbs_a, rgbs_b, depths_a, depths_b):
+        input_size = rgbs_a.shape[2:]
+        v_a, v_b, labels = self._encode_pair_fused(self.encoder, rgbs_a, rgbs_b, True, "rgb")
+        d_a, d_b, _ = self._encode_pair_fused(self.depth_encoder, depths_a, depths_b, False, "depth")
+        r_a, r_b = coattention_planes_ready(v_a, v_b, self.rgb_similarity_weights.weight, self.gate.weight, None, "rgb",
+                                            gated_only=True)
+        q_a, q_b = coattention_planes_ready(d_a, d_b, self.depth_similarity_weights.weight, self.depth_gate.weight,
+                                            self.depth_gate.bias, "depth", gated_only=True)
+        wa, ba = self._folded_reduce("A", self.reduce_channels_A, self.bn_A)
+        wb, bb = self._folded_reduce("B", self.reduce_channels_B, self.bn_B)
+        wd, bd = self._folded_reduce("D", self.depth_reduce_channels, self.depth_bn, self.depth_weights)
+        z_a = self._split_conv_folded(wa, ba, self.reduce_channels_A, r_a, v_a)            # :188, :190
+        z_b = self._split_conv_folded(wb, bb, self.reduce_channels_B, r_b, v_b)            # :189, :191
+        dz_a = self._split_conv_folded(wd, bd, self.depth_reduce_channels, q_a, d_a)       # :239, :242, :245
+        dz_b = self._split_conv_folded(wd, bd, self.depth_reduce_channels, q_b, d_b)       # :240-247
+        z_a = self.prelu(z_a + dz_a)                            # :251, :256
+        z_b = self.prelu(z_b + dz_b)                            # :252, :257
+        x1 = self.softmax(F.interpolate(self.segmentation_classifier_A(z_a), input_size, mode="bilinear"))  # :260-265
+        x2 = self.softmax(F.interpolate(self.segmentation_classifier_B(z_b), input_size, mode="bilinear"))
+        return x1, x2, labels
+
     def _forward_eval(self, rgbs_a, rgbs_b, depths_a, depths_b):
         """Inference (eval mode, no autograd): the same operators as `forward`, with both encoders evaluated first so that
         the two co-attention calls -- independent of each other -- can share the GPU (`run_modalities`)."""
+        if (self.fuse_eval_path and rgbs_a.dtype == torch.float32 and hasattr(self.encoder, "aspp")
+                and hasattr(self.depth_encoder, "aspp") and self.encoder.aspp.prelu.weight.numel() == 1
+                and self.depth_encoder.aspp.prelu.weight.numel() == 1):
+            return self._forward_eval_fused(rgbs_a, rgbs_b, depths_a, depths_b)
         input_size = rgbs_a.shape[2:]
         v_a, v_b, labels = self._encode_pair(self.encoder, rgbs_a, rgbs_b, True)
         d_a, d_b, _ = self._encode_pair(self.depth_encoder, depths_a, depths_b, False)

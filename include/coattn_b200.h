@@ -113,6 +113,14 @@ enum {
 #define COATTN_FLAG_SPLIT_KEYS 256u
 
 /*
+ *   COATTN_FLAG_PLANES_READY  the 16-bit operand planes of V_a and V_b in the workspace were already written by
+ *                          coattn_stage_tail (the fused encoder tail, below): coattn_forward / coattn_stage_prep_project skip
+ *                          their cast kernel.  v_a / v_b are still read for the passthrough half of the concat.
+ *                          Default (channel-major) path only.
+ */
+#define COATTN_FLAG_PLANES_READY 512u
+
+/*
  * Status block: the first COATTN_STATUS_WORDS 32-bit words of every workspace.  With fp16 operands (the default) the
  * fp32 -> fp16 conversions of the features and of Q = W V_a clamp at +-65504; instead of clipping silently the kernels
  * record it here (sticky bits; the library never clears them -- coattn_status_clear, or zero the words yourself):
@@ -185,6 +193,23 @@ int coattn_forward_queries(const float* v_a, const float* v_b, const float* w, c
 int coattn_forward16(const void* v_a, const void* v_b, const float* w, const float* gate_w, const float* gate_b,
                      void* cat_a, void* cat_b, float* lse, float* mask, void* workspace, int64_t workspace_bytes,
                      int nq, int refs, int c, int h, int w_, unsigned flags, void* stream);
+
+/*
+ * Producer side: the tail of the ASPP encoder head, deeplab/deeplabv3_encoder.py:80-82,
+ *     features = PReLU(BatchNorm(bottleneck(x)))         in eval mode (BN with running statistics),
+ * fused with the 16-bit operand cast of the co-attention that consumes the features:
+ *   x      [N, 256, H, W]  output of the 3x3 bottleneck conv (bias included)
+ *   scale, shift [256]     eval-mode BN as an affine map: gamma / sqrt(var + eps), beta - mean * scale
+ *   slope  [1]             the PReLU parameter
+ *   y      [N, 256, H, W]  fp32 features (what the reference's encoder returns), or NULL if nobody needs them
+ *   frame  0: these are frame A's features (V_a), 1: frame B's (V_b)
+ * and writes the zero-padded 16-bit plane of that frame into `workspace` (laid out for n pairs, as coattn_forward
+ * expects); a following coattn_forward(..., COATTN_FLAG_PLANES_READY) with the same workspace, n and operand format
+ * starts at the projection.  One HBM pass instead of four (BN, PReLU, and the cast's read + write).
+ */
+int coattn_stage_tail(const float* x, const float* scale, const float* shift, const float* slope, float* y,
+                      void* workspace, int64_t workspace_bytes, int frame, int n, int c, int h, int w_,
+                      unsigned flags, void* stream);
 
 /* ---- the four stages, exported individually for unit parity tests and per-kernel timing ---- */
 

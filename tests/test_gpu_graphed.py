@@ -71,3 +71,24 @@ def test_graph_replay_grouped_queries(dtype):
         wa = coattention_forward16_raw(va, vb, *rgb, refs=r)[0]
         wd = coattention_forward16_raw(da, db, *depth, refs=r)[0]
     assert torch.equal(cat_a, wa) and torch.equal(dcat_a, wd)
+
+
+def test_whole_model_eval_graph_matches_eager():
+    """GraphedEvalModel: the drop-in model's eval forward (fused tails, planes-ready operators, folded reduce convs) captured
+    once and replayed on new inputs equals the eager forward."""
+    from cosnet_b200.backbone import Bottleneck
+    from cosnet_b200.graphed import GraphedEvalModel
+    from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
+    dev = torch.device("cuda:0")
+    torch.manual_seed(21)
+    model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).to(dev).eval()
+    mk = lambda c: torch.randn(1, c, 97, 97, device=dev)
+    gm = GraphedEvalModel(model, mk(3), mk(3), mk(1), mk(1))
+    for _ in range(2):
+        x = (mk(3), mk(3), mk(1), mk(1))
+        got = [t.clone() for t in gm(*x)]
+        with torch.no_grad():
+            want = model(*x)
+        torch.cuda.synchronize()
+        for a, b in zip(got, want):
+            assert torch.isfinite(a).all() and (a - b).abs().max().item() < 1e-5

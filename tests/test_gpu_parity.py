@@ -599,3 +599,58 @@ def test_grouped_queries_equal_repeated_queries(op, q, refs, h, w, gated):
     got = coattention_queries_raw(v_a, v_b, W, g, b, refs=refs, gated_only=gated)
     torch.cuda.synchronize()
     assert got.shape == want.shape and torch.equal(got, want)
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 12, 11), (1, 60, 60), (1, 31, 41)])
+def test_fused_encoder_tail_and_planes_ready(op, n, h, w):
+    """SURVEY.md 8f row N4 (producer side): coattn_stage_tail = PReLU(BN_eval(x)) + the 16-bit operand cast in one kernel.
+    Its fp32 features equal torch's to rounding, and the co-attention started from its planes (COATTN_FLAG_PLANES_READY)
+    equals the ordinary call on those features BIT FOR BIT (the plane is the cast of the same fp32 values)."""
+    from cosnet_b200.coattention import bn_eval_affine, coattention_planes_ready, encoder_tail
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    bn = torch.nn.BatchNorm2d(C).to(dev).eval()
+    bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.normal_(1, 0.2); bn.bias.data.normal_(0, 0.3)
+    prelu = torch.nn.PReLU().to(dev)
+    xa, xb = torch.randn(n, C, h, w, device=dev), torch.randn(n, C, h, w, device=dev)
+    W, g, b = (torch.from_numpy(t).to(dev) for t in orc.synthetic_weights(21, bias=True))
+    scale, shift = bn_eval_affine(bn)
+    with torch.no_grad():
+        v_a = encoder_tail(xa, scale, shift, prelu.weight, 0, "t")
+        v_b = encoder_tail(xb, scale, shift, prelu.weight, 1, "t")
+        assert (v_a - prelu(bn(xa))).abs().max() < 2e-6 and (v_b - prelu(bn(xb))).abs().max() < 2e-6
+        for gated in (False, True):
+            got = coattention_planes_ready(v_a, v_b, W, g, b, "t", gated_only=gated)
+            want = op(v_a, v_b, W, g, b, want_z=False, gated_only=gated)
+            torch.cuda.synchronize()
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        # features are not needed by a gated-only consumer that keeps them elsewhere: planes only
+        assert encoder_tail(xa, scale, shift, prelu.weight, 0, "t2", want_features=False) is None
+
+
+def test_fused_eval_path_matches_plain_eval_path(op):
+    """The drop-in model's eval forward with the fused tail + planes-ready operators + folded split reduce convs (rows N3 /
+    N4) against the same model with fuse_eval_path = False: same parameters, outputs equal to fp32 rounding."""
+    from cosnet_b200.backbone import Bottleneck
+    from cosnet_b200.rgbd_segmentation_raa import RGBDSegmentation_RAA
+    dev = torch.device("cuda:0")
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(11)
+        model = RGBDSegmentation_RAA(Bottleneck, [1, 1, 1, 1], [1, 1, 1, 1], num_classes=1).to(dev).eval()
+        for m in model.modules():           # non-trivial running statistics everywhere
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.05); m.running_var.uniform_(0.8, 1.2)
+        x = torch.randn(2, 3, 97, 129, device=dev); d = torch.randn(2, 1, 97, 129, device=dev)
+        with torch.no_grad():
+            model.fuse_eval_path = True
+            got = model(x, x.flip(0), d, d.flip(0))
+            model.fuse_eval_path = False
+            want = model(x, x.flip(0), d, d.flip(0))
+        for a, b_ in zip(got, want):
+            assert a.shape == b_.shape
+            assert (a - b_).abs().max().item() < 2e-5, (a - b_).abs().max().item()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32

@@ -210,3 +210,35 @@ def test_train_mode_forward_backward_matches_reference(frozen):
         assert (pr.grad is None) == (pm.grad is None), k
         if pr.grad is not None:
             assert float((pr.grad - pm.grad).norm()) <= 2e-3 * float(pr.grad.norm()) + 1e-5 * top, k
+
+
+def test_bn_and_pointwise_fold_equal_the_unfused_operators():
+    """SURVEY.md 8f row N3 (second half): conv -> BN_eval (-> 1x1 conv) evaluated as ONE split convolution with folded
+    weights equals the reference's operator sequence (rgbd_segmentation_RAA.py:188-191, :239-247)."""
+    torch.manual_seed(0)
+    m = small_model().eval()
+    for bn in (m.bn_A, m.bn_B, m.depth_bn):
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.normal_(1, 0.1); bn.bias.data.normal_()
+    g, v = torch.randn(2, 256, 9, 7), torch.randn(2, 256, 9, 7)
+    with torch.no_grad():
+        want = m.bn_A(m.reduce_channels_A(torch.cat([g, v], 1)))
+        got = m._split_conv_folded(*m._folded_reduce("A", m.reduce_channels_A, m.bn_A), m.reduce_channels_A, g, v)
+        assert (want - got).abs().max() < 1e-5
+        want = m.depth_weights(m.depth_bn(m.depth_reduce_channels(torch.cat([g, v], 1))))
+        got = m._split_conv_folded(*m._folded_reduce("D", m.depth_reduce_channels, m.depth_bn, m.depth_weights),
+                                   m.depth_reduce_channels, g, v)
+        assert (want - got).abs().max() < 1e-5
+        # the cache follows parameter updates
+        w0, _ = m._folded_reduce("A", m.reduce_channels_A, m.bn_A)
+        m.bn_A.weight.mul_(2.0)
+        w1, _ = m._folded_reduce("A", m.reduce_channels_A, m.bn_A)
+        assert torch.allclose(w1, 2.0 * w0)
+
+
+def test_aspp_pre_tail_composes_to_forward():
+    from cosnet_b200.backbone import ASPP
+    torch.manual_seed(1)
+    aspp = ASPP(64, 256, 32, [2, 3, 7], [2, 3, 7]).eval()
+    x = torch.randn(1, 64, 9, 11)
+    with torch.no_grad():
+        assert torch.equal(aspp(x), aspp.prelu(aspp.bn(aspp.pre_tail(x))))

@@ -85,6 +85,28 @@ def main():
             row[name] = {"ms_per_forward": ms, "ms_per_frame_pair": ms / n, "peak_gib": gib}
         print(json.dumps(row), flush=True)
 
+    # the whole eval forward as one CUDA graph (cosnet_b200.graphed.GraphedEvalModel): what the host-bound batch-1 case costs
+    # once the ~700 launches are replayed instead of issued
+    from cosnet_b200.graphed import GraphedEvalModel
+    model.coattention_impl = coattention
+    for n in args.batch:
+        x = inputs(n)
+        row = {"workload": "model_probe", "mode": "eval forward, whole-model CUDA graph", "pairs": n, "input": [s, s]}
+        for fuse in (True, False):
+            model.fuse_eval_path = fuse
+            gm = GraphedEvalModel(model, *x)
+            with torch.no_grad():
+                want = model(*x)
+            got = gm(*x)
+            torch.cuda.synchronize()
+            err = max(float((a - b).abs().max()) for a, b in zip(got, want))
+            ms, gib = timed(lambda: gm(*x), 3, args.steps)
+            row["fused_eval_path" if fuse else "plain_eval_path"] = {"ms_per_forward": ms, "ms_per_frame_pair": ms / n,
+                                                                      "max_abs_diff_vs_eager": err}
+            del gm
+        model.fuse_eval_path = True
+        print(json.dumps(row), flush=True)
+
     # the same model in half precision (`model.half()`): fp16 encoders on cuDNN hand fp16 features to coattn_forward16
     import copy
     half = copy.deepcopy(model).half().eval()
