@@ -27,6 +27,7 @@ FLAG_KMAJOR = 64  # COATTN_FLAG_KMAJOR
 FLAG_SOFTMAX16 = 128  # COATTN_FLAG_SOFTMAX16
 FLAG_SPLIT_KEYS = 256  # COATTN_FLAG_SPLIT_KEYS
 FLAG_PLANES_READY = 512  # COATTN_FLAG_PLANES_READY
+FLAG_UNFOLDED = 1024  # COATTN_FLAG_UNFOLDED
 STATUS_WORDS = 8  # COATTN_STATUS_WORDS
 STATUS_OVERFLOW_B, STATUS_OVERFLOW_A, STATUS_OVERFLOW_Q = 1, 2, 4
 

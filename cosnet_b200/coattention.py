@@ -171,12 +171,13 @@ def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
 
 def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False,
                             unfused_gate=False, want_mask=False, want_z=True, single_cta=False, a_only=False, unfused_prep=False, gated_only=False, kmajor=False,
-                            softmax16=False, split_keys=False):
+                            softmax16=False, split_keys=False, unfolded=False):
     """Runs the CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L]
     (plus mask [2,N,L] when want_mask=True; fused path only).
 
     bf16_operands=False (default): fp16 tensor-core operands with fp32 accumulation (COATTN_FLAG_BF16 unset);
     True: bf16 operands (see include/coattn_b200.h for the trade-off).
+    unfolded=True: COATTN_FLAG_UNFOLDED, Q = W V_a by the stand-alone projection kernel instead of inside the attend kernel.
     split_keys=True: COATTN_FLAG_SPLIT_KEYS, the latency mode for one or two pairs (key range of every item swept in parts
     by different CTA pairs + a merge kernel; equal to the default path to fp32 rounding, not bit for bit).
     """
@@ -202,7 +203,7 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)
                  | (_lib.FLAG_SINGLE_CTA if single_cta else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
                  | (_lib.FLAG_UNFUSED_PREP if unfused_prep else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0) | (_lib.FLAG_KMAJOR if kmajor else 0) | (_lib.FLAG_SOFTMAX16 if softmax16 else 0)
-                 | (_lib.FLAG_SPLIT_KEYS if split_keys else 0))
+                 | (_lib.FLAG_SPLIT_KEYS if split_keys else 0) | (_lib.FLAG_UNFOLDED if unfolded else 0))
         code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
                                   None if gb is None else gb.data_ptr(), cat_a.data_ptr(),
                                   None if cat_b is None else cat_b.data_ptr(),
@@ -547,9 +548,9 @@ class HostPipeline:
                 self.slots.append(s)
         self.h2d_bytes = 2 * n * c * h * w * esize
         self.d2h_bytes = 2 * n * (c if (host_passthrough or gated_only) else 2 * c) * h * w * esize
-        # fp32: cast, cast_w, project_mn, attend2;  16-bit features read in place: cast_w, project_mn, attend2
+        # fp32: cast, cast_w, attend2 (which projects its query tiles itself);  16-bit features read in place: cast_w, attend2
         in_place = self.io16 and (h * w) % 8 == 0
-        self.launches_per_call = (3 if in_place else 4) * ((n + self.chunk - 1) // self.chunk)
+        self.launches_per_call = (2 if in_place else 3) * ((n + self.chunk - 1) // self.chunk)
         self._worker = None
 
     def _host_copy(self, v_a, v_b, out_a, out_b, lo, hi):

@@ -99,6 +99,7 @@ struct Attend2Params {
   int xb_row0;   // V_b in tmap_k
   int v0_row0;   // values of pass 0 (V_b) in tmap_v
   int v1_row0;   // values of pass 1 (V_a) in tmap_v1
+  unsigned* status;   // status block of the workspace or null (FOLD: |Q| beyond the fp16 range raises COATTN_STATUS_OVERFLOW_Q)
 };
 
 // exchange one float between the G threads that own the same query row (warps quad, quad + 4, ...): every thread gets
@@ -131,13 +132,22 @@ __device__ __forceinline__ float group_exchange_sum(float v, float* xbuf, uint32
 //             operands may then be read straight from the caller's tensors (one tensor map per tensor, see *_row0).
 // SPLIT = true: the work units are (item, key-range part) pairs (Attend2Params::splits > 1); the default instantiation
 //             has splits == 1 folded away at compile time, so its loops are the plain per-item sweeps.
-template <bool BF16, bool MN, int G, bool IO16 = false, bool SPLIT = false>
+// FOLD = true (MN only): the W projection (:158-159) happens INSIDE the kernel.  Every item first projects its own 256-row
+//             query tile on the tensor cores -- pass 0: Q_I = (W A_I), pass 1: Q'_J = (W^T B_J), so that S^T = Q'^T A needs no
+//             projected KEYS -- from the raw feature tile (TMA, MN-major A operand) and W (two 32 KB blocks through the key
+//             ring) into the TMEM columns of S and P, which are idle between items; the softmax warps round it to 16 bits
+//             and write it back over the raw tile as a K-major operand.  The projected plane Q16 and the project_mn launch
+//             no longer exist in the forward; tmap_q then holds V_a and xq_row0 its first row.
+template <bool BF16, bool MN, int G, bool IO16 = false, bool SPLIT = false, bool FOLD = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Attend2Cfg<G>::kThreads, 1)
-attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C], box {64, 128};  MN: holds Q16, rows [..][C] x Lp, box {64, 256}
+attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C], box {64, 128};  MN: holds Q16 (FOLD: V_a), rows [..][C] x Lp, box {64, 256}
                const __grid_constant__ CUtensorMap tmap_k,  // !MN: T [2*N*Lp][C], box {64, 64};   MN: holds V_b, box {64, 256}
                const __grid_constant__ CUtensorMap tmap_v,  // holds V_b (values of pass 0), box {64, 128}
                const __grid_constant__ CUtensorMap tmap_v1, // holds V_a (values of pass 1), box {64, 128}
+               const __grid_constant__ CUtensorMap tmap_w0, // FOLD: W16 [C][C], box {64, 64}  (K-major blocks, pass 0)
+               const __grid_constant__ CUtensorMap tmap_w1, // FOLD: W16 [C][C], box {64, 256} (MN-major block = W^T, pass 1)
                Attend2Params p) {
+  static_assert(!FOLD || MN, "the in-kernel projection reads channel-major feature tiles");
   using Cfg = Attend2Cfg<G>;
   const int kSplits = SPLIT ? p.splits : 1;
   constexpr int k2KStages = Cfg::kKStages;
@@ -162,7 +172,9 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
   uint64_t* p_full = s_full + 2;                // (L) [2] one arrival per softmax warp of each CTA
   uint64_t* o_full = p_full + 2;                // [2] PV(j) complete, on barrier j & 1: a waiter can then never be two
                                                 //     phases behind (the next completion on the same barrier needs P(j+2))
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* proj_full = o_full + 2;             // FOLD: the projected query tile of the item is complete in TMEM (both CTAs)
+  uint64_t* qk_ready = o_full + 3;              // FOLD (L): every softmax warp of the pair has written its rows of Q to shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -179,6 +191,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     tma_prefetch_desc(&tmap_v1);
+    if constexpr (FOLD) { tma_prefetch_desc(&tmap_w0); tma_prefetch_desc(&tmap_w1); }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     for (int s = 0; s < k2KStages; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
@@ -188,6 +201,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     for (int b = 0; b < 2; ++b) mbar_init(p_full + b, 2 * k2SoftmaxWarps);
     mbar_init(o_full + 0, 1);
     mbar_init(o_full + 1, 1);
+    mbar_init(proj_full, 1);
+    mbar_init(qk_ready, 2 * k2SoftmaxWarps);
     fence_mbar_init();
   }
   if (warp == k2MmaWarp) {
@@ -219,6 +234,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * k2QBytes);
         if constexpr (MN) {
           // pass 0: queries Q16 (tmap_q), keys V_b (tmap_k);  pass 1: queries V_b, keys Q16
+          // FOLD: tmap_q holds V_a: pass 0 queries = (W V_a) projected here, keys V_b; pass 1 queries = (W^T V_b), keys V_a
           const CUtensorMap* mq = pass ? &tmap_k : &tmap_q;
           const CUtensorMap* mk = pass ? &tmap_q : &tmap_k;
           const int nq = pass ? n : n / p.q_group;      // q_group > 1 only with passes == 1 (pass 0: queries from V_a)
@@ -228,6 +244,25 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
 #pragma unroll
           for (int mc = 0; mc < 2; ++mc)     // two 64-position chunks x 256 channel rows
             tma_load_2d_pair(sQ + mc * 32768, mq, q_full_l, qpos0 + mc * 64, qch0);
+          if constexpr (FOLD) {
+            // W through the key ring, one 32 KB block per half of the 256 projected channels.  Block h, CTA r:
+            //   pass 0  B operand [N = c_out][K = c_in] K-major: rows c_out in [128 h + 64 r, + 64), four 64-wide k-blocks
+            //   pass 1  B operand W^T = [N = c_in][K = c_out] MN-major: columns c_in in [128 h + 64 r, + 64), all 256 rows
+            for (int hh = 0; hh < 2; ++hh, ++cnt) {
+              const uint32_t s = cnt % k2KStages, ph = (cnt / k2KStages) & 1;
+              mbar_wait(k_empty + s, ph ^ 1, 4);
+              if (rank == 0) mbar_arrive_expect_tx(k_full + s, 2 * k2KBytes);
+              const uint32_t full_l = mapa_u32(smem_u32(k_full + s), 0);
+              const int c0 = 128 * hh + 64 * (int)rank;
+              if (pass == 0) {
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+                  tma_load_2d_pair(sK + s * k2KBytes + kb * ((k2BN / 2) * 128), &tmap_w0, full_l, kb * 64, c0);
+              } else {
+                tma_load_2d_pair(sK + s * k2KBytes, &tmap_w1, full_l, c0, 0);
+              }
+            }
+          }
           for (int j = j0; j < j1; ++j, ++cnt) {
             const uint32_t s = cnt % k2KStages, ph = (cnt / k2KStages) & 1;
             mbar_wait(k_empty + s, ph ^ 1, 2);
@@ -329,15 +364,18 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
   } else if (warp == k2MmaWarp) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA; uniform control flow)
     if (rank == 0) {
-      constexpr uint32_t idesc_s = make_idesc_16_major(2 * k2BM, k2BN, BF16, MN, MN);
+      // FOLD: the query tile is the projected one, written by the softmax warps as a K-major operand
+      constexpr bool QMN = MN && !FOLD;
+      constexpr uint32_t idesc_s = make_idesc_16_major(2 * k2BM, k2BN, BF16, QMN, MN);
       constexpr uint32_t idesc_o = make_idesc_16(2 * k2BM, kC, BF16);
-      const uint32_t idesc_s_last = make_idesc_16_major(2 * k2BM, (uint32_t)n_last, BF16, MN, MN);
+      const uint32_t idesc_s_last = make_idesc_16_major(2 * k2BM, (uint32_t)n_last, BF16, QMN, MN);
       const int ksteps_last = n_last / 16;
       uint32_t it = 0, kcnt = 0, vcnt = 0;
+      uint32_t rcnt = 0;      // blocks taken from the key ring (FOLD: S tiles + W blocks; otherwise == kcnt)
       uint32_t pphase0 = 0, pphase1 = 0;
       const uint32_t tO = tmem + k2TmemO;
       const uint32_t tS = tmem + k2TmemS;
-      const uint64_t qd0 = MN ? make_sdesc_mn_sw128(smem_u32(sQ), 32768, 1024) : make_sdesc_k_sw128(smem_u32(sQ));
+      const uint64_t qd0 = QMN ? make_sdesc_mn_sw128(smem_u32(sQ), 32768, 1024) : make_sdesc_k_sw128(smem_u32(sQ));
       const uint32_t sK_addr = smem_u32(sK);
       const uint32_t sV_addr = smem_u32(sV);
       for (int unit = cluster_id; unit < p.num_items * kSplits; unit += num_clusters, ++it) {
@@ -345,7 +383,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         const int j0 = (T * part) / kSplits, j1 = (T * (part + 1)) / kSplits;   // key tiles [j0, j1) of this unit
         // S(j) of this item; kcnt counts every S tile of the kernel (key stage ring and s_free phases)
         auto issue_s = [&](int j) {
-          const uint32_t s = kcnt % k2KStages, ph = (kcnt / k2KStages) & 1;
+          const uint32_t s = rcnt % k2KStages, ph = (rcnt / k2KStages) & 1;
           warp_mbar_wait(k_full + s, ph, lane, 10);
           // the single S buffer: every softmax warp of the pair has pulled the previous tile into registers
           if (kcnt > 0) warp_mbar_wait(s_free, (kcnt - 1) & 1, lane, 12);
@@ -356,7 +394,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
 #pragma unroll
             for (int kk = 0; kk < kC / 16; ++kk) {
               // K-major: k-block kk/4 + 32 B per 16 channels inside the 128-byte row;  MN-major: 16 channel rows = 2048 B
-              const uint64_t ad = qd0 + (uint64_t)((MN ? kk * 2048 : ((kk >> 2) * (k2BM * 128) + (kk & 3) * 32)) >> 4);
+              const uint64_t ad = qd0 + (uint64_t)((QMN ? kk * 2048 : ((kk >> 2) * (k2BM * 128) + (kk & 3) * 32)) >> 4);
               const uint64_t bd = kd0 + (uint64_t)((MN ? kk * 2048 : ((kk >> 2) * ((k2BN / 2) * 128) + (kk & 3) * 32)) >> 4);
               umma2_ss(tS, ad, bd, idesc, kk > 0);
             }
@@ -366,11 +404,44 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           }
           __syncwarp();
           ++kcnt;
+          ++rcnt;
         };
         TRG(0);
         warp_mbar_wait(q_full, it & 1, lane, 11);
         tc_fence_after();
         TRG(1);
+        if constexpr (FOLD) {
+          // Projection of this item's query tile into the TMEM columns of S and P (idle between items: the previous item's
+          // PVs precede these MMAs in the pipe, its last S sits in registers once s_free says so):
+          //   D[i, c] = sum_k raw[k, i] Wop[c, k]     M 256 (query rows of the pair) x N 128 per block x K 256
+          const int np_ = (unit / kSplits) / p.q_pairs;
+          const int pass_ = (p.passes == 2) ? (np_ & 1) : 0;
+          const uint64_t rawd0 = make_sdesc_mn_sw128(smem_u32(sQ), 32768, 1024);
+          const uint32_t idesc_p = pass_ ? make_idesc_16_major(2 * k2BM, 128, BF16, true, true)
+                                         : make_idesc_16_major(2 * k2BM, 128, BF16, true, false);
+          for (int hh = 0; hh < 2; ++hh, ++rcnt) {
+            const uint32_t s = rcnt % k2KStages, ph = (rcnt / k2KStages) & 1;
+            warp_mbar_wait(k_full + s, ph, lane, 15);
+            if (hh == 0 && kcnt > 0) warp_mbar_wait(s_free, (kcnt - 1) & 1, lane, 16);
+            tc_fence_after();
+            const uint32_t sb = sK_addr + s * k2KBytes;
+            const uint64_t wk0 = make_sdesc_k_sw128(sb), wm0 = make_sdesc_mn_sw128(sb, 32768, 1024);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < kC / 16; ++kk) {
+                const uint64_t ad = rawd0 + (uint64_t)((kk * 2048) >> 4);
+                const uint64_t bd = pass_ ? wm0 + (uint64_t)((kk * 2048) >> 4)
+                                          : wk0 + (uint64_t)(((kk >> 2) * ((k2BN / 2) * 128) + (kk & 3) * 32) >> 4);
+                umma2_ss(tmem + k2TmemS + (uint32_t)hh * 128, ad, bd, idesc_p, kk > 0);
+              }
+              umma2_commit_mc(k_empty + s, 3);
+              if (hh == 1) umma2_commit_mc(proj_full, 3);
+            }
+            __syncwarp();
+          }
+          warp_mbar_wait(qk_ready, it & 1, lane, 17);      // Q (16-bit, K-major) replaced the raw tile in shared memory
+          tc_fence_after();
+        }
         // Tensor-pipe order per item: S(0) S(1) | S(2) PV(0) | S(3) PV(1) | ... | PV(T-1).  S(j+2) only needs the S buffer
         // back (s_free(j+1): the softmax warps hold S(j+1) in registers) and is computed while they work on tile j+1;
         // PV(j) follows when P(j) is complete.  Both conditions arrive when softmax(j) ends, and the affinity tile goes
@@ -455,6 +526,42 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       // rows of this warp that lie entirely in the padding of the last query tile: no softmax math, P = 0
       // (zero MMA operands also draw less power, and this kernel runs against the power cap)
       const bool warp_is_padding = (qp * (2 * k2BM) + (int)rank * k2BM + quad * 32) >= p.L;
+      if constexpr (FOLD) {
+        // the projected query tile: TMEM columns [256, 512) hold Q[row][c], c = column - 256 -> 16 bits -> shared memory as the
+        // K-major operand of the affinity MMAs (four 64-channel k-blocks of [128 rows x 128 B], 16-byte chunks XOR row % 8),
+        // over the raw tile, which every projection MMA has finished reading (proj_full)
+        warp_mbar_wait(proj_full, it & 1, lane, 25);
+        tc_fence_after();
+        uint8_t* qrow = sQ + rloc * 128;
+        float qmax = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < kChunks; ++ch) {
+          uint32_t o[32];
+          tmem_ld32(tmem + lane_base + k2TmemS + (uint32_t)(g * kChans + ch * 32), o);
+          tmem_ld_wait();
+          if constexpr (!BF16) {      // fp16 range guard (the pack below saturates at +-65504)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) qmax = fmaxf(qmax, fabsf(__uint_as_float(o[k])));
+          }
+          const int c = g * kChans + ch * 32;          // first channel of this chunk
+          uint8_t* kb = qrow + (c >> 6) * (k2BM * 128);
+          const int j0 = (c & 63) >> 3;                // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(kb + (((j0 + q) ^ (rloc & 7)) << 4)) =
+                make_uint4(pack16x2<BF16>(__uint_as_float(o[8 * q + 0]), __uint_as_float(o[8 * q + 1])),
+                           pack16x2<BF16>(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3])),
+                           pack16x2<BF16>(__uint_as_float(o[8 * q + 4]), __uint_as_float(o[8 * q + 5])),
+                           pack16x2<BF16>(__uint_as_float(o[8 * q + 6]), __uint_as_float(o[8 * q + 7])));
+        }
+        if constexpr (!BF16) {
+          if (p.status != nullptr && __any_sync(0xffffffffu, !(qmax <= 65504.0f)) && lane == 0) atomicOr(p.status, 4u);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(qk_ready), 0));
+      }
       float m = -INFINITY, l = 0.0f;
       if (warp == 0) TRG(8);
       for (int j = j0; j < j1; ++j) {

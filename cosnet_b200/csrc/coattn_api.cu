@@ -19,6 +19,7 @@ using namespace coattn;
 
 constexpr int64_t kAlign = 1024;
 constexpr unsigned kInternalPrepOnlyB = 1u << 30;   // internal: prep converts V_b only (V_a goes through project_fused)
+constexpr unsigned kInternalNeedQ16 = 1u << 29;     // internal: the caller (backward) needs the projected plane Q16 in the workspace
 inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
@@ -264,8 +265,9 @@ static int prep_and_project_fused(const float* v_a, const float* v_b, const floa
 //   in16: 0 = fp32 features (cast), 1 = 16-bit features copied into the padded planes (pad16_kernel),
 //         2 = 16-bit features consumed in place: nothing is copied and the projection reads V_a through its own map
 static int cast_project_core(const void* v_a, const void* v_b, const float* w, unsigned short* x, unsigned short* w16,
-                             int n, const Layout& ly, bool bf16, bool project, cudaStream_t st, int n_a = -1,
+                             int n, const Layout& ly, bool bf16, int project, cudaStream_t st, int n_a = -1,
                              int in16 = 0, unsigned* status = nullptr) {
+  // project: 0 = cast only, 1 = cast + W16 + Q16 = W V_a (project_mn), 2 = cast + W16 (the attend kernel projects itself)
   if (n_a < 0) n_a = n;       // samples of V_a (query frames); the planes are laid out for n samples either way
   CastParams cp;
   cp.va = static_cast<const float*>(v_a);   // fp32 features; with in16 == 1 pad16_kernel reads the same pointers as 16-bit data
@@ -287,6 +289,7 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   if (!project) return (int)cudaGetLastError();
   if (bf16) cast_w_kernel<true><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
   else cast_w_kernel<false><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+  if (project == 2) return (int)cudaGetLastError();
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return COATTN_E_DRIVER;
   CUtensorMap tm_w, tm_x;
@@ -312,6 +315,11 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   return (int)cudaGetLastError();
 }
 
+// the attend kernel projects its query tiles itself (FOLD) on the default channel-major path
+static inline bool uses_fold(unsigned flags) {
+  return !(flags & (COATTN_FLAG_UNFOLDED | COATTN_FLAG_KMAJOR | COATTN_FLAG_UNFUSED_PREP | COATTN_FLAG_SINGLE_CTA | COATTN_FLAG_SOFTMAX16));
+}
+
 static int cast_and_project_mn(const float* v_a, const float* v_b, const float* w, void* workspace, int64_t workspace_bytes,
                                int n, int c, int h, int w_, unsigned flags, void* stream) {
   if (int e = check_dims(n, c, h, w_)) return e;
@@ -320,8 +328,8 @@ static int cast_and_project_mn(const float* v_a, const float* v_b, const float* 
   if (int e = check_arch(nullptr)) return e;
   return cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
                            reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
-                           (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), -1,
-                           (flags & COATTN_FLAG_PLANES_READY) ? 3 : 0,
+                           (flags & COATTN_FLAG_BF16) != 0, (uses_fold(flags) && !(flags & kInternalNeedQ16)) ? 2 : 1,
+                           static_cast<cudaStream_t>(stream), -1, (flags & COATTN_FLAG_PLANES_READY) ? 3 : 0,
                            reinterpret_cast<unsigned*>(seg(workspace, ly.off_status)));
 }
 
@@ -384,15 +392,25 @@ static int launch_attend(const void* v_a, const void* v_b, void* cat_a, void* ca
   if (!(flags & COATTN_FLAG_SINGLE_CTA)) {
     // default: CTA-pair kernel (cluster of 2, tcgen05 cta_group::2)
     const bool mn = !(flags & (COATTN_FLAG_KMAJOR | COATTN_FLAG_UNFUSED_PREP));
-    CUtensorMap tm_q, tm_k2, tm_v2, tm_v3;
+    CUtensorMap tm_q, tm_k2, tm_v2, tm_v3, tm_w0, tm_w1;
     Attend2Params q;
     if (in16 && !mn) return COATTN_E_UNSUPPORTED;
+    const bool fold = mn && uses_fold(flags);
+    if (fold) {
+      if (int e = make_tmap(enc, &tm_w0, seg(workspace, ly.off_w16), kC, kC, 64, bf16)) return e;
+      if (int e = make_tmap(enc, &tm_w1, seg(workspace, ly.off_w16), kC, kC, 256, bf16)) return e;
+    } else {
+      memset(&tm_w0, 0, sizeof(tm_w0));
+      memset(&tm_w1, 0, sizeof(tm_w1));
+    }
     if (in16 == 2) {
       // 16-bit features consumed in place: one map per tensor (positions past L are zero-filled by TMA); Q16 is the
       // only operand that lives in the workspace
       const int n_a = n / q_group;
       const uint8_t* q16 = seg(workspace, ly.off_vv) + 2 * ly.t_pass_elems() * 2;
-      if (int e = make_tmap(enc, &tm_q, q16, (uint64_t)n * kC, ly.Lp, kC, bf16)) return e;
+      if (fold) {      // queries are projected in the kernel from V_a itself
+        if (int e = make_tmap(enc, &tm_q, v_a, (uint64_t)n_a * kC, ly.L, kC, bf16)) return e;
+      } else if (int e = make_tmap(enc, &tm_q, q16, (uint64_t)n * kC, ly.Lp, kC, bf16)) return e;
       if (int e = make_tmap(enc, &tm_k2, v_b, (uint64_t)n * kC, ly.L, kC, bf16)) return e;
       if (int e = make_tmap(enc, &tm_v2, v_b, (uint64_t)n * kC, ly.L, kC / 2, bf16)) return e;
       if (int e = make_tmap(enc, &tm_v3, v_a, (uint64_t)n_a * kC, ly.L, kC / 2, bf16)) return e;
@@ -408,8 +426,9 @@ static int launch_attend(const void* v_a, const void* v_b, void* cat_a, void* ca
       }
       if (int e = make_tmap(enc, &tm_v2, seg(workspace, ly.off_vv), (uint64_t)3 * n * kC, ly.Lp, kC / 2, bf16)) return e;
       tm_v3 = tm_v2;
-      q.xq_row0 = 2 * n * kC; q.xb_row0 = 0; q.v0_row0 = 0; q.v1_row0 = n * kC;
+      q.xq_row0 = (fold ? 1 : 2) * n * kC; q.xb_row0 = 0; q.v0_row0 = 0; q.v1_row0 = n * kC;      // fold: "queries" = plane A16
     }
+    q.status = reinterpret_cast<unsigned*>(seg(workspace, ly.off_status));
     q.z = z;
     q.lse = lse ? lse : reinterpret_cast<float*>(seg(workspace, ly.off_lse));
     q.cat_a = cat_a; q.cat_b = cat_b; q.mask = mask; q.gate_w = gate_w; q.gate_b = gate_b;
@@ -428,13 +447,17 @@ static int launch_attend(const void* v_a, const void* v_b, void* cat_a, void* ca
     // 8 softmax warps (two column groups per TMEM lane quadrant) by default; COATTN_FLAG_SOFTMAX16 selects the 16-warp
     // layout (four groups)
     const bool g4 = (flags & COATTN_FLAG_SOFTMAX16) != 0;
-    void (*kern2)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Attend2Params);
+    void (*kern2)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Attend2Params);
     if (in16) {
       if (g4) return COATTN_E_UNSUPPORTED;
-      kern2 = bf16 ? attend2_kernel<true, true, 2, true> : attend2_kernel<false, true, 2, true>;
+      if (fold) kern2 = bf16 ? attend2_kernel<true, true, 2, true, false, true> : attend2_kernel<false, true, 2, true, false, true>;
+      else kern2 = bf16 ? attend2_kernel<true, true, 2, true> : attend2_kernel<false, true, 2, true>;
     } else if (splits != 1) {
       if (g4) return COATTN_E_UNSUPPORTED;
-      kern2 = bf16 ? attend2_kernel<true, true, 2, false, true> : attend2_kernel<false, true, 2, false, true>;
+      if (fold) kern2 = bf16 ? attend2_kernel<true, true, 2, false, true, true> : attend2_kernel<false, true, 2, false, true, true>;
+      else kern2 = bf16 ? attend2_kernel<true, true, 2, false, true> : attend2_kernel<false, true, 2, false, true>;
+    } else if (fold) {
+      kern2 = bf16 ? attend2_kernel<true, true, 2, false, false, true> : attend2_kernel<false, true, 2, false, false, true>;
     } else if (g4) kern2 = mn ? (bf16 ? attend2_kernel<true, true, 4> : attend2_kernel<false, true, 4>)
                        : (bf16 ? attend2_kernel<true, false, 4> : attend2_kernel<false, false, 4>);
     else    kern2 = mn ? (bf16 ? attend2_kernel<true, true, 2> : attend2_kernel<false, true, 2>)
@@ -445,7 +468,7 @@ static int launch_attend(const void* v_a, const void* v_b, void* cat_a, void* ca
     if (e2 != cudaSuccess) return (int)e2;
     int clusters = sms / 2;
     if (q.num_items * splits < clusters) clusters = q.num_items * splits;
-    kern2<<<2 * clusters, threads2, smem2, st>>>(tm_q, tm_k2, tm_v2, tm_v3, q);
+    kern2<<<2 * clusters, threads2, smem2, st>>>(tm_q, tm_k2, tm_v2, tm_v3, tm_w0, tm_w1, q);
 #ifdef COATTN_TRACE2
     {
       static int calls = 0;
@@ -652,7 +675,7 @@ int coattn_forward_queries(const float* v_a, const float* v_b, const float* w, c
   // the query side (16-bit cast of V_a and Q = W V_a) is prepared once per query frame, not once per pair
   if (int e = cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
                                 reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
-                                (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq, 0,
+                                (flags & COATTN_FLAG_BF16) != 0, uses_fold(flags) ? 2 : 1, static_cast<cudaStream_t>(stream), nq, 0,
                                 reinterpret_cast<unsigned*>(seg(workspace, ly.off_status))))
     return e;
   int parts = 1;
@@ -686,7 +709,7 @@ int coattn_forward16(const void* v_a, const void* v_b, const float* w, const flo
   const int in16 = in_place ? 2 : 1;
   if (int e = cast_project_core(v_a, v_b, w, reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv)),
                                 reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
-                                (flags & COATTN_FLAG_BF16) != 0, true, static_cast<cudaStream_t>(stream), nq, in16,
+                                (flags & COATTN_FLAG_BF16) != 0, uses_fold(flags) ? 2 : 1, static_cast<cudaStream_t>(stream), nq, in16,
                                 reinterpret_cast<unsigned*>(seg(workspace, ly.off_status))))
     return e;
   return launch_attend(v_a, v_b, cat_a, cat_b, nullptr, lse, mask, gate_w, gate_b,
@@ -857,13 +880,13 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   // forward used, so that exp(S - lse) is the forward's softmax).  Every other product multiplies by a bf16 gradient
   // operand, and tcgen05 kind::f16 needs both operands in one format, so with an fp16 forward a second, bf16 copy of
   // the planes is cast as well (its Q16 plane is only needed for counterpart gradients).
-  if (int e = cast_and_project_mn(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags, stream)) return e;
+  if (int e = cast_and_project_mn(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags | kInternalNeedQ16, stream)) return e;
   unsigned short* xf = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv));     // forward format
   unsigned short* xg = xf;                                                                // bf16
   if (!fbf16) {
     xg = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_g));
     if (int e = cast_project_core(v_a, v_b, w, xg, reinterpret_cast<unsigned short*>(seg(workspace, bl.off_w16g)), n, ly, true,
-                                  counterpart, st))
+                                  counterpart ? 1 : 0, st))
       return e;
   }
   unsigned short* b16f = xf;                              // B, forward format

@@ -121,6 +121,16 @@ enum {
 #define COATTN_FLAG_PLANES_READY 512u
 
 /*
+ *   COATTN_FLAG_UNFOLDED   compute Q = W V_a with the stand-alone projection kernel (project_mn) into the workspace and let
+ *                          the attend kernel read it as queries (pass 0) and KEYS (pass 1), as in the first version.
+ *                          Default: the attend kernel projects the query tile of every work item itself (pass 0: W V_a,
+ *                          pass 1: W^T V_b, so no projected keys are needed) -- north_star item 2, "the W projection is
+ *                          pre-folded into V_a in the same kernel".  Same math; the frame-B outputs differ by the 16-bit
+ *                          rounding of W^T V_b instead of W V_a (~1e-4 rel-L2).  Kept as a cross-check and for A/B timing.
+ */
+#define COATTN_FLAG_UNFOLDED 1024u
+
+/*
  * Status block: the first COATTN_STATUS_WORDS 32-bit words of every workspace.  With fp16 operands (the default) the
  * fp32 -> fp16 conversions of the features and of Q = W V_a clamp at +-65504; instead of clipping silently the kernels
  * record it here (sticky bits; the library never clears them -- coattn_status_clear, or zero the words yourself):

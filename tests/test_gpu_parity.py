@@ -395,14 +395,20 @@ def test_fused_and_unfused_prep_agree(op):
         W, g, b = orc.synthetic_weights(86, bias=True)
         dev = torch.device("cuda:0")
         t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
-        mn = op(t(v_a), t(v_b), t(W), t(g), t(b))                       # default: channel-major (MN-major) operands
+        mn = op(t(v_a), t(v_b), t(W), t(g), t(b), unfolded=True)        # channel-major (MN-major) operands, stand-alone projection
         kmajor = op(t(v_a), t(v_b), t(W), t(g), t(b), kmajor=True)      # transposing prep + fused convert/projection
         unfused = op(t(v_a), t(v_b), t(W), t(g), t(b), unfused_prep=True)
+        folded = op(t(v_a), t(v_b), t(W), t(g), t(b))                   # default: projection inside the attend kernel
         torch.cuda.synchronize()
         for x, y in zip(kmajor, unfused):
             assert torch.equal(x, y)      # same conversions, same MMAs: bit-identical
         for x, y in zip(mn, unfused):     # same operand values, different operand layout
             assert (x - y).abs().max() < 1e-5
+        # the in-kernel projection: frame-A side from the same Q = W V_a (same MMAs, fp32 accumulation order may differ in the
+        # last bit); frame-B side from W^T V_b rounded to 16 bits instead of W V_a -- equal to that rounding
+        assert (folded[0] - mn[0]).abs().max() < 1e-5 * max(1.0, float(mn[0].abs().max()))
+        assert rel_l2(folded[1][:, :C].cpu().numpy(), mn[1][:, :C].cpu().numpy()) < 5e-4
+        assert torch.equal(folded[1][:, C:], mn[1][:, C:])
 
 
 @pytest.mark.parametrize("n,h,w", [(2, 12, 11), (1, 40, 40)])
@@ -541,7 +547,7 @@ def test_softmax16_cross_check_kernel(op, n, h, w):
     W, g, b = orc.synthetic_weights(90, bias=True)
     dev = torch.device("cuda:0")
     t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
-    narrow = op(t(v_a), t(v_b), t(W), t(g), t(b))
+    narrow = op(t(v_a), t(v_b), t(W), t(g), t(b), unfolded=True)     # the 16-warp variant keeps the stand-alone projection
     wide = op(t(v_a), t(v_b), t(W), t(g), t(b), softmax16=True)
     torch.cuda.synchronize()
     ref = orc.coattention(v_a, v_b, W, g, b)
