@@ -3,7 +3,8 @@
 // The softmax matrices are NOT kept from the forward pass (the reference keeps S_row and S_column, 104 MB per
 // sample and modality at L = 3600): S is recomputed from the 16-bit operands and the saved log-sum-exp vectors.
 //
-//   bwd_prep      d_cat_a/b, Z, mask, g  ->  dZ_a, dZ_b (bf16 planes [C][Lp]), delta_a, delta_b, d_gate, dA init
+//   bwd_stats / bwd_planes   d_cat_a/b, Z, mask, g  ->  delta_a, delta_b, d_gate, max |dZ|; then the scaled 16-bit planes
+//                 s dZ_a, s dZ_b [C][Lp] (fp16 with an fp16 forward, bf16 with a bf16 forward) and the passthrough gradients
 //   bwd_flash     (bwd_flash_kernel.cuh) everything of size L x L, flash style: S, dP_a, dP_b are recomputed tile by tile
 //                 in TMEM and consumed there -- dQ = dS B^T, dA += P_b dZ_b^T (and dB with counterpart gradients)
 //   gemm_nt  x2   dA += dQ W;  dW += dQ^T A^T
@@ -183,8 +184,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K]
 //   delta  = sum_c dZ_x Z_x
 //   d_gate_w += sum_i d_ta[i] Z_a[:, i]               d_gate_b += sum_i d_ta[i]
 //   dA      = d_cat_a[:, C:2C]                        (passthrough half of the concat, :186)
-// dZ_a / dZ_b leave as bf16 planes [N][C][Lp] -- the orientation every consumer takes (MN-major operands of the
-// tile kernel, K-major operands of the position-contracting GEMMs).
+// Two passes, because the 16-bit gradient planes are SCALED: with fp16 forward operands the gradient operands of the
+// flash sweeps are fp16 as well (one operand format per tcgen05 product; 11 significant bits instead of bf16's 8, which
+// is what the gradient parity rides on), and fp16 needs the values in range -- every dZ is multiplied by ONE power of two
+// s chosen from max |dZ| over the whole call.
+//   PASS 0  reads d_cat (gated halves), Z, mask: d_ta -> buffer, delta, d_gate, max |dZ| (one atomicMax per block)
+//   PASS 1  reads d_cat, mask, d_ta, the maximum: writes s dZ_a, s dZ_b as 16-bit planes [N][C][Lp] (the orientation every
+//           consumer takes) and the passthrough gradients
+// With bf16 forward operands the planes are bf16 and s = 1.
 // ==============================================================================================
 struct BwdPrepParams {
   const float* d_cat_a;   // [N][2C][L]
@@ -192,10 +199,12 @@ struct BwdPrepParams {
   const float* z;         // [2][N][C][L]
   const float* mask;      // [2][N][L]
   const float* gate_w;    // [C]
-  unsigned short* dza16;  // [N][C][Lp] bf16
-  unsigned short* dzb16;  // [N][C][Lp] bf16
+  unsigned short* dza16;  // [N][C][Lp] 16-bit, scaled
+  unsigned short* dzb16;  // [N][C][Lp] 16-bit, scaled
   float* d_vb;            // [N][C][L] or null: initialised with the passthrough gradient d_cat_b[:, C:2C]
-  float* delta;           // [2][N][L]
+  float* delta;           // [2][N][L]  (unscaled)
+  float* d_ta;            // [N][L] scratch between the passes
+  unsigned* absmax;       // [1] bits of max |dZ| (caller zeroes)
   float* d_gate_w;        // [C]   (accumulated with atomics; caller zeroes)
   float* d_gate_b;        // [1] or null
   float* d_va;            // [N][C][L]  initialised with the passthrough gradient
@@ -204,6 +213,17 @@ struct BwdPrepParams {
 
 constexpr int kBwdPrepThreads = 256;
 constexpr int kBwdPrepPos = 32;
+
+// The power of two that brings max |dZ| into [2^-5, 2^-4): products with O(1) features summed over 256 channels and
+// multiplied by softmax weights <= 1 then stay far inside the fp16 range, and values down to 2^-20 of the maximum are
+// still representable.  bits = 0 (all gradients zero) -> 1.
+__device__ __forceinline__ float grad_scale_from_absmax(unsigned bits) {
+  const float m = __uint_as_float(bits);
+  if (!(m > 0.f) || !(m < 3.0e38f)) return 1.0f;
+  int e;
+  (void)frexpf(m, &e);          // m = f 2^e, f in [0.5, 1)
+  return ldexpf(1.0f, -e - 4);
+}
 
 // sum over the 32 lanes of v[k] for every k: after the five exchange steps lane l holds the total of element
 // k = bitreverse5(l) ... expressed here simply as "the element this lane ends up with"; 31 shuffles instead of 160
@@ -247,8 +267,10 @@ __device__ __forceinline__ float warp_multi_reduce32(float (&v)[32], int lane, i
   return v[0];
 }
 
-__global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams p) {
+// PASS 0: statistics
+__global__ void __launch_bounds__(kBwdPrepThreads) bwd_stats_kernel(BwdPrepParams p) {
   __shared__ float red[8][kBwdPrepPos];
+  __shared__ float redm[8];
   const int n = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int wrp = threadIdx.x >> 5;      // channels [32 wrp, 32 wrp + 32)
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
   const float ma = valid ? __ldg(p.mask + (size_t)n * p.L + l) : 0.f;
   const float mb = (valid && has_b) ? __ldg(p.mask + (size_t)(p.N + n) * p.L + l) : 0.f;
 
-  // ---- A side, pass 1: this thread's 32 channels of dZag and Z_a stay in registers
+  // ---- A side: this thread's 32 channels of dZag and Z_a stay in registers
   float g[32], zz[32];
   float acc = 0.f;
 #pragma unroll
@@ -278,32 +300,19 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
   for (int w = 0; w < 8; ++w) dta += red[w][lane];
   dta *= ma * (1.f - ma);
   __syncthreads();
-  // ---- pass 2: dZ_a, delta_a partial, d_gate_w partials
-  float dl = 0.f;
-  unsigned short* dza = p.dza16 + ((size_t)n * kC + c0) * p.Lp + l;
+  if (wrp == 0 && valid) p.d_ta[(size_t)n * p.L + l] = dta;
+  float dl = 0.f, amax = 0.f;
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     const float dz = fmaf(__ldg(p.gate_w + c0 + k), dta, g[k] * ma);
     dl = fmaf(dz, zz[k], dl);
-    dza[(size_t)k * p.Lp] = cvt16<true>(dz);     // positions >= L get 0 (g = 0, dta = 0)
+    amax = fmaxf(amax, fabsf(dz));
     zz[k] *= dta;                                // d_gate_w contribution of this position
   }
   red[wrp][lane] = dl;
   int owner;
   const float gsum = warp_multi_reduce32(zz, lane, owner);
   atomicAdd(p.d_gate_w + c0 + owner, gsum);
-  // passthrough half of the concat -> gradient of V_a
-  {
-    const float* src = p.d_cat_a + ((size_t)n * 2 * kC + kC + c0) * p.L + l;
-    float* dst = p.d_va + ((size_t)n * kC + c0) * p.L + l;
-    if (valid) {
-      float t[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) t[k] = __ldcs(src + (size_t)k * p.L);
-#pragma unroll
-      for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, t[k]);
-    }
-  }
   __syncthreads();
   if (wrp == 0) {
     float t = 0.f;
@@ -319,9 +328,8 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
   }
   __syncthreads();
   // ---- B side: dZ_b = dZbg * m_b (the mask is a constant), delta_b
-  dl = 0.f;
-  unsigned short* dzb = p.dzb16 + ((size_t)n * kC + c0) * p.Lp + l;
   if (has_b) {
+    dl = 0.f;
     const float* dcb = p.d_cat_b + ((size_t)n * 2 * kC + c0) * p.L + l;
     const float* zb = p.z + ((size_t)(p.N + n) * kC + c0) * p.L + l;
 #pragma unroll
@@ -330,8 +338,70 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
     for (int k = 0; k < 32; ++k) {
       const float dz = g[k] * mb;
       dl = fmaf(dz, zz[k], dl);
-      dzb[(size_t)k * p.Lp] = cvt16<true>(dz);
+      amax = fmaxf(amax, fabsf(dz));
     }
+    red[wrp][lane] = dl;
+    __syncthreads();
+    if (wrp == 0 && valid) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][lane];
+      p.delta[(size_t)(p.N + n) * p.L + l] = t;
+    }
+  }
+  // ---- max |dZ| of the block -> one atomic (the bits of a non-negative float order like the float)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  if (lane == 0) redm[wrp] = amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = redm[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, redm[w]);
+    if (m > 0.f) atomicMax(p.absmax, __float_as_uint(m));
+  }
+}
+
+// PASS 1: scaled 16-bit planes + passthrough gradients.  BF16: bf16 planes, no scaling.
+template <bool BF16>
+__global__ void __launch_bounds__(kBwdPrepThreads) bwd_planes_kernel(BwdPrepParams p) {
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int wrp = threadIdx.x >> 5;
+  const int l = blockIdx.x * kBwdPrepPos + lane;
+  const bool valid = l < p.L;
+  const int c0 = wrp * 32;
+  const bool has_b = p.d_cat_b != nullptr;
+  const float s = BF16 ? 1.0f : grad_scale_from_absmax(__ldg(p.absmax));
+  const float ma = valid ? __ldg(p.mask + (size_t)n * p.L + l) : 0.f;
+  const float mb = (valid && has_b) ? __ldg(p.mask + (size_t)(p.N + n) * p.L + l) : 0.f;
+  const float dta = valid ? __ldg(p.d_ta + (size_t)n * p.L + l) : 0.f;
+  float g[32];
+  {
+    const float* dca = p.d_cat_a + ((size_t)n * 2 * kC + c0) * p.L + l;
+    unsigned short* dza = p.dza16 + ((size_t)n * kC + c0) * p.Lp + l;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) g[k] = valid ? __ldcs(dca + (size_t)k * p.L) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)       // positions >= L get 0 (g = 0, dta = 0)
+      dza[(size_t)k * p.Lp] = cvt16<BF16>(fmaf(__ldg(p.gate_w + c0 + k), dta, g[k] * ma) * s);
+    // passthrough half of the concat -> gradient of V_a
+    if (valid) {
+      const float* src = dca + (size_t)kC * p.L;
+      float* dst = p.d_va + ((size_t)n * kC + c0) * p.L + l;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) g[k] = __ldcs(src + (size_t)k * p.L);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, g[k]);
+    }
+  }
+  if (has_b) {
+    const float* dcb = p.d_cat_b + ((size_t)n * 2 * kC + c0) * p.L + l;
+    unsigned short* dzb = p.dzb16 + ((size_t)n * kC + c0) * p.Lp + l;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) g[k] = valid ? __ldcs(dcb + (size_t)k * p.L) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) dzb[(size_t)k * p.Lp] = cvt16<BF16>(g[k] * mb * s);
     if (p.d_vb != nullptr && valid) {
       const float* src = dcb + (size_t)kC * p.L;
       float* dst = p.d_vb + ((size_t)n * kC + c0) * p.L + l;
@@ -340,22 +410,11 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_prep_kernel(BwdPrepParams
 #pragma unroll
       for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, g[k]);
     }
-  } else {
+  } else if (p.d_vb != nullptr && valid) {
     // depth modality: the B branch is gradient dead, nothing reads dZ_b or delta_b
-    if (p.d_vb != nullptr && valid) {
-      float* dst = p.d_vb + ((size_t)n * kC + c0) * p.L + l;
+    float* dst = p.d_vb + ((size_t)n * kC + c0) * p.L + l;
 #pragma unroll 8
-      for (int k = 0; k < 32; ++k) dst[(size_t)k * p.L] = 0.f;
-    }
-  }
-  if (!has_b) return;
-  red[wrp][lane] = dl;
-  __syncthreads();
-  if (wrp == 0 && valid) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][lane];
-    p.delta[(size_t)(p.N + n) * p.L + l] = t;
+    for (int k = 0; k < 32; ++k) dst[(size_t)k * p.L] = 0.f;
   }
 }
 

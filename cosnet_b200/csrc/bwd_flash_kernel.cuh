@@ -14,6 +14,8 @@
 // online softmax (the normalisers are known) plus the second product.
 //
 // A work item = (kind, sample, 256-row tile) runs 1-3 PHASES that accumulate into the same O:
+// (all gradient operands -- dZ_a, dZ_b and X -- are in the forward's operand format; with fp16 they carry the call-wide
+//  power-of-two scale s of bwd_planes_kernel, delta is scaled on load and O is unscaled in the drain)
 //   kind DQ   : phase A  S = Q_I^T B_J,  T = dZ_a,I^T B_J,  X = P_a (T - delta_a[I]),  V = B      (row vectors)
 //               phase B  S = Q_I^T B_J,  T = A_I^T dZ_b,J,  X = P_b (T - delta_b[J]),  V = B      (column vectors)
 //               -> dQ as bf16 in both layouts ([Lp][C] and [C][Lp]) for the two small GEMMs that follow
@@ -32,6 +34,7 @@
 //   profiles/r2_bwd_flash_trace_v1.txt) for 3.1 k cycles of MMA.
 #pragma once
 #include "attend2_kernel.cuh"
+#include "backward_kernels.cuh"
 
 namespace coattn {
 
@@ -95,8 +98,10 @@ struct FlashParams {
   int q_pairs;             // ceil(L / 256)
   int kv_tiles;            // ceil(L / 128)
   uint32_t idesc_s, idesc_s_last;     // S: forward operand format, M 256 x N 128 (n_last in the ragged tile), MN-major operands
-  uint32_t idesc_t, idesc_t_last;     // T: bf16
-  uint32_t idesc_o;                   // PV: bf16, M 256 x N 256, K-major
+  uint32_t idesc_t, idesc_t_last;     // T: gradient operand format (= forward format; the gradient planes are scaled, see bwd_planes_kernel)
+  uint32_t idesc_o;                   // PV: same format, M 256 x N 256, K-major
+  const unsigned* absmax;             // bits of max |dZ| of the call: the gradient planes hold s dZ, s = grad_scale_from_absmax
+                                      // (fp16 only; null: s = 1).  delta is multiplied by s on load, O by 1 / s in the drain.
 };
 
 // Static schedule.  Cluster k of K runs its kind-0 items (k, k + K, ...) first and then a contiguous range of kind-1 items.
@@ -125,7 +130,8 @@ __device__ __forceinline__ FlashSched flash_schedule(int k, int K, int n0, int n
   return s;
 }
 
-template <int G>
+// XBF: X (and the gradient planes) are bf16 (bf16 forward) instead of scaled fp16
+template <int G, bool XBF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FlashCfg<G>::kThreads, 1)
 bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__ FlashParams p) {
   using Cfg = FlashCfg<G>;
@@ -223,8 +229,11 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           // of its own slot, so a parity wait can never be two phases behind).  With T: C1(j) -> slot 0, C2(j) -> slot 1 --
           // S runs about a tile ahead of T and one in-order producer would hold C1(j+2) back behind C2(j+1).  Without T:
           // C1(j) alternates, even tiles here, odd tiles in the other warp.
+          // C1 == C2 (phase A with one operand format: S and dP_a both multiply B_J): ONE load per tile serves both products
+          // and the two slots alternate like in a phase without T -- the column tiles are then double buffered.
+          const bool alt = !has_t || ph.c2 == ph.c1;
           for (int j = 0; j < T; ++j) {
-            if (!has_t && (j & 1)) continue;
+            if (alt && (j & 1)) continue;
             // this CTA's half of the column positions: 64 (n_last / 2 in the ragged last tile) x 256 channel rows
             const int kpos = j * k2BN + (int)rank * ((j == T - 1) ? (n_last / 2) : (k2BN / 2));
             mbar_wait(k_empty + 0, (kuse0 & 1) ^ 1, 3);
@@ -247,12 +256,13 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
         for (int pi = K.phase0; pi < K.phase0 + K.phases; ++pi) {
           const FlashPhase& ph = p.ph[pi];
           const bool has_t = ph.r2 >= 0;
+          const bool alt = !has_t || ph.c2 == ph.c1;
           for (int j = 0; j < T; ++j) {
-            if (!has_t && !(j & 1)) continue;
+            if (alt && !(j & 1)) continue;
             const int kpos = j * k2BN + (int)rank * ((j == T - 1) ? (n_last / 2) : (k2BN / 2));
             mbar_wait(k_empty + 1, (kuse1 & 1) ^ 1, 5);
             if (rank == 0) mbar_arrive_expect_tx(k_full + 1, 2 * kFKBytes);
-            tma_load_2d_pair(sK + kFKBytes, &maps.m[has_t ? ph.c2 : ph.c1], mapa_u32(smem_u32(k_full + 1), 0), kpos, n * kC);
+            tma_load_2d_pair(sK + kFKBytes, &maps.m[alt ? ph.c1 : ph.c2], mapa_u32(smem_u32(k_full + 1), 0), kpos, n * kC);
             ++kuse1;
           }
         }
@@ -300,10 +310,14 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
         // one affinity-type product of column tile j: S into the S buffer (needs the previous S in registers), or T into
         // the T buffer (follows the previous PV in the pipe, which read X out of that buffer; T itself was in registers
         // before that X existed)
+        bool shared_c = false;      // this phase's S and T read the same column tile
         auto issue_set = [&](bool is_t, int j, bool phase_has_t) {
-          const uint32_t s = phase_has_t ? (is_t ? 1u : 0u) : (uint32_t)(j & 1);
-          const uint32_t phs = (s ? kuse1 : kuse0) & 1;
-          warp_mbar_wait(k_full + s, phs, lane, 10);
+          const bool alt = !phase_has_t || shared_c;
+          const uint32_t s = alt ? (uint32_t)(j & 1) : (is_t ? 1u : 0u);
+          // shared tile: S waits for it, T reuses it (its use count was taken by S) and releases it
+          const bool reuse = shared_c && is_t;
+          const uint32_t phs = ((s ? kuse1 : kuse0) - (reuse ? 1u : 0u)) & 1;
+          if (!reuse) warp_mbar_wait(k_full + s, phs, lane, 10);
           if (pi0_trace && !is_t) FTR(j - 1, 13);
           if (!is_t && scnt > 0) warp_mbar_wait(s_free, (scnt - 1) & 1, lane, 12);
           if (pi0_trace && !is_t) FTR(j - 1, 14);
@@ -316,11 +330,11 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
 #pragma unroll
             for (int kk = 0; kk < kC / 16; ++kk)      // MN-major operands: 16 channel rows = 2048 B per K step
               umma2_ss(td, rd0 + (uint64_t)((kk * 2048) >> 4), kd0 + (uint64_t)((kk * 2048) >> 4), idesc, kk > 0);
-            umma2_commit_mc(k_empty + s, 3);
+            if (!(shared_c && !is_t)) umma2_commit_mc(k_empty + s, 3);
             umma2_commit_mc(is_t ? t_full : s_full, 3);
           }
           __syncwarp();
-          if (s) ++kuse1; else ++kuse0;
+          if (!reuse) { if (s) ++kuse1; else ++kuse0; }
           if (!is_t) ++scnt;
         };
         warp_mbar_wait(r1_full, it & 1, lane, 11);
@@ -330,6 +344,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           const bool has_t = p.ph[pi].r2 >= 0;
           if (has_t) { warp_mbar_wait(r2_full, r2cnt & 1, lane, 15); tc_fence_after(); }
           pi0_trace = (pi == K.phase0);
+          shared_c = has_t && p.ph[pi].c2 == p.ph[pi].c1;
           issue_set(false, 0, has_t);
           if (has_t) issue_set(true, 0, has_t);
           for (int j = 0; j < T; ++j) {
@@ -390,6 +405,8 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
     uint32_t scnt = 0, tcnt = 0, cvcnt = 0, nt_tile = 0;
     uint32_t xuse0 = 0, xuse1 = 0;
     uint32_t last_xb = 0;
+    const float gs = (!XBF && p.absmax != nullptr) ? grad_scale_from_absmax(__ldg(p.absmax)) : 1.0f;
+    const float inv_gs = 1.0f / gs;      // a power of two: exact
     for (int idx = 0; idx < my_items; ++idx) {
       int kd, item;
       decode(idx, kd, item);
@@ -405,13 +422,13 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
         const float* dv = has_t ? ph.dvec + (size_t)n * p.L : nullptr;
         // row vectors live in registers for the whole phase
         const float nrow = (!vcol && vrow) ? -__ldg(nv + row) * kLog2e : 0.f;
-        const float drow = (!vcol && vrow && has_t) ? __ldg(dv + row) : 0.f;
+        const float drow = (!vcol && vrow && has_t) ? __ldg(dv + row) * gs : 0.f;
         // column vectors: thread et stages element et & 127 of the normaliser (et < 128) or of delta; fetched one tile ahead
         auto fetch_col = [&](int j) -> float {
           const int pos = j * k2BN + (et & 127);
           if (!vcol || pos >= p.L) return 0.f;
           if (et < 128) return -__ldg(nv + pos) * kLog2e;
-          return has_t ? __ldg(dv + pos) : 0.f;
+          return has_t ? __ldg(dv + pos) * gs : 0.f;
         };
         float cnext = fetch_col(0);
         for (int j = 0; j < T; ++j) {
@@ -479,13 +496,13 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
                 const float x1 = pr[c * 32 + k + 1] * (__uint_as_float(tv[k + 1]) - dc.y);
                 const float x2 = pr[c * 32 + k + 2] * (__uint_as_float(tv[k + 2]) - dc.z);
                 const float x3 = pr[c * 32 + k + 3] * (__uint_as_float(tv[k + 3]) - dc.w);
-                pk[c * 16 + (k >> 1)] = pack_bf16x2(x0, x1);
-                pk[c * 16 + (k >> 1) + 1] = pack_bf16x2(x2, x3);
+                pk[c * 16 + (k >> 1)] = pack16x2<XBF>(x0, x1);
+                pk[c * 16 + (k >> 1) + 1] = pack16x2<XBF>(x2, x3);
               }
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < kCols / 2; ++k) pk[k] = pack_bf16x2(pr[2 * k], pr[2 * k + 1]);
+            for (int k = 0; k < kCols / 2; ++k) pk[k] = pack16x2<XBF>(pr[2 * k], pr[2 * k + 1]);
           }
           // X -> buffer xb once the PV that read its previous content has completed.  With T: always buffer 0, the first 64
           // columns of the T buffer -- every warp of this CTA must have T in registers before any of them overwrites it
@@ -521,7 +538,8 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           tmem_ld_wait();
           uint32_t w[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) w[k] = vrow ? pack_bf16x2(__uint_as_float(o[2 * k]), __uint_as_float(o[2 * k + 1])) : 0u;
+          for (int k = 0; k < 16; ++k)
+            w[k] = vrow ? pack_bf16x2(__uint_as_float(o[2 * k]) * inv_gs, __uint_as_float(o[2 * k + 1]) * inv_gs) : 0u;
           uint4* d4 = reinterpret_cast<uint4*>(ot + ch * 32);
 #pragma unroll
           for (int q = 0; q < 4; ++q) d4[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
@@ -541,7 +559,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < 32; ++k) old[k] = acc[(size_t)(ch * 32 + k) * p.L];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) acc[(size_t)(ch * 32 + k) * p.L] = old[k] + __uint_as_float(o[k]);
+            for (int k = 0; k < 32; ++k) acc[(size_t)(ch * 32 + k) * p.L] = fmaf(__uint_as_float(o[k]), inv_gs, old[k]);
           }
         }
       }

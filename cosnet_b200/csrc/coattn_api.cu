@@ -274,6 +274,7 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   cp.vb = static_cast<const float*>(v_b);
   cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp; cp.Na = n_a;
   cp.status = status;
+  cp.first_plane = 0;
   const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   const dim3 cgrid(n * kC, 2);
   if (in16 == 1) {
@@ -759,8 +760,8 @@ int coattn_forward(const float* v_a, const float* v_b, const float* w, const flo
 namespace {
 struct BwdLayout {
   Layout fwd;
-  int64_t off_g;   // bf16 copies of the channel-major planes [B16, A16, (Q16)] (operands of the gradient products)
-  int64_t off_w16g, off_dza16, off_dzb16, off_delta, off_dqt, off_dq16, off_wt, total;
+  int64_t off_g;   // bf16 copy of the plane A16 (operand of dW = dQ A^T, whose other operand dQ is bf16); fp16 forward only
+  int64_t off_dza16, off_dzb16, off_delta, off_dta, off_dqt, off_dq16, off_wt, total;
 };
 // Nothing of size L x L: 16-bit planes [N][C][Lp] and vectors only (the softmax matrices are recomputed tile by tile in
 // TMEM, bwd_flash_kernel.cuh).
@@ -771,10 +772,10 @@ BwdLayout make_bwd_layout(int n, int h, int w) {
   const int64_t plane = (int64_t)n * Lp * kC * 2;
   int64_t off = b.fwd.total;
   auto take = [&](int64_t bytes) { const int64_t o = off; off = round_up(off + bytes, kAlign); return o; };
-  b.off_g = take(3 * plane);
-  b.off_w16g = take((int64_t)kC * kC * 2);
+  b.off_g = take(plane);
   b.off_dza16 = take(plane); b.off_dzb16 = take(plane);
   b.off_delta = take((int64_t)2 * n * L * 4);
+  b.off_dta = take((int64_t)n * L * 4 + 64);      // d_ta [N][L] + the max |dZ| word
   b.off_dqt = take(plane); b.off_dq16 = take(plane);
   b.off_wt = take((int64_t)kC * kC * 2);
   b.total = off;
@@ -805,14 +806,15 @@ int launch_flash(cudaStream_t st, const FlashMaps& maps, FlashParams& fp, int sm
   const uint32_t n_last = (uint32_t)(((ly.L - (fp.kv_tiles - 1) * k2BN) + 15) & ~15);
   fp.idesc_s = make_idesc_16_major(2 * k2BM, k2BN, fbf16, true, true);
   fp.idesc_s_last = make_idesc_16_major(2 * k2BM, n_last, fbf16, true, true);
-  fp.idesc_t = make_idesc_16_major(2 * k2BM, k2BN, true, true, true);
-  fp.idesc_t_last = make_idesc_16_major(2 * k2BM, n_last, true, true, true);
-  fp.idesc_o = make_idesc_16(2 * k2BM, kC, true);
+  fp.idesc_t = make_idesc_16_major(2 * k2BM, k2BN, fbf16, true, true);
+  fp.idesc_t_last = make_idesc_16_major(2 * k2BM, n_last, fbf16, true, true);
+  fp.idesc_o = make_idesc_16(2 * k2BM, kC, fbf16);
   // X-producer warps per lane quadrant: 2 (8 warps, 64 tile columns per thread).  COATTN_FLASH_G=4 selects the 16-warp
   // layout of the tuning runs (same arithmetic, identical results): measured SLOWER, 572 vs 540 us for the RGB backward of
   // 8 pairs at 60x60 -- the chain is bound by the MUFU pipe and the hand-offs, not by the warp count (as in attend2).
   static const int g_sel = []() { const char* e = getenv("COATTN_FLASH_G"); return (e && e[0] == '4') ? 4 : 2; }();
-  auto kern = g_sel == 2 ? bwd_flash_kernel<2> : bwd_flash_kernel<4>;
+  auto kern = g_sel == 2 ? (fbf16 ? bwd_flash_kernel<2, true> : bwd_flash_kernel<2, false>)
+                         : (fbf16 ? bwd_flash_kernel<4, true> : bwd_flash_kernel<4, false>);
   const int threads = g_sel == 2 ? FlashCfg<2>::kThreads : FlashCfg<4>::kThreads;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFSmemBytes);
   if (e != cudaSuccess) return (int)e;
@@ -876,27 +878,30 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   const int64_t plane_elems = ly.t_pass_elems();
 
   // Operands of the forward pass are regenerated rather than kept alive between forward and backward: the 16-bit
-  // channel-major planes X = [B16, A16, Q16] in the forward's format (S must be recomputed from exactly the operands the
-  // forward used, so that exp(S - lse) is the forward's softmax).  Every other product multiplies by a bf16 gradient
-  // operand, and tcgen05 kind::f16 needs both operands in one format, so with an fp16 forward a second, bf16 copy of
-  // the planes is cast as well (its Q16 plane is only needed for counterpart gradients).
+  // channel-major planes X = [B16, A16, Q16] in the forward's format (S must be recomputed from the operands the forward
+  // used, so that exp(S - lse) is the forward's softmax).  The gradient operands of the flash sweeps (dZ_a, dZ_b, X) are in
+  // the SAME format -- scaled by one power of two with fp16 (bwd_planes_kernel) -- so the sweeps need no second copy of
+  // the features; only dW = dQ A^T, whose dQ is bf16, wants A in bf16.
   if (int e = cast_and_project_mn(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags | kInternalNeedQ16, stream)) return e;
   unsigned short* xf = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv));     // forward format
-  unsigned short* xg = xf;                                                                // bf16
+  unsigned short* b16f = xf;                              // B
+  unsigned short* a16f = xf + plane_elems;                // A
+  unsigned short* q16f = xf + 2 * plane_elems;            // Q = W A
+  unsigned short* a16 = a16f;                             // A, bf16
   if (!fbf16) {
-    xg = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_g));
-    if (int e = cast_project_core(v_a, v_b, w, xg, reinterpret_cast<unsigned short*>(seg(workspace, bl.off_w16g)), n, ly, true,
-                                  counterpart ? 1 : 0, st))
-      return e;
+    a16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_g));
+    CastParams cp;
+    cp.va = v_a; cp.vb = v_b;
+    cp.x = a16 - plane_elems;      // the kernel writes plane 1 of x
+    cp.N = n; cp.L = L; cp.Lp = Lp; cp.Na = n; cp.status = nullptr; cp.first_plane = 1;
+    const bool vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_a) & 15) == 0);
+    if (vec) cast_kernel<true, 4><<<dim3(n * kC, 1), 256, 0, st>>>(cp); else cast_kernel<true, 1><<<dim3(n * kC, 1), 256, 0, st>>>(cp);
   }
-  unsigned short* b16f = xf;                              // B, forward format
-  unsigned short* q16f = xf + 2 * plane_elems;            // Q, forward format
-  unsigned short* b16 = xg;                               // B, bf16
-  unsigned short* a16 = xg + plane_elems;                 // A, bf16
-  unsigned short* q16g = xg + 2 * plane_elems;            // Q, bf16 (counterpart gradients only)
   unsigned short* dza16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dza16));
   unsigned short* dzb16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb16));
   float* delta = reinterpret_cast<float*>(seg(workspace, bl.off_delta));
+  float* d_ta = reinterpret_cast<float*>(seg(workspace, bl.off_dta));
+  unsigned* absmax = reinterpret_cast<unsigned*>(d_ta + (size_t)n * L);
   unsigned short* dqt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dqt));
   unsigned short* dq16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dq16));
   unsigned short* wt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_wt));
@@ -905,13 +910,16 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   if ((ce = cudaMemsetAsync(d_w, 0, (size_t)kC * kC * 4, st)) != cudaSuccess) return (int)ce;
   if ((ce = cudaMemsetAsync(d_gate_w, 0, (size_t)kC * 4, st)) != cudaSuccess) return (int)ce;
   if (d_gate_b && (ce = cudaMemsetAsync(d_gate_b, 0, 4, st)) != cudaSuccess) return (int)ce;
+  if ((ce = cudaMemsetAsync(absmax, 0, 4, st)) != cudaSuccess) return (int)ce;
 
   BwdPrepParams bp;
   bp.d_cat_a = d_cat_a; bp.d_cat_b = d_cat_b; bp.z = z; bp.mask = mask; bp.gate_w = gate_w;
   bp.d_vb = d_v_b;
-  bp.dza16 = dza16; bp.dzb16 = dzb16; bp.delta = delta;
+  bp.dza16 = dza16; bp.dzb16 = dzb16; bp.delta = delta; bp.d_ta = d_ta; bp.absmax = absmax;
   bp.d_gate_w = d_gate_w; bp.d_gate_b = d_gate_b; bp.d_va = d_v_a; bp.N = n; bp.L = L; bp.Lp = Lp;
-  bwd_prep_kernel<<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
+  bwd_stats_kernel<<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
+  if (fbf16) bwd_planes_kernel<true><<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
+  else bwd_planes_kernel<false><<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
   transpose_w_kernel<<<kC, kC, 0, st>>>(w, wt);
   if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
 
@@ -921,11 +929,12 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   FlashMaps maps;
   enum { mQf = 0, mBf = 1, mDza = 2, mBg = 3, mAg = 4, mDzb = 5, vBg = 6, vDzb = 7, vQg = 8, vDza = 9 };
   {
-    struct { int idx; const void* base; uint32_t box; bool bf; } defs[kFMaps] = {
-        {mQf, q16f, 256, fbf16}, {mBf, b16f, 256, fbf16}, {mDza, dza16, 256, true}, {mBg, b16, 256, true}, {mAg, a16, 256, true},
-        {mDzb, dzb16, 256, true}, {vBg, b16, 128, true}, {vDzb, dzb16, 128, true}, {vQg, q16g, 128, true}, {vDza, dza16, 128, true}};
+    // every operand of the sweeps is in the forward's format (the "g" maps used to be bf16 copies)
+    struct { int idx; const void* base; uint32_t box; } defs[kFMaps] = {
+        {mQf, q16f, 256}, {mBf, b16f, 256}, {mDza, dza16, 256}, {mBg, b16f, 256}, {mAg, a16f, 256},
+        {mDzb, dzb16, 256}, {vBg, b16f, 128}, {vDzb, dzb16, 128}, {vQg, q16f, 128}, {vDza, dza16, 128}};
     for (const auto& d : defs)
-      if (int e = make_tmap(enc, &maps.m[d.idx], d.base, rowsC, Lp, d.box, d.bf)) return e;
+      if (int e = make_tmap(enc, &maps.m[d.idx], d.base, rowsC, Lp, d.box, fbf16)) return e;
   }
   const float* lse_a = lse;
   const float* lse_b = lse + (size_t)n * L;
@@ -936,7 +945,12 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
     // frame-A side: dQ (phase A [+ phase B]) and dA += P_b dZ_b^T
     FlashParams fp{};
     fp.N = n;
-    fp.ph[0] = FlashPhase{mQf, mBf, mDza, mBg, vBg, 0, lse_a, del_a};
+    fp.absmax = fbf16 ? nullptr : absmax;
+    // S and dP_a both multiply B_J.  COATTN_FLASH_SHARED=1 loads that tile ONCE per column tile (c1 == c2: the two ring
+    // slots then alternate, double buffered); measured 1 % SLOWER than two loads of the same tile (560 vs 556 us, RGB
+    // backward of 8 pairs at 60x60, A/B on one box): the sweep is bound by the T -> X -> PV -> T chain, not by the loads.
+    static const bool share = []() { const char* e = getenv("COATTN_FLASH_SHARED"); return e && e[0] == '1'; }();
+    fp.ph[0] = FlashPhase{mQf, mBf, mDza, share ? mBf : mBg, vBg, 0, lse_a, del_a};
     fp.ph[1] = FlashPhase{mQf, mBf, mAg, mDzb, vBg, 1, lse_b, del_b};
     fp.ph[2] = FlashPhase{mQf, mBf, -1, -1, vDzb, 1, lse_b, nullptr};
     fp.kind[0] = FlashKind{0, has_b ? 2 : 1, 0, dqt, dq16, nullptr};
@@ -951,6 +965,7 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
     //   dB[:, j] += sum_i dS[i, j] Q[:, i] + sum_i P_a[i, j] dZ_a[:, i]
     FlashParams fp{};
     fp.N = n;
+    fp.absmax = fbf16 ? nullptr : absmax;
     fp.ph[0] = FlashPhase{mBf, mQf, mBg, mDza, vQg, 1, lse_a, del_a};        // P_a (dP_a - delta_a): vectors follow the columns (i)
     fp.ph[1] = FlashPhase{mBf, mQf, -1, -1, vDza, 1, lse_a, nullptr};         // P_a dZ_a
     fp.ph[2] = FlashPhase{mBf, mQf, mDzb, mAg, vQg, 0, lse_b, del_b};        // P_b (dP_b - delta_b): vectors follow the rows (j)

@@ -414,6 +414,7 @@ struct CastParams {
   int N, L, Lp;
   int Na;              // samples of V_a (= N, or the number of query frames when each is paired with several references)
   unsigned* status;    // status block of the workspace (include/coattn_b200.h, COATTN_STATUS_*) or null
+  int first_plane;     // 0: both planes (grid.y = 2); 1 with grid.y = 1: V_a only
 };
 
 // fp16 operand range guard: the block's largest |v| goes into the status block (atomicMax on the bits of a non-negative
@@ -438,7 +439,7 @@ __device__ __forceinline__ void report_absmax(float m, bool nan, unsigned* statu
 template <bool BF16, int VEC>
 __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
   const int row = blockIdx.x;                 // n * C + c
-  const int plane = blockIdx.y;               // 0: V_b, 1: V_a
+  const int plane = blockIdx.y + p.first_plane;   // 0: V_b, 1: V_a
   if (plane == 1 && row >= p.Na * kC) return;
   const float* src = (plane ? p.va : p.vb) + (size_t)row * p.L;
   unsigned short* dst = p.x + ((size_t)plane * p.N * kC + row) * p.Lp;

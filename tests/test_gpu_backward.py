@@ -1,8 +1,11 @@
 """Gradient parity of the CUDA backward (through the autograd bridge and the C ABI) against the reference's autograd
 (golden fixtures) and the analytic oracle.  Needs a B200: `pytest -m gpu`.
 
-Tolerance: the backward runs its GEMMs on bf16/fp16 operands with fp32 accumulation (dS, dQ and the dZ operands are
-rounded to bf16), so gradients are compared with rel-L2 <= GRAD_TOL = 1e-2.
+Tolerance: the flash sweeps run on the forward's operand format with fp32 accumulation -- fp16 by default, the gradient
+operands dZ_a, dZ_b, dS scaled by one power of two per call (11 significant bits) -- and dQ is rounded to bf16 for the two
+small GEMMs behind them (dW = dQ A^T, dA += W^T dQ).  Measured against the fp64 oracle (tools/grad_err.py): d_v_a 3e-4 ... 2e-3,
+d_w 2.5e-3 ... 3.1e-3, d_gate_w 2e-4 ... 1.7e-3 up to sigma = 1.0, independent of the cotangent scale (1e-4 ... 1e3).
+GRAD_TOL = 5e-3 (it was 1e-2 while the gradient operands were bf16).
 """
 import numpy as np
 import pytest
@@ -12,7 +15,7 @@ from oracle import coattn_oracle as orc
 from tests.helpers import golden_inputs, load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
-GRAD_TOL = 1e-2
+GRAD_TOL = 5e-3
 
 
 @pytest.fixture(scope="module")
@@ -192,6 +195,10 @@ def _train_step_parity(fx, dev, Bottleneck, RGBDSegmentation_RAA, TrainStep, HOT
         delta = (after[k].detach() - before[k]).cpu().numpy()
         ref = fx["delta__" + k]
         assert np.isfinite(delta).all()
+        # 2e-2: with REAL cotangents (smooth maps coming back through the reduce convs) dS = P (dP - delta) is a difference
+        # of nearly equal terms, and the 16-bit operands of the recomputed S alone move it by ~1e-2 (measured 1.3e-2 on
+        # W, 3e-3 on the gate; an eager fp32 operator in the same harness gives 7e-5, tools/train_step_diag.py).  The
+        # random-cotangent tests above hold 5e-3.
         assert rel_l2(delta, ref) < 2e-2, (k, rel_l2(delta, ref))
     # a second step keeps everything finite (momentum buffers, BN statistics)
     loss2 = float(step(rgb[0], rgb[1], dep[0], dep[1], gt[0], gt[1]))
