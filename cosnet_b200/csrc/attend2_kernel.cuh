@@ -182,10 +182,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
-  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
-    printf("attend2: dynamic shared memory is not 1024-byte aligned\n");
-    __trap();
-  }
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();      // the swizzled operand tiles need 1024-byte alignment
   if (warp == k2KProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);

@@ -273,3 +273,28 @@ def test_split_reduce_conv_module_forward_and_backward(coattention):
     for k in grads[False]:
         ref = grads[False][k]
         assert (grads[True][k] - ref).norm() <= 5e-3 * ref.norm() + 1e-12, k   # bf16 rounding flips on ~1e-6 input differences
+
+
+def test_feature_gradients_are_run_to_run_identical(coattention):
+    """A race in the flash sweeps (barrier phases, TMEM buffer reuse, the two TMA producers of the column ring) would show
+    as run-to-run differences: d_v_a and d_v_b are accumulated in a fixed order (no atomics), so 12 runs over shapes whose
+    CTA pairs walk several items of both kinds must agree BIT FOR BIT.  (compute-sanitizer is closed on this pool,
+    profiles/r2_racecheck.txt; d_w is reduced with fp32 atomics across samples and is compared to rounding instead.)"""
+    dev = torch.device("cuda:0")
+    for (n, h, w) in ((3, 31, 41), (10, 20, 20)):
+        v_a, v_b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_features(600 + n, n, h, w, 0.66))
+        W, g, b = (torch.from_numpy(x).to(dev) for x in orc.synthetic_weights(601, bias=True))
+        r = torch.randn(2, n, 512, h, w, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+        first = None
+        for _ in range(12):
+            va = v_a.clone().requires_grad_(True); vb = v_b.clone().requires_grad_(True)
+            wt = W.clone().requires_grad_(True)
+            ca, cb = coattention(va, vb, wt, g.view(1, -1, 1, 1), b)
+            ((ca * r[0]).sum() + (cb * r[1]).sum()).backward()
+            torch.cuda.synchronize()
+            got = (va.grad.clone(), vb.grad.clone(), wt.grad.clone())
+            if first is None:
+                first = got
+            else:
+                assert torch.equal(got[0], first[0]) and torch.equal(got[1], first[1])
+                assert (got[2] - first[2]).abs().max() <= 1e-5 * first[2].abs().max()
