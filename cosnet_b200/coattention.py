@@ -394,11 +394,7 @@ class _CoAttentionFn(torch.autograd.Function):
         lib = _lib.load()
         with torch.cuda.device(dev):
             if d_cat_a is None:
-                d_cat_a = torch.zeros((n, 2 * c, h, w), dtype=torch.float32, device=dev)
-            elif ctx.gated_only:      # the C ABI takes concat-shaped cotangents; the passthrough half has no gradient here
-                d_cat_a = torch.cat([d_cat_a.float(), torch.zeros_like(d_cat_a, dtype=torch.float32)], 1)
-            if d_cat_b is not None and ctx.gated_only:
-                d_cat_b = torch.cat([d_cat_b.float(), torch.zeros_like(d_cat_b, dtype=torch.float32)], 1)
+                d_cat_a = torch.zeros((n, (c if ctx.gated_only else 2 * c), h, w), dtype=torch.float32, device=dev)
             d_cat_a = d_cat_a.contiguous().float()
             d_cat_b = None if d_cat_b is None else d_cat_b.contiguous().float()
             wt = weight.detach().float().contiguous()
@@ -409,13 +405,15 @@ class _CoAttentionFn(torch.autograd.Function):
             d_gb = torch.empty((1,), dtype=torch.float32, device=dev) if ctx.has_bias else None
             d_v_b = torch.empty(v_b.shape, dtype=torch.float32, device=dev) if ctx.v_b_needs_grad else None
             nbytes = backward_workspace_bytes(n, c, h, w, ctx.v_b_needs_grad)
-            ws = _workspace(dev, nbytes)
+            # per call, through the caching allocator (stream-ordered reuse is safe; nothing stays pinned between steps)
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             code = lib.coattn_backward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(), z.data_ptr(),
                                        lse.data_ptr(), mask.data_ptr(), d_cat_a.data_ptr(),
                                        None if d_cat_b is None else d_cat_b.data_ptr(), d_v_a.data_ptr(),
                                        None if d_v_b is None else d_v_b.data_ptr(), d_w.data_ptr(), d_gw.data_ptr(), None if d_gb is None else d_gb.data_ptr(),
-                                       _aligned_ptr(ws), nbytes, n, c, h, w, _lib.FLAG_BF16 if ctx.bf16 else 0, stream)
+                                       _aligned_ptr(ws), nbytes, n, c, h, w,
+                                       (_lib.FLAG_BF16 if ctx.bf16 else 0) | (_lib.FLAG_GATED_ONLY if ctx.gated_only else 0), stream)
             _lib.check(code, "coattn_backward")
         return d_v_a, d_v_b, d_w.to(weight.dtype), d_gw.view_as(gate_weight).to(gate_weight.dtype), d_gb, None, None
 

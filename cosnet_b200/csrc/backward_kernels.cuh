@@ -209,6 +209,8 @@ struct BwdPrepParams {
   float* d_gate_b;        // [1] or null
   float* d_va;            // [N][C][L]  initialised with the passthrough gradient
   int N, L, Lp;
+  int cat_ch;             // channels per sample of d_cat_a / d_cat_b: 2C (concat), or C (COATTN_FLAG_GATED_ONLY: the gated half
+                          // only -- no passthrough gradient, d_va / d_vb start from zero)
 };
 
 constexpr int kBwdPrepThreads = 256;
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_stats_kernel(BwdPrepParam
   const int l = blockIdx.x * kBwdPrepPos + lane;
   const bool valid = l < p.L;
   const int c0 = wrp * 32;
-  const float* dca = p.d_cat_a + ((size_t)n * 2 * kC + c0) * p.L + l;
+  const float* dca = p.d_cat_a + ((size_t)n * p.cat_ch + c0) * p.L + l;
   const float* za = p.z + ((size_t)n * kC + c0) * p.L + l;
   const bool has_b = p.d_cat_b != nullptr;
   const float ma = valid ? __ldg(p.mask + (size_t)n * p.L + l) : 0.f;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_stats_kernel(BwdPrepParam
   // ---- B side: dZ_b = dZbg * m_b (the mask is a constant), delta_b
   if (has_b) {
     dl = 0.f;
-    const float* dcb = p.d_cat_b + ((size_t)n * 2 * kC + c0) * p.L + l;
+    const float* dcb = p.d_cat_b + ((size_t)n * p.cat_ch + c0) * p.L + l;
     const float* zb = p.z + ((size_t)(p.N + n) * kC + c0) * p.L + l;
 #pragma unroll
     for (int k = 0; k < 32; ++k) { g[k] = valid ? __ldcs(dcb + (size_t)k * p.L) : 0.f; zz[k] = valid ? __ldcs(zb + (size_t)k * p.L) : 0.f; }
@@ -378,8 +380,9 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_planes_kernel(BwdPrepPara
   const float dta = valid ? __ldg(p.d_ta + (size_t)n * p.L + l) : 0.f;
   float g[32];
   {
-    const float* dca = p.d_cat_a + ((size_t)n * 2 * kC + c0) * p.L + l;
+    const float* dca = p.d_cat_a + ((size_t)n * p.cat_ch + c0) * p.L + l;
     unsigned short* dza = p.dza16 + ((size_t)n * kC + c0) * p.Lp + l;
+    const bool pass = p.cat_ch == 2 * kC;
 #pragma unroll
     for (int k = 0; k < 32; ++k) g[k] = valid ? __ldcs(dca + (size_t)k * p.L) : 0.f;
 #pragma unroll
@@ -390,13 +393,13 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_planes_kernel(BwdPrepPara
       const float* src = dca + (size_t)kC * p.L;
       float* dst = p.d_va + ((size_t)n * kC + c0) * p.L + l;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) g[k] = __ldcs(src + (size_t)k * p.L);
+      for (int k = 0; k < 32; ++k) g[k] = pass ? __ldcs(src + (size_t)k * p.L) : 0.f;
 #pragma unroll
       for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, g[k]);
     }
   }
   if (has_b) {
-    const float* dcb = p.d_cat_b + ((size_t)n * 2 * kC + c0) * p.L + l;
+    const float* dcb = p.d_cat_b + ((size_t)n * p.cat_ch + c0) * p.L + l;
     unsigned short* dzb = p.dzb16 + ((size_t)n * kC + c0) * p.Lp + l;
 #pragma unroll
     for (int k = 0; k < 32; ++k) g[k] = valid ? __ldcs(dcb + (size_t)k * p.L) : 0.f;
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_planes_kernel(BwdPrepPara
       const float* src = dcb + (size_t)kC * p.L;
       float* dst = p.d_vb + ((size_t)n * kC + c0) * p.L + l;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) g[k] = __ldcs(src + (size_t)k * p.L);
+      for (int k = 0; k < 32; ++k) g[k] = (p.cat_ch == 2 * kC) ? __ldcs(src + (size_t)k * p.L) : 0.f;
 #pragma unroll
       for (int k = 0; k < 32; ++k) __stcs(dst + (size_t)k * p.L, g[k]);
     }

@@ -917,6 +917,7 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   bp.d_vb = d_v_b;
   bp.dza16 = dza16; bp.dzb16 = dzb16; bp.delta = delta; bp.d_ta = d_ta; bp.absmax = absmax;
   bp.d_gate_w = d_gate_w; bp.d_gate_b = d_gate_b; bp.d_va = d_v_a; bp.N = n; bp.L = L; bp.Lp = Lp;
+  bp.cat_ch = (flags & COATTN_FLAG_GATED_ONLY) ? kC : 2 * kC;
   bwd_stats_kernel<<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
   if (fbf16) bwd_planes_kernel<true><<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
   else bwd_planes_kernel<false><<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);

@@ -264,7 +264,9 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
  *   inputs   v_a, v_b, w, gate_w           as in coattn_forward
  *            z [2,N,256,L], lse [2,N,L], mask [2,N,L]      saved outputs of coattn_forward
  *            d_cat_a, d_cat_b [N,512,H,W]  gradients w.r.t. the two concat tensors; d_cat_b may be NULL
- *                                          (depth modality: the B branch is gradient dead, :240-247)
+ *                                          (depth modality: the B branch is gradient dead, :240-247).  With
+ *                                          COATTN_FLAG_GATED_ONLY they are [N,256,H,W], the gradients of the gated halves a
+ *                                          gated-only forward returned (no passthrough term)
  *   outputs  d_v_a [N,256,H,W], d_w [256,256] (16-byte aligned, else COATTN_E_ALIGN), d_gate_w [256], d_gate_b [1]
  *            (may be NULL); all overwritten
  *            d_v_b [N,256,H,W] or NULL: gradient for the counterpart frame, only needed with
