@@ -496,6 +496,17 @@ def test_host_pipeline_matches_resident_path(op, host_passthrough):
         torch.cuda.synchronize()
         pipe.wait_host()
         assert torch.equal(out_a, want[0].cpu()) and torch.equal(out_b, want[1].cpu())
+    # streamed: consecutive calls without the join in between (the bench's e2e leg), one join at the end
+    if not host_passthrough:
+        out_a.zero_(); out_b.zero_()
+        out_a2 = torch.empty_like(out_a).pin_memory(); out_b2 = torch.empty_like(out_b).pin_memory()
+        pipe(v_a.pin_memory(), v_b.pin_memory(), W, g, b, out_a, out_b, join=False)
+        pipe(v_b.pin_memory(), v_a.pin_memory(), W, g, b, out_a2, out_b2, join=False)
+        pipe.join()
+        torch.cuda.synchronize()
+        swapped = op(v_b.to(dev), v_a.to(dev), W, g, b)
+        assert torch.equal(out_a, want[0].cpu()) and torch.equal(out_b, want[1].cpu())
+        assert torch.equal(out_a2, swapped[0].cpu()) and torch.equal(out_b2, swapped[1].cpu())
 
 
 def test_forward_is_cuda_graph_capturable(op):
