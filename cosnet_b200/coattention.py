@@ -37,6 +37,7 @@ class _Workspace:
         # status of graphed calls is read with check_overflow-style synchronous reads by whoever owns the graph)
         self.host = None if torch.cuda.is_current_stream_capturing() else torch.zeros(_lib.STATUS_WORDS, dtype=torch.int32).pin_memory()
         self.event = None
+        self._event = None
 
     def numel(self):
         return self.buf.numel()
@@ -46,7 +47,9 @@ class _Workspace:
         if OVERFLOW_CHECK == "off" or self.host is None or torch.cuda.is_current_stream_capturing():
             return
         self.host.copy_(self.status, non_blocking=True)
-        self.event = torch.cuda.Event()
+        if self._event is None:
+            self._event = torch.cuda.Event()
+        self.event = self._event
         self.event.record(stream)
         if OVERFLOW_CHECK == "sync":
             self.raise_if_clipped(wait=True)
@@ -96,7 +99,7 @@ class capture_scope:
         _capture_local.cache = None
 
 
-def _workspace_entry(device: torch.device, nbytes: int, tag=None) -> _Workspace:
+def _workspace_entry(device: torch.device, nbytes: int, tag=None, cur=None) -> _Workspace:
     if torch.cuda.is_current_stream_capturing():
         # a buffer allocated during capture lives in the graph's private pool: never cache it for eager use
         scope = getattr(_capture_local, "cache", None)
@@ -107,7 +110,7 @@ def _workspace_entry(device: torch.device, nbytes: int, tag=None) -> _Workspace:
             ent = scope[tag] = _Workspace(device, nbytes)
         return ent
     key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream, threading.get_ident(), tag)
+           (cur if cur is not None else torch.cuda.current_stream(device)).cuda_stream, threading.get_ident(), tag)
     with _ws_lock:
         ent = _ws_cache.get(key)
     if ent is not None:
@@ -152,6 +155,25 @@ def _aligned_ptr(buf: torch.Tensor) -> int:
     return (p + 1023) // 1024 * 1024
 
 
+def _f32(t, dev):
+    """fp32 contiguous view of a parameter on `dev` -- the tensor itself when it already is one (the usual case)."""
+    t = t.detach()
+    if t.dtype is torch.float32 and t.device == dev and t.is_contiguous():
+        return t
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+_ws_bytes_cache = {}
+
+
+def _workspace_bytes_cached(n, c, h, w):
+    key = (n, c, h, w)
+    r = _ws_bytes_cache.get(key)
+    if r is None:
+        r = _ws_bytes_cache[key] = workspace_bytes(n, c, h, w)
+    return r
+
+
 def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
     if not (v_a.is_cuda and v_b.is_cuda):
         raise _lib.CoattnError("co-attention runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
@@ -187,17 +209,17 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
     with torch.cuda.device(dev):
         v_a = v_a.contiguous()
         v_b = v_b.contiguous()
-        wt = weight.detach().to(device=dev, dtype=torch.float32).contiguous()
-        gw = gate_weight.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
-        gb = None if gate_bias is None else gate_bias.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
+        wt = _f32(weight, dev)
+        gw = _f32(gate_weight, dev).view(-1)
+        gb = None if gate_bias is None else _f32(gate_bias, dev).view(-1)
         oc = c if gated_only else 2 * c
         cat_a = torch.empty((n, oc, h, w), dtype=torch.float32, device=dev)
         cat_b = None if a_only else torch.empty((n, oc, h, w), dtype=torch.float32, device=dev)
         z = torch.empty((2, n, c, h * w), dtype=torch.float32, device=dev) if (want_z or unfused_gate) else None
         lse = torch.empty((2, n, h * w), dtype=torch.float32, device=dev)
-        nbytes = workspace_bytes(n, c, h, w)
-        ws = _workspace_entry(dev, nbytes)
+        nbytes = _workspace_bytes_cached(n, c, h, w)
         cur = torch.cuda.current_stream(dev)
+        ws = _workspace_entry(dev, nbytes, cur=cur)
         stream = cur.cuda_stream
         mask = torch.empty((2, n, h * w), dtype=torch.float32, device=dev) if want_mask else None
         flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)

@@ -25,8 +25,8 @@
 //
 // Shared memory (per CTA): two RESIDENT row-side operand tiles R1 (S) and R2 (T), 64 KB each; a 2-slot ring of 32 KB
 // column-side operand halves (C1 and C2 of a tile alternate); one 32 KB V slot.  TMEM (per CTA): [0,256) O |
-// [256,384) S | [384,512) T.  X(j) is written over the first 64 columns of the T buffer once T(j) sits in registers (a phase
-// without T uses [384,448) and [448,512) as two alternating X buffers).
+// [256,384) S | [384,512) T.  X(j) is written over T once T(j) sits in registers: every warp over the first half of its own
+// T columns (a phase without T uses [384,448) and [448,512) as two alternating X buffers).
 // Tensor-pipe order inside a phase with T:  S(0) T(0) | S(1) PV(0) T(1) | S(2) PV(1) T(2) | ...
 //   S(j+1) only needs S(j) in registers and runs early; T(j+1) follows PV(j) IN THE PIPE (the MMAs of one issuing thread
 //   execute in order), which is what makes overwriting X(j) safe without a barrier.  The first version shared ONE buffer
@@ -366,7 +366,10 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
               for (int kk = 0; kk < k2BN / 16; ++kk) {
                 if (kk < ksteps) {
                   const uint64_t bd = vd0 + (uint64_t)(((kk >> 2) * ((kC / 2) * 128) + (kk & 3) * 32) >> 4);
-                  umma2_ts(tO, tX + kk * 8, bd, p.idesc_o, (!first_pv || kk > 0) ? 1u : 0u);
+                  // with T, group g's X sits at the start of ITS OWN T columns (16 tile columns per K step, 8 TMEM columns)
+                  const uint32_t xa = has_t ? tmem + kFTmemT + (uint32_t)((kk / (kCols / 16)) * kCols + (kk % (kCols / 16)) * 8)
+                                            : tX + kk * 8;
+                  umma2_ts(tO, xa, bd, p.idesc_o, (!first_pv || kk > 0) ? 1u : 0u);
                 }
               }
               umma2_commit_mc(v_empty, 3);
@@ -504,15 +507,16 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < kCols / 2; ++k) pk[k] = pack16x2<XBF>(pr[2 * k], pr[2 * k + 1]);
           }
-          // X -> buffer xb once the PV that read its previous content has completed.  With T: always buffer 0, the first 64
-          // columns of the T buffer -- every warp of this CTA must have T in registers before any of them overwrites it
-          // (the named barrier), and t_full(j) already implies PV(j - 1), so the wait below returns at once.
+          // X -> buffer xb once the PV that read its previous content has completed.  With T ("buffer 0"): every warp writes
+          // its X over the first half of the T columns IT just pulled into registers -- no other warp's T is touched, so no
+          // barrier between the warps of a lane quadrant is needed (the first version packed X into columns [384, 448) and
+          // needed one) -- and t_full(j) already implies PV(j - 1), so the wait below returns at once.
           const uint32_t xb = has_t ? 0u : (nt_tile++ & 1u);
-          if (has_t) named_bar_sync(2 + quad, 32 * G);  // the warps of a lane quadrant: X overlaps the T columns of the lower groups
           const uint32_t xu = xb ? xuse1 : xuse0;
           if (xu > 0) { warp_mbar_wait(o_full + xb, (xu - 1) & 1, lane, 24); tc_fence_after(); }
-          if constexpr (kCols == 64) tmem_st32(tmem + lane_base + kFTmemX + xb * (k2BN / 2) + (uint32_t)(g * 32), pk);
-          else tmem_st16(tmem + lane_base + kFTmemX + xb * (k2BN / 2) + (uint32_t)(g * 16), pk);
+          const uint32_t xaddr = has_t ? tTg : tmem + lane_base + kFTmemX + xb * (k2BN / 2) + (uint32_t)(g * (kCols / 2));
+          if constexpr (kCols == 64) tmem_st32(xaddr, pk);
+          else tmem_st16(xaddr, pk);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -76,18 +77,31 @@ int check_workspace(const void* ws, int64_t bytes, const Layout& ly) {
   return COATTN_OK;
 }
 
+// Immutable per-device attributes, queried once per device and process (the only state the library keeps).
+// Written with relaxed atomics: every thread that races here writes the same values.
+constexpr int kMaxDevices = 64;
+std::atomic<int> g_dev_major[kMaxDevices];
+std::atomic<int> g_dev_sms[kMaxDevices];
+
 int check_arch(int* sm_count) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
-  int major = 0;
-  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  if (e != cudaSuccess) return (int)e;
-  if (major != 10) return COATTN_E_ARCH;
-  if (sm_count) {
-    e = cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev);
+  int major = 0, sms = 0;
+  if (dev >= 0 && dev < kMaxDevices && (major = g_dev_major[dev].load(std::memory_order_relaxed)) != 0) {
+    sms = g_dev_sms[dev].load(std::memory_order_relaxed);
+  } else {
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < kMaxDevices) {
+      g_dev_sms[dev].store(sms, std::memory_order_relaxed);
+      g_dev_major[dev].store(major, std::memory_order_relaxed);
+    }
   }
+  if (major != 10) return COATTN_E_ARCH;
+  if (sm_count) *sm_count = sms;
   return COATTN_OK;
 }
 
@@ -96,13 +110,22 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-EncodeTiledFn get_encode_fn() {
+EncodeTiledFn resolve_encode_fn() {
   // resolved through the runtime so the library has no link-time dependency on libcuda
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess) return nullptr;
   if (qres != cudaDriverEntryPointSuccess) return nullptr;
   return reinterpret_cast<EncodeTiledFn>(fn);
+}
+EncodeTiledFn get_encode_fn() {
+  static std::atomic<EncodeTiledFn> cached{nullptr};      // the entry point does not change during the life of the process
+  EncodeTiledFn fn = cached.load(std::memory_order_relaxed);
+  if (!fn) {
+    fn = resolve_encode_fn();
+    if (fn) cached.store(fn, std::memory_order_relaxed);
+  }
+  return fn;
 }
 
 // 2-D 16-bit row-major tensor [rows][cols]; box = {64 columns (128 B), box_rows}; 128-byte swizzle.
