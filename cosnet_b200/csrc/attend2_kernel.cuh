@@ -501,6 +501,50 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
     float greg[kChunks];
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) greg[ch] = (p.cat_a != nullptr) ? __ldg(p.gate_w + g * kChans + ch * 32 + lane) : 0.f;
+    // FOLD: round the projected query tile of item `item_it` to 16 bits and publish it as the affinity MMAs' A operand.
+    // Called for the first item before its sweep, and for every following item from the MIDDLE of the previous item's drain
+    // (after the gate-dot sweep over O, before the store sweep): the projection MMAs -- queued behind the last PV -- have
+    // finished by then, and S(0), S(1) of the next item are computed while the stores drain, as they were before the
+    // projection moved into the kernel.
+    auto convert_q = [&](uint32_t item_it) {
+        // the projected query tile: TMEM columns [256, 512) hold Q[row][c], c = column - 256 -> 16 bits -> shared memory as the
+        // K-major operand of the affinity MMAs (four 64-channel k-blocks of [128 rows x 128 B], 16-byte chunks XOR row % 8),
+        // over the raw tile, which every projection MMA has finished reading (proj_full)
+        warp_mbar_wait(proj_full, item_it & 1, lane, 25);
+        tc_fence_after();
+        uint8_t* qrow = sQ + rloc * 128;
+        float qmax = 0.f;
+        // all of this thread's columns leave TMEM with ONE wait (four dependent load -> wait -> store rounds cost ~2.5 k
+        // cycles per item on the path between the drain and the next item's first softmax; few other registers are live here)
+        uint32_t o[kChunks][32];
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) tmem_ld32(tmem + lane_base + k2TmemS + (uint32_t)(g * kChans + ch * 32), o[ch]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+          if constexpr (!BF16) {      // fp16 range guard (the pack below saturates at +-65504)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) qmax = fmaxf(qmax, fabsf(__uint_as_float(o[ch][k])));
+          }
+          const int c = g * kChans + ch * 32;          // first channel of this chunk
+          uint8_t* kb = qrow + (c >> 6) * (k2BM * 128);
+          const int j0 = (c & 63) >> 3;                // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(kb + (((j0 + q) ^ (rloc & 7)) << 4)) =
+                make_uint4(pack16x2<BF16>(__uint_as_float(o[ch][8 * q + 0]), __uint_as_float(o[ch][8 * q + 1])),
+                           pack16x2<BF16>(__uint_as_float(o[ch][8 * q + 2]), __uint_as_float(o[ch][8 * q + 3])),
+                           pack16x2<BF16>(__uint_as_float(o[ch][8 * q + 4]), __uint_as_float(o[ch][8 * q + 5])),
+                           pack16x2<BF16>(__uint_as_float(o[ch][8 * q + 6]), __uint_as_float(o[ch][8 * q + 7])));
+        }
+        if constexpr (!BF16) {
+          if (p.status != nullptr && __any_sync(0xffffffffu, !(qmax <= 65504.0f)) && lane == 0) atomicOr(p.status, 4u);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(qk_ready), 0));
+    };
     uint32_t pv_acc0 = 0, pv_acc1 = 0;      // PV tiles of even / odd local index completed by the earlier units
     for (int unit = cluster_id; unit < p.num_items * kSplits; unit += num_clusters, ++it) {
       const int item = unit / kSplits, part = unit - item * kSplits;
@@ -524,40 +568,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       // (zero MMA operands also draw less power, and this kernel runs against the power cap)
       const bool warp_is_padding = (qp * (2 * k2BM) + (int)rank * k2BM + quad * 32) >= p.L;
       if constexpr (FOLD) {
-        // the projected query tile: TMEM columns [256, 512) hold Q[row][c], c = column - 256 -> 16 bits -> shared memory as the
-        // K-major operand of the affinity MMAs (four 64-channel k-blocks of [128 rows x 128 B], 16-byte chunks XOR row % 8),
-        // over the raw tile, which every projection MMA has finished reading (proj_full)
-        warp_mbar_wait(proj_full, it & 1, lane, 25);
-        tc_fence_after();
-        uint8_t* qrow = sQ + rloc * 128;
-        float qmax = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < kChunks; ++ch) {
-          uint32_t o[32];
-          tmem_ld32(tmem + lane_base + k2TmemS + (uint32_t)(g * kChans + ch * 32), o);
-          tmem_ld_wait();
-          if constexpr (!BF16) {      // fp16 range guard (the pack below saturates at +-65504)
-#pragma unroll
-            for (int k = 0; k < 32; ++k) qmax = fmaxf(qmax, fabsf(__uint_as_float(o[k])));
-          }
-          const int c = g * kChans + ch * 32;          // first channel of this chunk
-          uint8_t* kb = qrow + (c >> 6) * (k2BM * 128);
-          const int j0 = (c & 63) >> 3;                // first 16-byte chunk inside the 128-byte row
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(kb + (((j0 + q) ^ (rloc & 7)) << 4)) =
-                make_uint4(pack16x2<BF16>(__uint_as_float(o[8 * q + 0]), __uint_as_float(o[8 * q + 1])),
-                           pack16x2<BF16>(__uint_as_float(o[8 * q + 2]), __uint_as_float(o[8 * q + 3])),
-                           pack16x2<BF16>(__uint_as_float(o[8 * q + 4]), __uint_as_float(o[8 * q + 5])),
-                           pack16x2<BF16>(__uint_as_float(o[8 * q + 6]), __uint_as_float(o[8 * q + 7])));
-        }
-        if constexpr (!BF16) {
-          if (p.status != nullptr && __any_sync(0xffffffffu, !(qmax <= 65504.0f)) && lane == 0) atomicOr(p.status, 4u);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(qk_ready), 0));
+        if (it == 0) convert_q(0);
       }
       float m = -INFINITY, l = 0.0f;
       if (warp == 0) TRG(8);
@@ -692,8 +703,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
       if (warp == 0) TRG(11);
       l = group_exchange_sum<G>(l, xbuf, seq++, g, rloc, quad);
       if (warp == 0) TRG(5);
+      const bool has_next = (unit + num_clusters) < p.num_items * kSplits;
       if (warp_is_padding) {     // nothing to store; keep the exchange sequence of the gate dot in step
         if (p.cat_a != nullptr) (void)group_exchange_sum<G>(0.f, xbuf, seq++, g, rloc, quad);
+        if constexpr (FOLD) { if (has_next) convert_q(it + 1); }
         continue;
       }
       const float inv = 1.0f / l;
@@ -741,6 +754,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         if (warp == 0) TRG(13);
         dot = group_exchange_sum<G>(dot, xbuf, seq++, g, rloc, quad);   // same summation order in every group
         if (warp == 0) TRG(14);
+        if constexpr (FOLD) { if (has_next) convert_q(it + 1); }      // between the two sweeps over O
         const float logit = dot * inv + (p.gate_b ? __ldg(p.gate_b) : 0.f);
         const float gate = 1.0f / (1.0f + __expf(-logit));
         const float sc = inv * gate;
@@ -772,6 +786,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
         }
         if (valid && g == 0 && p.mask != nullptr) p.mask[(size_t)(pass * p.N + n) * p.L + row] = gate;
       }
+      if constexpr (FOLD) { if (has_next && p.cat_a == nullptr) convert_q(it + 1); }      // no fused gate: after the only sweep
       if (valid && g == 0) p.lse[out_idx * p.L + row] = m + __logf(l);
       if (warp == 0) TRG(12);
     }
