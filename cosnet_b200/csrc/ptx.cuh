@@ -324,6 +324,11 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
                    "r"(smem_u32(bar)), "h"(mask)
                : "memory");
 }
+// Register re-allocation between warpgroups (4 consecutive warps; all of them execute the same instruction).  The kernel is
+// compiled for the launch-time budget (65536 / threads); a warpgroup that gives registers back (dec) lets another one take
+// more than that (inc blocks until they are available).  Values: multiples of 8 in [24, 256].
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 // named barrier among `nthreads` threads of the CTA (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
