@@ -25,10 +25,11 @@ ca, cb = torch.empty(n, 2 * C, H, W, device=dev), torch.empty(n, 2 * C, H, W, de
 lse = torch.empty(2, n, H * W, device=dev)
 nb = workspace_bytes(n, C, H, W); ws = torch.empty(nb + 1024, dtype=torch.uint8, device=dev); wp = (ws.data_ptr() + 1023) // 1024 * 1024
 st = torch.cuda.current_stream().cuda_stream
+NOPASS = os.environ.get("AB_NOPASS") == "1"      # attend without the passthrough copy warp's traffic (v_a / v_b = NULL)
 def step():
     _lib.check(lib.coattn_stage_prep_project(va.data_ptr(), vb.data_ptr(), wt.data_ptr(), wp, nb, n, C, H, W, 0, st), "p")
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
-    _lib.check(lib.coattn_stage_attend_gate(va.data_ptr(), vb.data_ptr(), ca.data_ptr(), cb.data_ptr(), None, lse.data_ptr(), None, gw.data_ptr(), None, wp, nb, n, C, H, W, 0, st), "a")
+    _lib.check(lib.coattn_stage_attend_gate(None if NOPASS else va.data_ptr(), None if NOPASS else vb.data_ptr(), ca.data_ptr(), cb.data_ptr(), None, lse.data_ptr(), None, gw.data_ptr(), None, wp, nb, n, C, H, W, 0, st), "a")
     e1.record(); return e0, e1
 for _ in range(5): step()
 torch.cuda.synchronize()
