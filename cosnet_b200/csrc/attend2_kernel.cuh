@@ -585,7 +585,8 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(s_free_l);
-          (void)group_exchange_max<G>(0.f, xbuf, seq++, g, rloc, quad);
+          if (jr == 0) (void)group_exchange_max<G>(0.f, xbuf, seq++, g, rloc, quad);
+          else if (named_bar_red_or(1 + quad, 32 * G, false)) (void)group_exchange_max<G>(0.f, xbuf, seq++, g, rloc, quad);
           uint32_t zero[kCols / 2];
 #pragma unroll
           for (int k = 0; k < kCols / 2; ++k) zero[k] = 0u;
@@ -631,18 +632,51 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             h2 = fmaxf(h2, __uint_as_float(sv[c][k + 2])); h3 = fmaxf(h3, __uint_as_float(sv[c][k + 3]));
           }
         const float hmax = fmaxf(fmaxf(h0, h1), fmaxf(h2, h3));
-        // all groups of the row agree on the tile max
-        const float tmax = group_exchange_max<G>(hmax, xbuf, seq++, g, rloc, quad);
+        uint32_t pk[kCols / 2];
+        // P = 2^(S log2e - m) for this thread's columns -> pk, returns their sum.  x = S log2e - m and the row sum run on
+        // packed fp32 pairs (FFMA2 / FADD2): the pair ops halve two of the four per-element instructions, and every lane
+        // rounds exactly like the scalar op did
+        auto exp_tile = [&](float m_ref) -> float {
+          const float neg_m = -m_ref * kLog2e;
+          const uint64_t log2e2 = f32x2_pack(kLog2e, kLog2e), neg_m2 = f32x2_pack(neg_m, neg_m);
+          uint64_t la = f32x2_pack(0.f, 0.f), lb = la;      // {l0, l1} (even pairs), {l2, l3} (odd pairs)
+#pragma unroll
+          for (int c = 0; c < kLoads; ++c)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              float x0, x1;
+              f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(sv[c][2 * k]), __uint_as_float(sv[c][2 * k + 1])), log2e2, neg_m2), x0, x1);
+              const float p0 = fast_exp2(x0);
+              const float p1 = fast_exp2(x1);
+              const uint32_t w = pack16x2<BF16>(p0, p1);
+              pk[c * 16 + k] = w;
+              const uint64_t pp = BF16 ? f32x2_pack(bf16lo_to_f32(w), bf16hi_to_f32(w)) : f32x2_pack(p0, p1);
+              if (k & 1) lb = f32x2_add(lb, pp); else la = f32x2_add(la, pp);
+            }
+          float l0, l1, l2, l3;
+          f32x2_unpack(la, l0, l1);
+          f32x2_unpack(lb, l2, l3);
+          return (l0 + l1) + (l2 + l3);
+        };
+        float lt;
         if (jr == 0) {
-          m = tmax;
+          // all groups of the row agree on the first tile's max: the reference point of the row
+          m = group_exchange_max<G>(hmax, xbuf, seq++, g, rloc, quad);
+          lt = exp_tile(m);
         } else {
           // lazy rescale: the reference max only moves when the row max jumps by more than 2^13 (fp16 P stays below
           // 8192 < 65504 and keeps its 11-bit precision at any magnitude; bf16 has the range for 2^24).  The slow
-          // path costs ~3 k cycles and stalls the whole CTA pair, and `__any_sync` takes it for all 32 rows of a warp, so
+          // path costs ~3 k cycles and stalls the whole CTA pair, and it is taken for all 32 rows of a lane quadrant, so
           // with the usual 2^8 threshold spiky features (logit sigma ~ 6 in log2 units) hit it on most early tiles.
+          // The tile is exponentiated against the CURRENT reference first; whether any row of the quadrant needs a new one is
+          // then decided by ONE barrier-with-OR among the warps that own these rows (the per-tile exchange of the row maxima
+          // through shared memory used to sit between the TMEM load and the first exponential of every tile), and only the
+          // slow path exchanges the maxima and exponentiates again.  Decisions and results are the ones of the exchange.
           constexpr float kThreshold = BF16 ? 24.0f : 13.0f;
-          const bool need = (tmax - m) * kLog2e > kThreshold;
-          if (__any_sync(0xffffffffu, need)) {
+          lt = exp_tile(m);
+          const bool need = (hmax - m) * kLog2e > kThreshold;
+          if (named_bar_red_or(1 + quad, 32 * G, need)) {
+            const float tmax = group_exchange_max<G>(hmax, xbuf, seq++, g, rloc, quad);
             const float m_new = fmaxf(m, tmax);
             const float scale = fast_exp2((m - m_new) * kLog2e);
             // S(j) follows PV(j-3) in the tensor pipe, so s_full(j) implies PV(j-3) is complete
@@ -660,28 +694,10 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
             tmem_st_wait();
             l *= scale;
             m = m_new;
+            lt = exp_tile(m);
           }
         }
-        const float neg_m = -m * kLog2e;
-        uint32_t pk[kCols / 2];
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll
-        for (int c = 0; c < kLoads; ++c)
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float x0 = fmaf(__uint_as_float(sv[c][2 * k]), kLog2e, neg_m);
-            const float x1 = fmaf(__uint_as_float(sv[c][2 * k + 1]), kLog2e, neg_m);
-            const float p0 = fast_exp2(x0);
-            const float p1 = fast_exp2(x1);
-            const uint32_t w = pack16x2<BF16>(p0, p1);
-            pk[c * 16 + k] = w;
-            if constexpr (BF16) {
-              if (k & 1) { l2 += bf16lo_to_f32(w); l3 += bf16hi_to_f32(w); } else { l0 += bf16lo_to_f32(w); l1 += bf16hi_to_f32(w); }
-            } else {
-              if (k & 1) { l2 += p0; l3 += p1; } else { l0 += p0; l1 += p1; }
-            }
-          }
-        l += (l0 + l1) + (l2 + l3);
+        l += lt;
         // packed P: the kCols keys of this group -> kCols / 2 columns of P buffer b, once PV(j-2) has read its previous
         // content (S(j) is issued ahead of PV(j-2), so s_full(j) does not imply it; the wait is almost always over)
         if (jr >= 2) { wait_pv(jr - 2, 24); tc_fence_after(); }
