@@ -740,7 +740,7 @@ def run_ours(args):
     io16_block = {
         "value": total_pairs * io16_steps / (io16_ms * 1e-3), "unit": UNIT, "ms_per_step": io16_ms / io16_steps,
         "steps": io16_steps, "feature_dtype": str(dt16), "gpu_launches_per_step": 4,
-        # whole modality call (cast_w + project_mn + attend2), algorithmic flops 6 L^2 C + 2 L C^2 per pair
+        # whole modality call (cast_w + attend2 with the projection inside), algorithmic flops 6 L^2 C + 2 L C^2 per pair
         "whole_call_tflops": 2 * n * FLOPS_PER_PAIR_MODALITY / (io16_ms / io16_steps * 1e-3) / 1e12,
         "whole_call_frac_of_burst_peak": 2 * n * FLOPS_PER_PAIR_MODALITY / (io16_ms / io16_steps * 1e-3) / 1e12 / peaks["bf16_tflops"],
         "rel_l2_vs_fp32_interface": rel16,
@@ -820,7 +820,7 @@ def run_ours(args):
         "clocks": clk,
         "e2e": e2e_block,
         "io16": io16_block,
-        "gpu_launches": 6 * args.steps,   # per modality call: cast(V_a, V_b), cast_w, attend2 (projection + gate + concat inside)
+        "gpu_launches": 4 * args.steps,   # per modality call: cast (V_a, V_b and W), attend2 (projection + gate + concat inside)
         "roofline": roofline,
         "sustained": sustained_block,
         "operands_" + other_name: other_block,

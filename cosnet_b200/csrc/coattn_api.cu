@@ -298,6 +298,11 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   cp.x = x; cp.N = n; cp.L = ly.L; cp.Lp = ly.Lp; cp.Na = n_a;
   cp.status = status;
   cp.first_plane = 0;
+  // W is cast by the first C blocks of the feature cast (256 threads = one row each); a launch of its own only when the
+  // features need no cast kernel (16-bit interfaces, planes written by the fused encoder tail)
+  const bool w_in_cast = project != 0 && in16 == 0;
+  cp.w = w_in_cast ? w : nullptr;
+  cp.w16 = w16;
   const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
   const dim3 cgrid(n * kC, 2);
   if (in16 == 1) {
@@ -311,8 +316,10 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
     if (vec) cast_kernel<false, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<false, 1><<<cgrid, 256, 0, st>>>(cp);
   }
   if (!project) return (int)cudaGetLastError();
-  if (bf16) cast_w_kernel<true><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
-  else cast_w_kernel<false><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+  if (!w_in_cast) {
+    if (bf16) cast_w_kernel<true><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+    else cast_w_kernel<false><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
+  }
   if (project == 2) return (int)cudaGetLastError();
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return COATTN_E_DRIVER;
@@ -916,7 +923,7 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
     CastParams cp;
     cp.va = v_a; cp.vb = v_b;
     cp.x = a16 - plane_elems;      // the kernel writes plane 1 of x
-    cp.N = n; cp.L = L; cp.Lp = Lp; cp.Na = n; cp.status = nullptr; cp.first_plane = 1;
+    cp.N = n; cp.L = L; cp.Lp = Lp; cp.Na = n; cp.status = nullptr; cp.first_plane = 1; cp.w = nullptr; cp.w16 = nullptr;
     const bool vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_a) & 15) == 0);
     if (vec) cast_kernel<true, 4><<<dim3(n * kC, 1), 256, 0, st>>>(cp); else cast_kernel<true, 1><<<dim3(n * kC, 1), 256, 0, st>>>(cp);
   }

@@ -415,6 +415,8 @@ struct CastParams {
   int Na;              // samples of V_a (= N, or the number of query frames when each is paired with several references)
   unsigned* status;    // status block of the workspace (include/coattn_b200.h, COATTN_STATUS_*) or null
   int first_plane;     // 0: both planes (grid.y = 2); 1 with grid.y = 1: V_a only
+  const float* w;      // [C][C] fp32 similarity weights or null: the first C blocks of plane 0 also cast one row of W each
+  unsigned short* w16; // [C][C] 16-bit (the cast_w launch of its own, 3 us + a launch gap per modality call, is gone)
 };
 
 // fp16 operand range guard: the block's largest |v| goes into the status block (atomicMax on the bits of a non-negative
@@ -440,6 +442,7 @@ template <bool BF16, int VEC>
 __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
   const int row = blockIdx.x;                 // n * C + c
   const int plane = blockIdx.y + p.first_plane;   // 0: V_b, 1: V_a
+  if (p.w != nullptr && blockIdx.y == 0 && row < kC) p.w16[row * kC + threadIdx.x] = cvt16<BF16>(p.w[row * kC + threadIdx.x]);
   if (plane == 1 && row >= p.Na * kC) return;
   const float* src = (plane ? p.va : p.vb) + (size_t)row * p.L;
   unsigned short* dst = p.x + ((size_t)plane * p.N * kC + row) * p.Lp;
