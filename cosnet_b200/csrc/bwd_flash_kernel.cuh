@@ -64,8 +64,12 @@ constexpr int kFMaps = 10;
 #ifdef COATTN_TRACE_FLASH
 __device__ long long g_flash_trace[64 * 16];
 #define FTR(j, slot) do { if (blockIdx.x == 0 && lane == 0 && idx == 1 && (j) < 64) g_flash_trace[(j) * 16 + (slot)] = clock64(); } while (0)
+// per item of cluster 0 (X warp 0): 0 item start | 1 + k end of phase k's sweep (last X stored) | 5 O complete | 6 drain done | 7 kind
+__device__ long long g_flash_items[32 * 8];
+#define FTI(slot, v) do { if (blockIdx.x == 0 && warp == 0 && lane == 0 && idx < 32) g_flash_items[idx * 8 + (slot)] = (v); } while (0)
 #else
 #define FTR(j, slot) do {} while (0)
+#define FTI(slot, v) do {} while (0)
 #endif
 
 struct FlashMaps {
@@ -417,6 +421,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
       const int qp = item % p.q_pairs, n = item / p.q_pairs;
       const int row = qp * (2 * k2BM) + (int)rank * k2BM + rloc;
       const bool vrow = row < p.L;
+      FTI(1, 0ll); FTI(2, 0ll); FTI(3, 0ll); FTI(0, clock64()); FTI(7, (long long)kd);
       for (int pi = K.phase0; pi < K.phase0 + K.phases; ++pi) {
         const FlashPhase& ph = p.ph[pi];
         const bool has_t = ph.r2 >= 0;
@@ -525,10 +530,12 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           if (xb) ++xuse1; else ++xuse0;
           last_xb = xb;
         }
+        FTI(1 + (pi - K.phase0), clock64());
       }
       // ---- drain: PV completions arrive in order; the last PV of the item read buffer last_xb
       warp_mbar_wait(o_full + last_xb, ((last_xb ? xuse1 : xuse0) - 1) & 1, lane, 22);
       tc_fence_after();
+      FTI(5, clock64());
       const int c0 = g * kCh;
       if (K.out_mode == 0) {
         // dQ: bf16, position-major [N][Lp][C] (contiguous 64-byte pieces per chunk) and channel-major [N][C][Lp]
@@ -567,6 +574,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           }
         }
       }
+      FTI(6, clock64());
     }
   }
   tc_fence_before();

@@ -868,6 +868,15 @@ int launch_flash(cudaStream_t st, const FlashMaps& maps, FlashParams& fp, int sm
                r[13] - r[0], r[14] - r[13], r[1] - r[14], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[8] - t0, r[9] - r[8], r[10] - r[9],
                r[11] - r[10], r[12] - r[11]);
       }
+      long long ib[32 * 8];
+      cudaMemcpyFromSymbol(ib, g_flash_items, sizeof(ib));
+      for (int i = 0; i < 32; ++i) {
+        const long long* r = ib + i * 8;
+        if (r[0] == 0) break;
+        printf("item %2d kind %lld: start +%8lld | sweep A %7lld | B %7lld | C %7lld | wait O %5lld | drain %6lld | total %7lld\n", i, r[7],
+               r[0] - ib[0], r[1] - r[0], r[2] ? r[2] - r[1] : 0ll, r[3] ? r[3] - r[2] : 0ll, r[5] - (r[3] ? r[3] : r[2] ? r[2] : r[1]),
+               r[6] - r[5], r[6] - r[0]);
+      }
     }
   }
 #endif
