@@ -161,7 +161,8 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
   uint64_t* x_full = bars + 12;     // (L) [2] one per X buffer
   uint64_t* o_full = bars + 14;     // [2] the PV that read X buffer b has completed
   uint64_t* t_full = bars + 16;     // T complete (both CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* t_free = bars + 18;     // (L) T sits in the registers of every X-producer warp of the pair
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,6 +179,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
     mbar_init(s_full, 1);
     mbar_init(t_full, 1);
     mbar_init(s_free, 2 * kXWarps);
+    mbar_init(t_free, 2 * kXWarps);
     for (int b = 0; b < 2; ++b) { mbar_init(x_full + b, 2 * kXWarps); mbar_init(o_full + b, 1); }
     fence_mbar_init();
   }
@@ -298,7 +300,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
     // ------------------------------------------------------------------ MMA issuer (leader CTA; uniform control flow)
     if (rank == 0) {
       const int ksteps_last = n_last / 16;
-      uint32_t it = 0, vcnt = 0, scnt = 0, r2cnt = 0;
+      uint32_t it = 0, vcnt = 0, scnt = 0, r2cnt = 0, tcnt = 0;
       uint32_t kuse0 = 0, kuse1 = 0;
       uint32_t xuse0 = 0, xuse1 = 0;   // uses of X buffer 0 / 1 so far (phase of x_full[b] / o_full[b])
       uint32_t nt_tile = 0;            // tiles of phases without T so far (they alternate between the two X buffers)
@@ -324,6 +326,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           if (!reuse) warp_mbar_wait(k_full + s, phs, lane, 10);
           if (pi0_trace && !is_t) FTR(j - 1, 13);
           if (!is_t && scnt > 0) warp_mbar_wait(s_free, (scnt - 1) & 1, lane, 12);
+          if (is_t && tcnt > 0) warp_mbar_wait(t_free, (tcnt - 1) & 1, lane, 16);
           if (pi0_trace && !is_t) FTR(j - 1, 14);
           tc_fence_after();
           const uint64_t kd0 = make_sdesc_mn_sw128(sK_addr + s * kFKBytes, 32768, 1024);
@@ -339,7 +342,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           }
           __syncwarp();
           if (!reuse) { if (s) ++kuse1; else ++kuse0; }
-          if (!is_t) ++scnt;
+          if (!is_t) ++scnt; else ++tcnt;
         };
         warp_mbar_wait(r1_full, it & 1, lane, 11);
         tc_fence_after();
@@ -349,11 +352,17 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           if (has_t) { warp_mbar_wait(r2_full, r2cnt & 1, lane, 15); tc_fence_after(); }
           pi0_trace = (pi == K.phase0);
           shared_c = has_t && p.ph[pi].c2 == p.ph[pi].c1;
+          // Order of the products.  Without T:  S(0) | S(1) PV(0) | S(2) PV(1) | ...   (X alternates between two buffers)
+          // With T:  S(0) T(0) S(1) | T(1) PV(0) S(2) | T(2) PV(1) S(3) | ...   X(j) lives in the S buffer (written over
+          // S(j+1), which every warp pulls into registers first), so T(j+1) only waits for T(j) to sit in registers and runs
+          // while X(j) is produced, and S(j+2) follows PV(j) -- the reader of X(j) -- in the pipe.  (X used to be written
+          // over T: every tile then paid the serial chain T(j) -> X(j) -> PV(j) -> T(j+1), 4.5 k cycles for 3.07 k of MMA.)
           issue_set(false, 0, has_t);
-          if (has_t) issue_set(true, 0, has_t);
+          if (has_t) { issue_set(true, 0, has_t); if (T > 1) issue_set(false, 1, has_t); }
           for (int j = 0; j < T; ++j) {
             if (pi == K.phase0) FTR(j, 0);
-            if (j + 1 < T) issue_set(false, j + 1, has_t);
+            if (has_t) { if (j + 1 < T) issue_set(true, j + 1, has_t); }
+            else if (j + 1 < T) issue_set(false, j + 1, has_t);
             if (pi == K.phase0) FTR(j, 1);
             // O += X(j) V(j)
             const uint32_t xb = has_t ? 0u : (nt_tile++ & 1u);
@@ -370,8 +379,8 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
               for (int kk = 0; kk < k2BN / 16; ++kk) {
                 if (kk < ksteps) {
                   const uint64_t bd = vd0 + (uint64_t)(((kk >> 2) * ((kC / 2) * 128) + (kk & 3) * 32) >> 4);
-                  // with T, group g's X sits at the start of ITS OWN T columns (16 tile columns per K step, 8 TMEM columns)
-                  const uint32_t xa = has_t ? tmem + kFTmemT + (uint32_t)((kk / (kCols / 16)) * kCols + (kk % (kCols / 16)) * 8)
+                  // with T, group g's X sits at the start of ITS OWN S columns (16 tile columns per K step, 8 TMEM columns)
+                  const uint32_t xa = has_t ? tmem + kFTmemS + (uint32_t)((kk / (kCols / 16)) * kCols + (kk % (kCols / 16)) * 8)
                                             : tX + kk * 8;
                   umma2_ts(tO, xa, bd, p.idesc_o, (!first_pv || kk > 0) ? 1u : 0u);
                 }
@@ -383,7 +392,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
             first_pv = false;
             ++vcnt;
             if (xb) ++xuse1; else ++xuse0;
-            if (has_t && j + 1 < T) issue_set(true, j + 1, has_t);
+            if (has_t && j + 2 < T) issue_set(false, j + 2, has_t);
             if (pi == K.phase0) FTR(j, 4);
           }
           if (has_t) {
@@ -407,6 +416,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
     const uint32_t tTg = tmem + lane_base + kFTmemT + (uint32_t)(g * kCols);
     const uint32_t tOg = tmem + lane_base + kFTmemO + (uint32_t)(g * kCh);
     const uint32_t s_free_l = mapa_u32(smem_u32(s_free), 0);
+    const uint32_t t_free_l = mapa_u32(smem_u32(t_free), 0);
     const uint32_t x_full_l0 = mapa_u32(smem_u32(x_full + 0), 0);
     const uint32_t x_full_l1 = mapa_u32(smem_u32(x_full + 1), 0);
     uint32_t scnt = 0, tcnt = 0, cvcnt = 0, nt_tile = 0;
@@ -439,56 +449,95 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           return has_t ? __ldg(dv + pos) * gs : 0.f;
         };
         float cnext = fetch_col(0);
-        for (int j = 0; j < T; ++j) {
-          float* cv = colv + (cvcnt & 1) * 256;
+        // publish the column vectors of tile j (vcol phases) in the buffer of the current parity, prefetch those of tile j + 1.
+        // The barrier also keeps a fast warp from overwriting the buffer of the tile before last.
+        auto stage_cols = [&](int j) -> float* {
+          float* cvj = colv + (cvcnt & 1) * 256;
           if (vcol) {
-            if (et < 256) cv[et] = cnext;
-            named_bar_sync(1, 128 * G);   // also keeps a fast warp from overwriting the buffer of the tile before last
+            if (et < 256) cvj[et] = cnext;
+            named_bar_sync(1, 128 * G);
             ++cvcnt;
             if (j + 1 < T && et < 256) cnext = fetch_col(j + 1);
           }
-          const int jc0 = j * k2BN + g * kCols;              // first column position of this thread
-          const bool ragged = (j == T - 1) && (jc0 + kCols > p.L);
-          // ---- S
+          return cvj;
+        };
+        // the next S tile -> registers; the buffer goes back to the issuer at once
+        auto load_s = [&](uint32_t (&sv)[kLd][32]) {
           warp_mbar_wait(s_full, scnt & 1, lane, 20);
-          if (warp == 0 && pi == K.phase0) FTR(j, 8);
           ++scnt;
           tc_fence_after();
-          float pr[kCols];
-          {
-            uint32_t sv[kLd][32];
 #pragma unroll
-            for (int c = 0; c < kLd; ++c) tmem_ld32(tSg + c * 32, sv[c]);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(s_free_l);
-            if (warp == 0 && pi == K.phase0) FTR(j, 9);
+          for (int c = 0; c < kLd; ++c) tmem_ld32(tSg + c * 32, sv[c]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(s_free_l);
+        };
+        // P = exp(S - n) of tile j for this thread's columns (padding rows / ragged columns -> 0)
+        auto exp_s = [&](const uint32_t (&sv)[kLd][32], const float* cvj, int j, float (&pr)[kCols]) {
 #pragma unroll
-            for (int c = 0; c < kLd; ++c)
+          for (int c = 0; c < kLd; ++c)
 #pragma unroll
-              for (int k = 0; k < 32; k += 4) {
-                float4 nc = make_float4(nrow, nrow, nrow, nrow);
-                if (vcol) nc = *reinterpret_cast<const float4*>(cv + g * kCols + c * 32 + k);
-                pr[c * 32 + k + 0] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 0]), kLog2e, nc.x));
-                pr[c * 32 + k + 1] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 1]), kLog2e, nc.y));
-                pr[c * 32 + k + 2] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 2]), kLog2e, nc.z));
-                pr[c * 32 + k + 3] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 3]), kLog2e, nc.w));
-              }
-          }
+            for (int k = 0; k < 32; k += 4) {
+              float4 nc = make_float4(nrow, nrow, nrow, nrow);
+              if (vcol) nc = *reinterpret_cast<const float4*>(cvj + g * kCols + c * 32 + k);
+              pr[c * 32 + k + 0] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 0]), kLog2e, nc.x));
+              pr[c * 32 + k + 1] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 1]), kLog2e, nc.y));
+              pr[c * 32 + k + 2] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 2]), kLog2e, nc.z));
+              pr[c * 32 + k + 3] = fast_exp2(fmaf(__uint_as_float(sv[c][k + 3]), kLog2e, nc.w));
+            }
+          const int jc0 = j * k2BN + g * kCols;              // first column position of this thread
           if (!vrow) {
 #pragma unroll
             for (int k = 0; k < kCols; ++k) pr[k] = 0.f;
-          } else if (ragged) {
+          } else if ((j == T - 1) && (jc0 + kCols > p.L)) {
 #pragma unroll
             for (int k = 0; k < kCols; ++k) if (jc0 + k >= p.L) pr[k] = 0.f;
           }
-          uint32_t pk[kCols / 2];
-          if (warp == 0 && pi == K.phase0) FTR(j, 10);
-          if (has_t) {
-            // ---- T, in two 32-column chunks (P x 64 + T x 64 + the packed result would not fit the register file)
+        };
+        if (!has_t) {
+          // ---- X = P: S(j) -> registers -> P -> one of the two X buffers in the T columns
+          for (int j = 0; j < T; ++j) {
+            float* cv = stage_cols(j);
+            float pr[kCols];
+            {
+              uint32_t sv[kLd][32];
+              load_s(sv);
+              exp_s(sv, cv, j, pr);
+            }
+            uint32_t pk[kCols / 2];
+#pragma unroll
+            for (int k = 0; k < kCols / 2; ++k) pk[k] = pack16x2<XBF>(pr[2 * k], pr[2 * k + 1]);
+            // X -> buffer xb once the PV that read its previous content has completed
+            const uint32_t xb = nt_tile++ & 1u;
+            const uint32_t xu = xb ? xuse1 : xuse0;
+            if (xu > 0) { warp_mbar_wait(o_full + xb, (xu - 1) & 1, lane, 24); tc_fence_after(); }
+            const uint32_t xaddr = tmem + lane_base + kFTmemX + xb * (k2BN / 2) + (uint32_t)(g * (kCols / 2));
+            if constexpr (kCols == 64) tmem_st32(xaddr, pk);
+            else tmem_st16(xaddr, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(xb ? x_full_l1 : x_full_l0);
+            if (xb) ++xuse1; else ++xuse0;
+            last_xb = xb;
+          }
+        } else {
+          // ---- X = P (T - d), software-pipelined: P(j) is in registers when T(j) arrives; T(j) -> X(j) in registers (the T
+          // buffer goes back to the issuer), then S(j+1) -> registers, then X(j) is stored over the first half of the S columns
+          // this warp has just read (no other warp's columns are touched, and s_full(j+1) implies that PV(j-1), which read
+          // X(j-1) from there, has completed), then P(j+1) is exponentiated while PV(j) and T(j+1) run.
+          float pr[kCols];
+          float* cv = stage_cols(0);
+          {
+            uint32_t sv[kLd][32];
+            load_s(sv);
+            exp_s(sv, cv, 0, pr);
+          }
+          // T(j) -> X(j) = P(j) (T(j) - d) packed to 16 bits, in two 32-column chunks (P x 64 + T x 64 + the packed result
+          // would not fit the register file); the T buffer goes back to the issuer as soon as the last chunk has left TMEM
+          auto t_to_x = [&](const float* cvj, uint32_t (&pk)[kCols / 2]) {
             warp_mbar_wait(t_full, tcnt & 1, lane, 21);
-            if (warp == 0 && pi == K.phase0) FTR(j, 11);
             ++tcnt;
             tc_fence_after();
 #pragma unroll
@@ -496,10 +545,15 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
               uint32_t tv[32];
               tmem_ld32(tTg + c * 32, tv);
               tmem_ld_wait();
+              if (c == kLd - 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(t_free_l);
+              }
 #pragma unroll
               for (int k = 0; k < 32; k += 4) {
                 float4 dc = make_float4(drow, drow, drow, drow);
-                if (vcol) dc = *reinterpret_cast<const float4*>(cv + 128 + g * kCols + c * 32 + k);
+                if (vcol) dc = *reinterpret_cast<const float4*>(cvj + 128 + g * kCols + c * 32 + k);
                 const float x0 = pr[c * 32 + k + 0] * (__uint_as_float(tv[k + 0]) - dc.x);
                 const float x1 = pr[c * 32 + k + 1] * (__uint_as_float(tv[k + 1]) - dc.y);
                 const float x2 = pr[c * 32 + k + 2] * (__uint_as_float(tv[k + 2]) - dc.z);
@@ -508,27 +562,37 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
                 pk[c * 16 + (k >> 1) + 1] = pack16x2<XBF>(x2, x3);
               }
             }
-          } else {
-#pragma unroll
-            for (int k = 0; k < kCols / 2; ++k) pk[k] = pack16x2<XBF>(pr[2 * k], pr[2 * k + 1]);
+          };
+          auto store_x = [&](const uint32_t (&pk)[kCols / 2]) {
+            // only the last tile of a phase (no S(j+1) before it) really waits here
+            if (xuse0 > 0) { warp_mbar_wait(o_full + 0, (xuse0 - 1) & 1, lane, 24); tc_fence_after(); }
+            if constexpr (kCols == 64) tmem_st32(tSg, pk);
+            else tmem_st16(tSg, pk);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(x_full_l0);
+            ++xuse0;
+          };
+#pragma unroll 1
+          for (int j = 0; j + 1 < T; ++j) {
+            uint32_t pk[kCols / 2];
+            t_to_x(cv, pk);
+            if (warp == 0 && pi == K.phase0) FTR(j, 11);
+            cv = stage_cols(j + 1);
+            uint32_t sv[kLd][32];
+            load_s(sv);
+            if (warp == 0 && pi == K.phase0) FTR(j, 9);
+            store_x(pk);
+            if (warp == 0 && pi == K.phase0) FTR(j, 12);
+            exp_s(sv, cv, j + 1, pr);
           }
-          // X -> buffer xb once the PV that read its previous content has completed.  With T ("buffer 0"): every warp writes
-          // its X over the first half of the T columns IT just pulled into registers -- no other warp's T is touched, so no
-          // barrier between the warps of a lane quadrant is needed (the first version packed X into columns [384, 448) and
-          // needed one) -- and t_full(j) already implies PV(j - 1), so the wait below returns at once.
-          const uint32_t xb = has_t ? 0u : (nt_tile++ & 1u);
-          const uint32_t xu = xb ? xuse1 : xuse0;
-          if (xu > 0) { warp_mbar_wait(o_full + xb, (xu - 1) & 1, lane, 24); tc_fence_after(); }
-          const uint32_t xaddr = has_t ? tTg : tmem + lane_base + kFTmemX + xb * (k2BN / 2) + (uint32_t)(g * (kCols / 2));
-          if constexpr (kCols == 64) tmem_st32(xaddr, pk);
-          else tmem_st16(xaddr, pk);
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(xb ? x_full_l1 : x_full_l0);
-          if (warp == 0 && pi == K.phase0) FTR(j, 12);
-          if (xb) ++xuse1; else ++xuse0;
-          last_xb = xb;
+          {
+            uint32_t pk[kCols / 2];
+            t_to_x(cv, pk);
+            store_x(pk);
+          }
+          last_xb = 0;
         }
         FTI(1 + (pi - K.phase0), clock64());
       }
