@@ -154,15 +154,17 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
   uint64_t* r2_empty = bars + 3;    // every T MMA of the phase completed
   uint64_t* k_full = bars + 4;      // (L) [2]
   uint64_t* k_empty = bars + 6;     // [2]
-  uint64_t* v_full = bars + 8;      // (L)
-  uint64_t* v_empty = bars + 9;
+  // V slots: slot 0 = sV; slots 1 and 2 = the two halves of R2, used by the phases WITHOUT T (R2 holds nothing then): with one
+  // slot PV(j+1) can only start a TMA round trip after PV(j) has completed, which bounds a T-less tile at ~2.4 k cycles + hand-offs
+  uint64_t* v_full = bars + 19;     // (L) [3]
+  uint64_t* v_empty = bars + 22;    // [3]
   uint64_t* s_full = bars + 10;     // S complete (both CTAs)
   uint64_t* s_free = bars + 11;     // (L) S sits in the registers of every softmax warp of the pair
   uint64_t* x_full = bars + 12;     // (L) [2] one per X buffer
   uint64_t* o_full = bars + 14;     // [2] the PV that read X buffer b has completed
   uint64_t* t_full = bars + 16;     // T complete (both CTAs)
   uint64_t* t_free = bars + 18;     // (L) T sits in the registers of every X-producer warp of the pair
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -175,7 +177,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
     for (int i = 0; i < kFMaps; ++i) tma_prefetch_desc(&maps.m[i]);
     mbar_init(r1_full, 1); mbar_init(r1_empty, 1); mbar_init(r2_full, 1); mbar_init(r2_empty, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
-    mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    for (int v = 0; v < 3; ++v) { mbar_init(v_full + v, 1); mbar_init(v_empty + v, 1); }
     mbar_init(s_full, 1);
     mbar_init(t_full, 1);
     mbar_init(s_free, 2 * kXWarps);
@@ -209,6 +211,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
       const uint32_t r2_full_l = mapa_u32(smem_u32(r2_full), 0);
       uint32_t it = 0, r2cnt = 0;
       uint32_t kuse0 = 0;              // loads that went through column slot 0 so far (phase of k_empty[0] / k_full[0])
+      uint32_t ntv = 0, vuse1 = 0, vuse2 = 0;   // V tiles of T-less phases so far (slot = ntv % 3), uses of V slots 1 / 2
       for (int idx = 0; idx < my_items; ++idx, ++it) {
         int kd, item;
         decode(idx, kd, item);
@@ -225,6 +228,9 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           const bool has_t = ph.r2 >= 0;
           if (has_t) {
             mbar_wait(r2_empty, (r2cnt & 1) ^ 1, 2);
+            // ... and the PVs of earlier T-less phases that read V tiles out of R2 have completed
+            if (vuse1 > 0) mbar_wait(v_empty + 1, (vuse1 - 1) & 1, 6);
+            if (vuse2 > 0) mbar_wait(v_empty + 2, (vuse2 - 1) & 1, 6);
             if (rank == 0) mbar_arrive_expect_tx(r2_full, 2 * kFRBytes);
 #pragma unroll
             for (int mc = 0; mc < 2; ++mc)
@@ -237,6 +243,9 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           // C1(j) alternates, even tiles here, odd tiles in the other warp.
           // C1 == C2 (phase A with one operand format: S and dP_a both multiply B_J): ONE load per tile serves both products
           // and the two slots alternate like in a phase without T -- the column tiles are then double buffered.
+          if (!has_t) {
+            for (int j = 0; j < T; ++j, ++ntv) { const uint32_t vs = ntv % 3; if (vs == 1) ++vuse1; else if (vs == 2) ++vuse2; }
+          }
           const bool alt = !has_t || ph.c2 == ph.c1;
           for (int j = 0; j < T; ++j) {
             if (alt && (j & 1)) continue;
@@ -277,8 +286,8 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
   } else if (warp == kFVProducerWarp) {
     // ------------------------------------------------------------------ TMA producer: V tiles
     if (lane == 0) {
-      const uint32_t v_full_l = mapa_u32(smem_u32(v_full), 0);
-      uint32_t vcnt = 0;
+      uint32_t vu0 = 0, vu1 = 0, vu2 = 0;      // loads that went through each V slot so far
+      uint32_t ntv = 0, r2done = 0;      // V tiles of T-less phases so far; phases with T so far (completions of r2_empty)
       for (int idx = 0; idx < my_items; ++idx) {
         int kd, item;
         decode(idx, kd, item);
@@ -286,13 +295,22 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
         const int n = item / p.q_pairs;
         for (int pi = K.phase0; pi < K.phase0 + K.phases; ++pi) {
           const CUtensorMap* mv = &maps.m[p.ph[pi].v];
-          for (int j = 0; j < T; ++j, ++vcnt) {
-            mbar_wait(v_empty, (vcnt & 1) ^ 1, 4);
-            if (rank == 0) mbar_arrive_expect_tx(v_full, 2 * kFVBytes);
+          const bool has_t = p.ph[pi].r2 >= 0;
+          // a T-less phase borrows R2: every T MMA of the last phase that read it must have completed
+          if (!has_t && r2done > 0) mbar_wait(r2_empty, (r2done - 1) & 1, 7);
+          for (int j = 0; j < T; ++j) {
+            const uint32_t vs = has_t ? 0u : (ntv++ % 3u);
+            uint8_t* slot = vs == 0 ? sV : sR2 + (vs - 1) * kFVBytes;
+            const uint32_t vu = vs == 0 ? vu0 : (vs == 1 ? vu1 : vu2);
+            mbar_wait(v_empty + vs, (vu & 1) ^ 1, 4);
+            if (vs == 0) ++vu0; else if (vs == 1) ++vu1; else ++vu2;
+            if (rank == 0) mbar_arrive_expect_tx(v_full + vs, 2 * kFVBytes);
+            const uint32_t v_full_l = mapa_u32(smem_u32(v_full + vs), 0);
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb)
-              tma_load_2d_pair(sV + kb * ((kC / 2) * 128), mv, v_full_l, j * k2BN + kb * 64, n * kC + (int)rank * (kC / 2));
+              tma_load_2d_pair(slot + kb * ((kC / 2) * 128), mv, v_full_l, j * k2BN + kb * 64, n * kC + (int)rank * (kC / 2));
           }
+          if (has_t) ++r2done;
         }
       }
     }
@@ -300,14 +318,15 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
     // ------------------------------------------------------------------ MMA issuer (leader CTA; uniform control flow)
     if (rank == 0) {
       const int ksteps_last = n_last / 16;
-      uint32_t it = 0, vcnt = 0, scnt = 0, r2cnt = 0, tcnt = 0;
+      uint32_t it = 0, scnt = 0, r2cnt = 0, tcnt = 0;
+      uint32_t vu0 = 0, vu1 = 0, vu2 = 0, ntv = 0;
       uint32_t kuse0 = 0, kuse1 = 0;
       uint32_t xuse0 = 0, xuse1 = 0;   // uses of X buffer 0 / 1 so far (phase of x_full[b] / o_full[b])
       uint32_t nt_tile = 0;            // tiles of phases without T so far (they alternate between the two X buffers)
       const uint32_t tO = tmem + kFTmemO, tS = tmem + kFTmemS, tT = tmem + kFTmemT;
       const uint64_t r1d0 = make_sdesc_mn_sw128(smem_u32(sR1), 32768, 1024);
       const uint64_t r2d0 = make_sdesc_mn_sw128(smem_u32(sR2), 32768, 1024);
-      const uint32_t sK_addr = smem_u32(sK), sV_addr = smem_u32(sV);
+      const uint32_t sK_addr = smem_u32(sK), sV_addr = smem_u32(sV), sR2_addr = smem_u32(sR2);
       for (int idx = 0; idx < my_items; ++idx, ++it) {
         int kd, item;
         decode(idx, kd, item);
@@ -366,13 +385,16 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
             if (pi == K.phase0) FTR(j, 1);
             // O += X(j) V(j)
             const uint32_t xb = has_t ? 0u : (nt_tile++ & 1u);
-            warp_mbar_wait(v_full, vcnt & 1, lane, 14);
+            const uint32_t vs = has_t ? 0u : (ntv++ % 3u);
+            const uint32_t vu = vs == 0 ? vu0 : (vs == 1 ? vu1 : vu2);
+            warp_mbar_wait(v_full + vs, vu & 1, lane, 14);
+            if (vs == 0) ++vu0; else if (vs == 1) ++vu1; else ++vu2;
             if (pi == K.phase0) FTR(j, 2);
             warp_mbar_wait(x_full + xb, (xb ? xuse1 : xuse0) & 1, lane, 13);
             if (pi == K.phase0) FTR(j, 3);
             tc_fence_after();
             const uint32_t tX = tmem + kFTmemX + xb * (k2BN / 2);
-            const uint64_t vd0 = make_sdesc_k_sw128(sV_addr);
+            const uint64_t vd0 = make_sdesc_k_sw128(vs == 0 ? sV_addr : sR2_addr + (vs - 1) * kFVBytes);
             const int ksteps = (j == T - 1) ? ksteps_last : k2BN / 16;
             if (elect_one()) {
 #pragma unroll
@@ -385,12 +407,11 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
                   umma2_ts(tO, xa, bd, p.idesc_o, (!first_pv || kk > 0) ? 1u : 0u);
                 }
               }
-              umma2_commit_mc(v_empty, 3);
+              umma2_commit_mc(v_empty + vs, 3);
               umma2_commit_mc(o_full + xb, 3);
             }
             __syncwarp();
             first_pv = false;
-            ++vcnt;
             if (xb) ++xuse1; else ++xuse0;
             if (has_t && j + 2 < T) issue_set(false, j + 2, has_t);
             if (pi == K.phase0) FTR(j, 4);
