@@ -154,8 +154,8 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
   uint64_t* r2_empty = bars + 3;    // every T MMA of the phase completed
   uint64_t* k_full = bars + 4;      // (L) [2]
   uint64_t* k_empty = bars + 6;     // [2]
-  // V slots: slot 0 = sV; slots 1 and 2 = the two halves of R2, used by the phases WITHOUT T (R2 holds nothing then): with one
-  // slot PV(j+1) can only start a TMA round trip after PV(j) has completed, which bounds a T-less tile at ~2.4 k cycles + hand-offs
+  // V slots: slot 0 = sV; slots 1 and 2 = the two halves of R2, borrowed by the T-less items that run last (R2 holds nothing
+  // then): with one slot PV(j+1) can only start a TMA round trip after PV(j) has completed (~2.4 k cycles per tile + hand-offs)
   uint64_t* v_full = bars + 19;     // (L) [3]
   uint64_t* v_empty = bars + 22;    // [3]
   uint64_t* s_full = bars + 10;     // S complete (both CTAs)
@@ -211,7 +211,6 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
       const uint32_t r2_full_l = mapa_u32(smem_u32(r2_full), 0);
       uint32_t it = 0, r2cnt = 0;
       uint32_t kuse0 = 0;              // loads that went through column slot 0 so far (phase of k_empty[0] / k_full[0])
-      uint32_t ntv = 0, vuse1 = 0, vuse2 = 0;   // V tiles of T-less phases so far (slot = ntv % 3), uses of V slots 1 / 2
       for (int idx = 0; idx < my_items; ++idx, ++it) {
         int kd, item;
         decode(idx, kd, item);
@@ -228,9 +227,6 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           const bool has_t = ph.r2 >= 0;
           if (has_t) {
             mbar_wait(r2_empty, (r2cnt & 1) ^ 1, 2);
-            // ... and the PVs of earlier T-less phases that read V tiles out of R2 have completed
-            if (vuse1 > 0) mbar_wait(v_empty + 1, (vuse1 - 1) & 1, 6);
-            if (vuse2 > 0) mbar_wait(v_empty + 2, (vuse2 - 1) & 1, 6);
             if (rank == 0) mbar_arrive_expect_tx(r2_full, 2 * kFRBytes);
 #pragma unroll
             for (int mc = 0; mc < 2; ++mc)
@@ -243,9 +239,6 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
           // C1(j) alternates, even tiles here, odd tiles in the other warp.
           // C1 == C2 (phase A with one operand format: S and dP_a both multiply B_J): ONE load per tile serves both products
           // and the two slots alternate like in a phase without T -- the column tiles are then double buffered.
-          if (!has_t) {
-            for (int j = 0; j < T; ++j, ++ntv) { const uint32_t vs = ntv % 3; if (vs == 1) ++vuse1; else if (vs == 2) ++vuse2; }
-          }
           const bool alt = !has_t || ph.c2 == ph.c1;
           for (int j = 0; j < T; ++j) {
             if (alt && (j & 1)) continue;
@@ -296,10 +289,14 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
         for (int pi = K.phase0; pi < K.phase0 + K.phases; ++pi) {
           const CUtensorMap* mv = &maps.m[p.ph[pi].v];
           const bool has_t = p.ph[pi].r2 >= 0;
-          // a T-less phase borrows R2: every T MMA of the last phase that read it must have completed
-          if (!has_t && r2done > 0) mbar_wait(r2_empty, (r2done - 1) & 1, 7);
+          // Items of kind 1 that consist of ONE T-less phase borrow R2 for two more V slots.  They run after all kind-0 items
+          // of the cluster (flash_schedule), so no phase with T -- no load of R2 -- can follow them: the R producer needs no
+          // guard (it runs phases ahead of the PVs, and a parity wait cannot look back more than one completion).  Here:
+          // every T MMA of the last phase that read R2 must have completed (this warp is at most one tile ahead of the PVs).
+          const bool borrow = !has_t && K.phases == 1 && kd == 1;
+          if (borrow && r2done > 0) mbar_wait(r2_empty, (r2done - 1) & 1, 7);
           for (int j = 0; j < T; ++j) {
-            const uint32_t vs = has_t ? 0u : (ntv++ % 3u);
+            const uint32_t vs = borrow ? (ntv++ % 3u) : 0u;
             uint8_t* slot = vs == 0 ? sV : sR2 + (vs - 1) * kFVBytes;
             const uint32_t vu = vs == 0 ? vu0 : (vs == 1 ? vu1 : vu2);
             mbar_wait(v_empty + vs, (vu & 1) ^ 1, 4);
@@ -385,7 +382,7 @@ bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__
             if (pi == K.phase0) FTR(j, 1);
             // O += X(j) V(j)
             const uint32_t xb = has_t ? 0u : (nt_tile++ & 1u);
-            const uint32_t vs = has_t ? 0u : (ntv++ % 3u);
+            const uint32_t vs = (!has_t && K.phases == 1 && kd == 1) ? (ntv++ % 3u) : 0u;      // see the V producer
             const uint32_t vu = vs == 0 ? vu0 : (vs == 1 ? vu1 : vu2);
             warp_mbar_wait(v_full + vs, vu & 1, lane, 14);
             if (vs == 0) ++vu0; else if (vs == 1) ++vu1; else ++vu2;

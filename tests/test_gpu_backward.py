@@ -94,7 +94,10 @@ def test_gradients_with_bf16_forward(coattention, n, h, w, bias, with_b):
     assert np.isfinite(got["d_v_a"]).all()
 
 
-@pytest.mark.parametrize("n,h,w,bias", [(1, 4, 5, False), (2, 12, 11, True)])
+# (1, 17, 44) and (3, 40, 14): several row tiles AND six / five column tiles per sweep -- the sizes at which a pipeline
+# hazard between the phases of one work item (a phase with T, one without, one with) shows; the small shapes cannot
+@pytest.mark.parametrize("n,h,w,bias", [(1, 4, 5, False), (2, 12, 11, True), (1, 17, 44, True), (3, 40, 14, False),
+                                        (1, 37, 40, True)])
 def test_counterpart_gradients(coattention, n, h, w, bias):
     """no_grad_for_counterpart=False (:147-148): V_b receives gradient too."""
     v_a, v_b = orc.synthetic_features(400 + h * w, n, h, w, 0.66)
