@@ -354,7 +354,8 @@ def extra_workloads(args, dev, world, rank, barrier):
     def bwd5(m, wsp, st):
         _lib.check(lib.coattn_backward(P(m["a"]), P(m["b"]), P(m["w"]), P(m["gw"]), P(m["z"]), P(m["lse"]), P(m["mask"]),
                                        P(ra), P(rb) if m["has_b"] else None, P(m["dva"]), None, P(m["dw"]), P(m["dgw"]),
-                                       P(m["dgb"]) if m["gb"] is not None else None, wsp, nb_b, n, C, h, w, 0, st),
+                                       P(m["dgb"]) if m["gb"] is not None else None, wsp, nb_b, n, C, h, w,
+                                       _lib.FLAG_PLANES_READY, st),      # the forward above ran on this very workspace
                    "coattn_backward")
 
     def step5(record=False):
@@ -392,8 +393,9 @@ def extra_workloads(args, dev, world, rank, barrier):
         "pairs_per_gpu": n, "feat_hw": [h, w], "backward_ms": bwd_ms,
         "backward_tflops_algorithmic": bwd_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms else None,
         "backward_workspace_bytes": nb_b, "forward_workspace_bytes": nb_f,
-        "note": "coattn_forward + coattn_backward of both modalities through the C ABI (preallocated buffers; RGB and depth on two "
-                "streams, joined before the collective), then one NCCL all-reduce of the 131 585 hot-path gradients; includes "
+        "note": "coattn_forward + coattn_backward of both modalities through the C ABI (preallocated buffers, one workspace per "
+                "modality shared by its forward and backward: COATTN_FLAG_PLANES_READY, the backward reuses the forward's 16-bit "
+                "planes; RGB and depth on two streams, joined before the collective), then one NCCL all-reduce of the 131 585 hot-path gradients; includes "
                 "the all-reduce"}
     return out
 

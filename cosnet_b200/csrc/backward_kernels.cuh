@@ -421,11 +421,27 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_planes_kernel(BwdPrepPara
   }
 }
 
-// W [C_out][C_in] fp32 -> Wt [C_in][C_out] bf16 (B operand of dA += dQ W: dA[i][c] = sum_d dQt[i][d] Wt[c][d])
-__global__ void transpose_w_kernel(const float* __restrict__ w, unsigned short* __restrict__ wt) {
-  const int c = blockIdx.x;       // C_in
-  const int d = threadIdx.x;      // C_out
+// Start of a backward call, ONE launch instead of four memsets and two small kernels (each ~2.5 us of launch gap in a call
+// whose small kernels add up to a quarter of its time): grid = C blocks of C threads.
+//   Wt [C_in][C_out] bf16 = W^T   (B operand of dA += dQ W: dA[i][c] = sum_d dQt[i][d] Wt[c][d])
+//   W16 [C_out][C_in] = W in the forward's operand format (w16 != null: the feature cast, which would have done it, is skipped)
+//   d_w, d_gate_w, d_gate_b, absmax = 0   (accumulated with atomics by the kernels that follow)
+template <bool BF16>
+__global__ void bwd_init_kernel(const float* __restrict__ w, unsigned short* __restrict__ wt, unsigned short* __restrict__ w16,
+                                float* __restrict__ d_w, float* __restrict__ d_gate_w, float* __restrict__ d_gate_b,
+                                unsigned* __restrict__ absmax) {
+  const int c = blockIdx.x;
+  const int d = threadIdx.x;
   wt[c * kC + d] = cvt16<true>(w[d * kC + c]);
+  if (w16 != nullptr) w16[c * kC + d] = cvt16<BF16>(w[c * kC + d]);
+  d_w[c * kC + d] = 0.f;
+  if (c == 0) {
+    d_gate_w[d] = 0.f;
+    if (d == 0) {
+      if (d_gate_b != nullptr) *d_gate_b = 0.f;
+      *absmax = 0u;
+    }
+  }
 }
 
 }  // namespace coattn

@@ -21,6 +21,7 @@ using namespace coattn;
 constexpr int64_t kAlign = 1024;
 constexpr unsigned kInternalPrepOnlyB = 1u << 30;   // internal: prep converts V_b only (V_a goes through project_fused)
 constexpr unsigned kInternalNeedQ16 = 1u << 29;     // internal: the caller (backward) needs the projected plane Q16 in the workspace
+constexpr unsigned kInternalW16Ready = 1u << 28;    // internal: W16 of the workspace is already written (bwd_init_kernel)
 inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct Layout {
@@ -289,7 +290,7 @@ static int prep_and_project_fused(const float* v_a, const float* v_b, const floa
 //         2 = 16-bit features consumed in place: nothing is copied and the projection reads V_a through its own map
 static int cast_project_core(const void* v_a, const void* v_b, const float* w, unsigned short* x, unsigned short* w16,
                              int n, const Layout& ly, bool bf16, int project, cudaStream_t st, int n_a = -1,
-                             int in16 = 0, unsigned* status = nullptr) {
+                             int in16 = 0, unsigned* status = nullptr, bool w_ready = false) {
   // project: 0 = cast only, 1 = cast + W16 + Q16 = W V_a (project_mn), 2 = cast + W16 (the attend kernel projects itself)
   if (n_a < 0) n_a = n;       // samples of V_a (query frames); the planes are laid out for n samples either way
   CastParams cp;
@@ -300,7 +301,7 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   cp.first_plane = 0;
   // W is cast by the first C blocks of the feature cast (256 threads = one row each); a launch of its own only when the
   // features need no cast kernel (16-bit interfaces, planes written by the fused encoder tail)
-  const bool w_in_cast = project != 0 && in16 == 0;
+  const bool w_in_cast = project != 0 && in16 == 0 && !w_ready;
   cp.w = w_in_cast ? w : nullptr;
   cp.w16 = w16;
   const bool vec = (ly.L % 4 == 0) && (((reinterpret_cast<uintptr_t>(v_a) | reinterpret_cast<uintptr_t>(v_b)) & 15) == 0);
@@ -316,7 +317,7 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
     if (vec) cast_kernel<false, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<false, 1><<<cgrid, 256, 0, st>>>(cp);
   }
   if (!project) return (int)cudaGetLastError();
-  if (!w_in_cast) {
+  if (!w_in_cast && !w_ready) {
     if (bf16) cast_w_kernel<true><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
     else cast_w_kernel<false><<<(kC * kC + 255) / 256, 256, 0, st>>>(w, w16, kC * kC);
   }
@@ -361,7 +362,7 @@ static int cast_and_project_mn(const float* v_a, const float* v_b, const float* 
                            reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16)), n, ly,
                            (flags & COATTN_FLAG_BF16) != 0, (uses_fold(flags) && !(flags & kInternalNeedQ16)) ? 2 : 1,
                            static_cast<cudaStream_t>(stream), -1, (flags & COATTN_FLAG_PLANES_READY) ? 3 : 0,
-                           reinterpret_cast<unsigned*>(seg(workspace, ly.off_status)));
+                           reinterpret_cast<unsigned*>(seg(workspace, ly.off_status)), (flags & kInternalW16Ready) != 0);
 }
 
 extern "C" int coattn_stage_tail(const float* x, const float* scale, const float* shift, const float* slope, float* y,
@@ -921,7 +922,17 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   // used, so that exp(S - lse) is the forward's softmax).  The gradient operands of the flash sweeps (dZ_a, dZ_b, X) are in
   // the SAME format -- scaled by one power of two with fp16 (bwd_planes_kernel) -- so the sweeps need no second copy of
   // the features; only dW = dQ A^T, whose dQ is bf16, wants A in bf16.
-  if (int e = cast_and_project_mn(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_, flags | kInternalNeedQ16, stream)) return e;
+  // COATTN_FLAG_PLANES_READY: the caller ran the forward of this call on THIS workspace (a backward workspace starts with the
+  // forward layout) and nothing has touched it since -- planes B16 and A16 are still there and the feature cast is skipped.
+  unsigned short* wt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_wt));
+  unsigned* absmax = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(seg(workspace, bl.off_dta)) + (size_t)n * ly.L);
+  {
+    unsigned short* w16 = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16));
+    if (fbf16) bwd_init_kernel<true><<<kC, kC, 0, st>>>(w, wt, w16, d_w, d_gate_w, d_gate_b, absmax);
+    else bwd_init_kernel<false><<<kC, kC, 0, st>>>(w, wt, w16, d_w, d_gate_w, d_gate_b, absmax);
+  }
+  if (int e = cast_and_project_mn(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_,
+                                  flags | kInternalNeedQ16 | kInternalW16Ready, stream)) return e;
   unsigned short* xf = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_vv));     // forward format
   unsigned short* b16f = xf;                              // B
   unsigned short* a16f = xf + plane_elems;                // A
@@ -940,16 +951,10 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   unsigned short* dzb16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb16));
   float* delta = reinterpret_cast<float*>(seg(workspace, bl.off_delta));
   float* d_ta = reinterpret_cast<float*>(seg(workspace, bl.off_dta));
-  unsigned* absmax = reinterpret_cast<unsigned*>(d_ta + (size_t)n * L);
   unsigned short* dqt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dqt));
   unsigned short* dq16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dq16));
-  unsigned short* wt = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_wt));
 
   cudaError_t ce;
-  if ((ce = cudaMemsetAsync(d_w, 0, (size_t)kC * kC * 4, st)) != cudaSuccess) return (int)ce;
-  if ((ce = cudaMemsetAsync(d_gate_w, 0, (size_t)kC * 4, st)) != cudaSuccess) return (int)ce;
-  if (d_gate_b && (ce = cudaMemsetAsync(d_gate_b, 0, 4, st)) != cudaSuccess) return (int)ce;
-  if ((ce = cudaMemsetAsync(absmax, 0, 4, st)) != cudaSuccess) return (int)ce;
 
   BwdPrepParams bp;
   bp.d_cat_a = d_cat_a; bp.d_cat_b = d_cat_b; bp.z = z; bp.mask = mask; bp.gate_w = gate_w;
@@ -960,7 +965,6 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   bwd_stats_kernel<<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
   if (fbf16) bwd_planes_kernel<true><<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
   else bwd_planes_kernel<false><<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
-  transpose_w_kernel<<<kC, kC, 0, st>>>(w, wt);
   if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
 
   const uint64_t rowsL = (uint64_t)n * Lp, rowsC = (uint64_t)n * kC;

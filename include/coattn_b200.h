@@ -274,6 +274,12 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
  *            and a bf16 projection.  `counterpart` in the size query is kept for ABI stability and ignored.
  * Nothing of size L x L exists in the workspace: S, dP_a and dP_b are recomputed per 256 x 128 tile in TMEM
  * (csrc/bwd_flash_kernel.cuh); the scratch is 16-bit planes [N][256][round_up(L, 256)] and a few vectors, linear in L.
+ *
+ * A backward workspace BEGINS with the forward layout.  A caller that ran coattn_forward of the same call (same n, shape,
+ * operand format, features) on this very buffer -- sized by coattn_backward_workspace_bytes -- and has not let anything
+ * else write to it since may pass COATTN_FLAG_PLANES_READY: the 16-bit planes of V_a and V_b are then taken as they are
+ * and the feature cast (the forward's operands regenerated from v_a / v_b) is skipped; results are bit-identical.  Without
+ * the flag the backward assumes nothing about the workspace's content.
  */
 int64_t coattn_backward_workspace_bytes(int n, int c, int h, int w, int counterpart);
 int coattn_backward(const float* v_a, const float* v_b, const float* w, const float* gate_w, const float* z,

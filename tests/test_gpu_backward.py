@@ -301,3 +301,47 @@ def test_feature_gradients_are_run_to_run_identical(coattention):
             else:
                 assert torch.equal(got[0], first[0]) and torch.equal(got[1], first[1])
                 assert (got[2] - first[2]).abs().max() <= 1e-5 * first[2].abs().max()
+
+
+def test_backward_reuses_the_forward_planes_bit_exactly(coattention):
+    """COATTN_FLAG_PLANES_READY in coattn_backward: forward and backward of one call share a workspace (a backward workspace
+    begins with the forward layout), the backward skips the feature cast -- same gradients, bit for bit, as the plain call."""
+    from cosnet_b200 import _lib
+    from cosnet_b200.coattention import backward_workspace_bytes, workspace_bytes
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    n, h, w, C = 2, 23, 37, 256
+    L = h * w
+    v_a, v_b = orc.synthetic_features(77, n, h, w, 0.66)
+    W, g, b = orc.synthetic_weights(78, bias=True)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    va, vb, wt, gw, gb = t(v_a), t(v_b), t(W), t(g), t(b)
+    gen = torch.Generator(device=dev); gen.manual_seed(3)
+    ra = torch.randn((n, 2 * C, h, w), generator=gen, device=dev)
+    rb = torch.randn((n, 2 * C, h, w), generator=gen, device=dev)
+    ca, cb = torch.empty((n, 2 * C, h, w), device=dev), torch.empty((n, 2 * C, h, w), device=dev)
+    z, lse, mask = torch.empty((2, n, C, L), device=dev), torch.empty((2, n, L), device=dev), torch.empty((2, n, L), device=dev)
+    nbf, nbb = workspace_bytes(n, C, h, w), backward_workspace_bytes(n, C, h, w, False)
+    assert nbb >= nbf
+    st = torch.cuda.current_stream(dev).cuda_stream
+    P = lambda x: None if x is None else x.data_ptr()
+    outs = []
+    for flags in (0, _lib.FLAG_PLANES_READY):
+        ws = torch.full((nbb + 1024,), 0x5A, dtype=torch.uint8, device=dev)      # garbage: the plain call must not depend on it
+        wsp = (ws.data_ptr() + 1023) // 1024 * 1024
+        _lib.check(lib.coattn_status_clear(wsp, st), "clear")
+        _lib.check(lib.coattn_forward(P(va), P(vb), P(wt), P(gw), P(gb), P(ca), P(cb), P(z), P(lse), P(mask), wsp, nbb,
+                                      n, C, h, w, 0, st), "fwd")
+        dva, dw = torch.empty((n, C, h, w), device=dev), torch.empty((C, C), device=dev)
+        dgw, dgb = torch.empty(C, device=dev), torch.empty(1, device=dev)
+        _lib.check(lib.coattn_backward(P(va), P(vb), P(wt), P(gw), P(z), P(lse), P(mask), P(ra), P(rb), P(dva), None, P(dw),
+                                       P(dgw), P(dgb), wsp, nbb, n, C, h, w, flags, st), "bwd")
+        torch.cuda.synchronize()
+        outs.append((dva, dgw, dgb, dw))
+    assert torch.equal(outs[0][0], outs[1][0])
+    # d_gate_w, d_gate_b and d_w are reduced with fp32 atomics (the order varies from run to run)
+    for k in (1, 2, 3):
+        assert float((outs[0][k] - outs[1][k]).norm() / outs[0][k].norm()) < 1e-5
+    ref = orc.coattention_grads(v_a, v_b, W, g, b, ra.cpu().numpy(), rb.cpu().numpy(), counterpart_grad=False)
+    assert rel_l2(outs[1][0].cpu().numpy(), ref["d_v_a"]) < GRAD_TOL
+    assert rel_l2(outs[1][3].cpu().numpy(), ref["d_w"]) < GRAD_TOL

@@ -11,6 +11,7 @@ from cosnet_b200.coattention import backward_workspace_bytes, workspace_bytes
 
 n = int(os.environ.get("PAIRS", "8")); h = int(os.environ.get("FH", "60")); w = int(os.environ.get("FW", "60")); C = 256
 reps = int(os.environ.get("REPS", "1"))
+bflags = int(os.environ.get("BWD_FLAGS", "0"))      # 512 = COATTN_FLAG_PLANES_READY: the backward reuses the forward's planes
 dev = torch.device("cuda:0")
 lib = _lib.load()
 g = torch.Generator(device=dev); g.manual_seed(1)
@@ -35,6 +36,6 @@ for has_b in (True, False):
         if r == 2:
             torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e0.record()
         _lib.check(lib.coattn_backward(P(va), P(vb), P(W), P(gw), P(z), P(lse), P(mask), P(ra), P(rb) if has_b else None, P(dva), None,
-                                       P(dw), P(dgw), P(dgb), wsp, nbb, n, C, h, w, 0, st), "bwd")
+                                       P(dw), P(dgw), P(dgb), wsp, nbb, n, C, h, w, bflags, st), "bwd")
     e1.record(); torch.cuda.synchronize()
     print(f"backward has_b={has_b}: {e0.elapsed_time(e1) / reps * 1e3:.1f} us per call ({n} pairs {h}x{w})", flush=True)
