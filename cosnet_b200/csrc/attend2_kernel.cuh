@@ -155,6 +155,7 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
   constexpr int k2KProducerWarp = Cfg::kKProducerWarp, k2MmaWarp = Cfg::kMmaWarp, k2VProducerWarp = Cfg::kVProducerWarp,
                 k2CopyWarp = Cfg::kCopyWarp;
   constexpr int k2ScratchBytes = Cfg::kScratchBytes;
+  pdl_wait();      // launched with programmatic stream serialization (the cast kernel before it may still be draining)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + k2QBytes;

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(kNumThreads, 2)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a,  // [batch*a_rows][K], box {64, 128}
                const __grid_constant__ CUtensorMap tmap_b,  // [batch*b_rows][K], box {64, 128}
                GemmParams p) {
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
@@ -271,6 +272,7 @@ __device__ __forceinline__ float warp_multi_reduce32(float (&v)[32], int lane, i
 
 // PASS 0: statistics
 __global__ void __launch_bounds__(kBwdPrepThreads) bwd_stats_kernel(BwdPrepParams p) {
+  pdl_wait();
   __shared__ float red[8][kBwdPrepPos];
   __shared__ float redm[8];
   const int n = blockIdx.y;
@@ -367,6 +369,7 @@ __global__ void __launch_bounds__(kBwdPrepThreads) bwd_stats_kernel(BwdPrepParam
 // PASS 1: scaled 16-bit planes + passthrough gradients.  BF16: bf16 planes, no scaling.
 template <bool BF16>
 __global__ void __launch_bounds__(kBwdPrepThreads) bwd_planes_kernel(BwdPrepParams p) {
+  pdl_wait();
   const int n = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int wrp = threadIdx.x >> 5;
@@ -430,6 +433,7 @@ template <bool BF16>
 __global__ void bwd_init_kernel(const float* __restrict__ w, unsigned short* __restrict__ wt, unsigned short* __restrict__ w16,
                                 float* __restrict__ d_w, float* __restrict__ d_gate_w, float* __restrict__ d_gate_b,
                                 unsigned* __restrict__ absmax) {
+  pdl_wait();
   const int c = blockIdx.x;
   const int d = threadIdx.x;
   wt[c * kC + d] = cvt16<true>(w[d * kC + c]);

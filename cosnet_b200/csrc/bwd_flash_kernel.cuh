@@ -138,6 +138,7 @@ __device__ __forceinline__ FlashSched flash_schedule(int k, int K, int n0, int n
 template <int G, bool XBF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FlashCfg<G>::kThreads, 1)
 bwd_flash_kernel(const __grid_constant__ FlashMaps maps, const __grid_constant__ FlashParams p) {
+  pdl_wait();
   using Cfg = FlashCfg<G>;
   constexpr int kXWarps = Cfg::kXWarps, kCols = Cfg::kCols, kLd = Cfg::kLd, kCh = Cfg::kCh;
   constexpr int kFProducerWarp = kXWarps, kFMmaWarp = kXWarps + 1, kFVProducerWarp = kXWarps + 2, kFC2ProducerWarp = kXWarps + 3;

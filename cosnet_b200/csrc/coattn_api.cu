@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <utility>
 #include "coattn_kernels.cuh"
 #include "attend2_kernel.cuh"
 #include "backward_kernels.cuh"
@@ -143,6 +144,23 @@ int make_tmap(EncodeTiledFn enc, CUtensorMap* out, const void* base, uint64_t ro
 }
 
 inline uint8_t* seg(void* ws, int64_t off) { return static_cast<uint8_t*>(ws) + off; }
+
+// Launch with programmatic stream serialization: the grid may be scheduled while its predecessor in the stream drains; the
+// kernel itself waits (pdl_wait, first statement) until the predecessor has completed.  Only for kernels that do so.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 }  // namespace
 
@@ -312,9 +330,9 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   } else if (in16 == 2 || in16 == 3) {
     // 2: 16-bit features consumed in place; 3: the planes were already written by coattn_stage_tail
   } else if (bf16) {
-    if (vec) cast_kernel<true, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<true, 1><<<cgrid, 256, 0, st>>>(cp);
+    if (cudaError_t e = launch_pdl(vec ? cast_kernel<true, 4> : cast_kernel<true, 1>, cgrid, dim3(256), 0, st, cp)) return (int)e;
   } else {
-    if (vec) cast_kernel<false, 4><<<cgrid, 256, 0, st>>>(cp); else cast_kernel<false, 1><<<cgrid, 256, 0, st>>>(cp);
+    if (cudaError_t e = launch_pdl(vec ? cast_kernel<false, 4> : cast_kernel<false, 1>, cgrid, dim3(256), 0, st, cp)) return (int)e;
   }
   if (!project) return (int)cudaGetLastError();
   if (!w_in_cast && !w_ready) {
@@ -343,7 +361,8 @@ static int cast_project_core(const void* v_a, const void* v_b, const float* w, u
   auto kern = bf16 ? project_mn_kernel<true> : project_mn_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kProjMnSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  kern<<<pp.num_tiles < sms ? pp.num_tiles : sms, kProjMnThreads, kProjMnSmemBytes, st>>>(tm_w, tm_x, pp);
+  if ((e = launch_pdl(kern, dim3(pp.num_tiles < sms ? pp.num_tiles : sms), dim3(kProjMnThreads), kProjMnSmemBytes, st, tm_w, tm_x, pp)) !=
+      cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
 }
 
@@ -500,7 +519,8 @@ static int launch_attend(const void* v_a, const void* v_b, void* cat_a, void* ca
     if (e2 != cudaSuccess) return (int)e2;
     int clusters = sms / 2;
     if (q.num_items * splits < clusters) clusters = q.num_items * splits;
-    kern2<<<2 * clusters, threads2, smem2, st>>>(tm_q, tm_k2, tm_v2, tm_v3, tm_w0, tm_w1, q);
+    if ((e2 = launch_pdl(kern2, dim3(2 * clusters), dim3(threads2), smem2, st, tm_q, tm_k2, tm_v2, tm_v3, tm_w0, tm_w1, q)) != cudaSuccess)
+      return (int)e2;
 #ifdef COATTN_TRACE2
     {
       static int calls = 0;
@@ -826,7 +846,8 @@ int launch_gemm(EncodeTiledFn enc, cudaStream_t st, const void* a, uint64_t a_ro
   auto kern = gemm_nt_kernel<MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
   if (e != cudaSuccess) return (int)e;
-  kern<<<dim3(m_tiles, n_tiles, batch * k_split), kNumThreads, kGemmSmemBytes, st>>>(ta, tb, gp);
+  if ((e = launch_pdl(kern, dim3(m_tiles, n_tiles, batch * k_split), dim3(kNumThreads), kGemmSmemBytes, st, ta, tb, gp)) != cudaSuccess)
+    return (int)e;
   return (int)cudaGetLastError();
 }
 
@@ -852,7 +873,7 @@ int launch_flash(cudaStream_t st, const FlashMaps& maps, FlashParams& fp, int sm
   int clusters = sms / 2;
   if (fp.items[0] + fp.items[1] < clusters) clusters = fp.items[0] + fp.items[1];
   if (clusters < 1) return COATTN_OK;
-  kern<<<2 * clusters, threads, kFSmemBytes, st>>>(maps, fp);
+  if ((e = launch_pdl(kern, dim3(2 * clusters), dim3(threads), kFSmemBytes, st, maps, fp)) != cudaSuccess) return (int)e;
 #ifdef COATTN_TRACE_FLASH
   {
     static int calls = 0;
@@ -928,8 +949,8 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   unsigned* absmax = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(seg(workspace, bl.off_dta)) + (size_t)n * ly.L);
   {
     unsigned short* w16 = reinterpret_cast<unsigned short*>(seg(workspace, ly.off_w16));
-    if (fbf16) bwd_init_kernel<true><<<kC, kC, 0, st>>>(w, wt, w16, d_w, d_gate_w, d_gate_b, absmax);
-    else bwd_init_kernel<false><<<kC, kC, 0, st>>>(w, wt, w16, d_w, d_gate_w, d_gate_b, absmax);
+    if (cudaError_t e = launch_pdl(fbf16 ? bwd_init_kernel<true> : bwd_init_kernel<false>, dim3(kC), dim3(kC), 0, st, w, wt, w16, d_w,
+                                   d_gate_w, d_gate_b, absmax)) return (int)e;
   }
   if (int e = cast_and_project_mn(v_a, v_b, w, workspace, workspace_bytes, n, c, h, w_,
                                   flags | kInternalNeedQ16 | kInternalW16Ready, stream)) return e;
@@ -945,7 +966,7 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
     cp.x = a16 - plane_elems;      // the kernel writes plane 1 of x
     cp.N = n; cp.L = L; cp.Lp = Lp; cp.Na = n; cp.status = nullptr; cp.first_plane = 1; cp.w = nullptr; cp.w16 = nullptr;
     const bool vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(v_a) & 15) == 0);
-    if (vec) cast_kernel<true, 4><<<dim3(n * kC, 1), 256, 0, st>>>(cp); else cast_kernel<true, 1><<<dim3(n * kC, 1), 256, 0, st>>>(cp);
+    if (cudaError_t e = launch_pdl(vec ? cast_kernel<true, 4> : cast_kernel<true, 1>, dim3(n * kC, 1), dim3(256), 0, st, cp)) return (int)e;
   }
   unsigned short* dza16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dza16));
   unsigned short* dzb16 = reinterpret_cast<unsigned short*>(seg(workspace, bl.off_dzb16));
@@ -962,9 +983,9 @@ int coattn_backward(const float* v_a, const float* v_b, const float* w, const fl
   bp.dza16 = dza16; bp.dzb16 = dzb16; bp.delta = delta; bp.d_ta = d_ta; bp.absmax = absmax;
   bp.d_gate_w = d_gate_w; bp.d_gate_b = d_gate_b; bp.d_va = d_v_a; bp.N = n; bp.L = L; bp.Lp = Lp;
   bp.cat_ch = (flags & COATTN_FLAG_GATED_ONLY) ? kC : 2 * kC;
-  bwd_stats_kernel<<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
-  if (fbf16) bwd_planes_kernel<true><<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
-  else bwd_planes_kernel<false><<<dim3(Lp / kBwdPrepPos, n), kBwdPrepThreads, 0, st>>>(bp);
+  if ((ce = launch_pdl(bwd_stats_kernel, dim3(Lp / kBwdPrepPos, n), dim3(kBwdPrepThreads), 0, st, bp)) != cudaSuccess) return (int)ce;
+  if ((ce = launch_pdl(fbf16 ? bwd_planes_kernel<true> : bwd_planes_kernel<false>, dim3(Lp / kBwdPrepPos, n), dim3(kBwdPrepThreads), 0, st,
+                       bp)) != cudaSuccess) return (int)ce;
   if ((ce = cudaGetLastError()) != cudaSuccess) return (int)ce;
 
   const uint64_t rowsL = (uint64_t)n * Lp, rowsC = (uint64_t)n * kC;

@@ -440,6 +440,7 @@ __device__ __forceinline__ void report_absmax(float m, bool nan, unsigned* statu
 
 template <bool BF16, int VEC>
 __global__ void __launch_bounds__(256) cast_kernel(CastParams p) {
+  pdl_wait();
   const int row = blockIdx.x;                 // n * C + c
   const int plane = blockIdx.y + p.first_plane;   // 0: V_b, 1: V_a
   if (p.w != nullptr && blockIdx.y == 0 && row < kC) p.w16[row * kC + threadIdx.x] = cvt16<BF16>(p.w[row * kC + threadIdx.x]);
@@ -585,6 +586,7 @@ __global__ void __launch_bounds__(kProjMnThreads, 1)
 project_mn_kernel(const __grid_constant__ CUtensorMap tmap_w,   // W16 [C][C], box {64, 128}
                   const __grid_constant__ CUtensorMap tmap_x,   // X [3*N*C][Lp], box {64, 256}
                   ProjectMnParams p) {
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_1024(smem_raw);
   uint8_t* sW = smem;                 // 2 m-tiles x 4 k-blocks x [128 rows x 128 B] = 128 KB

@@ -334,6 +334,14 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Programmatic dependent launch (a launch with cudaLaunchAttributeProgrammaticStreamSerialization is scheduled as soon as the
+// CTAs of its predecessor in the stream have exited, before that grid's completion has been processed): pdl_wait() returns
+// once the predecessor grids have COMPLETED and their writes are visible -- every kernel that can be launched that way calls
+// it before it touches global memory; a no-op in an ordinary launch.  Saves ~2 us per kernel boundary (16 us of a 465 us
+// backward call).  An explicit early griddepcontrol.launch_dependents was measured and is NOT used: the successor's CTAs
+// then take SM slots from the predecessor's last waves (+15 us per call instead of -16).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // named barrier + OR reduction of one predicate among `nthreads` threads (every participant gets the result)
 __device__ __forceinline__ bool named_bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
   uint32_t r;
