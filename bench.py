@@ -30,8 +30,10 @@ SIGMA = 0.66
 FLOPS_ATTEND_PER_PAIR_MODALITY = 6.0 * L * L * C
 FLOPS_PER_PAIR_MODALITY = FLOPS_ATTEND_PER_PAIR_MODALITY + 2.0 * L * C * C
 # one attend2 launch at batch 32, 60x60, fp16 operands, fp32 concat (ncu --set full; NOT re-measured by bench.py)
-ATTEND_TRAFFIC_BYTES = 868.3e6
-ATTEND_TRAFFIC_SOURCE = "profiles/r1_ncu_kernels.txt (ncu --set full: 440.3 MB read + 427.9 MB written; round-1 kernel)"
+ATTEND_TRAFFIC_BYTES = 795.4e6
+ATTEND_TRAFFIC_SOURCE = ("profiles/r2_ncu_kernels.txt, final section (ncu --set full of this kernel: 375.2 MB read + 420.2 MB written; "
+                         "algorithmic: 126 MB of 16-bit operand planes + 236 MB fp32 passthrough read, 472 MB concat written minus the "
+                         "padding rows)")
 # tensor-core flops the attend kernel executes per algorithmic flop: two symmetric passes (8 L^2 C for 6 L^2 C) x query
 # rows padded to 256-row tiles (3840 / 3600)
 EXECUTED_OVER_ALGORITHMIC = (8.0 / 6.0) * (3840.0 / 3600.0)
