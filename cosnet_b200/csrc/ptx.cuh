@@ -402,77 +402,4 @@ __device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-// Programmatic dependent launch (a launch with cudaLaunchAttributeProgrammaticStreamSerialization is scheduled as soon as the
-// CTAs of its predecessor in the stream have exited, before that grid's completion has been processed): pdl_wait() returns
-// once the predecessor grids have COMPLETED and their writes are visible -- every kernel that can be launched that way calls
-// it before it touches global memory; a no-op in an ordinary launch.  Saves ~2 us per kernel boundary (16 us of a 465 us
-// backward call).  An explicit early griddepcontrol.launch_dependents was measured and is NOT used: the successor's CTAs
-// then take SM slots from the predecessor's last waves (+15 us per call instead of -16).
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-// named barrier + OR reduction of one predicate among `nthreads` threads (every participant gets the result)
-__device__ __forceinline__ bool named_bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
-  uint32_t r;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %3, 0;\n\tbar.red.or.pred p, %1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(r)
-      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
-      : "memory");
-  return r != 0;
-}
-
-// two fp32 -> packed bf16x2 (lo = a, hi = b), round-to-nearest-even
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
-// two fp32 -> packed f16x2 (lo = a, hi = b), round-to-nearest-even, saturating to +-65504
-__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
-// format-generic helpers: BF16 = true -> bfloat16, false -> IEEE half (saturating)
-template <bool BF16>
-__device__ __forceinline__ uint32_t pack16x2(float a, float b) {
-  if constexpr (BF16) return pack_bf16x2(a, b);
-  else return pack_f16x2(a, b);
-}
-template <bool BF16>
-__device__ __forceinline__ unsigned short cvt16(float a) {
-  return static_cast<unsigned short>(pack16x2<BF16>(a, 0.0f) & 0xFFFFu);
-}
-__device__ __forceinline__ float bf16lo_to_f32(uint32_t p) { return __uint_as_float(p << 16); }
-__device__ __forceinline__ float bf16hi_to_f32(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// Packed fp32 pairs (sm_100: FFMA2 / FADD2 -- one issue slot for two results; each lane rounds like the scalar op).
-__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 }  // namespace coattn
