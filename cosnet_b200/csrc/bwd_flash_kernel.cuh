@@ -24,14 +24,16 @@
 // The depth modality (B branch gradient dead, :240-247) runs phase A only.
 //
 // Shared memory (per CTA): two RESIDENT row-side operand tiles R1 (S) and R2 (T), 64 KB each; a 2-slot ring of 32 KB
-// column-side operand halves (C1 and C2 of a tile alternate); one 32 KB V slot.  TMEM (per CTA): [0,256) O |
-// [256,384) S | [384,512) T.  X(j) is written over T once T(j) sits in registers: every warp over the first half of its own
-// T columns (a phase without T uses [384,448) and [448,512) as two alternating X buffers).
-// Tensor-pipe order inside a phase with T:  S(0) T(0) | S(1) PV(0) T(1) | S(2) PV(1) T(2) | ...
-//   S(j+1) only needs S(j) in registers and runs early; T(j+1) follows PV(j) IN THE PIPE (the MMAs of one issuing thread
-//   execute in order), which is what makes overwriting X(j) safe without a barrier.  The first version shared ONE buffer
-//   between S and T: every tile then paid two full MMA -> warps -> MMA round trips (6.0 k cycles per tile, clock64 trace in
-//   profiles/r2_bwd_flash_trace_v1.txt) for 3.1 k cycles of MMA.
+// column-side operand halves (C1 and C2 of a tile alternate); one 32 KB V slot (the T-less items that run last in a
+// cluster's list borrow the idle R2 for two more).  TMEM (per CTA): [0,256) O | [256,384) S | [384,512) T.
+// A phase with T: X(j) is written over the S BUFFER -- a warp turns T(j) into X(j) in registers (t_free: the T buffer goes
+// back), pulls S(j+1) into registers and stores X(j) over the first half of the S columns it has just read; a phase without
+// T uses [384,448) and [448,512) as two alternating X buffers.
+// Tensor-pipe order inside a phase with T:  S(0) T(0) S(1) | T(1) PV(0) S(2) | T(2) PV(1) S(3) | ...
+//   T(j+1) only needs T(j) in registers and runs while X(j) is produced; S(j+2) follows PV(j) -- the reader of X(j) -- IN THE
+//   PIPE (the MMAs of one issuing thread execute in order), which is what makes overwriting X(j) safe without a barrier.
+//   History (clock64 traces under profiles/): ONE buffer shared by S and T, 6.0 k cycles per tile for 3.1 k of MMA; separate
+//   buffers with X written over T (T(j+1) behind PV(j): the serial chain T -> X -> PV -> T), 4.5 k; this layout, 3.3 k.
 #pragma once
 #include "attend2_kernel.cuh"
 #include "backward_kernels.cuh"
@@ -59,8 +61,8 @@ constexpr int kFMaxPhases = 6;
 constexpr int kFMaps = 10;
 
 // Debug builds (-DCOATTN_TRACE_FLASH): clock64 stamps of cluster 0's second item, per column tile:
-//   MMA issuer  0 loop top | 1 S(j+1) issued | 2 v_full seen | 3 x_full seen (PV issue) | 4 T(j+1) issued
-//   softmax w0  8 S seen | 9 S in registers | 10 P done | 11 T seen | 12 X stored + arrived | 13 k_full wait of S (issuer) | 14 st_free wait
+//   MMA issuer  0 loop top | 1 T(j+1) issued | 2 v_full seen | 3 x_full seen (PV issue) | 4 S(j+2) issued
+//   X warp 0    9 S(j+1) in registers | 11 T(j) seen | 12 X stored + arrived        (phase with T; other slots: older layouts)
 #ifdef COATTN_TRACE_FLASH
 __device__ long long g_flash_trace[64 * 16];
 #define FTR(j, slot) do { if (blockIdx.x == 0 && lane == 0 && idx == 1 && (j) < 64) g_flash_trace[(j) * 16 + (slot)] = clock64(); } while (0)
