@@ -596,7 +596,7 @@ def run_ours(args):
 
     # the same through the gated-only contract (the consumer splits the reduce conv, so the passthrough
     # half of the concat -- a copy of the inputs the host already holds -- is neither produced nor sent back)
-    gpipe = HostPipeline(n, C, H, W, chunk=4, slots=4, device=dev, bf16_operands=bool(FLAGS & _lib.FLAG_BF16), gated_only=True)
+    gpipe = HostPipeline(n, C, H, W, chunk=8, slots=4, device=dev, bf16_operands=bool(FLAGS & _lib.FLAG_BF16), gated_only=True)
     gout = [torch.empty((n, C, H, W), dtype=torch.float32).pin_memory() for _ in range(4)]
 
     def e2e_gated_step():      # streamed: no join between the modality calls or the steps; every step moves its own bytes
@@ -668,7 +668,7 @@ def run_ours(args):
         io16_ms, e2e16_s = float(t[0].item()), float(t[1].item())
     same16 = bool(torch.equal(hout16[0], c16[0].cpu()) and torch.equal(hout16[3], c16[3].cpu()))
     # ... and with the gated-only contract on top (16-bit, no passthrough half on the wire): the least PCIe traffic per pair
-    gpipe16 = HostPipeline(n, C, H, W, chunk=4, slots=4, device=dev, feature_dtype=dt16, gated_only=True)
+    gpipe16 = HostPipeline(n, C, H, W, chunk=8, slots=4, device=dev, feature_dtype=dt16, gated_only=True)
     gout16 = [torch.empty((n, C, H, W), dtype=dt16).pin_memory() for _ in range(4)]
 
     def e2e16_gated_step():
@@ -732,7 +732,7 @@ def run_ours(args):
         "value": total_pairs * e2e_steps / e2e_gated_s, "unit": UNIT, "h2d_bytes_per_step": 2 * gpipe.h2d_bytes * world,
         "d2h_bytes_per_step": 2 * gpipe.d2h_bytes * world, "steps": e2e_steps, "matches_resident_path": same_gated,
         "h2d_GBps_per_gpu": gbps(2 * gpipe.h2d_bytes, e2e_gated_s), "d2h_GBps_per_gpu": gbps(2 * gpipe.d2h_bytes, e2e_gated_s),
-        "api": "cosnet_b200.coattention.HostPipeline(gated_only=True): pinned host in/out, 4 streams x chunks of 4 pairs, calls "
+        "api": "cosnet_b200.coattention.HostPipeline(gated_only=True): pinned host in/out, 4 streams x chunks of 8 pairs (tools/e2e_sweep_streamed.py: +8 % over chunks of 4), calls "
                "streamed back to back (join=False) and joined once before the clock stops; "
                "outputs = Z * sigmoid(gate(Z)) [n,256,h,w]; the concat's passthrough half is the caller's own input tensor "
                "and is not copied back",
