@@ -527,7 +527,7 @@ class HostPipeline:
     traffic for host memory bandwidth, so it stays opt-in.
     """
 
-    def __init__(self, n: int, c: int, h: int, w: int, chunk: int = 4, slots: int = 3, device="cuda:0",
+    def __init__(self, n: int, c: int, h: int, w: int, chunk: int = 8, slots: int = 4, device="cuda:0",
                  bf16_operands: bool = False, host_passthrough: bool = False, gated_only: bool = False,
                  feature_dtype: torch.dtype = torch.float32):
         self.n, self.c, self.h, self.w = n, c, h, w
