@@ -345,3 +345,61 @@ def test_backward_reuses_the_forward_planes_bit_exactly(coattention):
     ref = orc.coattention_grads(v_a, v_b, W, g, b, ra.cpu().numpy(), rb.cpu().numpy(), counterpart_grad=False)
     assert rel_l2(outs[1][0].cpu().numpy(), ref["d_v_a"]) < GRAD_TOL
     assert rel_l2(outs[1][3].cpu().numpy(), ref["d_w"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("has_b,counterpart", [(True, False), (False, False), (True, True)])
+def test_batch_of_eight_equals_eight_single_sample_calls(coattention, has_b, counterpart):
+    """cfg 5's shape (8 pairs, 60x60): every CTA pair of bwd_flash then runs SEVERAL work items in a row (two long dQ items,
+    then T-less ones that borrow the R2 tile) -- the regime in which hand-off bugs between items show, and which the small
+    shapes never reach.  The feature gradient of every sample must equal, bit for bit, the one a single-sample call produces
+    (fixed accumulation order; the per-call power-of-two scale of the fp16 gradient operands cancels exactly)."""
+    from cosnet_b200 import _lib
+    from cosnet_b200.coattention import backward_workspace_bytes
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    n, h, w, C = 8, 60, 60, 256
+    L = h * w
+    gen = torch.Generator(device=dev); gen.manual_seed(11)
+    feats = lambda: torch.nn.functional.prelu(torch.randn((n, C, h, w), generator=gen, device=dev), torch.tensor([0.25], device=dev)) * 0.66
+    va, vb = feats(), feats()
+    wt = (torch.rand((C, C), generator=gen, device=dev) * 2 - 1) / 16
+    gw = torch.randn((C,), generator=gen, device=dev) * 0.01
+    gb = torch.zeros(1, device=dev)
+    ra = torch.randn((n, 2 * C, h, w), generator=gen, device=dev) * 1e-3
+    rb = torch.randn((n, 2 * C, h, w), generator=gen, device=dev) * 1e-3
+    ra[:, 0, 0, 0] = 0.0078125      # the same largest cotangent in every sample: the same scale in every call
+    st = torch.cuda.current_stream(dev).cuda_stream
+    P = lambda x: None if x is None else x.data_ptr()
+
+    def run(lo, hi):
+        m = hi - lo
+        nbb = backward_workspace_bytes(m, C, h, w, False)
+        ws = torch.empty(nbb + 1024, dtype=torch.uint8, device=dev)
+        wsp = (ws.data_ptr() + 1023) // 1024 * 1024
+        a, b_ = va[lo:hi].contiguous(), vb[lo:hi].contiguous()
+        ca, cb = torch.empty((m, 2 * C, h, w), device=dev), torch.empty((m, 2 * C, h, w), device=dev)
+        z, lse, mask = torch.empty((2, m, C, L), device=dev), torch.empty((2, m, L), device=dev), torch.empty((2, m, L), device=dev)
+        _lib.check(lib.coattn_status_clear(wsp, st), "clear")
+        _lib.check(lib.coattn_forward(P(a), P(b_), P(wt), P(gw), P(gb), P(ca), P(cb), P(z), P(lse), P(mask), wsp, nbb, m, C, h, w,
+                                      0, st), "fwd")
+        dva, dw = torch.empty((m, C, h, w), device=dev), torch.empty((C, C), device=dev)
+        dgw, dgb = torch.empty(C, device=dev), torch.empty(1, device=dev)
+        r_a, r_b = ra[lo:hi].contiguous(), rb[lo:hi].contiguous()
+        dvb = torch.empty((m, C, h, w), device=dev) if counterpart else None      # (:147-148: the three-phase frame-B items)
+        _lib.check(lib.coattn_backward(P(a), P(b_), P(wt), P(gw), P(z), P(lse), P(mask), P(r_a), P(r_b) if has_b else None, P(dva),
+                                       P(dvb), P(dw), P(dgw), P(dgb), wsp, nbb, m, C, h, w, _lib.FLAG_PLANES_READY, st), "bwd")
+        torch.cuda.synchronize()
+        return dva, dw, dgw, dvb
+
+    dva8, dw8, dgw8, dvb8 = run(0, n)
+    assert torch.isfinite(dva8).all() and torch.isfinite(dw8).all()
+    dw_sum, dgw_sum = torch.zeros_like(dw8), torch.zeros_like(dgw8)
+    for i in range(n):
+        dva1, dw1, dgw1, dvb1 = run(i, i + 1)
+        assert torch.equal(dva1[0], dva8[i]), f"sample {i}: max abs diff {float((dva1[0] - dva8[i]).abs().max())}"
+        if counterpart:
+            assert torch.equal(dvb1[0], dvb8[i]), f"sample {i}: d_v_b max abs diff {float((dvb1[0] - dvb8[i]).abs().max())}"
+        dw_sum += dw1
+        dgw_sum += dgw1
+    assert float((dw8 - dw_sum).norm() / dw_sum.norm()) < 1e-5
+    assert float((dgw8 - dgw_sum).norm() / dgw_sum.norm()) < 1e-5
