@@ -347,8 +347,9 @@ def test_backward_reuses_the_forward_planes_bit_exactly(coattention):
     assert rel_l2(outs[1][3].cpu().numpy(), ref["d_w"]) < GRAD_TOL
 
 
-@pytest.mark.parametrize("has_b,counterpart", [(True, False), (False, False), (True, True)])
-def test_batch_of_eight_equals_eight_single_sample_calls(coattention, has_b, counterpart):
+@pytest.mark.parametrize("has_b,counterpart,n,h,w", [(True, False, 8, 60, 60), (False, False, 8, 60, 60), (True, True, 8, 60, 60),
+                                                      (True, False, 4, 61, 107), (True, True, 3, 61, 81)])
+def test_batch_of_eight_equals_eight_single_sample_calls(coattention, has_b, counterpart, n, h, w):
     """cfg 5's shape (8 pairs, 60x60): every CTA pair of bwd_flash then runs SEVERAL work items in a row (two long dQ items,
     then T-less ones that borrow the R2 tile) -- the regime in which hand-off bugs between items show, and which the small
     shapes never reach.  The feature gradient of every sample must equal, bit for bit, the one a single-sample call produces
@@ -357,7 +358,7 @@ def test_batch_of_eight_equals_eight_single_sample_calls(coattention, has_b, cou
     from cosnet_b200.coattention import backward_workspace_bytes
     lib = _lib.load()
     dev = torch.device("cuda:0")
-    n, h, w, C = 8, 60, 60, 256
+    C = 256      # (4, 61, 107) and (3, 61, 81): odd L (scalar load paths, ragged last tiles) with several items per CTA pair
     L = h * w
     gen = torch.Generator(device=dev); gen.manual_seed(11)
     feats = lambda: torch.nn.functional.prelu(torch.randn((n, C, h, w), generator=gen, device=dev), torch.tensor([0.25], device=dev)) * 0.66
