@@ -38,14 +38,22 @@ class _Workspace:
         self.host = None if torch.cuda.is_current_stream_capturing() else torch.zeros(_lib.STATUS_WORDS, dtype=torch.int32).pin_memory()
         self.event = None
         self._event = None
+        self.stream_obj = None      # the Stream this entry is keyed on (eager cache only), for post_call without a lookup
 
     def numel(self):
         return self.buf.numel()
 
-    def post_call(self, stream):
-        """Queue the status read-back of the call just issued on `stream` (lazy / sync modes)."""
-        if OVERFLOW_CHECK == "off" or self.host is None or torch.cuda.is_current_stream_capturing():
+    def post_call(self, stream=None, capturing=None):
+        """Queue the status read-back of the call just issued on `stream` (lazy / sync modes).  stream=None: the stream this
+        entry is keyed on, which is the current one; capturing: the caller's answer to is_current_stream_capturing()."""
+        if OVERFLOW_CHECK == "off" or self.host is None:
             return
+        if torch.cuda.is_current_stream_capturing() if capturing is None else capturing:
+            return
+        if stream is None:
+            stream = self.stream_obj
+            if stream is None:
+                stream = self.stream_obj = torch.cuda.current_stream(self.buf.device)
         self.host.copy_(self.status, non_blocking=True)
         if self._event is None:
             self._event = torch.cuda.Event()
@@ -99,7 +107,8 @@ class capture_scope:
         _capture_local.cache = None
 
 
-def _workspace_entry(device: torch.device, nbytes: int, tag=None, cur=None) -> _Workspace:
+def _workspace_entry(device: torch.device, nbytes: int, tag=None, cur=None, raw=None) -> _Workspace:
+    """raw: the current stream's handle when the caller has it already (saves building a Stream object per call)."""
     if torch.cuda.is_current_stream_capturing():
         # a buffer allocated during capture lives in the graph's private pool: never cache it for eager use
         scope = getattr(_capture_local, "cache", None)
@@ -109,14 +118,16 @@ def _workspace_entry(device: torch.device, nbytes: int, tag=None, cur=None) -> _
         if ent is None or ent.numel() < nbytes + 1024:
             ent = scope[tag] = _Workspace(device, nbytes)
         return ent
-    key = (device.index if device.index is not None else torch.cuda.current_device(),
-           (cur if cur is not None else torch.cuda.current_stream(device)).cuda_stream, threading.get_ident(), tag)
+    if raw is None:
+        raw = (cur if cur is not None else torch.cuda.current_stream(device)).cuda_stream
+    key = (device.index if device.index is not None else torch.cuda.current_device(), raw, threading.get_ident(), tag)
     with _ws_lock:
         ent = _ws_cache.get(key)
     if ent is not None:
         ent.raise_if_clipped()
     if ent is None or ent.numel() < nbytes + 1024:
         ent = _Workspace(device, nbytes)
+        ent.stream_obj = cur
         with _ws_lock:
             _ws_cache[key] = ent
     return ent
@@ -153,6 +164,23 @@ def release_workspaces(device=None):
 def _aligned_ptr(buf: torch.Tensor) -> int:
     p = buf.data_ptr()
     return (p + 1023) // 1024 * 1024
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on_device(dev: torch.device):
+    """Device guard that costs nothing when `dev` is current already (the usual case; `torch.cuda.device` is ~4 us of
+    host time per modality call, which matters at batch 1 where a call is ~55 us of GPU time)."""
+    return _NO_GUARD if torch._C._cuda_getDevice() == dev.index else torch.cuda.device(dev)
 
 
 def _f32(t, dev):
@@ -193,9 +221,9 @@ def _check_inputs(v_a, v_b, weight, gate_weight, gate_bias):
 
 def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=False,
                             unfused_gate=False, want_mask=False, want_z=True, single_cta=False, a_only=False, unfused_prep=False, gated_only=False, kmajor=False,
-                            softmax16=False, split_keys=False, unfolded=False):
+                            softmax16=False, split_keys=False, unfolded=False, want_lse=True):
     """Runs the CUDA stages.  Returns (cat_a, cat_b, z, lse) with z [2,N,C,L] and lse [2,N,L]
-    (plus mask [2,N,L] when want_mask=True; fused path only).
+    (plus mask [2,N,L] when want_mask=True; fused path only); z / lse are None with want_z / want_lse False.
 
     bf16_operands=False (default): fp16 tensor-core operands with fp32 accumulation (COATTN_FLAG_BF16 unset);
     True: bf16 operands (see include/coattn_b200.h for the trade-off).
@@ -206,7 +234,7 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
     n, c, h, w = _check_inputs(v_a, v_b, weight, gate_weight, gate_bias)
     lib = _lib.load()
     dev = v_a.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         v_a = v_a.contiguous()
         v_b = v_b.contiguous()
         wt = _f32(weight, dev)
@@ -216,25 +244,29 @@ def coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_
         cat_a = torch.empty((n, oc, h, w), dtype=torch.float32, device=dev)
         cat_b = None if a_only else torch.empty((n, oc, h, w), dtype=torch.float32, device=dev)
         z = torch.empty((2, n, c, h * w), dtype=torch.float32, device=dev) if (want_z or unfused_gate) else None
-        lse = torch.empty((2, n, h * w), dtype=torch.float32, device=dev)
+        # want_lse=False (inference): the library keeps the row statistics in its workspace segment instead
+        lse = torch.empty((2, n, h * w), dtype=torch.float32, device=dev) if (want_lse or unfused_gate or split_keys) else None
         nbytes = _workspace_bytes_cached(n, c, h, w)
-        cur = torch.cuda.current_stream(dev)
-        ws = _workspace_entry(dev, nbytes, cur=cur)
-        stream = cur.cuda_stream
+        stream = torch._C._cuda_getCurrentRawStream(dev.index)      # the handle only: no Stream object per call
+        capturing = torch.cuda.is_current_stream_capturing()
+        ws = _workspace_entry(dev, nbytes, raw=stream) if not capturing else _workspace_entry(dev, nbytes)
         mask = torch.empty((2, n, h * w), dtype=torch.float32, device=dev) if want_mask else None
-        flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)
-                 | (_lib.FLAG_SINGLE_CTA if single_cta else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
-                 | (_lib.FLAG_UNFUSED_PREP if unfused_prep else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0) | (_lib.FLAG_KMAJOR if kmajor else 0) | (_lib.FLAG_SOFTMAX16 if softmax16 else 0)
-                 | (_lib.FLAG_SPLIT_KEYS if split_keys else 0) | (_lib.FLAG_UNFOLDED if unfolded else 0))
+        flags = 0
+        if bf16_operands or unfused_gate or single_cta or a_only or unfused_prep or gated_only or kmajor or softmax16 or split_keys or unfolded:
+            flags = ((_lib.FLAG_BF16 if bf16_operands else 0) | (_lib.FLAG_UNFUSED_GATE if unfused_gate else 0)
+                     | (_lib.FLAG_SINGLE_CTA if single_cta else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
+                     | (_lib.FLAG_UNFUSED_PREP if unfused_prep else 0) | (_lib.FLAG_GATED_ONLY if gated_only else 0) | (_lib.FLAG_KMAJOR if kmajor else 0) | (_lib.FLAG_SOFTMAX16 if softmax16 else 0)
+                     | (_lib.FLAG_SPLIT_KEYS if split_keys else 0) | (_lib.FLAG_UNFOLDED if unfolded else 0))
         code = lib.coattn_forward(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
                                   None if gb is None else gb.data_ptr(), cat_a.data_ptr(),
                                   None if cat_b is None else cat_b.data_ptr(),
-                                  None if z is None else z.data_ptr(), lse.data_ptr(),
+                                  None if z is None else z.data_ptr(), None if lse is None else lse.data_ptr(),
                                   None if mask is None else mask.data_ptr(),
                                   ws.ptr, nbytes, n, c, h, w, flags, stream)
-        _lib.check(code, "coattn_forward")
+        if code:
+            _lib.check(code, "coattn_forward")
         if not bf16_operands:
-            ws.post_call(cur)
+            ws.post_call(capturing=capturing)
     if want_mask:
         return cat_a, cat_b, z, lse, mask
     return cat_a, cat_b, z, lse
@@ -298,11 +330,11 @@ def coattention_forward16_raw(v_a, v_b, weight, gate_weight, gate_bias=None, ref
     a_only = a_only or refs > 1
     lib = _lib.load()
     dev = v_a.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         v_a = v_a.contiguous(); v_b = v_b.contiguous()
-        wt = weight.detach().to(device=dev, dtype=torch.float32).contiguous()
-        gw = gate_weight.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
-        gb = None if gate_bias is None else gate_bias.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
+        wt = _f32(weight, dev)
+        gw = _f32(gate_weight, dev).view(-1)
+        gb = None if gate_bias is None else _f32(gate_bias, dev).view(-1)
         n = nq * refs
         oc = c if gated_only else 2 * c
         cat_a = torch.empty((n, oc, h, w), dtype=v_a.dtype, device=dev)
@@ -310,19 +342,21 @@ def coattention_forward16_raw(v_a, v_b, weight, gate_weight, gate_bias=None, ref
         passes = 1 if a_only else 2
         lse = torch.empty((passes, n, h * w), dtype=torch.float32, device=dev) if want_lse else None
         mask = torch.empty((passes, n, h * w), dtype=torch.float32, device=dev) if want_lse else None
-        nbytes = workspace_bytes(n, c, h, w)
-        ws = _workspace_entry(dev, nbytes)
+        nbytes = _workspace_bytes_cached(n, c, h, w)
+        stream = torch._C._cuda_getCurrentRawStream(dev.index)
+        capturing = torch.cuda.is_current_stream_capturing()
+        ws = _workspace_entry(dev, nbytes, raw=stream) if not capturing else _workspace_entry(dev, nbytes)
         flags = ((_lib.FLAG_BF16 if v_a.dtype == torch.bfloat16 else 0) | (_lib.FLAG_A_ONLY if a_only else 0)
                  | (_lib.FLAG_GATED_ONLY if gated_only else 0))
         code = lib.coattn_forward16(v_a.data_ptr(), v_b.data_ptr(), wt.data_ptr(), gw.data_ptr(),
                                     None if gb is None else gb.data_ptr(), cat_a.data_ptr(),
                                     None if cat_b is None else cat_b.data_ptr(),
                                     None if lse is None else lse.data_ptr(), None if mask is None else mask.data_ptr(),
-                                    ws.ptr, nbytes, nq, refs, c, h, w, flags,
-                                    torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(code, "coattn_forward16")
+                                    ws.ptr, nbytes, nq, refs, c, h, w, flags, stream)
+        if code:
+            _lib.check(code, "coattn_forward16")
         if v_a.dtype == torch.float16:
-            ws.post_call(torch.cuda.current_stream(dev))
+            ws.post_call(capturing=capturing)
     if want_lse:
         return cat_a, cat_b, lse, mask
     return cat_a, cat_b
@@ -462,7 +496,7 @@ def coattention(v_a, v_b, weight, gate_weight, gate_bias=None, bf16_operands=Fal
     if needs_grad:
         return _CoAttentionFn.apply(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands, gated_only)
     cat_a, cat_b, _, _ = coattention_forward_raw(v_a, v_b, weight, gate_weight, gate_bias, bf16_operands, want_z=False,
-                                                 gated_only=gated_only)
+                                                 gated_only=gated_only, want_lse=False)
     return cat_a, cat_b
 
 
@@ -501,8 +535,11 @@ def run_modalities(rgb_call, depth_call, depth_inputs, overlap: bool):
     cur = torch.cuda.current_stream(dev)
     side = _side_stream(dev)
     side.wait_stream(cur)
-    with torch.cuda.stream(side):
+    torch.cuda.set_stream(side)      # same device: cheaper than the `torch.cuda.stream` context (host time counts at batch 1)
+    try:
         d_out = depth_call()
+    finally:
+        torch.cuda.set_stream(cur)
     r_out = rgb_call()
     cur.wait_stream(side)
     for t in depth_inputs:

@@ -436,10 +436,7 @@ static int launch_attend(const void* v_a, const void* v_b, void* cat_a, void* ca
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return COATTN_E_DRIVER;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CUtensorMap tm_k, tm_v;
   const uint64_t t_rows = (uint64_t)2 * n * ly.Lp;
-  if (int e = make_tmap(enc, &tm_k, seg(workspace, ly.off_t), t_rows, kC, kBN, bf16)) return e;
-  if (int e = make_tmap(enc, &tm_v, seg(workspace, ly.off_vv), (uint64_t)2 * n * kC, ly.Lp, kC, bf16)) return e;
   if (!(flags & COATTN_FLAG_SINGLE_CTA)) {
     // default: CTA-pair kernel (cluster of 2, tcgen05 cta_group::2)
     const bool mn = !(flags & (COATTN_FLAG_KMAJOR | COATTN_FLAG_UNFUSED_PREP));
@@ -558,6 +555,9 @@ static int launch_attend(const void* v_a, const void* v_b, void* cat_a, void* ca
     return (int)cudaGetLastError();
   }
   if (flags & (COATTN_FLAG_A_ONLY | COATTN_FLAG_GATED_ONLY)) return COATTN_E_UNSUPPORTED;   // cross-check kernel: full concat only
+  CUtensorMap tm_k, tm_v;
+  if (int e = make_tmap(enc, &tm_k, seg(workspace, ly.off_t), t_rows, kC, kBN, bf16)) return e;
+  if (int e = make_tmap(enc, &tm_v, seg(workspace, ly.off_vv), (uint64_t)2 * n * kC, ly.Lp, kC, bf16)) return e;
   AttendParams p;
   p.t = reinterpret_cast<const unsigned short*>(seg(workspace, ly.off_t));
   p.z = z;

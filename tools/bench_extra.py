@@ -91,11 +91,11 @@ def main():
         from cosnet_b200.coattention import run_modalities
         def step():
             if args.two_streams:      # what the drop-in module's eval forward does at this size
-                return run_modalities(lambda: coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False, split_keys=sk),
-                                      lambda: coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, split_keys=sk),
+                return run_modalities(lambda: coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False, want_lse=False, split_keys=sk),
+                                      lambda: coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, want_lse=False, split_keys=sk),
                                       (da, db), True)
-            coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False, split_keys=sk)
-            coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, split_keys=sk)
+            coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False, want_lse=False, split_keys=sk)
+            coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, want_lse=False, split_keys=sk)
         pairs = n
         desc = ("one frame pair per step (60x60x256, RGB + depth call)" + (", COATTN_FLAG_SPLIT_KEYS" if sk else ", default path")
                 + (", eager calls on two streams" if args.two_streams else ""))
