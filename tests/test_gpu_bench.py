@@ -27,6 +27,9 @@ def test_bench_line_has_the_contract_keys():
     rf = d["roofline"]
     assert rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s" and 0.2 < rf["frac"] < 1.0
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert rf["launches_timed"] >= 2 and rf["events_on_every_kth_step"] >= 1
+    ep = d["epilogue_roofline"]      # stand-alone gate / concat kernel, timed first (cool part): HBM-bound
+    assert ep["bound"] == "hbm" and 0.6 < ep["frac"] < 1.05
     e = d["e2e"]
     # headline e2e contract: the gated half comes back, the passthrough half is the caller's own input (not copied)
     assert e["h2d_bytes_per_step"] == 4 * 32 * 256 * 3600 * 4 and e["d2h_bytes_per_step"] == e["h2d_bytes_per_step"]
