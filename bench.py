@@ -349,15 +349,17 @@ def extra_workloads(args, dev, world, rank, barrier):
                          dw=torch.empty((C, C), device=dev), dgw=torch.empty((C,), device=dev), dgb=torch.empty((1,), device=dev)))
     fwd_ev = []
 
+    op5 = [0]      # operand format of the step: 0 = fp16 (default), _lib.FLAG_BF16 = bf16 (BASELINE cfg 5 says "bf16")
+
     def fwd5(m, wsp, st):
         _lib.check(lib.coattn_forward(P(m["a"]), P(m["b"]), P(m["w"]), P(m["gw"]), P(m["gb"]), P(m["ca"]), P(m["cb"]),
-                                      P(m["z"]), P(m["lse"]), P(m["mask"]), wsp, nb_f, n, C, h, w, 0, st), "coattn_forward")
+                                      P(m["z"]), P(m["lse"]), P(m["mask"]), wsp, nb_f, n, C, h, w, op5[0], st), "coattn_forward")
 
     def bwd5(m, wsp, st):
         _lib.check(lib.coattn_backward(P(m["a"]), P(m["b"]), P(m["w"]), P(m["gw"]), P(m["z"]), P(m["lse"]), P(m["mask"]),
                                        P(ra), P(rb) if m["has_b"] else None, P(m["dva"]), None, P(m["dw"]), P(m["dgw"]),
                                        P(m["dgb"]) if m["gb"] is not None else None, wsp, nb_b, n, C, h, w,
-                                       _lib.FLAG_PLANES_READY, st),      # the forward above ran on this very workspace
+                                       _lib.FLAG_PLANES_READY | op5[0], st),      # the forward above ran on this very workspace
                    "coattn_backward")
 
     def step5(record=False):
@@ -388,6 +390,9 @@ def extra_workloads(args, dev, world, rank, barrier):
             marks.append((s0, fwd_ev[-1], s1))
         torch.cuda.synchronize()
         bwd_ms = sorted(m[1].elapsed_time(m[2]) for m in marks)[1]
+    op5[0] = _lib.FLAG_BF16      # the same step with bf16 operands (forward and backward)
+    ms_bf = _timed(step5, steps, 3, dev, world, barrier)
+    op5[0] = 0
     L5 = h * w
     bwd_flops = n * (8.0 + 4.0) * L5 * L5 * C        # algorithmic: 8 L^2 C (RGB, counterpart frozen) + 4 L^2 C (depth), SURVEY 7.3-4
     out["cfg5_train_step_8pairs"] = {
@@ -395,6 +400,7 @@ def extra_workloads(args, dev, world, rank, barrier):
         "pairs_per_gpu": n, "feat_hw": [h, w], "backward_ms": bwd_ms,
         "backward_tflops_algorithmic": bwd_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms else None,
         "backward_workspace_bytes": nb_b, "forward_workspace_bytes": nb_f,
+        "operands_bf16": {"value": n * world * steps / (ms_bf * 1e-3), "unit": UNIT, "ms_per_step": ms_bf / steps},
         "note": "coattn_forward + coattn_backward of both modalities through the C ABI (preallocated buffers, one workspace per "
                 "modality shared by its forward and backward: COATTN_FLAG_PLANES_READY, the backward reuses the forward's 16-bit "
                 "planes; RGB and depth on two streams, joined before the collective), then one NCCL all-reduce of the 131 585 hot-path gradients; includes "
