@@ -85,3 +85,33 @@ def test_inference_helper_is_identical_with_and_without_overlap(monkeypatch):
         got = inference.segment_with_references(model, tgt, tgt_d, refs, refs_d)
         torch.cuda.synchronize()
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("n,h,w,gated", [(1, 60, 60, False), (2, 12, 11, False), (3, 20, 17, True)])
+def test_coattention_pair_equals_two_calls(n, h, w, gated):
+    """`coattention_pair` (RGB call on the current stream, depth call on a side stream by handle) returns the bits of two
+    plain `coattention()` calls -- also when it is called repeatedly (workspace / event reuse) and on a non-default stream."""
+    from cosnet_b200 import coattention, coattention_pair
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev); gen.manual_seed(77 + n)
+    feats = [torch.randn(n, 256, h, w, generator=gen, device=dev) * 0.66 for _ in range(4)]
+    W = [torch.randn(256, 256, generator=gen, device=dev) / 16 for _ in range(2)]
+    G = [torch.randn(256, generator=gen, device=dev) * 0.05 for _ in range(2)]
+    b = torch.randn(1, generator=gen, device=dev) * 0.1
+    with torch.no_grad():
+        ref_rgb = coattention(feats[0], feats[1], W[0], G[0], None, gated_only=gated)
+        ref_dep = coattention(feats[2], feats[3], W[1], G[1], b, gated_only=gated)
+        for stream in (None, torch.cuda.Stream(dev)):
+            ctx = torch.cuda.stream(stream) if stream is not None else torch.no_grad()
+            if stream is not None:
+                stream.wait_stream(torch.cuda.current_stream(dev))
+            with ctx:
+                for _ in range(3):
+                    rgb, dep = coattention_pair((feats[0], feats[1], W[0], G[0], None), (feats[2], feats[3], W[1], G[1], b),
+                                                gated_only=gated)
+                    # consumer kernels on the calling stream right behind the call: both results must be complete there
+                    s_rgb = [t.clone() for t in rgb]
+                    s_dep = [t.clone() for t in dep]
+            torch.cuda.synchronize()
+            for got, ref in zip(s_rgb + s_dep, list(ref_rgb) + list(ref_dep)):
+                assert torch.equal(got, ref)

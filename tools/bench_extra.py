@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pairs", type=int, default=0, help="hd: pairs per GPU instead of 16 (cfg 3 strong-scaled over 8 GPUs = 2)")
+    ap.add_argument("--pair-call", action="store_true", help="latency + --two-streams: both modality calls through coattention_pair")
     ap.add_argument("--two-streams", action="store_true", help="hd / inference: the depth modality call runs on a second "
                     "stream, so its CTA pairs back-fill the tail wave of the RGB attend kernel")
     args = ap.parse_args()
@@ -90,6 +91,9 @@ def main():
         sk = args.workload == "latency_split"
         from cosnet_b200.coattention import run_modalities
         def step():
+            if args.two_streams and args.pair_call:      # both calls through coattention_pair (streams by handle)
+                from cosnet_b200 import coattention_pair
+                return coattention_pair((va, vb, W[0], G[0], None), (da, db, W[1], G[1], Bd))
             if args.two_streams:      # what the drop-in module's eval forward does at this size
                 return run_modalities(lambda: coattention_forward_raw(va, vb, W[0], G[0], None, want_z=False, want_lse=False, split_keys=sk),
                                       lambda: coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, want_lse=False, split_keys=sk),
@@ -98,7 +102,7 @@ def main():
             coattention_forward_raw(da, db, W[1], G[1], Bd, want_z=False, want_lse=False, split_keys=sk)
         pairs = n
         desc = ("one frame pair per step (60x60x256, RGB + depth call)" + (", COATTN_FLAG_SPLIT_KEYS" if sk else ", default path")
-                + (", eager calls on two streams" if args.two_streams else ""))
+                + (", eager calls on two streams" if args.two_streams else "") + (" through coattention_pair" if args.pair_call else ""))
     elif args.workload == "latency_graph":
         # the same single pair through GraphedCoAttention: one graph launch per step (host time included, like `latency`)
         from cosnet_b200.graphed import GraphedCoAttention
