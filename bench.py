@@ -573,7 +573,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     # ---------------- end to end: host buffers in, host buffers out, through the public host API
-    e2e_steps = max(4, min(args.steps, 10))
+    e2e_steps = max(4, min(args.steps, 20))      # the streamed legs pay one chunk of pipeline fill / drain per leg, not per step
     pipe = HostPipeline(n, C, H, W, chunk=4, slots=3, device=dev, bf16_operands=bool(FLAGS & _lib.FLAG_BF16))
     hin = [t.cpu().pin_memory() for t in (v_a, v_b, d_a, d_b)]
     hout = [torch.empty((n, 2 * C, H, W), dtype=torch.float32).pin_memory() for _ in range(4)]
