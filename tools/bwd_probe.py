@@ -30,7 +30,7 @@ ws = torch.empty(max(nbf, nbb) + 1024, dtype=torch.uint8, device=dev)
 wsp = (ws.data_ptr() + 1023) // 1024 * 1024
 st = torch.cuda.current_stream(dev).cuda_stream
 P = lambda t: None if t is None else t.data_ptr()
-_lib.check(lib.coattn_forward(P(va), P(vb), P(W), P(gw), P(gb), P(ca), P(cb), P(z), P(lse), P(mask), wsp, nbf, n, C, h, w, 0, st), "fwd")
+_lib.check(lib.coattn_forward(P(va), P(vb), P(W), P(gw), P(gb), P(ca), P(cb), P(z), P(lse), P(mask), wsp, nbf, n, C, h, w, bflags & 1, st), "fwd")      # bit 0 = COATTN_FLAG_BF16: forward and backward in one format
 for has_b in (True, False):
     for r in range(reps + 2):
         if r == 2:
