@@ -343,15 +343,15 @@ attend2_kernel(const __grid_constant__ CUtensorMap tmap_q,  // !MN: T [2*N*Lp][C
           }
         } else {
 #pragma unroll 1
-          for (int c = 0; c < kC; c += 2) {
-            Elem t[8];
+          for (int c = 0; c < kC; c += 4) {
+            Elem t[16];      // four channels x four row groups in flight
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 16; ++u) {
               const int r = row0 + (u & 3) * 32 + lane;
               t[u] = (r < p.L) ? __ldcs(src + (size_t)(c + (u >> 2)) * p.L + r) : Elem(0);
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 16; ++u) {
               const int r = row0 + (u & 3) * 32 + lane;
               if (r < p.L) __stcs(dst + (size_t)(c + (u >> 2)) * p.L + r, t[u]);
             }
